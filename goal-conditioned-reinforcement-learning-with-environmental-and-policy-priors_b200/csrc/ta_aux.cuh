@@ -1,0 +1,219 @@
+// ta_aux.cuh -- reset / observe / state export-import / featurise kernels.
+//
+//   reset_*            MiniGridEnv.reset             gym_minigrid/minigrid.py:947-980
+//                      Twoarmy_v4._gen_grid          gym_minigrid/envs/twoarmy_v4.py:38-80
+//                      Twoarmy_v4.__init__ (hard)    gym_minigrid/envs/twoarmy_v4.py:9-36
+//   observe_kernel     MiniGridEnv.gen_obs           gym_minigrid/minigrid.py:1443-1496
+//   state_matrix_*     Env_transact.matrix_env       soa/env_buffer.py:300-318
+//                      Env_transact.data_env         soa/env_buffer.py:320-334
+//   stack_roll_kernel  frame-stack roll              soa/train_ppo.py:116-121,
+//                      np.tile at episode start      soa/env_buffer.py:420-423
+#pragma once
+#include "ta_common.cuh"
+
+namespace ta {
+
+// One thread per (env, cell): rebuild the grid of masked envs.
+__global__ void reset_grid_kernel(uint8_t *grid, const uint8_t *mask, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * NCELL) return;
+    const long long e = i / NCELL;
+    if (mask && !mask[e]) return;
+    const int c = (int)(i - e * NCELL);
+    grid[i] = (uint8_t)initial_cell(c / GS, c % GS);  // column-major: c = x*17 + y
+}
+
+// One thread per env: agent, step_count, ball objects; hard also re-runs __init__'s flags.
+__global__ void reset_scalar_kernel(uint4 *sc0, uint4 *sc1, const uint8_t *mask, int hard, long long n) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mask && !mask[e]) return;
+    uint4 s0 = sc0[e], s1 = sc1[e];
+    uint32_t fl = (s0.x >> 16) & 0xFFu, risk = s0.x >> 24, err = (s1.w >> 16) & 0xFFu;
+    if (hard) {
+        fl = FLAGS_INIT;
+        risk = 0;
+        err = 0;
+        s0.z = 0;  // step_move
+    }
+    s0.x = 3u | (15u << 8) | (fl << 16) | (risk << 24);
+    s0.y = 0;  // step_count
+    s1.x = MID_INIT;
+    s1.y = ALL_NONE3;
+    s1.z = ALL_NONE3;
+    s1.w = NOPOS | (err << 16);
+    sc0[e] = s0;
+    sc1[e] = s1;
+}
+
+// One thread per (env, view cell): gen_obs of the current state.
+__global__ void observe_kernel(const uint8_t *grid, const uint4 *sc0, uint8_t *obs, int V, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int VV = V * V;
+    if (i >= n * VV) return;
+    const long long e = i / VV;
+    const int k = (int)(i - e * VV), vi = k / V, vj = k - vi * V;
+    const uint32_t m = sc0[e].x;
+    const int x = (int)(m & 0xFFu) - V / 2 + vi, y = (int)((m >> 8) & 0xFFu) - (V - 1) + vj;
+    uint32_t code = inb(x, y) ? grid[e * NCELL + x * GS + y] : C_WALL;
+    if (vi == V / 2 && vj == V - 1) code = C_EMPTY;
+    uint8_t *o = obs + i * 3;
+    o[0] = (uint8_t)(0x08060201u >> (8 * code));
+    o[1] = (uint8_t)(0x01040500u >> (8 * code));
+    o[2] = 0;
+}
+
+// Export / import: ta_env_state records (328 B, see include/twoarmy_b200.h).
+struct EnvStateRec {
+    uint8_t grid[289];
+    uint8_t agent_x, agent_y, flags, risk_count, error;
+    uint8_t balls[10][2];
+    uint8_t pad_[2];
+    int32_t step_count, step_move;
+    uint32_t t;
+};
+static_assert(sizeof(EnvStateRec) == 328, "ta_env_state layout");
+
+__device__ __forceinline__ void unpack_ball(uint32_t p, uint8_t *o) {
+    if (p == NOPOS) {
+        o[0] = 0xFF;
+        o[1] = 0xFF;
+    } else {
+        o[0] = (uint8_t)pos_x(p);
+        o[1] = (uint8_t)pos_y(p);
+    }
+}
+__device__ __forceinline__ uint32_t pack_ball(const uint8_t *o) {
+    return (o[0] == 0xFF) ? NOPOS : pack_pos(o[0] & 31, o[1] & 31);
+}
+
+__global__ void export_kernel(const uint8_t *grid, const uint4 *sc0, const uint4 *sc1, EnvStateRec *out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * NCELL) return;
+    const long long e = i / NCELL;
+    const int c = (int)(i - e * NCELL);  // reference order c = y*17 + x
+    const int y = c / GS, x = c - y * GS;
+    out[e].grid[c] = grid[e * NCELL + x * GS + y];
+    if (c == 0) {
+        const uint4 s0 = sc0[e], s1 = sc1[e];
+        EnvStateRec &r = out[e];
+        r.agent_x = (uint8_t)(s0.x & 0xFFu);
+        r.agent_y = (uint8_t)((s0.x >> 8) & 0xFFu);
+        r.flags = (uint8_t)((s0.x >> 16) & 0xFFu);
+        r.risk_count = (uint8_t)(s0.x >> 24);
+        r.error = (uint8_t)((s1.w >> 16) & 0xFFu);
+        for (int k = 0; k < 3; k++) unpack_ball(ball_get(s1.x, k), r.balls[k]);
+        for (int k = 0; k < 3; k++) unpack_ball(ball_get(s1.y, k), r.balls[3 + k]);
+        for (int k = 0; k < 3; k++) unpack_ball(ball_get(s1.z, k), r.balls[6 + k]);
+        unpack_ball(ball_get(s1.w, 0), r.balls[9]);
+        r.pad_[0] = r.pad_[1] = 0;
+        r.step_count = (int32_t)s0.y;
+        r.step_move = (int32_t)s0.z;
+        r.t = s0.w;
+    }
+}
+
+__global__ void import_kernel(uint8_t *grid, uint4 *sc0, uint4 *sc1, const EnvStateRec *in, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * NCELL) return;
+    const long long e = i / NCELL;
+    const int c = (int)(i - e * NCELL);
+    const int y = c / GS, x = c - y * GS;
+    grid[e * NCELL + x * GS + y] = in[e].grid[c] & 3u;
+    if (c == 0) {
+        const EnvStateRec &r = in[e];
+        uint4 s0, s1;
+        s0.x = (uint32_t)r.agent_x | ((uint32_t)r.agent_y << 8) | ((uint32_t)r.flags << 16) | ((uint32_t)r.risk_count << 24);
+        s0.y = (uint32_t)r.step_count;
+        s0.z = (uint32_t)r.step_move;
+        s0.w = r.t;
+        s1.x = pack_ball(r.balls[0]) | (pack_ball(r.balls[1]) << 10) | (pack_ball(r.balls[2]) << 20);
+        s1.y = pack_ball(r.balls[3]) | (pack_ball(r.balls[4]) << 10) | (pack_ball(r.balls[5]) << 20);
+        s1.z = pack_ball(r.balls[6]) | (pack_ball(r.balls[7]) << 10) | (pack_ball(r.balls[8]) << 20);
+        s1.w = pack_ball(r.balls[9]) | ((uint32_t)r.error << 16);
+        sc0[e] = s0;
+        sc1[e] = s1;
+    }
+}
+
+// matrix_env (env_buffer.py:300-318): None 0.9, wall -0.9, ball -0.5, goal 0.9, then the
+// agent's cell 0.3; index y*17 + x.  The float64 LUT is cast to float32 exactly as
+// train_ppo.py:122 does on store.  Compact code: 0 -> 0.9, 1 -> -0.9, 2 -> -0.5, 4 -> 0.3.
+__device__ __forceinline__ uint32_t matrix_code(uint32_t cell, bool agent) {
+    return agent ? 4u : (cell == C_GOAL ? 0u : cell);
+}
+__device__ __forceinline__ float matrix_value(uint32_t mc) {
+    return mc == 0u ? 0.9f : (mc == 1u ? -0.9f : (mc == 2u ? -0.5f : 0.3f));
+}
+
+// One CTA of 320 threads handles 4 envs: the column-major grids are staged through shared
+// memory so that both the HBM read and the row-major write are contiguous.
+constexpr int SM_ENVS = 4;
+__global__ void __launch_bounds__(320) state_matrix_kernel(const uint8_t *grid, const uint4 *sc0, uint8_t *codes,
+                                                          float *matrix, float *place, long long n) {
+    __shared__ uint8_t sg[SM_ENVS * NCELL];
+    __shared__ uint32_t sa[SM_ENVS];
+    const long long e0 = (long long)blockIdx.x * SM_ENVS;
+    const int cnt = (int)((n - e0) < SM_ENVS ? (n - e0) : SM_ENVS);
+    for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) sg[i] = grid[e0 * NCELL + i];
+    if (threadIdx.x < cnt) {
+        const uint32_t m = sc0[e0 + threadIdx.x].x;
+        sa[threadIdx.x] = m & 0xFFFFu;
+        if (place) {
+            place[(e0 + threadIdx.x) * 2 + 0] = (float)((m >> 8) & 0xFFu);  // (row, col) = (y, x)
+            place[(e0 + threadIdx.x) * 2 + 1] = (float)(m & 0xFFu);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) {
+        const int e = i / NCELL, c = i - e * NCELL, y = c / GS, x = c - y * GS;
+        const uint32_t a = sa[e];
+        const uint32_t mc = matrix_code(sg[e * NCELL + x * GS + y], x == (int)(a & 0xFFu) && y == (int)(a >> 8));
+        if (codes) codes[e0 * NCELL + i] = (uint8_t)mc;
+        if (matrix) matrix[e0 * NCELL + i] = matrix_value(mc);
+    }
+}
+
+// Frame-stack roll fused with matrix_env: s [n][5][289], p [n][5][2].
+__global__ void __launch_bounds__(320) stack_roll_kernel(const uint8_t *grid, const uint4 *sc0, float *s, float *p,
+                                                        const uint8_t *init_mask, int init, long long n) {
+    __shared__ uint8_t sg[SM_ENVS * NCELL];
+    __shared__ uint32_t sa[SM_ENVS];
+    __shared__ uint8_t sinit[SM_ENVS];
+    const long long e0 = (long long)blockIdx.x * SM_ENVS;
+    const int cnt = (int)((n - e0) < SM_ENVS ? (n - e0) : SM_ENVS);
+    for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) sg[i] = grid[e0 * NCELL + i];
+    if (threadIdx.x < cnt) {
+        sa[threadIdx.x] = sc0[e0 + threadIdx.x].x & 0xFFFFu;
+        sinit[threadIdx.x] = (uint8_t)(init && (!init_mask || init_mask[e0 + threadIdx.x]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) {
+        const int e = i / NCELL, c = i - e * NCELL, y = c / GS, x = c - y * GS;
+        const uint32_t a = sa[e];
+        const float v = matrix_value(matrix_code(sg[e * NCELL + x * GS + y], x == (int)(a & 0xFFu) && y == (int)(a >> 8)));
+        float *row = s + (e0 + e) * 5 * NCELL + c;
+        if (sinit[e]) {
+#pragma unroll
+            for (int f = 0; f < 5; f++) row[f * NCELL] = v;
+        } else {
+            const float f1 = row[1 * NCELL], f2 = row[2 * NCELL], f3 = row[3 * NCELL], f4 = row[4 * NCELL];
+            row[0] = f1; row[1 * NCELL] = f2; row[2 * NCELL] = f3; row[3 * NCELL] = f4; row[4 * NCELL] = v;
+        }
+    }
+    if (p && threadIdx.x < cnt * 2) {
+        const int e = threadIdx.x >> 1, comp = threadIdx.x & 1;
+        const uint32_t a = sa[e];
+        const float v = comp == 0 ? (float)(a >> 8) : (float)(a & 0xFFu);
+        float *row = p + (e0 + e) * 10 + comp;
+        if (sinit[e]) {
+#pragma unroll
+            for (int f = 0; f < 5; f++) row[f * 2] = v;
+        } else {
+            const float f1 = row[2], f2 = row[4], f3 = row[6], f4 = row[8];
+            row[0] = f1; row[2] = f2; row[4] = f3; row[6] = f4; row[8] = v;
+        }
+    }
+}
+
+}  // namespace ta

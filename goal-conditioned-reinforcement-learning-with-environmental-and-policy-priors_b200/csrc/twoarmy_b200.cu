@@ -1,0 +1,351 @@
+// twoarmy_b200.cu -- C ABI (include/twoarmy_b200.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/twoarmy_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ta_aux.cuh"
+#include "ta_gae.cuh"
+#include "ta_step.cuh"
+
+using namespace ta;
+
+static_assert(sizeof(ta_env_state) == sizeof(EnvStateRec), "public and device record must match");
+
+namespace {
+
+thread_local char g_cuda_err[512] = "";
+long long g_launches = 0;
+
+int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return TA_E_CUDA;
+}
+#define CK(call)                                        \
+    do {                                                \
+        cudaError_t e_ = (call);                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+inline int launch_ok(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    g_launches++;
+    return TA_OK;
+}
+
+inline unsigned blocks_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+}  // namespace
+
+struct ta_batch {
+    int version, view, device, sm_count;
+    long long n, npad;
+    uint64_t seed, env_id0;
+    uint8_t *grid = nullptr;
+    uint4 *sc0 = nullptr, *sc1 = nullptr;
+    uint8_t *tables = nullptr;
+    // host-call path (ta_step_host)
+    cudaStream_t own_stream = nullptr;
+    void *d_act = nullptr;
+    uint8_t *d_obs = nullptr;
+    float *d_rew = nullptr;
+    uint8_t *d_term = nullptr, *d_trunc = nullptr;
+    // timing
+    int timing = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+void build_tables(std::vector<uint8_t> &t) {
+    t.assign(TAB_BYTES, 0);
+    for (int ay = 0; ay < 17; ay++)
+        for (int j0 = 0; j0 < 17; j0++)
+            for (int b = 0; b < 16; b++) {
+                int j = (j0 + b) % 17;
+                t[TAB_TOP + (ay * 17 + j0) * 16 + b] = (j < 16 - ay) ? 0xFF : 0x00;
+            }
+    for (int cb = 0; cb < 4; cb++)
+        for (int j0 = 0; j0 < 17; j0++)
+            for (int b = 0; b < 16; b++) {
+                bool second = j0 + b >= 17;
+                bool off = second ? (cb & 2) : (cb & 1);
+                t[TAB_COL + (cb * 17 + j0) * 16 + b] = off ? 0xFF : 0x00;
+            }
+    for (int x = 0; x < GS; x++)
+        for (int y = 0; y < GS; y++) t[TAB_TEMPLATE + x * GS + y] = (uint8_t)initial_cell(x, y);
+}
+
+template <int V, bool FAST>
+int launch_step_t(ta_batch *h, const StepArgs &a, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    auto kern = step_obs_kernel<V, FAST>;
+    if (!attr_set[h->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM));
+        attr_set[h->device & 63] = true;
+    }
+    int grid = a.ntiles < h->sm_count ? a.ntiles : h->sm_count;
+    kern<<<grid, STEP_WARPS * 32, STEP_SMEM, st>>>(a);
+    return launch_ok("step_obs_kernel");
+}
+
+int g_force_generic = 0;
+
+int launch_step(ta_batch *h, const StepArgs &a, cudaStream_t st) {
+    switch (h->view) {
+        case 3: return launch_step_t<3, false>(h, a, st);
+        case 5: return launch_step_t<5, false>(h, a, st);
+        case 7: return launch_step_t<7, false>(h, a, st);
+        case 9: return launch_step_t<9, false>(h, a, st);
+        case 11: return launch_step_t<11, false>(h, a, st);
+        case 13: return launch_step_t<13, false>(h, a, st);
+        case 15: return launch_step_t<15, false>(h, a, st);
+        case 17: return g_force_generic ? launch_step_t<17, false>(h, a, st) : launch_step_t<17, true>(h, a, st);
+    }
+    return TA_E_UNSUPPORTED;
+}
+
+int do_reset(ta_batch *h, const uint8_t *mask, int hard, uint8_t *obs_out, cudaStream_t st, bool pad_too) {
+    // padded tail envs (>= n) are reset only at creation
+    const long long cnt = pad_too ? h->npad : h->n;
+    reset_grid_kernel<<<blocks_for(cnt * NCELL, 256), 256, 0, st>>>(h->grid, mask, cnt);
+    if (int rc = launch_ok("reset_grid_kernel")) return rc;
+    reset_scalar_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(h->sc0, h->sc1, mask, hard, cnt);
+    if (int rc = launch_ok("reset_scalar_kernel")) return rc;
+    if (obs_out) {
+        observe_kernel<<<blocks_for(h->n * h->view * h->view, 256), 256, 0, st>>>(h->grid, h->sc0, obs_out, h->view, h->n);
+        if (int rc = launch_ok("observe_kernel")) return rc;
+    }
+    return TA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ta_abi_version(void) { return TA_ABI_VERSION; }
+
+const char *ta_strerror(int code) {
+    switch (code) {
+        case TA_OK: return "ok";
+        case TA_E_INVALID: return "invalid argument";
+        case TA_E_CUDA: return "CUDA runtime error (see ta_last_cuda_error)";
+        case TA_E_NOMEM: return "out of memory";
+        case TA_E_UNSUPPORTED: return "unsupported configuration";
+    }
+    return "unknown error";
+}
+
+const char *ta_last_cuda_error(void) { return g_cuda_err; }
+int64_t ta_launch_count(void) { return g_launches; }
+
+int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device, uint64_t seed, uint64_t env_id0) {
+    if (!out || (version != 4 && version != 6) || n_envs <= 0 || view < 3 || view > 17 || (view & 1) == 0)
+        return TA_E_INVALID;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return TA_E_INVALID;
+    CK(cudaSetDevice(device));
+    ta_batch *h = new (std::nothrow) ta_batch();
+    if (!h) return TA_E_NOMEM;
+    h->version = version; h->view = view; h->device = device;
+    h->n = n_envs; h->npad = (n_envs + TILE - 1) / TILE * TILE;
+    h->seed = seed; h->env_id0 = env_id0;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                 prop.major, prop.minor);
+        delete h;
+        return TA_E_UNSUPPORTED;
+    }
+    CK(cudaMalloc(&h->grid, (size_t)h->npad * NCELL));
+    CK(cudaMalloc(&h->sc0, (size_t)h->npad * sizeof(uint4)));
+    CK(cudaMalloc(&h->sc1, (size_t)h->npad * sizeof(uint4)));
+    CK(cudaMalloc(&h->tables, TAB_BYTES));
+    CK(cudaMemset(h->sc0, 0, (size_t)h->npad * sizeof(uint4)));
+    CK(cudaMemset(h->sc1, 0, (size_t)h->npad * sizeof(uint4)));
+    std::vector<uint8_t> t;
+    build_tables(t);
+    CK(cudaMemcpy(h->tables, t.data(), TAB_BYTES, cudaMemcpyHostToDevice));
+    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    if (int rc = do_reset(h, nullptr, 1, nullptr, nullptr, true)) return rc;
+    CK(cudaDeviceSynchronize());
+    *out = h;
+    return TA_OK;
+}
+
+int ta_destroy(ta_handle h) {
+    if (!h) return TA_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaFree(h->grid); cudaFree(h->sc0); cudaFree(h->sc1); cudaFree(h->tables);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return TA_OK;
+}
+
+int64_t ta_num_envs(ta_handle h) { return h ? h->n : 0; }
+int ta_view(ta_handle h) { return h ? h->view : 0; }
+int ta_version(ta_handle h) { return h ? h->version : 0; }
+
+int ta_reset(ta_handle h, const uint8_t *mask, int hard, uint8_t *obs_out, void *stream) {
+    if (!h) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    return do_reset(h, mask, hard, obs_out, (cudaStream_t)stream, false);
+}
+
+int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags, uint8_t *obs_out,
+            float *reward_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *consumed_out, void *stream) {
+    if (!h || !actions || !obs_out || !reward_out || !term_out || !trunc_out) return TA_E_INVALID;
+    if (action_dtype < 0 || action_dtype > 2) return TA_E_INVALID;
+    if (((uintptr_t)obs_out & 15u) || (draws && ((uintptr_t)draws & 7u))) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    StepArgs a;
+    a.grid = h->grid; a.sc0 = h->sc0; a.sc1 = h->sc1; a.tables = h->tables;
+    a.actions = actions; a.draws = draws;
+    a.obs = obs_out; a.reward = reward_out; a.term = term_out; a.trunc = trunc_out; a.consumed = consumed_out;
+    a.n = h->n; a.ntiles = (int)(h->npad / TILE);
+    a.version = h->version; a.flags = flags; a.action_dtype = action_dtype;
+    a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32);
+    a.env_id0 = h->env_id0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->timing) CK(cudaEventRecord(h->ev0, st));
+    int rc = launch_step(h, a, st);
+    if (h->timing) CK(cudaEventRecord(h->ev1, st));
+    return rc;
+}
+
+int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, uint8_t *obs_out, float *reward_out,
+                 uint8_t *term_out, uint8_t *trunc_out) {
+    if (!h || !actions || !obs_out || !reward_out || !term_out || !trunc_out) return TA_E_INVALID;
+    if (action_dtype < 0 || action_dtype > 2) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const size_t asz = action_dtype == TA_ACT_I32 ? 4 : (action_dtype == TA_ACT_U8 ? 1 : 8);
+    const size_t obs_bytes = (size_t)h->n * 3 * h->view * h->view;
+    if (!h->d_obs) {
+        CK(cudaMalloc(&h->d_act, (size_t)h->n * 8));
+        CK(cudaMalloc(&h->d_obs, obs_bytes));
+        CK(cudaMalloc(&h->d_rew, (size_t)h->n * 4));
+        CK(cudaMalloc(&h->d_term, (size_t)h->n));
+        CK(cudaMalloc(&h->d_trunc, (size_t)h->n));
+    }
+    cudaStream_t st = h->own_stream;
+    CK(cudaMemcpyAsync(h->d_act, actions, (size_t)h->n * asz, cudaMemcpyHostToDevice, st));
+    int rc = ta_step(h, h->d_act, action_dtype, nullptr, flags, h->d_obs, h->d_rew, h->d_term, h->d_trunc, nullptr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(obs_out, h->d_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(reward_out, h->d_rew, (size_t)h->n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(term_out, h->d_term, (size_t)h->n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(trunc_out, h->d_trunc, (size_t)h->n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TA_OK;
+}
+
+int ta_rollout(ta_handle h, const void *actions, int action_dtype, int T, uint8_t *obs_out, float *reward_out,
+               uint8_t *term_out, uint8_t *trunc_out, void *stream) {
+    if (!h || T <= 0) return TA_E_INVALID;
+    const size_t asz = action_dtype == TA_ACT_I32 ? 4 : (action_dtype == TA_ACT_U8 ? 1 : 8);
+    const size_t obs_env = (size_t)3 * h->view * h->view;
+    if ((obs_env * (size_t)h->n) & 15u) return TA_E_INVALID;  // every step's obs block must stay 16 B aligned
+    for (int t = 0; t < T; t++) {
+        int rc = ta_step(h, (const uint8_t *)actions + (size_t)t * h->n * asz, action_dtype, nullptr, TA_STEP_AUTORESET,
+                         obs_out + (size_t)t * h->n * obs_env, reward_out + (size_t)t * h->n, term_out + (size_t)t * h->n,
+                         trunc_out + (size_t)t * h->n, nullptr, stream);
+        if (rc) return rc;
+    }
+    return TA_OK;
+}
+
+int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *place_out, void *stream) {
+    if (!h) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    state_matrix_kernel<<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, codes_out, matrix_out,
+                                                                                   place_out, h->n);
+    return launch_ok("state_matrix_kernel");
+}
+
+int ta_stack_roll(ta_handle h, float *s_stack, float *p_stack, const uint8_t *init_mask, int init, void *stream) {
+    if (!h || !s_stack) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    stack_roll_kernel<<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, s_stack, p_stack,
+                                                                                 init_mask, init, h->n);
+    return launch_ok("stack_roll_kernel");
+}
+
+int ta_export_state(ta_handle h, ta_env_state *out, void *stream) {
+    if (!h || !out) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    export_kernel<<<blocks_for(h->n * NCELL, 256), 256, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, h->sc1,
+                                                                                 reinterpret_cast<EnvStateRec *>(out), h->n);
+    return launch_ok("export_kernel");
+}
+
+int ta_import_state(ta_handle h, const ta_env_state *in, void *stream) {
+    if (!h || !in) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    import_kernel<<<blocks_for(h->n * NCELL, 256), 256, 0, (cudaStream_t)stream>>>(
+        h->grid, h->sc0, h->sc1, reinterpret_cast<const EnvStateRec *>(in), h->n);
+    return launch_ok("import_kernel");
+}
+
+int ta_gae(const float *reward, const float *v, const float *v_next, const float *last_v, const uint8_t *done, float gamma,
+           float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, void *stream) {
+    if (!reward || !v || !adv_out || !ret_out || T <= 0 || n <= 0) return TA_E_INVALID;
+    if (!v_next && !last_v) return TA_E_INVALID;
+    if (use_mask && !done) return TA_E_INVALID;
+    int ch = (T + GAE_L - 1) / GAE_L;
+    if (ch > GAE_CH) ch = GAE_CH;
+    dim3 block(32, ch);
+    gae_kernel<<<blocks_for(n, 32), block, 0, (cudaStream_t)stream>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T,
+                                                                     n, adv_out, ret_out);
+    return launch_ok("gae_kernel");
+}
+
+int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream) {
+    if (!adv || !stats3 || count <= 0) return TA_E_INVALID;
+    CK(cudaMemsetAsync(stats3, 0, 3 * sizeof(double), (cudaStream_t)stream));
+    unsigned nb = blocks_for(count, 256 * 8);
+    if (nb > 148 * 8) nb = 148 * 8;
+    adv_stats_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(adv, count, stats3);
+    return launch_ok("adv_stats_kernel");
+}
+
+int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stream) {
+    if (!adv || !stats3 || count <= 0) return TA_E_INVALID;
+    unsigned nb = blocks_for(count, 256 * 4);
+    if (nb > 148 * 16) nb = 148 * 16;
+    adv_normalize_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(adv, count, stats3);
+    return launch_ok("adv_normalize_kernel");
+}
+
+int ta_set_timing(ta_handle h, int on) {
+    if (!h) return TA_E_INVALID;
+    h->timing = on;
+    return TA_OK;
+}
+
+int ta_last_step_ms(ta_handle h, float *ms) {
+    if (!h || !ms) return TA_E_INVALID;
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return TA_OK;
+}
+
+/* test hook: route V=17 through the generic per-cell observation builder (1) or the
+ * windowed fast path (0, default) so the two can be compared against each other */
+int ta_debug_force_generic_obs(int on) {
+    g_force_generic = on;
+    return TA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+/*
+ * twoarmy_b200.h -- C ABI of the B200 (sm_100a) batched Twoarmy hot path.
+ *
+ * This is the drop-in boundary: every entry point names the reference interface it
+ * replaces (paths relative to the reference repository root).  The reference is pure
+ * Python with no FFI of its own; the binding a maintainer would add is the ctypes stub in
+ * INTEGRATION.md (and the one this repo ships in
+ * goal-conditioned-reinforcement-learning-with-environmental-and-policy-priors_b200/_capi.py).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / C++ types.
+ *   - unless a function name ends in _host, every array argument is a DEVICE pointer owned
+ *     by the caller; the library never frees it.  obs pointers must be 16-byte aligned.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Kernels
+ *     are enqueued on it and the call returns without synchronising.
+ *   - a handle owns the per-env state (HBM, struct-of-arrays), is bound to one device and
+ *     is not thread-safe: one handle per GPU / process.
+ *   - return value: 0 on success, a negative TA_E_* code otherwise; nothing throws.
+ *   - there is no CPU fallback: without a CUDA device ta_create fails with TA_E_CUDA.
+ */
+#ifndef TWOARMY_B200_H
+#define TWOARMY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TA_ABI_VERSION 1
+
+/* error codes */
+#define TA_OK 0
+#define TA_E_INVALID (-1)   /* bad argument (version, view, n_envs, null pointer, alignment) */
+#define TA_E_CUDA (-2)      /* a CUDA runtime call failed; ta_last_cuda_error() has the text */
+#define TA_E_NOMEM (-3)
+#define TA_E_UNSUPPORTED (-4)
+
+/* per-env sticky error bits (reference raises a Python exception in these situations) */
+#define TA_ENV_ERR_BAD_ACTION 1 /* action 4,5 or <0: AttributeError at gym_minigrid/minigrid.py:1397 */
+#define TA_ENV_ERR_NONE_POS 2   /* patrol set but patrol balls unplaced (reset() mid-episode in v4):
+                                   TypeError at gym_minigrid/envs/twoarmy_v4.py:122/:243 */
+#define TA_ENV_ERR_OOB_MOVE 4   /* Grid.get assertion, gym_minigrid/minigrid.py:604-606 */
+
+/* ta_step flags */
+#define TA_STEP_AUTORESET 1 /* after a done step run reset() on that env (what the reference's
+                               caller does next, soa/train_ppo.py:104-105).  The obs returned for
+                               that step is still the terminal one, as env.step returns it. */
+
+/* action dtypes */
+#define TA_ACT_I32 0
+#define TA_ACT_U8 1
+#define TA_ACT_I64 2
+
+/* flag bits inside ta_env_state.flags (gym_minigrid/envs/twoarmy_v4.py:14-24) */
+#define TA_F_PONE 1
+#define TA_F_PATROL 2
+#define TA_F_UP1 4
+#define TA_F_RIGHT2 8
+#define TA_F_UPD_H 16
+#define TA_F_UPD_L 32
+#define TA_F_FIRST_ROOM2 64
+
+/* cell codes: 0 empty (None), 1 wall, 2 ball (yellow), 3 goal */
+
+/* One env as exported / imported for differential testing against the reference
+ * (everything Twoarmy.step reads or writes). 328 bytes. */
+typedef struct {
+    uint8_t grid[289];     /* reference order: index y*17+x (minigrid.py:599-607) */
+    uint8_t agent_x, agent_y;
+    uint8_t flags;         /* TA_F_* */
+    uint8_t risk_count;
+    uint8_t error;         /* TA_ENV_ERR_* */
+    uint8_t balls[10][2];  /* obstacles[0..2], obstacles1[0..2], obstacles2[0..3]: (x,y); 0xFF = cur_pos None */
+    uint8_t pad_[2];
+    int32_t step_count;    /* minigrid.py:972,1334 */
+    int32_t step_move;     /* twoarmy_v4.py:14,87,296 */
+    uint32_t t;            /* env steps since creation (Philox counter word) */
+} ta_env_state;
+
+typedef struct ta_batch *ta_handle;
+
+/* Replaces gym.make(id, agent_view_size=view) x n_envs
+ * (gym_minigrid/__init__.py:10-20 -> Twoarmy_v4.__init__ twoarmy_v4.py:9-36 ->
+ * MiniGridEnv.__init__ minigrid.py:866-945, which ends in reset()).
+ * version 4|6; view odd in [3,17]; env_id0 = global index of env 0 (sharding across
+ * GPUs keeps draws independent of the shard layout); seed keys the Philox stream. */
+int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device, uint64_t seed,
+              uint64_t env_id0);
+int ta_destroy(ta_handle h);
+
+int64_t ta_num_envs(ta_handle h);
+int ta_view(ta_handle h);
+int ta_version(ta_handle h);
+
+/* Replaces MiniGridEnv.reset (minigrid.py:947-980 -> _gen_grid twoarmy_v4.py:38-80) on the
+ * envs whose mask byte is non-zero (mask NULL = all).  Like the reference it rebuilds grid,
+ * balls, agent and step_count only; the Twoarmy flags carry over.  hard != 0 additionally
+ * re-runs __init__'s flag initialisation (a freshly constructed env) and clears the error
+ * bits.  obs_out (nullable): uint8 [n][V][V][3], the gen_obs() of EVERY env after the call. */
+int ta_reset(ta_handle h, const uint8_t *mask, int hard, uint8_t *obs_out, void *stream);
+
+/* Replaces Twoarmy_v4.step / Twoarmy_v6.step (twoarmy_v4.py:82-322, twoarmy_v6.py:83-325)
+ * including MiniGridEnv.step (minigrid.py:1333-1441) and gen_obs (minigrid.py:1443-1496),
+ * for all n envs in one fused kernel.
+ *   actions      [n] of action_dtype; >=7 is clamped to 0 (twoarmy_v4.py:84-85); 4, 5 and
+ *                negatives set TA_ENV_ERR_BAD_ACTION and leave that env untouched
+ *   draws        nullable.  NULL: production mode, draws come from Philox4x32-10 keyed by
+ *                (seed, global env id, env step index).  Non-NULL: verification mode, uint8
+ *                [n][8], the value np.random.choice returned at call-site slot s (SURVEY.md
+ *                section 3.5) is read from draws[i][s]
+ *   obs_out      uint8 [n][V][V][3], image[x][y][c] as Grid.encode lays it out
+ *   reward_out   float32 [n]  (the reference's Python float cast to float32)
+ *   term_out, trunc_out  uint8 [n]
+ *   consumed_out nullable uint8 [n]: bit s set iff call-site slot s executed this step */
+int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags,
+            uint8_t *obs_out, float *reward_out, uint8_t *term_out, uint8_t *trunc_out,
+            uint8_t *consumed_out, void *stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies actions in, launches, copies the
+ * four outputs back on the handle's own stream and synchronises before returning. This is
+ * the end-to-end path bench.py times. */
+int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, uint8_t *obs_out,
+                 float *reward_out, uint8_t *term_out, uint8_t *trunc_out);
+
+/* T consecutive steps with a pre-sampled action tensor [T][n] (random-policy rollouts,
+ * soa/datacol_predictor.py:106 style).  Outputs are [T][n]... ; always autoreset, Philox draws. */
+int ta_rollout(ta_handle h, const void *actions, int action_dtype, int T, uint8_t *obs_out,
+               float *reward_out, uint8_t *term_out, uint8_t *trunc_out, void *stream);
+
+/* Replaces Env_transact.matrix_env + data_env + the frame-stack roll
+ * (soa/env_buffer.py:300-334, soa/train_ppo.py:116-121).
+ *   codes_out  nullable uint8 [n][289], index y*17+x: 0 empty/goal(0.9) 1 wall(-0.9)
+ *              2 ball(-0.5) 4 agent(0.3)   (compact form of the float LUT)
+ *   matrix_out nullable float32 [n][289], the LUT applied
+ *   place_out  nullable float32 [n][2] = (agent y, agent x);  goal is the constant (2,14) */
+int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *place_out, void *stream);
+
+/* Frame-stack roll fused with matrix_env: s_stack float32 [n][5][289], p_stack [n][5][2] are
+ * shifted by one frame (oldest dropped) and the current frame appended, exactly
+ * np.delete(x,0,0); np.append(x,[new],0) of train_ppo.py:116-121.  With init != 0 all five
+ * frames are set to the current one (np.tile in Env_transact.reset, env_buffer.py:420-423)
+ * for envs whose mask byte is non-zero (mask NULL = all). */
+int ta_stack_roll(ta_handle h, float *s_stack, float *p_stack, const uint8_t *init_mask, int init,
+                  void *stream);
+
+/* Export / import the full env state (device buffers of n ta_env_state records). */
+int ta_export_state(ta_handle h, ta_env_state *out, void *stream);
+int ta_import_state(ta_handle h, const ta_env_state *in, void *stream);
+
+/* Advantage / returns over a rollout laid out [T][n] (time-major), fp32.
+ * Replaces soa/agent/PPO.py:112-115 (the lambda = 0, use_mask = 0, normalize = 0 mode:
+ * target_v = r + gamma*V(s'), adv = target_v - V(s)) and generalises it to GAE(gamma,lambda).
+ *   v_next  nullable [T][n]: V(s') per sample as the reference computes it; when NULL,
+ *           V(s_{t+1}) = v[t+1] and last_v [n] bootstraps the final step
+ *   done    nullable uint8 [T][n], used only when use_mask != 0
+ *   normalize != 0: adv <- (adv - mean) / (std + 1e-8) over all T*n (unbiased std, the
+ *           commented-out line PPO.py:115); stats [3] float64 device scratch receives
+ *           (sum, sum of squares, count) so several ranks can combine them first
+ *   adv_out, ret_out  float32 [T][n]  (ret = target_v in the reference's naming) */
+int ta_gae(const float *reward, const float *v, const float *v_next, const float *last_v,
+           const uint8_t *done, float gamma, float lam, int use_mask, int T, int64_t n,
+           float *adv_out, float *ret_out, void *stream);
+int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream);
+int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stream);
+
+/* introspection */
+int ta_abi_version(void);
+const char *ta_strerror(int code);
+const char *ta_last_cuda_error(void);
+/* kernels launched by this library since load (bench.py's gpu_launches claim) */
+int64_t ta_launch_count(void);
+/* duration in ms of the last `ta_step` kernel when timing is enabled (CUDA events on the
+ * launching stream); enable with ta_set_timing(h, 1). Synchronises. */
+int ta_set_timing(ta_handle h, int on);
+int ta_last_step_ms(ta_handle h, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWOARMY_B200_H */

@@ -1,0 +1,278 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(include/twoarmy_b200.h) via the package's ctypes binding; the oracle is only the checker."""
+import numpy as np
+import pytest
+
+from traj_check import FLAG_NAMES, check_traj
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _pkg():
+    import twoarmy_b200
+    return twoarmy_b200
+
+
+def _oracle():
+    from oracle import oracle as O
+    return O
+
+
+FLAG_BITS = {"pone": 1, "patrol": 2, "up1": 4, "right2": 8, "upd_h": 16, "upd_l": 32, "first_room2": 64}
+
+
+def state_to_fixture(st):
+    flags = np.zeros((len(st), 10), np.int32)
+    flags[:, 0], flags[:, 1], flags[:, 2] = st["step_count"], st["step_move"], st["risk_count"]
+    for k, name in enumerate(FLAG_NAMES[3:]):
+        flags[:, 3 + k] = (st["flags"] & FLAG_BITS[name]) != 0
+    balls = st["balls"].astype(np.int16)
+    balls[balls == 255] = -1
+    return dict(grid=st["grid"], agent=np.stack([st["agent_x"], st["agent_y"]], 1).astype(np.int8), flags=flags,
+                balls=balls.astype(np.int8))
+
+
+class GpuImpl:
+    def __init__(self, version, n, view, **kw):
+        self.env = _pkg().TwoarmyVecEnv(version, n, view, autoreset=False, **kw)
+
+    def reset(self):
+        return self.env.reset().cpu().numpy()
+
+    def step(self, actions, draws):
+        obs, rew, te, tr, info = self.env.step(torch.as_tensor(np.asarray(actions), dtype=torch.int32),
+                                               None if draws is None else torch.as_tensor(draws))
+        return dict(obs=obs.cpu().numpy(), reward=rew.cpu().numpy(), terminated=te.cpu().numpy(),
+                    truncated=tr.cpu().numpy(), consumed=info["consumed"].cpu().numpy())
+
+    def reset_masked(self, mask):
+        self.env.reset(torch.as_tensor(mask))
+
+    def obs_now(self):
+        return self.env.observe().cpu().numpy()
+
+    def state(self):
+        return state_to_fixture(self.env.export_state())
+
+
+@pytest.mark.parametrize("version", [4, 6])
+@pytest.mark.parametrize("view", [17, 7])
+def test_cuda_matches_reference_trajectories(golden, version, view):
+    """Bit-exact against the reference's own outputs (tests/golden/traj_v*.npz): obs, reward,
+    terminated, truncated, grid, agent, every flag and ball, RNG call sites, resets."""
+    fx = golden(f"traj_v{version}.npz")
+    check_traj(GpuImpl(version, fx["actions"].shape[1], view), fx, view)
+
+
+def test_cuda_v17_generic_and_windowed_obs_paths_agree(golden):
+    L = _pkg()._capi.lib()
+    fx = golden("traj_v4.npz")
+    try:
+        L.ta_debug_force_generic_obs(1)
+        check_traj(GpuImpl(4, fx["actions"].shape[1], 17), fx, 17, steps=80)
+    finally:
+        L.ta_debug_force_generic_obs(0)
+
+
+def test_scripted_goal_kat(golden):
+    fx = golden("kat_v6_goal.npz")
+    g = GpuImpl(6, 1, 17)
+    g.reset()
+    draws = np.array([[255, 255, 255, 255, 255, 1, 1, 255]], np.uint8)
+    for t, a in enumerate(fx["actions"]):
+        out = g.step([a], draws)
+        assert out["reward"][0] == np.float32(fx["reward"][t])
+        assert out["terminated"][0] == fx["term"][t] and out["truncated"][0] == fx["trunc"][t]
+        st = g.env.export_state()
+        assert (int(st["agent_x"][0]), int(st["agent_y"][0])) == tuple(fx["agent"][t])
+    assert out["terminated"][0] and t == 23
+
+
+def _random_actions(rng, n, with_clamped=True):
+    a = rng.choice(np.array([0, 1, 2, 3, 6], np.int32), size=n)
+    if with_clamped:
+        bad = rng.random(n) < 0.02
+        a[bad] = rng.choice(np.array([7, 8, 100], np.int32), size=int(bad.sum()))
+    # bias upwards/right so that room 2, patrols and the goal are reached
+    up = rng.random(n) < 0.35
+    a[up] = 2
+    right = rng.random(n) < 0.15
+    a[right] = 1
+    return a.astype(np.int32)
+
+
+def _compare_with_oracle(version, n, view, steps, seed, env_id0=0, check_state_every=25):
+    O = _oracle()
+    env = _pkg().TwoarmyVecEnv(version, n, view, seed=seed, env_id0=env_id0, autoreset=True)
+    ora = O.OracleBatch(version, n, view, seed=seed, env_id0=env_id0)
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset())
+    rng = np.random.default_rng(seed + 17)
+    dones = 0
+    for t in range(steps):
+        a = _random_actions(rng, n)
+        obs, rew, te, tr, info = env.step(torch.as_tensor(a), want_consumed=True)
+        want = ora.step(a, None, autoreset=True)
+        assert np.array_equal(obs.cpu().numpy(), want["obs"]), f"t={t} obs"
+        assert np.array_equal(rew.cpu().numpy(), want["reward"]), f"t={t} reward"
+        assert np.array_equal(te.cpu().numpy().astype(np.uint8), want["terminated"]), f"t={t} term"
+        assert np.array_equal(tr.cpu().numpy().astype(np.uint8), want["truncated"]), f"t={t} trunc"
+        assert np.array_equal(info["consumed"].cpu().numpy(), want["consumed"]), f"t={t} draw sites"
+        dones += int(want["terminated"].sum() + want["truncated"].sum())
+        if t % check_state_every == 0 or t == steps - 1:
+            st = state_to_fixture(env.export_state())
+            e = ora.envs
+            assert np.array_equal(st["grid"], e["grid"]), f"t={t} grid"
+            assert np.array_equal(st["agent"], np.stack([e["ax"], e["ay"]], 1).astype(np.int8))
+            assert np.array_equal(st["balls"], np.concatenate([e["mid"], e["o1"], e["o2"]], 1))
+            for k, name in enumerate(FLAG_NAMES):
+                assert np.array_equal(st["flags"][:, k], e[name].astype(np.int32)), f"t={t} {name}"
+    return dones
+
+
+def test_config2_v6_4096_envs_vs_oracle():
+    """BASELINE config 2: v6, 4096 envs, random actions, production (Philox) draws."""
+    for view in (17, 7):
+        dones = _compare_with_oracle(6, 4096, view, 160, seed=9981)
+        assert dones > 4096
+
+
+def test_config3_v4_65536_envs_vs_oracle():
+    """BASELINE config 3 at its full per-GPU size: v4, 65536 envs."""
+    dones = _compare_with_oracle(4, 65536, 17, 110, seed=9981, check_state_every=50)
+    assert dones > 65536
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 1000])
+@pytest.mark.parametrize("version", [4, 6])
+def test_ragged_batch_sizes(version, n):
+    _compare_with_oracle(version, n, 17, 70, seed=5)
+    _compare_with_oracle(version, n, 7, 70, seed=6)
+
+
+@pytest.mark.parametrize("view", [3, 5, 9, 11, 13, 15])
+def test_other_view_sizes(view):
+    _compare_with_oracle(4, 257, view, 60, seed=11)
+
+
+def test_sharding_is_invariant():
+    """Shard k of a global batch (env_id0 = offset) reproduces the slice of the single batch:
+    Philox draws are keyed by the global env id, so results do not depend on the GPU layout."""
+    P = _pkg()
+    n, parts = 2048, 4
+    whole = P.TwoarmyVecEnv(4, n, 17, seed=3)
+    shards = [P.TwoarmyVecEnv(4, n // parts, 17, seed=3, env_id0=k * (n // parts)) for k in range(parts)]
+    whole.reset()
+    for s in shards:
+        s.reset()
+    rng = np.random.default_rng(0)
+    for t in range(120):
+        a = _random_actions(rng, n)
+        o, r, te, tr, _ = whole.step(torch.as_tensor(a))
+        for k, s in enumerate(shards):
+            sl = slice(k * (n // parts), (k + 1) * (n // parts))
+            o2, r2, te2, tr2, _ = s.step(torch.as_tensor(a[sl]))
+            assert torch.equal(o[sl], o2) and torch.equal(r[sl], r2)
+            assert torch.equal(te[sl], te2) and torch.equal(tr[sl], tr2)
+
+
+def test_invalid_actions_set_error_and_freeze_env():
+    P = _pkg()
+    env = P.TwoarmyVecEnv(4, 64, 17, autoreset=False)
+    env.reset()
+    before = env.export_state()
+    a = np.full(64, 2, np.int32)
+    a[5], a[9], a[11] = 4, 5, -1
+    env.step(torch.as_tensor(a))
+    after = env.export_state()
+    for i in (5, 9, 11):
+        assert after["error"][i] == P._capi.ENV_ERR_BAD_ACTION
+        b, c = before[i].copy(), after[i].copy()
+        c["error"] = 0
+        assert b.tobytes() == c.tobytes()
+    ok = np.setdiff1d(np.arange(64), [5, 9, 11])
+    assert (after["error"][ok] == 0).all() and (after["step_count"][ok] == 1).all()
+
+
+def test_step_host_equals_device_step():
+    P = _pkg()
+    n = 4096
+    a_env = P.TwoarmyVecEnv(4, n, 17, seed=1)
+    b_env = P.TwoarmyVecEnv(4, n, 17, seed=1)
+    a_env.reset(); b_env.reset()
+    rng = np.random.default_rng(2)
+    obs = np.empty((n, 17, 17, 3), np.uint8); rew = np.empty(n, np.float32)
+    te = np.empty(n, np.uint8); tr = np.empty(n, np.uint8)
+    for t in range(60):
+        a = _random_actions(rng, n)
+        o, r, t1, t2, _ = a_env.step(torch.as_tensor(a))
+        b_env.step_host(a, obs, rew, te, tr)
+        assert np.array_equal(o.cpu().numpy(), obs) and np.array_equal(r.cpu().numpy(), rew)
+        assert np.array_equal(t1.cpu().numpy().astype(np.uint8), te)
+        assert np.array_equal(t2.cpu().numpy().astype(np.uint8), tr)
+
+
+def test_rollout_equals_stepwise():
+    P = _pkg()
+    n, T = 2048, 64  # 2048*867 is a multiple of 16
+    a_env = P.TwoarmyVecEnv(6, n, 17, seed=4)
+    b_env = P.TwoarmyVecEnv(6, n, 17, seed=4)
+    a_env.reset(); b_env.reset()
+    acts = torch.as_tensor(np.stack([_random_actions(np.random.default_rng(t), n) for t in range(T)]))
+    O, R, TE, TR = a_env.rollout(acts)
+    for t in range(T):
+        o, r, te, tr, _ = b_env.step(acts[t])
+        assert torch.equal(O[t], o) and torch.equal(R[t], r) and torch.equal(TE[t], te) and torch.equal(TR[t], tr)
+
+
+def test_state_export_import_roundtrip():
+    P = _pkg()
+    env = P.TwoarmyVecEnv(4, 500, 17, seed=8)
+    env.reset()
+    rng = np.random.default_rng(1)
+    for t in range(40):
+        env.step(torch.as_tensor(_random_actions(rng, 500)))
+    st = env.export_state()
+    other = P.TwoarmyVecEnv(4, 500, 17, seed=8)
+    other.import_state(st)
+    assert other.export_state().tobytes() == st.tobytes()
+    a = torch.as_tensor(_random_actions(rng, 500))
+    o1 = env.step(a); o2 = other.step(a)
+    assert torch.equal(o1[0], o2[0]) and torch.equal(o1[1], o2[1])
+
+
+def test_matrix_env_and_stack_roll_match_reference(golden):
+    """Env_transact.matrix_env / data_env and the 5-frame roll against the reference's values."""
+    for version in (4, 6):
+        fx = golden(f"traj_v{version}.npz")
+        n = fx["actions"].shape[1]
+        g = GpuImpl(version, n, 17)
+        g.reset()
+        dev = g.env.device
+        s = torch.zeros((n, 5, 289), dtype=torch.float32, device=dev)
+        p = torch.zeros((n, 5, 2), dtype=torch.float32, device=dev)
+        g.env.stack_roll(s, p, init=True)
+        m0, p0 = g.env.state_matrix()
+        assert torch.equal(s, m0[:, None, :].expand(n, 5, 289)) and torch.equal(p, p0[:, None, :].expand(n, 5, 2))
+        ref_s = np.repeat(m0.cpu().numpy()[:, None], 5, 1); ref_p = np.repeat(p0.cpu().numpy()[:, None], 5, 1)
+        for t in range(70):
+            g.step(fx["actions"][t], fx["draws"][t])
+            mat, place, codes = g.env.state_matrix(want_codes=True)
+            assert np.array_equal(mat.cpu().numpy(), fx["matrix"][t]), (version, t)
+            assert np.array_equal(place.cpu().numpy(), fx["place"][t])
+            lut = np.array([0.9, -0.9, -0.5, np.nan, 0.3], np.float32)
+            assert np.array_equal(lut[codes.cpu().numpy()], fx["matrix"][t])
+            g.env.stack_roll(s, p)
+            ref_s = np.concatenate([ref_s[:, 1:], fx["matrix"][t][:, None]], 1)  # np.delete + np.append
+            ref_p = np.concatenate([ref_p[:, 1:], fx["place"][t][:, None]], 1)
+            assert np.array_equal(s.cpu().numpy(), ref_s) and np.array_equal(p.cpu().numpy(), ref_p)
+            mask = (fx["term"][t] | fx["trunc"][t] | fx["forced_reset"][t]).astype(np.uint8)
+            if mask.any():
+                g.reset_masked(mask)
+                g.env.stack_roll(s, p, init_mask=torch.as_tensor(mask), init=True)
+                cur = g.env.state_matrix()
+                mm = mask.astype(bool)
+                ref_s[mm] = np.repeat(cur[0].cpu().numpy()[mm][:, None], 5, 1)
+                ref_p[mm] = np.repeat(cur[1].cpu().numpy()[mm][:, None], 5, 1)
+                assert np.array_equal(s.cpu().numpy(), ref_s)
