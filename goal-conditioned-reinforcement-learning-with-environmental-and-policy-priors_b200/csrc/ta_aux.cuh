@@ -13,14 +13,13 @@
 
 namespace ta {
 
-// One thread per (env, cell): rebuild the grid of masked envs.
-__global__ void reset_grid_kernel(uint8_t *grid, const uint8_t *mask, long long n) {
+// One thread per (env, record word): rebuild the packed grid of masked envs from the template.
+__global__ void reset_grid_kernel(uint32_t *grid, const uint32_t *tmpl, const uint8_t *mask, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * NCELL) return;
-    const long long e = i / NCELL;
+    if (i >= n * REC_WORDS) return;
+    const long long e = i / REC_WORDS;
     if (mask && !mask[e]) return;
-    const int c = (int)(i - e * NCELL);
-    grid[i] = (uint8_t)initial_cell(c / GS, c % GS);  // column-major: c = x*17 + y
+    grid[i] = tmpl[(int)(i - e * REC_WORDS)];
 }
 
 // One thread per env: agent, step_count, ball objects; hard also re-runs __init__'s flags.
@@ -47,7 +46,7 @@ __global__ void reset_scalar_kernel(uint4 *sc0, uint4 *sc1, const uint8_t *mask,
 }
 
 // One thread per (env, view cell): gen_obs of the current state.
-__global__ void observe_kernel(const uint8_t *grid, const uint4 *sc0, uint8_t *obs, int V, long long n) {
+__global__ void observe_kernel(const uint32_t *grid, const uint4 *sc0, uint8_t *obs, int V, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int VV = V * V;
     if (i >= n * VV) return;
@@ -55,7 +54,7 @@ __global__ void observe_kernel(const uint8_t *grid, const uint4 *sc0, uint8_t *o
     const int k = (int)(i - e * VV), vi = k / V, vj = k - vi * V;
     const uint32_t m = sc0[e].x;
     const int x = (int)(m & 0xFFu) - V / 2 + vi, y = (int)((m >> 8) & 0xFFu) - (V - 1) + vj;
-    uint32_t code = inb(x, y) ? grid[e * NCELL + x * GS + y] : C_WALL;
+    uint32_t code = inb(x, y) ? cell_get(grid + e * REC_WORDS, x, y) : C_WALL;
     if (vi == V / 2 && vj == V - 1) code = C_EMPTY;
     uint8_t *o = obs + i * 3;
     o[0] = (uint8_t)(0x08060201u >> (8 * code));
@@ -87,13 +86,13 @@ __device__ __forceinline__ uint32_t pack_ball(const uint8_t *o) {
     return (o[0] == 0xFF) ? NOPOS : pack_pos(o[0] & 31, o[1] & 31);
 }
 
-__global__ void export_kernel(const uint8_t *grid, const uint4 *sc0, const uint4 *sc1, EnvStateRec *out, long long n) {
+__global__ void export_kernel(const uint32_t *grid, const uint4 *sc0, const uint4 *sc1, EnvStateRec *out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * NCELL) return;
     const long long e = i / NCELL;
     const int c = (int)(i - e * NCELL);  // reference order c = y*17 + x
     const int y = c / GS, x = c - y * GS;
-    out[e].grid[c] = grid[e * NCELL + x * GS + y];
+    out[e].grid[c] = (uint8_t)cell_get(grid + e * REC_WORDS, x, y);
     if (c == 0) {
         const uint4 s0 = sc0[e], s1 = sc1[e];
         EnvStateRec &r = out[e];
@@ -113,14 +112,22 @@ __global__ void export_kernel(const uint8_t *grid, const uint4 *sc0, const uint4
     }
 }
 
-__global__ void import_kernel(uint8_t *grid, uint4 *sc0, uint4 *sc1, const EnvStateRec *in, long long n) {
+// One thread per (env, record word): gathers its 16 cells from the reference-order grid.
+__global__ void import_kernel(uint32_t *grid, uint4 *sc0, uint4 *sc1, const EnvStateRec *in, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * NCELL) return;
-    const long long e = i / NCELL;
-    const int c = (int)(i - e * NCELL);
-    const int y = c / GS, x = c - y * GS;
-    grid[e * NCELL + x * GS + y] = in[e].grid[c] & 3u;
-    if (c == 0) {
+    if (i >= n * REC_WORDS) return;
+    const long long e = i / REC_WORDS;
+    const int w = (int)(i - e * REC_WORDS);
+    uint32_t word = 0;
+    for (int b = 0; b < 16; b++) {
+        const int c = w * 16 + b;  // column-major cell index x*17 + y
+        if (c < NCELL) {
+            const int x = c / GS, y = c - x * GS;
+            word |= (uint32_t)(in[e].grid[y * GS + x] & 3u) << (2 * b);
+        }
+    }
+    grid[i] = word;
+    if (w == 0) {
         const EnvStateRec &r = in[e];
         uint4 s0, s1;
         s0.x = (uint32_t)r.agent_x | ((uint32_t)r.agent_y << 8) | ((uint32_t)r.flags << 16) | ((uint32_t)r.risk_count << 24);
@@ -146,16 +153,16 @@ __device__ __forceinline__ float matrix_value(uint32_t mc) {
     return mc == 0u ? 0.9f : (mc == 1u ? -0.9f : (mc == 2u ? -0.5f : 0.3f));
 }
 
-// One CTA of 320 threads handles 4 envs: the column-major grids are staged through shared
-// memory so that both the HBM read and the row-major write are contiguous.
+// One CTA of 320 threads handles 4 envs: the packed column-major records are staged through
+// shared memory so that both the HBM read and the row-major write are contiguous.
 constexpr int SM_ENVS = 4;
-__global__ void __launch_bounds__(320) state_matrix_kernel(const uint8_t *grid, const uint4 *sc0, uint8_t *codes,
+__global__ void __launch_bounds__(320) state_matrix_kernel(const uint32_t *grid, const uint4 *sc0, uint8_t *codes,
                                                           float *matrix, float *place, long long n) {
-    __shared__ uint8_t sg[SM_ENVS * NCELL];
+    __shared__ uint32_t sg[SM_ENVS * REC_WORDS];
     __shared__ uint32_t sa[SM_ENVS];
     const long long e0 = (long long)blockIdx.x * SM_ENVS;
     const int cnt = (int)((n - e0) < SM_ENVS ? (n - e0) : SM_ENVS);
-    for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) sg[i] = grid[e0 * NCELL + i];
+    for (int i = threadIdx.x; i < cnt * REC_WORDS; i += blockDim.x) sg[i] = grid[e0 * REC_WORDS + i];
     if (threadIdx.x < cnt) {
         const uint32_t m = sc0[e0 + threadIdx.x].x;
         sa[threadIdx.x] = m & 0xFFFFu;
@@ -168,31 +175,33 @@ __global__ void __launch_bounds__(320) state_matrix_kernel(const uint8_t *grid, 
     for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) {
         const int e = i / NCELL, c = i - e * NCELL, y = c / GS, x = c - y * GS;
         const uint32_t a = sa[e];
-        const uint32_t mc = matrix_code(sg[e * NCELL + x * GS + y], x == (int)(a & 0xFFu) && y == (int)(a >> 8));
+        const uint32_t mc = matrix_code(cell_get(sg + e * REC_WORDS, x, y), x == (int)(a & 0xFFu) && y == (int)(a >> 8));
         if (codes) codes[e0 * NCELL + i] = (uint8_t)mc;
         if (matrix) matrix[e0 * NCELL + i] = matrix_value(mc);
     }
 }
 
 // Frame-stack roll fused with matrix_env: s [n][5][289], p [n][5][2].
-__global__ void __launch_bounds__(320) stack_roll_kernel(const uint8_t *grid, const uint4 *sc0, float *s, float *p,
+__global__ void __launch_bounds__(320) stack_roll_kernel(const uint32_t *grid, const uint4 *sc0, float *s, float *p,
                                                         const uint8_t *init_mask, int init, long long n) {
-    __shared__ uint8_t sg[SM_ENVS * NCELL];
+    __shared__ uint32_t sg[SM_ENVS * REC_WORDS];
     __shared__ uint32_t sa[SM_ENVS];
     __shared__ uint8_t sinit[SM_ENVS];
     const long long e0 = (long long)blockIdx.x * SM_ENVS;
     const int cnt = (int)((n - e0) < SM_ENVS ? (n - e0) : SM_ENVS);
-    for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) sg[i] = grid[e0 * NCELL + i];
+    for (int i = threadIdx.x; i < cnt * REC_WORDS; i += blockDim.x) sg[i] = grid[e0 * REC_WORDS + i];
     if (threadIdx.x < cnt) {
         sa[threadIdx.x] = sc0[e0 + threadIdx.x].x & 0xFFFFu;
-        sinit[threadIdx.x] = (uint8_t)(init && (!init_mask || init_mask[e0 + threadIdx.x]));
+        // init call: masked envs are tiled, the others are left untouched (2 = skip)
+        sinit[threadIdx.x] = (uint8_t)(init ? ((!init_mask || init_mask[e0 + threadIdx.x]) ? 1 : 2) : 0);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) {
         const int e = i / NCELL, c = i - e * NCELL, y = c / GS, x = c - y * GS;
         const uint32_t a = sa[e];
-        const float v = matrix_value(matrix_code(sg[e * NCELL + x * GS + y], x == (int)(a & 0xFFu) && y == (int)(a >> 8)));
+        const float v = matrix_value(matrix_code(cell_get(sg + e * REC_WORDS, x, y), x == (int)(a & 0xFFu) && y == (int)(a >> 8)));
         float *row = s + (e0 + e) * 5 * NCELL + c;
+        if (sinit[e] == 2) continue;
         if (sinit[e]) {
 #pragma unroll
             for (int f = 0; f < 5; f++) row[f * NCELL] = v;
@@ -206,7 +215,8 @@ __global__ void __launch_bounds__(320) stack_roll_kernel(const uint8_t *grid, co
         const uint32_t a = sa[e];
         const float v = comp == 0 ? (float)(a >> 8) : (float)(a & 0xFFu);
         float *row = p + (e0 + e) * 10 + comp;
-        if (sinit[e]) {
+        if (sinit[e] == 2) {
+        } else if (sinit[e]) {
 #pragma unroll
             for (int f = 0; f < 5; f++) row[f * 2] = v;
         } else {

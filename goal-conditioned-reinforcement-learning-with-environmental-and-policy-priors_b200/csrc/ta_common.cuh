@@ -1,10 +1,12 @@
 // ta_common.cuh -- shared device-side definitions for the Twoarmy sm_100a kernels.
 //
 // HBM layout of one env batch (struct of arrays, owned by the handle):
-//   grid  uint8 [Npad][289]   cell codes 0 empty 1 wall 2 ball 3 goal, COLUMN-major inside an
-//                             env (index x*17+y) so that one column of the egocentric view is
-//                             a contiguous byte run; a 32-env tile is 9248 contiguous bytes
-//                             (578 x 16 B) and moves with one TMA bulk copy each way.
+//   grid  uint32 [Npad][20]   the 17x17 grid packed 2 bits per cell into 80 bytes (packed uint8,
+//                             16 cells per word): cell codes 0 empty 1 wall 2 ball 3 goal,
+//                             COLUMN-major inside an env (cell c = x*17+y sits at bits
+//                             [2c,2c+1]; cells 289..319 are padding) so that one column of the
+//                             egocentric view is a contiguous bit run.  A 32-env tile is 2560
+//                             contiguous bytes and moves with one TMA bulk copy each way.
 //   sc0   uint4 [Npad]        .x = agent_x | agent_y<<8 | flags<<16 | risk_count<<24
 //                             .y = step_count  .z = step_move  .w = t (steps since creation)
 //   sc1   uint4 [Npad]        ball positions, 10 bits each (x | y<<5, 0x3FF = cur_pos None):
@@ -19,8 +21,10 @@ namespace ta {
 
 constexpr int GS = 17;
 constexpr int NCELL = 289;
-constexpr int TILE = 32;  // envs per warp tile
-constexpr int HALF = 16;  // envs per obs staging buffer (16*3*V*V is always a multiple of 16 B)
+constexpr int TILE = 32;        // envs per tile
+constexpr int REC_WORDS = 20;   // packed grid record: 20 x uint32 = 80 B = 320 cell slots
+constexpr int REC_CELLS = 320;
+constexpr int REC_BYTES = 80;
 
 constexpr uint32_t C_EMPTY = 0, C_WALL = 1, C_BALL = 2, C_GOAL = 3;
 constexpr uint32_t NOPOS = 0x3FFu;
@@ -36,17 +40,30 @@ constexpr uint32_t ERR_BAD_ACTION = 1, ERR_NONE_POS = 2, ERR_OOB_MOVE = 4;
 // reward literals of twoarmy_v4.py:180,229,240,284,295 cast to float32
 enum { R_STEP = 0, R_RISK = 1, R_HIT = 2, R_ROOM2 = 3, R_GOAL = 4 };
 __device__ __forceinline__ float reward_value(int idx) {
-    return idx == R_STEP ? -0.01f : idx == R_RISK ? -0.1f : idx == R_HIT ? -0.9f : idx == R_ROOM2 ? 0.2f : 0.9f;
+    // bit patterns of float32(-0.01, -0.1, -0.9, 0.2, 0.9); selected without a jump table
+    uint32_t b = 0xBC23D70Au;
+    b = idx == R_RISK ? 0xBDCCCCCDu : b;
+    b = idx == R_HIT ? 0xBF666666u : b;
+    b = idx == R_ROOM2 ? 0x3E4CCCCDu : b;
+    b = idx == R_GOAL ? 0x3F666666u : b;
+    return __uint_as_float(b);
 }
 
 __host__ __device__ __forceinline__ uint32_t pack_pos(int x, int y) { return (uint32_t)x | ((uint32_t)y << 5); }
 __host__ __device__ __forceinline__ uint32_t ball_get(uint32_t w, int k) { return (w >> (10 * k)) & 0x3FFu; }
-__host__ __device__ __forceinline__ uint32_t ball_set(uint32_t w, int k, uint32_t p) {
-    return (w & ~(0x3FFu << (10 * k))) | (p << (10 * k));
-}
 __host__ __device__ __forceinline__ int pos_x(uint32_t p) { return (int)(p & 31u); }
 __host__ __device__ __forceinline__ int pos_y(uint32_t p) { return (int)(p >> 5); }
 __host__ __device__ __forceinline__ bool inb(int x, int y) { return (unsigned)x < (unsigned)GS && (unsigned)y < (unsigned)GS; }
+
+// packed-cell accessors on one env record (20 words)
+__host__ __device__ __forceinline__ uint32_t cell_get(const uint32_t *rec, int x, int y) {
+    const int c = x * GS + y;
+    return (rec[c >> 4] >> (2 * (c & 15))) & 3u;
+}
+__host__ __device__ __forceinline__ void cell_set(uint32_t *rec, int x, int y, uint32_t code) {
+    const int c = x * GS + y, sh = 2 * (c & 15);
+    rec[c >> 4] = (rec[c >> 4] & ~(3u << sh)) | (code << sh);
+}
 
 // _gen_grid (twoarmy_v4.py:38-80) as a pure function of the cell
 __host__ __device__ __forceinline__ uint32_t initial_cell(int x, int y) {
@@ -61,6 +78,19 @@ __host__ __device__ __forceinline__ uint32_t initial_cell(int x, int y) {
 }
 constexpr uint32_t MID_INIT = (7u | (8u << 5)) | ((8u | (8u << 5)) << 10) | ((9u | (8u << 5)) << 20);
 constexpr uint32_t ALL_NONE3 = 0x3FFFFFFFu;
+
+// Device-resident constant block (built on the host at ta_create).  The first TAB_SMEM_BYTES
+// are bulk-copied into shared memory by every CTA of the step kernel; the run table is read
+// straight from global memory (coalesced, L1-resident).
+constexpr int TAB_LUT = 0;                       // [256] uint4: 4 packed cells -> 12 obs bytes
+constexpr int TAB_TOP = 4096;                    // [17 ay][17 j0] u32: rows above the grid -> wall
+constexpr int TAB_COL = TAB_TOP + 1168;          // [4][17 j0] u32: columns off the grid -> wall
+constexpr int TAB_TEMPLATE = TAB_COL + 272;      // [20] u32: the initial grid record
+constexpr int TAB_SMEM_BYTES = TAB_TEMPLATE + 80;  // 5616
+// [608] u32, one per 16-cell run of a 32-env obs tile (V=17): e | k0<<5 | j0<<14 | (i0+1)<<19 |
+// crossing<<24 (the run straddles env e / e+1) | invalid<<25 (run >= 578)
+constexpr int TAB_RUN = TAB_SMEM_BYTES;
+constexpr int TAB_BYTES = TAB_RUN + 608 * 4;     // 8048
 
 // Philox4x32-10 (Random123); one block per (env, step). Draw contract:
 //   key = (seed lo, seed hi), ctr = (global env id lo, hi, t, 0)

@@ -8,33 +8,40 @@
 //                              Grid.slice :641-660, Grid.encode :749-772)
 //   MiniGridEnv.reset          gym_minigrid/minigrid.py:947-980 (autoreset tail)
 //
-// Mapping: one warp owns a tile of 32 envs.  The tile's grids (9248 B) arrive in shared
-// memory with one TMA bulk copy; lane e then runs env e's transition on its staged grid
-// (phase A: balls, patrols, agent move), the whole warp builds the 32 observations
-// cooperatively into a 16-env staging buffer that leaves with one TMA bulk store per half
-// tile (phase B), and lane e finishes the step (phase C: wall blocks, patrol spawn, reward,
-// episode end) before the grids go back with one more bulk store.  The obs is built between
-// A and C because the reference builds it inside MiniGridEnv.step, i.e. before the wall
-// blocks / patrol balls of the same step appear (ordering fact a).
+// Mapping: a CTA of 2 warps owns a tile of 32 envs; 14 CTAs are resident per SM, so the 2048
+// tiles of a 65536-env batch are all on chip at once.  The tile's packed grids (2560 B) arrive
+// in shared memory with one TMA bulk copy and the 32 envs' scalar state lives in warp 0's
+// registers for the whole launch.  For each of the launch's T steps (T = 1 for ta_step, the
+// rollout length for ta_rollout) warp 0 runs the per-env transition, lane e = env e (phase A:
+// balls, patrols, agent move); both warps then build the 32 observations cooperatively and
+// stream them to HBM with 16-byte stores (phase B); warp 0 finishes the step (phase C: wall
+// blocks, patrol spawn, reward, episode end, autoreset).  After the last step the state goes
+// back (grids with one TMA bulk store).  The obs is built between A and C because the
+// reference builds it inside MiniGridEnv.step, i.e. before the wall blocks / patrol balls of
+// the same step appear (ordering fact a).
 #pragma once
 #include "ta_common.cuh"
 
 namespace ta {
 
-constexpr int STEP_WARPS = 9;
-constexpr int G_BYTES = TILE * NCELL;  // 9248
-constexpr int G_PAD_BEFORE = 144;      // the V=17 window read may start up to 134 B before the tile
-constexpr int G_PAD_AFTER = 128;       // ... and end up to 121 B after it
-constexpr int TAB_TOP = 0;             // [17 ay][17 j0][16]  wall mask for rows above the grid
-constexpr int TAB_COL = 17 * 17 * 16;  // [4][17 j0][16]      wall mask for columns off the grid
-constexpr int TAB_TEMPLATE = TAB_COL + 4 * 17 * 16;  // 289 B initial grid, column-major
-constexpr int TAB_BYTES = TAB_TEMPLATE + 304;        // 6016
-constexpr int STAGE_MAX = HALF * 3 * GS * GS;        // 13872
-constexpr int WARP_SMEM = 16 + 128 + G_PAD_BEFORE + G_BYTES + G_PAD_AFTER + STAGE_MAX;  // 23536
-constexpr int STEP_SMEM = TAB_BYTES + 16 + STEP_WARPS * WARP_SMEM;
+constexpr int STEP_THREADS = 64;
+constexpr int STEP_WARPS = STEP_THREADS / 32;
+constexpr int STEP_CTAS_PER_SM = 14;  // 14 x 148 = 2072 resident tiles >= the 2048 tiles of 65536 envs
+constexpr int G_BYTES = TILE * REC_BYTES;  // 2560
+constexpr int G_PAD_BEFORE = 48;           // bytes: the V=17 window may start 134 cells early
+constexpr int G_PAD_AFTER = 48;            // ... and end 134 cells late
+constexpr int STAGE_BYTES = 6144;          // staging for the per-cell (generic view size) obs path
+// shared memory map (bytes)
+constexpr int SM_TAB = 0;
+constexpr int SM_BARS = TAB_SMEM_BYTES;                       // 2 mbarriers
+constexpr int SM_META = SM_BARS + 16;                    // 32 x u32: agent x | y<<8
+constexpr int SM_GPAD = SM_META + 128;                   // padded grid tile
+constexpr int SM_STAGE = SM_GPAD + G_PAD_BEFORE + G_BYTES + G_PAD_AFTER;
+constexpr int STEP_SMEM = SM_STAGE + STAGE_BYTES;        // 14560
+static_assert(SM_GPAD % 16 == 0 && SM_STAGE % 16 == 0 && (SM_GPAD + G_PAD_BEFORE) % 16 == 0, "alignment");
 
 struct StepArgs {
-    uint8_t *grid;
+    uint32_t *grid;
     uint4 *sc0;
     uint4 *sc1;
     const uint8_t *tables;
@@ -47,6 +54,7 @@ struct StepArgs {
     uint8_t *consumed;
     long long n;
     int ntiles;
+    int T;  // env steps per launch; outputs / actions / draws are [T][n]
     int version;
     int flags;
     int action_dtype;
@@ -54,47 +62,47 @@ struct StepArgs {
     unsigned long long env_id0;
 };
 
+// The step's draws, one byte per call-site slot: either the replay
+// record the caller supplied (verification mode) or the values of ONE Philox block computed up
+// front for every lane (production mode; cheaper than branching into it at each site).
 struct DrawSrc {
-    bool replay;
-    uint32_t rec_lo, rec_hi;  // replay record, slot s = byte s
-    uint32_t w[4];
-    bool have;
-    uint32_t k0, k1, c0, c1, t;
+    uint32_t rec_lo, rec_hi;  // slot s = byte s
     uint32_t consumed;
 };
 
-__device__ __forceinline__ int draw(DrawSrc &d, int slot, int lo) {
-    d.consumed |= 1u << slot;
-    if (d.replay) return (int)(((slot < 4 ? d.rec_lo : d.rec_hi) >> (8 * (slot & 3))) & 0xFFu);
-    if (!d.have) {
-        philox4x32_10(d.c0, d.c1, d.t, 0u, d.k0, d.k1, d.w);
-        d.have = true;
-    }
-    if (slot == 0) return lo + (int)__umulhi(d.w[0], 10u);
-    if (slot <= 3) return lo + (int)((d.w[1] >> (2 * (slot - 1))) & 3u);
-    return lo + (int)((d.w[2] >> (slot - 5)) & 1u);
+__device__ __forceinline__ void philox_record(DrawSrc &d, uint32_t c0, uint32_t c1, uint32_t t, uint32_t k0, uint32_t k1) {
+    uint32_t w[4];
+    philox4x32_10(c0, c1, t, 0u, k0, k1, w);
+    d.rec_lo = __umulhi(w[0], 10u) | ((9u + (w[1] & 3u)) << 8) | ((6u + ((w[1] >> 2) & 3u)) << 16) |
+               ((6u + ((w[1] >> 4) & 3u)) << 24);
+    d.rec_hi = (4u) | ((w[2] & 1u) << 8) | (((w[2] >> 1) & 1u) << 16);
 }
 
-__device__ __forceinline__ void put_cell(uint8_t *G, int x, int y, uint32_t code) {
-    if (inb(x, y)) G[x * GS + y] = (uint8_t)code;
+__device__ __forceinline__ int draw(DrawSrc &d, int slot) {
+    d.consumed |= 1u << slot;
+    return (int)(((slot < 4 ? d.rec_lo : d.rec_hi) >> (8 * (slot & 3))) & 0xFFu);
+}
+
+__device__ __forceinline__ void put_cell(uint32_t *G, int x, int y, uint32_t code) {
+    if (inb(x, y)) cell_set(G, x, y, code);
 }
 
 // clear every old cell, then put each ball at old+(dx,dy); a put that leaves the grid is the
 // swallowed AssertionError of twoarmy_v4.py:102-111 / :126-129: the ball keeps its cur_pos
 template <int NB>
-__device__ __forceinline__ void move_group(uint8_t *G, uint32_t (&p)[NB], int dx, int dy, bool fixed_y8) {
+__device__ __forceinline__ void move_group(uint32_t *G, uint32_t (&p)[NB], int dx, int dy, bool fixed_y8) {
     int ox[NB], oy[NB];
 #pragma unroll
     for (int k = 0; k < NB; k++) {
         ox[k] = pos_x(p[k]);
         oy[k] = pos_y(p[k]);
-        G[ox[k] * GS + oy[k]] = (uint8_t)C_EMPTY;
+        cell_set(G, ox[k], oy[k], C_EMPTY);
     }
 #pragma unroll
     for (int k = 0; k < NB; k++) {
         int nx = ox[k] + dx, ny = fixed_y8 ? 8 : oy[k] + dy;
         if (inb(nx, ny)) {
-            G[nx * GS + ny] = (uint8_t)C_BALL;
+            cell_set(G, nx, ny, C_BALL);
             p[k] = pack_pos(nx, ny);
         }
     }
@@ -108,116 +116,130 @@ __device__ __forceinline__ void move_group(uint8_t *G, uint32_t (&p)[NB], int dx
 constexpr uint32_t TYPE_LUT = 0x08060201u;   // empty 1, wall 2, ball 6, goal 8
 constexpr uint32_t COLOR_LUT = 0x01040500u;  // -, grey 5, yellow 4, green 1
 
-template <int V>
-__device__ __forceinline__ void fill_stage_generic(uint8_t *stage, const uint8_t *g, const uint32_t *meta, int half,
-                                                   int lane) {
-    constexpr int VV = V * V;
-    for (int c = lane; c < HALF * VV; c += 32) {
-        int e = c / VV, k = c - e * VV, i = k / V, j = k - i * V;
-        uint32_t m = meta[half * HALF + e];
-        int x = (int)(m & 0xFFu) - V / 2 + i, y = (int)((m >> 8) & 0xFFu) - (V - 1) + j;
-        uint32_t code = inb(x, y) ? g[(half * HALF + e) * NCELL + x * GS + y] : C_WALL;
-        if (i == V / 2 && j == V - 1) code = C_EMPTY;
-        stage[3 * c + 0] = (uint8_t)(TYPE_LUT >> (8 * code));
-        stage[3 * c + 1] = (uint8_t)(COLOR_LUT >> (8 * code));
-        stage[3 * c + 2] = 0;
-    }
+// Per-env record the scalar warp leaves for the observation builders:
+//   bits 0..15  cellbase = pad + e*320 + (ax-8)*17 + (ay-16): where view cell k=0 of env e sits
+//               in the padded shared-memory tile, in cells
+//   bits 16..20 agent y      bits 24..28 agent x
+__device__ __forceinline__ uint32_t make_meta(int e, int ax, int ay) {
+    return (uint32_t)(G_PAD_BEFORE * 4 + e * REC_CELLS + (ax - 8) * GS + (ay - 16)) | ((uint32_t)ay << 16) |
+           ((uint32_t)ax << 24);
 }
 
-// 16 consecutive view cells k0..k0+15 of env e (V = 17) as 16 code bytes.  Because the view
-// is as wide as the grid and the staged grid is column-major, they are the 16 bytes at
-// g[e][k0 + (ax-8)*17 + (ay-16)], except (a) rows above the grid and (b) columns off the grid,
-// which become walls through two 16-byte masks looked up by (ay, k0 mod 17) and by
-// (column-off-grid bits, k0 mod 17), and (c) the agent's own cell k = 152.
-__device__ __forceinline__ uint4 codes16_v17(const uint8_t *gpad, const uint8_t *tab, uint32_t m, int e, int k0) {
-    const int ax = (int)(m & 0xFFu), ay = (int)((m >> 8) & 0xFFu);
-    // i0 = floor(k0 / 17), valid for k0 in [-16, 288]
-    const int kk = k0 + 17;
-    const int i0 = kk / 17 - 1, j0 = kk - (i0 + 1) * 17;
-    const int addr = G_PAD_BEFORE + e * NCELL + k0 + (ax - 8) * GS + (ay - 16);
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(gpad) + (addr >> 2);
-    const uint32_t sh = (uint32_t)(addr & 3) * 8u;
-    uint32_t v0 = wp[0], v1 = wp[1], v2 = wp[2], v3 = wp[3], v4 = wp[4];
-    uint4 c;
-    c.x = __funnelshift_r(v0, v1, sh);
-    c.y = __funnelshift_r(v1, v2, sh);
-    c.z = __funnelshift_r(v2, v3, sh);
-    c.w = __funnelshift_r(v3, v4, sh);
-    const int x0 = ax - 8 + i0;
-    const int colbits = ((unsigned)x0 > 16u ? 1 : 0) | ((unsigned)(x0 + 1) > 16u ? 2 : 0);
-    const uint4 mt = *reinterpret_cast<const uint4 *>(tab + TAB_TOP + (ay * 17 + j0) * 16);
-    const uint4 mc = *reinterpret_cast<const uint4 *>(tab + TAB_COL + (colbits * 17 + j0) * 16);
-    uint32_t mx = mt.x | mc.x, my = mt.y | mc.y, mz = mt.z | mc.z, mw = mt.w | mc.w;
-    // (c & ~m) | (WALL & m)
-    c.x = (c.x & ~mx) | (0x01010101u & mx);
-    c.y = (c.y & ~my) | (0x01010101u & my);
-    c.z = (c.z & ~mz) | (0x01010101u & mz);
-    c.w = (c.w & ~mw) | (0x01010101u & mw);
-    // agent cell: view (8,16) -> k = 152
-    const int d = 152 - k0;
-    if ((unsigned)d < 16u) {
-        const uint32_t clr = ~(0xFFu << (8 * (d & 3)));
-        if ((d >> 2) == 0) c.x &= clr;
-        else if ((d >> 2) == 1) c.y &= clr;
-        else if ((d >> 2) == 2) c.z &= clr;
-        else c.w &= clr;
-    }
+// 16 consecutive view cells k0..k0+15 of one env (V = 17) as one word of 2-bit codes.  Because
+// the view is as wide as the grid and the record is column-major, they are the 32 bits at
+// cell offset cellbase + k0 -- one funnel shift -- except (a) rows above the grid and (b)
+// columns off the grid, which become walls through two masks looked up by (ay, j0) and by
+// (column-off-grid bits, j0), and (c) the agent's own cell k = 152.  i0p1 = floor(k0/17)+1,
+// j0 = k0 mod 17; valid for k0 in [-16, 288].
+__device__ __forceinline__ uint32_t codes16_v17(const uint32_t *gpadw, const uint8_t *tab, uint32_t m, int k0, int i0p1,
+                                                int j0) {
+    const int cell = (int)(m & 0xFFFFu) + k0;
+    const int ay = (int)((m >> 16) & 31u), ax = (int)(m >> 24);
+    const int wi = cell >> 4;
+    const uint32_t win = __funnelshift_r(gpadw[wi], gpadw[wi + 1], (uint32_t)(cell & 15) * 2u);
+    int s = ax + i0p1 - 1;  // grid column of view column i0, plus 8; columns < 0 or > 16 are walls
+    s = s > 31 ? 31 : (s < 0 ? 0 : s);
+    const uint32_t colbits = ((0xFE0000FFu >> s) & 1u) | (((0xFF00007Fu >> s) & 1u) << 1);
+    const uint32_t mk = reinterpret_cast<const uint32_t *>(tab + TAB_TOP)[ay * 17 + j0] |
+                        reinterpret_cast<const uint32_t *>(tab + TAB_COL)[colbits * 17 + j0];
+    uint32_t c = (win & ~mk) | (0x55555555u & mk);
+    const int d = 152 - k0;  // agent cell: view (8,16)
+    if ((unsigned)d < 16u) c &= ~(3u << (2 * d));
     return c;
 }
 
-// 4 code bytes -> 12 obs bytes (type,color,0 per cell) as 3 words
-__device__ __forceinline__ void expand4(uint32_t w, uint32_t &o0, uint32_t &o1, uint32_t &o2) {
-    const uint32_t sel = __byte_perm(w | (w >> 4), 0u, 0x4420u);  // c0 | c1<<4 | c2<<8 | c3<<12
-    const uint32_t t4 = __byte_perm(TYPE_LUT, 0u, sel);
-    const uint32_t c4 = __byte_perm(COLOR_LUT, 0u, sel);
-    o0 = __byte_perm(t4, c4, 0x1040u) & 0xFF00FFFFu;  // t0 c0 0 t1
-    o1 = __byte_perm(t4, c4, 0x6205u) & 0xFFFF00FFu;  // c1 0 t2 c2
-    o2 = __byte_perm(t4, c4, 0x0730u) & 0x00FFFF00u;  // 0 t3 c3 0
+// 16 packed cells -> 48 obs bytes through the 256-entry (4 cells -> 12 bytes) table, stored as
+// three 16-byte vectors at dst (16-byte aligned)
+__device__ __forceinline__ void expand16_store(uint32_t c, const uint8_t *tab, uint4 *dst) {
+    const uint4 *lut = reinterpret_cast<const uint4 *>(tab + TAB_LUT);
+    const uint4 a = lut[c & 0xFFu], b = lut[(c >> 8) & 0xFFu], cc = lut[(c >> 16) & 0xFFu], d = lut[c >> 24];
+    dst[0] = make_uint4(a.x, a.y, a.z, b.x);
+    dst[1] = make_uint4(b.y, b.z, cc.x, cc.y);
+    dst[2] = make_uint4(cc.z, d.x, d.y, d.z);
 }
 
-__device__ __forceinline__ void expand16_store(uint8_t *stage, int run, uint4 c) {
-    uint4 a, b, d;
-    expand4(c.x, a.x, a.y, a.z);
-    expand4(c.y, a.w, b.x, b.y);
-    expand4(c.z, b.z, b.w, d.x);
-    expand4(c.w, d.y, d.z, d.w);
-    uint4 *dst = reinterpret_cast<uint4 *>(stage + run * 48);
-    dst[0] = a;
-    dst[1] = b;
-    dst[2] = d;
-}
-
-// One half tile (16 envs x 289 cells = 289 runs of 16 cells -> 13872 B) for V = 17.
-__device__ __forceinline__ void fill_stage_v17(uint8_t *stage, const uint8_t *gpad, const uint8_t *tab,
-                                               const uint32_t *meta, int half, int lane) {
-    constexpr int RUNS = HALF * NCELL / 16;  // 289
-    for (int run = lane; run < RUNS; run += 32) {
-        const int q0 = run * 16;
-        const int e = q0 / NCELL, k0 = q0 - e * NCELL;
-        const int ge = half * HALF + e;
-        expand16_store(stage, run, codes16_v17(gpad, tab, meta[ge], ge, k0));
-    }
-    __syncwarp();
-    // runs that straddle two envs: run 18c holds the last c cells of env c-1 and the first
-    // 16-c cells of env c (c = 1..15); redo them with both halves merged
-    if (lane >= 1 && lane < HALF) {
-        const int c = lane, run = 18 * c;
-        const int ea = half * HALF + c - 1, eb = ea + 1;
-        uint4 ca = codes16_v17(gpad, tab, meta[ea], ea, NCELL - c);
-        uint4 cb = codes16_v17(gpad, tab, meta[eb], eb, -c);
-        // bytes [0,c) from ca, bytes [c,16) from cb
-        uint32_t mk[4];
+// V = 17, whole tile: the obs block (32 x 867 B = 27744 B) is 578 runs of 16 cells / 48 bytes.
+// Every lane builds one run per iteration; the 30 runs that straddle two envs are skipped in
+// the main loop and rebuilt by warp 3 (which has one block fewer) from both envs.
+// XPOSE: the warp's 32 x 48 B go through a shared-memory transposer so that each global store
+// instruction writes 512 contiguous bytes; otherwise every lane stores its own 48 bytes.
+template <bool XPOSE>
+__device__ __forceinline__ void emit_run(uint32_t c, bool valid, const uint8_t *tab, uint4 *d4, int run, uint4 *xp,
+                                         int lane) {
+    if (XPOSE) {
+        if (valid) expand16_store(c, tab, xp + 3 * lane);
+        __syncwarp();
+        const int u0 = (run - lane) * 3;  // first uint4 of this warp-iteration's 1536-byte block
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            int nb = c - 4 * w;  // how many low bytes of this word come from ca
-            mk[w] = nb <= 0 ? 0u : (nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u));
+        for (int k = 0; k < 3; k++) {
+            const int src_lane = (32 * k + lane) / 3;  // the lane whose run produced this uint4
+            const bool ok = __shfl_sync(0xFFFFFFFFu, (int)valid, src_lane) != 0;
+            if (ok) d4[u0 + 32 * k + lane] = xp[32 * k + lane];
         }
-        uint4 cm;
-        cm.x = (ca.x & mk[0]) | (cb.x & ~mk[0]);
-        cm.y = (ca.y & mk[1]) | (cb.y & ~mk[1]);
-        cm.z = (ca.z & mk[2]) | (cb.z & ~mk[2]);
-        cm.w = (ca.w & mk[3]) | (cb.w & ~mk[3]);
-        expand16_store(stage, run, cm);
+        __syncwarp();
+    } else {
+        if (valid) expand16_store(c, tab, d4 + 3 * run);
+    }
+}
+
+template <bool XPOSE>
+__device__ __forceinline__ void obs_tile_v17(uint8_t *dst, const uint32_t *gpadw, const uint8_t *tab,
+                                             const uint32_t *runtab, const uint32_t *meta, uint8_t *xpose, int warp,
+                                             int lane) {
+    constexpr int BLOCKS = 19;  // ceil(578 / 32)
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    uint4 *xp = reinterpret_cast<uint4 *>(xpose);
+#pragma unroll 2
+    for (int bi = warp; bi < BLOCKS; bi += STEP_WARPS) {
+        const int run = bi * 32 + lane;
+        const uint32_t rt = __ldg(runtab + run);  // coalesced, L1-resident after the first tile
+        const int e = (int)(rt & 31u), k0 = (int)((rt >> 5) & 511u), j0 = (int)((rt >> 14) & 31u),
+                  i0p1 = (int)((rt >> 19) & 31u);
+        const uint32_t c = codes16_v17(gpadw, tab, meta[e], k0, i0p1, j0);
+        emit_run<XPOSE>(c, (rt >> 24) == 0u, tab, d4, run, xp, lane);
+    }
+    if (warp == STEP_WARPS - 1) {
+        // boundary between env cidx-1 and env cidx; env 16 starts exactly on a run boundary
+        const int cidx = lane;
+        const bool valid = lane >= 1 && lane != 16;
+        const int run = (NCELL * cidx) >> 4;
+        const int k0a = valid ? 16 * run - NCELL * (cidx - 1) : 274;  // [274,288]: column 16 of env cidx-1
+        const int k0b = k0a - NCELL;                                   // [-15,-1]: "column -1" of env cidx
+        const uint32_t ca = codes16_v17(gpadw, tab, meta[valid ? cidx - 1 : 0], k0a, 17, k0a - 272);
+        const uint32_t cb = codes16_v17(gpadw, tab, meta[valid ? cidx : 1], k0b, 0, k0b + 17);
+        const uint32_t keep = (1u << (2 * (NCELL - k0a))) - 1u;
+        if (valid) expand16_store((ca & keep) | (cb & ~keep), tab, d4 + 3 * run);
+    }
+}
+
+// Any other odd V <= 17: CE envs at a time are expanded per cell into the shared staging area
+// and copied out with coalesced 4-byte stores.
+template <int V>
+__device__ __forceinline__ void obs_tile_generic(uint8_t *dst, long long limit_bytes, const uint32_t *gw,
+                                                 const uint32_t *meta, uint8_t *stage, int tid) {
+    constexpr int VV = V * V, OBS = 3 * VV;
+    constexpr int CE = (32 * OBS <= STAGE_BYTES) ? 32 : (16 * OBS <= STAGE_BYTES) ? 16 : (8 * OBS <= STAGE_BYTES) ? 8 : 4;
+    static_assert(CE * OBS <= STAGE_BYTES, "staging too small");
+    for (int e0 = 0; e0 < TILE; e0 += CE) {
+        for (int c = tid; c < CE * VV; c += STEP_THREADS) {
+            const int e = c / VV, k = c - e * VV, i = k / V, j = k - i * V;
+            const uint32_t m = meta[e0 + e];
+            const int x = (int)(m >> 24) - V / 2 + i, y = (int)((m >> 16) & 31u) - (V - 1) + j;
+            uint32_t code = inb(x, y) ? cell_get(gw + (e0 + e) * REC_WORDS, x, y) : C_WALL;
+            if (i == V / 2 && j == V - 1) code = C_EMPTY;
+            stage[3 * c + 0] = (uint8_t)(TYPE_LUT >> (8 * code));
+            stage[3 * c + 1] = (uint8_t)(COLOR_LUT >> (8 * code));
+            stage[3 * c + 2] = 0;
+        }
+        __syncthreads();
+        const long long base = (long long)e0 * OBS;
+        for (int w = tid; w < CE * OBS / 4; w += STEP_THREADS) {
+            const long long b0 = base + 4ll * w;
+            if (b0 + 4 <= limit_bytes) *reinterpret_cast<uint32_t *>(dst + b0) = reinterpret_cast<const uint32_t *>(stage)[w];
+            else if (b0 < limit_bytes)
+                for (int b = 0; b < (int)(limit_bytes - b0); b++) dst[b0 + b] = stage[4 * w + b];
+        }
+        __syncthreads();
     }
 }
 
@@ -229,291 +251,295 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, long 
 }
 
 template <int V, bool FAST>
-__global__ void __launch_bounds__(STEP_WARPS * 32, 1) step_obs_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(STEP_THREADS, STEP_CTAS_PER_SM) step_obs_kernel(const StepArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *tab = smem;
-    uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem + TAB_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *wbase = smem + TAB_BYTES + 16 + warp * WARP_SMEM;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
-    uint32_t *meta = reinterpret_cast<uint32_t *>(wbase + 16);
-    uint8_t *gpad = wbase + 16 + 128;
-    uint8_t *g = gpad + G_PAD_BEFORE;
-    uint8_t *stage = gpad + G_PAD_BEFORE + G_BYTES + G_PAD_AFTER;
+    uint8_t *tab = smem + SM_TAB;
+    uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem + SM_BARS);
+    uint64_t *bar = tab_bar + 1;
+    uint32_t *meta = reinterpret_cast<uint32_t *>(smem + SM_META);
+    uint8_t *gpad = smem + SM_GPAD;
+    uint32_t *gw = reinterpret_cast<uint32_t *>(gpad + G_PAD_BEFORE);
+    uint8_t *stage = smem + SM_STAGE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int OBS_ENV = 3 * V * V;
-    constexpr int STAGE_BYTES = HALF * OBS_ENV;
 
-    if (threadIdx.x == 0) mbar_init(tab_bar, 1);
-    if (lane == 0) mbar_init(bar, 1);
-    fence_mbar_init();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(tab_bar, TAB_BYTES);
-        bulk_g2s(tab, a.tables, TAB_BYTES, tab_bar);
+    if (tid == 0) {
+        mbar_init(tab_bar, 1);
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(tab_bar, TAB_SMEM_BYTES);
+        bulk_g2s(tab, a.tables, TAB_SMEM_BYTES, tab_bar);
     }
+    __syncthreads();
     uint32_t phase = 0;
-    bool tab_ready = false;
     const bool v4 = a.version == 4;
+    bool first = true;
+    const uint32_t *runtab = reinterpret_cast<const uint32_t *>(a.tables + TAB_RUN);
 
-    for (int it = warp;; it += STEP_WARPS) {
-        const long long tile = (long long)blockIdx.x + (long long)gridDim.x * it;
-        if (tile >= a.ntiles) break;
-        // previous tile's bulk stores must have finished reading g / stage
-        if (lane == 0) {
-            bulk_wait_read0();
-            mbar_expect_tx(bar, G_BYTES);
-            bulk_g2s(g, a.grid + tile * G_BYTES, G_BYTES, bar);
-        }
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        // ---- tile prologue (warp 0): state of 32 envs -> registers, packed grids -> smem -------
         const long long env = tile * TILE + lane;
         const bool live = env < a.n;
-        uint4 s0 = a.sc0[env], s1 = a.sc1[env];
-        int act = live ? load_action(a.actions, a.action_dtype, env) : 6;
-        DrawSrc d;
-        d.replay = a.draws != nullptr;
-        d.rec_lo = d.rec_hi = 0xFFFFFFFFu;
-        if (d.replay && live) {
-            uint2 r = reinterpret_cast<const uint2 *>(a.draws)[env];
-            d.rec_lo = r.x;
-            d.rec_hi = r.y;
-        }
-        d.have = false;
-        d.consumed = 0;
-        d.k0 = a.seed_lo;
-        d.k1 = a.seed_hi;
-        {
-            unsigned long long gid = a.env_id0 + (unsigned long long)env;
-            d.c0 = (uint32_t)gid;
-            d.c1 = (uint32_t)(gid >> 32);
-        }
-
-        int ax = (int)(s0.x & 0xFFu), ay = (int)((s0.x >> 8) & 0xFFu);
-        uint32_t fl = (s0.x >> 16) & 0xFFu;
-        int risk = (int)(s0.x >> 24);
-        int step_count = (int)s0.y, step_move = (int)s0.z;
-        uint32_t tcount = s0.w;
-        uint32_t mid[3] = {ball_get(s1.x, 0), ball_get(s1.x, 1), ball_get(s1.x, 2)};
-        uint32_t o1[3] = {ball_get(s1.y, 0), ball_get(s1.y, 1), ball_get(s1.y, 2)};
-        uint32_t o2[4] = {ball_get(s1.z, 0), ball_get(s1.z, 1), ball_get(s1.z, 2), ball_get(s1.w, 0)};
-        uint32_t err = (s1.w >> 16) & 0xFFu;
-
-        // ---- pre-checks: situations where the reference raises (documented divergence:
-        // the env is left untouched and an error bit is set) ---------------------------------
-        if (act >= 7) act = 0;  // twoarmy_v4.py:84-85
-        int adx = 0, ady = 0;
-        if (act == 0) adx = -1;
-        else if (act == 1) adx = 1;
-        else if (act == 2) ady = -1;
-        else if (act == 3) ady = 1;
-        bool skip = false;
-        if (!(act == 0 || act == 1 || act == 2 || act == 3 || act == 6)) {
-            err |= ERR_BAD_ACTION;
-            skip = true;
-        } else if ((fl & F_PATROL) && (o1[0] == NOPOS || o2[0] == NOPOS)) {
-            err |= ERR_NONE_POS;
-            skip = true;
-        } else if (!inb(ax + adx, ay + ady)) {
-            err |= ERR_OOB_MOVE;
-            skip = true;
-        }
-
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        uint8_t *G = g + lane * NCELL;
-        bool term = false, trunc = false;
-        d.t = tcount;
-
-        // ---- phase A: everything up to and including the agent move -------------------------
-        if (!skip) {
-            tcount += 1u;
-            step_move += 1;
-            const int m6 = step_move % 6, m4 = step_move & 3;
-            {  // mid-row balls, twoarmy_v4.py:95-111
-                const int dx = (m6 == 1 || m6 == 0) ? 1 : ((m6 == 2 || m6 == 3) ? -1 : 0);
-                move_group<3>(G, mid, dx, 0, true);
+        int ax = 0, ay = 0, risk = 0, step_count = 0, step_move = 0;
+        uint32_t fl = 0, tcount = 0, err = 0;
+        uint32_t mid[3] = {0, 0, 0}, o1[3] = {0, 0, 0}, o2[4] = {0, 0, 0, 0};
+        uint32_t *G = gw + lane * REC_WORDS;
+        long long nvalid = a.n - tile * TILE;
+        nvalid = nvalid > TILE ? TILE : nvalid;
+        if (warp == 0) {
+            if (lane == 0) {
+                bulk_wait_read0();  // the previous tile's grid store has finished reading smem
+                mbar_expect_tx(bar, G_BYTES);
+                bulk_g2s(gw, a.grid + tile * (G_BYTES / 4), G_BYTES, bar);
             }
-            if (v4) {
-                if (fl & F_UPD_L) {  // twoarmy_v4.py:115-144
-                    fl &= ~F_UPD_H;
-                    if (m4 == 2 || m6 == 3 || m6 == 0 || draw(d, 0, 0) == 6) {
-                        if (fl & F_PATROL) {
-                            if (fl & F_UP1) {
-                                move_group<3>(G, o1, 0, -1, false);
+            const uint4 s0 = a.sc0[env], s1 = a.sc1[env];
+            ax = (int)(s0.x & 0xFFu);
+            ay = (int)((s0.x >> 8) & 0xFFu);
+            fl = (s0.x >> 16) & 0xFFu;
+            risk = (int)(s0.x >> 24);
+            step_count = (int)s0.y;
+            step_move = (int)s0.z;
+            tcount = s0.w;
+            mid[0] = ball_get(s1.x, 0); mid[1] = ball_get(s1.x, 1); mid[2] = ball_get(s1.x, 2);
+            o1[0] = ball_get(s1.y, 0); o1[1] = ball_get(s1.y, 1); o1[2] = ball_get(s1.y, 2);
+            o2[0] = ball_get(s1.z, 0); o2[1] = ball_get(s1.z, 1); o2[2] = ball_get(s1.z, 2);
+            o2[3] = ball_get(s1.w, 0);
+            err = (s1.w >> 16) & 0xFFu;
+        }
+
+        // ---- T env steps on the resident tile -------------------------------------------------
+        for (int t = 0; t < a.T; t++) {
+            const long long out_idx = (long long)t * a.n + env;  // [T][n] outputs
+            bool skip = false, term = false, trunc = false;
+            DrawSrc d;
+            d.rec_lo = d.rec_hi = 0xFFFFFFFFu;
+            d.consumed = 0;
+            // ---- warp 0, phase A: everything up to and including the agent move -------------
+            if (warp == 0) {
+                int act = live ? load_action(a.actions, a.action_dtype, out_idx) : 6;
+                if (a.draws != nullptr) {
+                    if (live) {
+                        const uint2 r = reinterpret_cast<const uint2 *>(a.draws)[out_idx];
+                        d.rec_lo = r.x;
+                        d.rec_hi = r.y;
+                    }
+                } else {
+                    const unsigned long long gid = a.env_id0 + (unsigned long long)env;
+                    philox_record(d, (uint32_t)gid, (uint32_t)(gid >> 32), tcount, a.seed_lo, a.seed_hi);
+                }
+                // situations where the reference raises (documented divergence: the env is left
+                // untouched and an error bit is set)
+                if (act >= 7) act = 0;  // twoarmy_v4.py:84-85
+                int adx = 0, ady = 0;
+                if (act == 0) adx = -1;
+                else if (act == 1) adx = 1;
+                else if (act == 2) ady = -1;
+                else if (act == 3) ady = 1;
+                if (!(act == 0 || act == 1 || act == 2 || act == 3 || act == 6)) {
+                    err |= ERR_BAD_ACTION;
+                    skip = true;
+                } else if ((fl & F_PATROL) && (o1[0] == NOPOS || o2[0] == NOPOS)) {
+                    err |= ERR_NONE_POS;
+                    skip = true;
+                } else if (!inb(ax + adx, ay + ady)) {
+                    err |= ERR_OOB_MOVE;
+                    skip = true;
+                }
+                if (t == 0) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                }
+                if (!skip) {
+                    tcount += 1u;
+                    step_move += 1;
+                    const int m6 = step_move % 6, m4 = step_move & 3;
+                    {  // mid-row balls, twoarmy_v4.py:95-111
+                        const int dx = (m6 == 1 || m6 == 0) ? 1 : ((m6 == 2 || m6 == 3) ? -1 : 0);
+                        move_group<3>(G, mid, dx, 0, true);
+                    }
+                    if (v4) {
+                        bool mv1 = false, mv2 = false;
+                        if (fl & F_UPD_L) {  // twoarmy_v4.py:115-144 (the draw is short-circuited)
+                            fl &= ~F_UPD_H;
+                            if (m4 == 2 || m6 == 3 || m6 == 0 || draw(d, 0) == 6) mv1 = (fl & F_PATROL) != 0;
+                        }
+                        if (fl & F_UPD_H) {  // twoarmy_v4.py:147-176
+                            fl &= ~F_UPD_L;
+                            if (m6 != 1 || draw(d, 0) == 6) mv2 = (fl & F_PATROL) != 0;
+                        }
+                        if (mv1) {
+                            const bool up = (fl & F_UP1) != 0;
+                            move_group<3>(G, o1, 0, up ? -1 : 1, false);
+                            if (up) {
                                 if (pos_y(o1[0]) == 3) fl &= ~F_UP1;
-                            } else {
-                                move_group<3>(G, o1, 0, 1, false);
-                                if (pos_y(o1[2]) == 7) fl |= F_UP1;
+                            } else if (pos_y(o1[2]) == 7) {
+                                fl |= F_UP1;
                             }
                         }
-                    }
-                }
-                if (fl & F_UPD_H) {  // twoarmy_v4.py:147-176
-                    fl &= ~F_UPD_L;
-                    if (m6 == 0 || m6 == 2 || m6 == 3 || m6 == 5 || m6 == 4 || draw(d, 0, 0) == 6) {
-                        if (fl & F_PATROL) {
-                            if (fl & F_RIGHT2) {
-                                move_group<4>(G, o2, 1, 0, false);
+                        if (mv2) {
+                            const bool right = (fl & F_RIGHT2) != 0;
+                            move_group<4>(G, o2, right ? 1 : -1, 0, false);
+                            if (right) {
                                 if (pos_x(o2[3]) == 11) fl &= ~F_RIGHT2;
-                            } else {
-                                move_group<4>(G, o2, -1, 0, false);
-                                if (pos_x(o2[0]) == 5) fl |= F_RIGHT2;
+                            } else if (pos_x(o2[0]) == 5) {
+                                fl |= F_RIGHT2;
                             }
                         }
                     }
+                    // MiniGridEnv.step, minigrid.py:1333-1441
+                    step_count += 1;
+                    const int tx = ax + adx, ty = ay + ady;
+                    const uint32_t c = cell_get(G, tx, ty);
+                    if (c == C_EMPTY || c == C_GOAL) {
+                        ax = tx;
+                        ay = ty;
+                    }
+                    if (c == C_GOAL) term = true;
+                    if (step_count >= 50) trunc = true;
+                }
+                meta[lane] = make_meta(lane, ax, ay);
+            }
+            if (first) {  // LUT, masks and the reset template
+                mbar_wait(tab_bar, 0);
+                first = false;
+            }
+            __syncthreads();
+
+            // ---- phase B: observations of all 32 envs, every warp ----------------------------
+            {
+                uint8_t *dst = a.obs + ((long long)t * a.n + tile * TILE) * OBS_ENV;
+                if (FAST && nvalid == TILE && (((long long)t * a.n * OBS_ENV) & 15) == 0) {
+                    if (a.flags & 2)
+                        obs_tile_v17<true>(dst, reinterpret_cast<const uint32_t *>(gpad), tab, runtab, meta,
+                                           stage + warp * 1536, warp, lane);
+                    else
+                        obs_tile_v17<false>(dst, reinterpret_cast<const uint32_t *>(gpad), tab, runtab, meta, stage, warp,
+                                            lane);
+                } else {  // other view sizes, and the ragged last tile of a batch
+                    obs_tile_generic<V>(dst, nvalid * OBS_ENV, gw, meta, stage, tid);
                 }
             }
-            // MiniGridEnv.step, minigrid.py:1333-1441
-            step_count += 1;
-            const int tx = ax + adx, ty = ay + ady;
-            const uint32_t c = G[tx * GS + ty];
-            if (c == C_EMPTY || c == C_GOAL) {
-                ax = tx;
-                ay = ty;
-            }
-            if (c == C_GOAL) term = true;
-            if (step_count >= 50) trunc = true;
-        }
-        meta[lane] = (uint32_t)ax | ((uint32_t)ay << 8);
-        __syncwarp();
+            __syncthreads();
 
-        // ---- phase B: observations of all 32 envs, 16 at a time ----------------------------
-        if (!tab_ready) {  // mask tables (V=17 path) and the reset template
-            mbar_wait(tab_bar, 0);
-            tab_ready = true;
-        }
-#pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-            if (half == 1) {
-                if (lane == 0) bulk_wait_read0();
+            // ---- warp 0, phase C: rest of Twoarmy.step ----------------------------------------
+            if (warp == 0) {
+                int reward = R_STEP;  // twoarmy_v4.py:180
+                bool need_reset = false;
+                if (!skip) {
+                    if (!(fl & F_PONE) && (ax > 3 || ay < 14)) {  // twoarmy_v4.py:181-195, twoarmy_v6.py:182-198
+                        int i = v4 ? draw(d, 1) : 11;
+                        put_cell(G, 4, i, C_WALL); put_cell(G, 5, i, C_WALL);
+                        put_cell(G, 4, i + 1, C_WALL); put_cell(G, 5, i + 1, C_WALL);
+                        i = v4 ? draw(d, 2) : 8;
+                        put_cell(G, i, 11, C_WALL); put_cell(G, i, 12, C_WALL);
+                        put_cell(G, i + 1, 11, C_WALL); put_cell(G, i + 1, 12, C_WALL);
+                        fl |= F_PONE;
+                    }
+                    if (v4 && !(fl & F_PATROL) && ay <= 8) {  // twoarmy_v4.py:212-225
+                        const int i = draw(d, 3);
+                        const int bx[4] = {i, i + 1, i, i + 1}, by[4] = {4, 4, 5, 5};
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (inb(bx[k], by[k])) {
+                                cell_set(G, bx[k], by[k], C_BALL);
+                                o2[k] = pack_pos(bx[k], by[k]);
+                            }
+                        d.consumed |= 1u << 4;  // :221 choice(range(4,5)) == 4, no generator words
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            cell_set(G, 12, 4 + k, C_BALL);
+                            o1[k] = pack_pos(12, 4 + k);
+                        }
+                        fl |= F_PATROL;
+                    }
+                    const uint32_t ap = pack_pos(ax, ay);
+                    // twoarmy_v4.py:228-240
+                    if (ap == mid[0] || ap == mid[1] || ap == mid[2]) {
+                        reward = R_HIT;
+                        trunc = true;
+                    }
+                    if (ay == pos_y(mid[0]) + 1 && (ax == pos_x(mid[0]) || ax == pos_x(mid[1]) || ax == pos_x(mid[2])))
+                        reward = R_RISK;
+                    if (fl & F_PATROL) {  // twoarmy_v4.py:242-280
+                        if (ay == pos_y(o2[2]) + 1 && (ax == pos_x(o2[2]) || ax == pos_x(o2[3]))) reward = R_RISK;
+                        if (ax == pos_x(o2[0]) - 1 && (ay == pos_y(o2[0]) || ay == pos_y(o2[2]))) reward = R_RISK;
+                        if (ax == pos_x(o2[1]) + 1 && (ay == pos_y(o2[1]) || ay == pos_y(o2[3]))) reward = R_RISK;
+                        if (ax == pos_x(o1[0]) - 1 && (ay == pos_y(o1[0]) || ay == pos_y(o1[1]) || ay == pos_y(o1[2])))
+                            reward = R_RISK;
+                        if (ap == o1[0] || ap == o1[1] || ap == o1[2] || ap == o2[0] || ap == o2[1] || ap == o2[2] ||
+                            ap == o2[3]) {
+                            reward = R_HIT;
+                            trunc = true;
+                        }
+                    }
+                    if ((fl & F_FIRST) && ay == 7) {  // twoarmy_v4.py:282-285
+                        reward = R_ROOM2;
+                        fl &= ~F_FIRST;
+                    }
+                    if (reward == R_RISK) {  // twoarmy_v4.py:287-291
+                        risk += 1;
+                        if (risk > 5) trunc = true;
+                    }
+                    if (term || trunc) {  // twoarmy_v4.py:293-315
+                        if (term) reward = R_GOAL;
+                        step_move = 0;
+                        fl &= ~(F_PONE | F_PATROL);
+                        fl |= F_FIRST;
+                        risk = 0;
+                        if (draw(d, 5) == 1) fl = (fl & ~F_UP1) | F_RIGHT2;
+                        else fl = (fl | F_UP1) & ~F_RIGHT2;
+                        if (draw(d, 6) == 1) fl = (fl & ~F_UPD_H) | F_UPD_L;
+                        else fl = (fl | F_UPD_H) & ~F_UPD_L;
+                        need_reset = (a.flags & 1) != 0;
+                    }
+                }
+                if (live) {
+                    a.reward[out_idx] = reward_value(reward);
+                    a.term[out_idx] = term ? 1 : 0;
+                    a.trunc[out_idx] = trunc ? 1 : 0;
+                    if (a.consumed) a.consumed[out_idx] = (uint8_t)d.consumed;
+                }
+                // autoreset: MiniGridEnv.reset (minigrid.py:947-980) -- grid, balls, agent, step_count
+                if (need_reset) {
+                    ax = 3; ay = 15; step_count = 0;
+                    mid[0] = ball_get(MID_INIT, 0); mid[1] = ball_get(MID_INIT, 1); mid[2] = ball_get(MID_INIT, 2);
+                    o1[0] = o1[1] = o1[2] = NOPOS;
+                    o2[0] = o2[1] = o2[2] = o2[3] = NOPOS;
+                }
+                __syncwarp();
+                uint32_t rmask = __ballot_sync(0xFFFFFFFFu, need_reset);
+                while (rmask) {
+                    const int e = __ffs(rmask) - 1;
+                    rmask &= rmask - 1;
+                    if (lane < REC_WORDS)
+                        gw[e * REC_WORDS + lane] = reinterpret_cast<const uint32_t *>(tab + TAB_TEMPLATE)[lane];
+                }
                 __syncwarp();
             }
-            if (FAST) fill_stage_v17(stage, gpad, tab, meta, half, lane);
-            else fill_stage_generic<V>(stage, g, meta, half, lane);
+        }
+
+        // ---- tile epilogue (warp 0): registers -> state arrays, packed grids -> HBM ------------
+        if (warp == 0) {
+            uint4 s0, s1;
+            s0.x = (uint32_t)ax | ((uint32_t)ay << 8) | (fl << 16) | ((uint32_t)risk << 24);
+            s0.y = (uint32_t)step_count;
+            s0.z = (uint32_t)step_move;
+            s0.w = tcount;
+            s1.x = mid[0] | (mid[1] << 10) | (mid[2] << 20);
+            s1.y = o1[0] | (o1[1] << 10) | (o1[2] << 20);
+            s1.z = o2[0] | (o2[1] << 10) | (o2[2] << 20);
+            s1.w = o2[3] | (err << 16);
+            a.sc0[env] = s0;
+            a.sc1[env] = s1;
             fence_proxy_async();
             __syncwarp();
-            const long long e0 = tile * TILE + half * HALF;
-            long long nvalid = a.n - e0;
-            nvalid = nvalid < 0 ? 0 : (nvalid > HALF ? HALF : nvalid);
-            uint8_t *dst = a.obs + e0 * OBS_ENV;
-            if (nvalid == HALF) {
-                if (lane == 0) {
-                    bulk_s2g(dst, stage, STAGE_BYTES);
-                    bulk_commit();
-                }
-            } else {  // ragged last tile: plain stores
-                for (int i = lane; i < (int)nvalid * OBS_ENV; i += 32) dst[i] = stage[i];
-                __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(a.grid + tile * (G_BYTES / 4), gw, G_BYTES);
+                bulk_commit();
             }
-        }
-
-        // ---- phase C: rest of Twoarmy.step ---------------------------------------------------
-        int reward = R_STEP;  // twoarmy_v4.py:180
-        bool need_reset = false;
-        if (!skip) {
-            if (!(fl & F_PONE) && (ax > 3 || ay < 14)) {  // twoarmy_v4.py:181-195, twoarmy_v6.py:182-198
-                int i = v4 ? draw(d, 1, 9) : 11;
-                put_cell(G, 4, i, C_WALL); put_cell(G, 5, i, C_WALL);
-                put_cell(G, 4, i + 1, C_WALL); put_cell(G, 5, i + 1, C_WALL);
-                i = v4 ? draw(d, 2, 6) : 8;
-                put_cell(G, i, 11, C_WALL); put_cell(G, i, 12, C_WALL);
-                put_cell(G, i + 1, 11, C_WALL); put_cell(G, i + 1, 12, C_WALL);
-                fl |= F_PONE;
-            }
-            if (v4 && !(fl & F_PATROL) && ay <= 8) {  // twoarmy_v4.py:212-225
-                const int i = draw(d, 3, 6);
-                const int bx[4] = {i, i + 1, i, i + 1}, by[4] = {4, 4, 5, 5};
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (inb(bx[k], by[k])) {
-                        G[bx[k] * GS + by[k]] = (uint8_t)C_BALL;
-                        o2[k] = pack_pos(bx[k], by[k]);
-                    }
-                d.consumed |= 1u << 4;  // :221 choice(range(4,5)) == 4, no generator words
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    G[12 * GS + 4 + k] = (uint8_t)C_BALL;
-                    o1[k] = pack_pos(12, 4 + k);
-                }
-                fl |= F_PATROL;
-            }
-            const uint32_t ap = pack_pos(ax, ay);
-            // twoarmy_v4.py:228-240
-            if (ap == mid[0] || ap == mid[1] || ap == mid[2]) {
-                reward = R_HIT;
-                trunc = true;
-            }
-            if (ay == pos_y(mid[0]) + 1 && (ax == pos_x(mid[0]) || ax == pos_x(mid[1]) || ax == pos_x(mid[2])))
-                reward = R_RISK;
-            if (fl & F_PATROL) {  // twoarmy_v4.py:242-280
-                if (ay == pos_y(o2[2]) + 1 && (ax == pos_x(o2[2]) || ax == pos_x(o2[3]))) reward = R_RISK;
-                if (ax == pos_x(o2[0]) - 1 && (ay == pos_y(o2[0]) || ay == pos_y(o2[2]))) reward = R_RISK;
-                if (ax == pos_x(o2[1]) + 1 && (ay == pos_y(o2[1]) || ay == pos_y(o2[3]))) reward = R_RISK;
-                if (ax == pos_x(o1[0]) - 1 && (ay == pos_y(o1[0]) || ay == pos_y(o1[1]) || ay == pos_y(o1[2])))
-                    reward = R_RISK;
-                if (ap == o1[0] || ap == o1[1] || ap == o1[2] || ap == o2[0] || ap == o2[1] || ap == o2[2] ||
-                    ap == o2[3]) {
-                    reward = R_HIT;
-                    trunc = true;
-                }
-            }
-            if ((fl & F_FIRST) && ay == 7) {  // twoarmy_v4.py:282-285
-                reward = R_ROOM2;
-                fl &= ~F_FIRST;
-            }
-            if (reward == R_RISK) {  // twoarmy_v4.py:287-291
-                risk += 1;
-                if (risk > 5) trunc = true;
-            }
-            if (term || trunc) {  // twoarmy_v4.py:293-315
-                if (term) reward = R_GOAL;
-                step_move = 0;
-                fl &= ~(F_PONE | F_PATROL);
-                fl |= F_FIRST;
-                risk = 0;
-                if (draw(d, 5, 0) == 1) fl = (fl & ~F_UP1) | F_RIGHT2;
-                else fl = (fl | F_UP1) & ~F_RIGHT2;
-                if (draw(d, 6, 0) == 1) fl = (fl & ~F_UPD_H) | F_UPD_L;
-                else fl = (fl | F_UPD_H) & ~F_UPD_L;
-                need_reset = (a.flags & 1) != 0;
-            }
-        }
-        if (live) {
-            a.reward[env] = reward_value(reward);
-            a.term[env] = term ? 1 : 0;
-            a.trunc[env] = trunc ? 1 : 0;
-            if (a.consumed) a.consumed[env] = (uint8_t)d.consumed;
-        }
-        // autoreset: MiniGridEnv.reset (minigrid.py:947-980) -- grid, balls, agent, step_count
-        if (need_reset) {
-            ax = 3; ay = 15; step_count = 0;
-            mid[0] = ball_get(MID_INIT, 0); mid[1] = ball_get(MID_INIT, 1); mid[2] = ball_get(MID_INIT, 2);
-            o1[0] = o1[1] = o1[2] = NOPOS;
-            o2[0] = o2[1] = o2[2] = o2[3] = NOPOS;
-        }
-        __syncwarp();
-        uint32_t rmask = __ballot_sync(0xFFFFFFFFu, need_reset);
-        while (rmask) {
-            const int e = __ffs(rmask) - 1;
-            rmask &= rmask - 1;
-            for (int i = lane; i < NCELL; i += 32) g[e * NCELL + i] = tab[TAB_TEMPLATE + i];
-        }
-        s0.x = (uint32_t)ax | ((uint32_t)ay << 8) | (fl << 16) | ((uint32_t)risk << 24);
-        s0.y = (uint32_t)step_count;
-        s0.z = (uint32_t)step_move;
-        s0.w = tcount;
-        s1.x = mid[0] | (mid[1] << 10) | (mid[2] << 20);
-        s1.y = o1[0] | (o1[1] << 10) | (o1[2] << 20);
-        s1.z = o2[0] | (o2[1] << 10) | (o2[2] << 20);
-        s1.w = o2[3] | (err << 16);
-        a.sc0[env] = s0;
-        a.sc1[env] = s1;
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(a.grid + tile * G_BYTES, g, G_BYTES);
-            bulk_commit();
         }
     }
-    if (lane == 0) bulk_wait_all0();
+    if (tid == 0) bulk_wait_all0();
 }
 
 }  // namespace ta

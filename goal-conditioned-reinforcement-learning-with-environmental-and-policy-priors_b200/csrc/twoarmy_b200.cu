@@ -3,6 +3,7 @@
 #include "../../include/twoarmy_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -45,8 +46,10 @@ struct ta_batch {
     int version, view, device, sm_count;
     long long n, npad;
     uint64_t seed, env_id0;
-    uint8_t *grid = nullptr;
+    uint32_t *grid = nullptr;
     uint4 *sc0 = nullptr, *sc1 = nullptr;
+    int ctas_per_sm = STEP_CTAS_PER_SM;
+    int kernel_flags = 2;  // bit 1: transpose obs stores through shared memory (coalesced 512 B stores)
     uint8_t *tables = nullptr;
     // host-call path (ta_step_host)
     cudaStream_t own_stream = nullptr;
@@ -63,21 +66,45 @@ namespace {
 
 void build_tables(std::vector<uint8_t> &t) {
     t.assign(TAB_BYTES, 0);
+    static const uint8_t type_of[4] = {1, 2, 6, 8}, color_of[4] = {0, 5, 4, 1};
+    for (int b = 0; b < 256; b++)  // 4 packed cells -> (type,color,0) x 4
+        for (int k = 0; k < 4; k++) {
+            int c = (b >> (2 * k)) & 3;
+            t[TAB_LUT + b * 16 + 3 * k + 0] = type_of[c];
+            t[TAB_LUT + b * 16 + 3 * k + 1] = color_of[c];
+            t[TAB_LUT + b * 16 + 3 * k + 2] = 0;
+        }
+    uint32_t *top = reinterpret_cast<uint32_t *>(t.data() + TAB_TOP);
     for (int ay = 0; ay < 17; ay++)
-        for (int j0 = 0; j0 < 17; j0++)
-            for (int b = 0; b < 16; b++) {
-                int j = (j0 + b) % 17;
-                t[TAB_TOP + (ay * 17 + j0) * 16 + b] = (j < 16 - ay) ? 0xFF : 0x00;
-            }
+        for (int j0 = 0; j0 < 17; j0++) {
+            uint32_t m = 0;
+            for (int b = 0; b < 16; b++)
+                if ((j0 + b) % 17 < 16 - ay) m |= 3u << (2 * b);
+            top[ay * 17 + j0] = m;
+        }
+    uint32_t *col = reinterpret_cast<uint32_t *>(t.data() + TAB_COL);
     for (int cb = 0; cb < 4; cb++)
-        for (int j0 = 0; j0 < 17; j0++)
+        for (int j0 = 0; j0 < 17; j0++) {
+            uint32_t m = 0;
             for (int b = 0; b < 16; b++) {
                 bool second = j0 + b >= 17;
-                bool off = second ? (cb & 2) : (cb & 1);
-                t[TAB_COL + (cb * 17 + j0) * 16 + b] = off ? 0xFF : 0x00;
+                if (second ? (cb & 2) : (cb & 1)) m |= 3u << (2 * b);
             }
+            col[cb * 17 + j0] = m;
+        }
+    uint32_t *rt = reinterpret_cast<uint32_t *>(t.data() + TAB_RUN);
+    for (int run = 0; run < 608; run++) {
+        if (run >= 578) {
+            rt[run] = 1u << 25;
+            continue;
+        }
+        int q0 = run * 16, e = q0 / NCELL, k0 = q0 - e * NCELL, i0 = k0 / 17, j0 = k0 - 17 * i0;
+        rt[run] = (uint32_t)e | ((uint32_t)k0 << 5) | ((uint32_t)j0 << 14) | ((uint32_t)(i0 + 1) << 19) |
+                  ((k0 > NCELL - 16) ? (1u << 24) : 0u);
+    }
+    uint32_t *tm = reinterpret_cast<uint32_t *>(t.data() + TAB_TEMPLATE);
     for (int x = 0; x < GS; x++)
-        for (int y = 0; y < GS; y++) t[TAB_TEMPLATE + x * GS + y] = (uint8_t)initial_cell(x, y);
+        for (int y = 0; y < GS; y++) cell_set(tm, x, y, initial_cell(x, y));
 }
 
 template <int V, bool FAST>
@@ -88,8 +115,9 @@ int launch_step_t(ta_batch *h, const StepArgs &a, cudaStream_t st) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM));
         attr_set[h->device & 63] = true;
     }
-    int grid = a.ntiles < h->sm_count ? a.ntiles : h->sm_count;
-    kern<<<grid, STEP_WARPS * 32, STEP_SMEM, st>>>(a);
+    const int max_ctas = h->sm_count * h->ctas_per_sm;
+    int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
+    kern<<<grid, STEP_THREADS, STEP_SMEM, st>>>(a);
     return launch_ok("step_obs_kernel");
 }
 
@@ -112,7 +140,8 @@ int launch_step(ta_batch *h, const StepArgs &a, cudaStream_t st) {
 int do_reset(ta_batch *h, const uint8_t *mask, int hard, uint8_t *obs_out, cudaStream_t st, bool pad_too) {
     // padded tail envs (>= n) are reset only at creation
     const long long cnt = pad_too ? h->npad : h->n;
-    reset_grid_kernel<<<blocks_for(cnt * NCELL, 256), 256, 0, st>>>(h->grid, mask, cnt);
+    reset_grid_kernel<<<blocks_for(cnt * REC_WORDS, 256), 256, 0, st>>>(
+        h->grid, reinterpret_cast<const uint32_t *>(h->tables + TAB_TEMPLATE), mask, cnt);
     if (int rc = launch_ok("reset_grid_kernel")) return rc;
     reset_scalar_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(h->sc0, h->sc1, mask, hard, cnt);
     if (int rc = launch_ok("reset_scalar_kernel")) return rc;
@@ -158,13 +187,18 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("TA_XPOSE")) h->kernel_flags = atoi(e) ? 2 : 0;
+    if (const char *e = getenv("TA_CTAS_PER_SM")) {  // tuning knob for experiments
+        int v = atoi(e);
+        if (v >= 1 && v <= 16) h->ctas_per_sm = v;
+    }
     if (prop.major < 10) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; this library is built for sm_100a only", device,
                  prop.major, prop.minor);
         delete h;
         return TA_E_UNSUPPORTED;
     }
-    CK(cudaMalloc(&h->grid, (size_t)h->npad * NCELL));
+    CK(cudaMalloc(&h->grid, (size_t)h->npad * REC_BYTES));
     CK(cudaMalloc(&h->sc0, (size_t)h->npad * sizeof(uint4)));
     CK(cudaMalloc(&h->sc1, (size_t)h->npad * sizeof(uint4)));
     CK(cudaMalloc(&h->tables, TAB_BYTES));
@@ -204,9 +238,10 @@ int ta_reset(ta_handle h, const uint8_t *mask, int hard, uint8_t *obs_out, void 
     return do_reset(h, mask, hard, obs_out, (cudaStream_t)stream, false);
 }
 
-int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags, uint8_t *obs_out,
-            float *reward_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *consumed_out, void *stream) {
-    if (!h || !actions || !obs_out || !reward_out || !term_out || !trunc_out) return TA_E_INVALID;
+static int step_launch(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags, int T,
+                       uint8_t *obs_out, float *reward_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *consumed_out,
+                       void *stream) {
+    if (!h || !actions || !obs_out || !reward_out || !term_out || !trunc_out || T <= 0) return TA_E_INVALID;
     if (action_dtype < 0 || action_dtype > 2) return TA_E_INVALID;
     if (((uintptr_t)obs_out & 15u) || (draws && ((uintptr_t)draws & 7u))) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
@@ -214,8 +249,8 @@ int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *d
     a.grid = h->grid; a.sc0 = h->sc0; a.sc1 = h->sc1; a.tables = h->tables;
     a.actions = actions; a.draws = draws;
     a.obs = obs_out; a.reward = reward_out; a.term = term_out; a.trunc = trunc_out; a.consumed = consumed_out;
-    a.n = h->n; a.ntiles = (int)(h->npad / TILE);
-    a.version = h->version; a.flags = flags; a.action_dtype = action_dtype;
+    a.n = h->n; a.ntiles = (int)(h->npad / TILE); a.T = T;
+    a.version = h->version; a.flags = (flags & 1) | h->kernel_flags; a.action_dtype = action_dtype;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32);
     a.env_id0 = h->env_id0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -223,6 +258,12 @@ int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *d
     int rc = launch_step(h, a, st);
     if (h->timing) CK(cudaEventRecord(h->ev1, st));
     return rc;
+}
+
+int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags, uint8_t *obs_out,
+            float *reward_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *consumed_out, void *stream) {
+    return step_launch(h, actions, action_dtype, draws, flags, 1, obs_out, reward_out, term_out, trunc_out, consumed_out,
+                       stream);
 }
 
 int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, uint8_t *obs_out, float *reward_out,
@@ -253,17 +294,9 @@ int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, 
 
 int ta_rollout(ta_handle h, const void *actions, int action_dtype, int T, uint8_t *obs_out, float *reward_out,
                uint8_t *term_out, uint8_t *trunc_out, void *stream) {
-    if (!h || T <= 0) return TA_E_INVALID;
-    const size_t asz = action_dtype == TA_ACT_I32 ? 4 : (action_dtype == TA_ACT_U8 ? 1 : 8);
-    const size_t obs_env = (size_t)3 * h->view * h->view;
-    if ((obs_env * (size_t)h->n) & 15u) return TA_E_INVALID;  // every step's obs block must stay 16 B aligned
-    for (int t = 0; t < T; t++) {
-        int rc = ta_step(h, (const uint8_t *)actions + (size_t)t * h->n * asz, action_dtype, nullptr, TA_STEP_AUTORESET,
-                         obs_out + (size_t)t * h->n * obs_env, reward_out + (size_t)t * h->n, term_out + (size_t)t * h->n,
-                         trunc_out + (size_t)t * h->n, nullptr, stream);
-        if (rc) return rc;
-    }
-    return TA_OK;
+    // one persistent launch: the env state stays on chip for all T steps
+    return step_launch(h, actions, action_dtype, nullptr, TA_STEP_AUTORESET, T, obs_out, reward_out, term_out, trunc_out,
+                       nullptr, stream);
 }
 
 int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *place_out, void *stream) {
@@ -293,7 +326,7 @@ int ta_export_state(ta_handle h, ta_env_state *out, void *stream) {
 int ta_import_state(ta_handle h, const ta_env_state *in, void *stream) {
     if (!h || !in) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
-    import_kernel<<<blocks_for(h->n * NCELL, 256), 256, 0, (cudaStream_t)stream>>>(
+    import_kernel<<<blocks_for(h->n * REC_WORDS, 256), 256, 0, (cudaStream_t)stream>>>(
         h->grid, h->sc0, h->sc1, reinterpret_cast<const EnvStateRec *>(in), h->n);
     return launch_ok("import_kernel");
 }
