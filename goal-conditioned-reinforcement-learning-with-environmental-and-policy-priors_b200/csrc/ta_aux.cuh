@@ -124,6 +124,8 @@ __global__ void import_kernel(uint32_t *grid, uint4 *sc0, uint4 *sc1, const EnvS
         if (c < NCELL) {
             const int x = c / GS, y = c - x * GS;
             word |= (uint32_t)(in[e].grid[y * GS + x] & 3u) << (2 * b);
+        } else {
+            word |= C_WALL << (2 * b);  // padding cells always hold the wall code (ta_step.cuh)
         }
     }
     grid[i] = word;

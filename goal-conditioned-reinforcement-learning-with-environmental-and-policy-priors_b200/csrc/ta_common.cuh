@@ -4,9 +4,9 @@
 //   grid  uint32 [Npad][20]   the 17x17 grid packed 2 bits per cell into 80 bytes (packed uint8,
 //                             16 cells per word): cell codes 0 empty 1 wall 2 ball 3 goal,
 //                             COLUMN-major inside an env (cell c = x*17+y sits at bits
-//                             [2c,2c+1]; cells 289..319 are padding) so that one column of the
-//                             egocentric view is a contiguous bit run.  A 32-env tile is 2560
-//                             contiguous bytes and moves with one TMA bulk copy each way.
+//                             [2c,2c+1]; cells 289..319 are padding and always hold the wall code) so that one column of the
+//                             egocentric view is a contiguous bit run.  Records are 16-byte
+//                             aligned and move to / from shared memory with TMA bulk copies.
 //   sc0   uint4 [Npad]        .x = agent_x | agent_y<<8 | flags<<16 | risk_count<<24
 //                             .y = step_count  .z = step_move  .w = t (steps since creation)
 //   sc1   uint4 [Npad]        ball positions, 10 bits each (x | y<<5, 0x3FF = cur_pos None):
@@ -79,19 +79,6 @@ __host__ __device__ __forceinline__ uint32_t initial_cell(int x, int y) {
 constexpr uint32_t MID_INIT = (7u | (8u << 5)) | ((8u | (8u << 5)) << 10) | ((9u | (8u << 5)) << 20);
 constexpr uint32_t ALL_NONE3 = 0x3FFFFFFFu;
 
-// Device-resident constant block (built on the host at ta_create).  The first TAB_SMEM_BYTES
-// are bulk-copied into shared memory by every CTA of the step kernel; the run table is read
-// straight from global memory (coalesced, L1-resident).
-constexpr int TAB_LUT = 0;                       // [256] uint4: 4 packed cells -> 12 obs bytes
-constexpr int TAB_TOP = 4096;                    // [17 ay][17 j0] u32: rows above the grid -> wall
-constexpr int TAB_COL = TAB_TOP + 1168;          // [4][17 j0] u32: columns off the grid -> wall
-constexpr int TAB_TEMPLATE = TAB_COL + 272;      // [20] u32: the initial grid record
-constexpr int TAB_SMEM_BYTES = TAB_TEMPLATE + 80;  // 5616
-// [608] u32, one per 16-cell run of a 32-env obs tile (V=17): e | k0<<5 | j0<<14 | (i0+1)<<19 |
-// crossing<<24 (the run straddles env e / e+1) | invalid<<25 (run >= 578)
-constexpr int TAB_RUN = TAB_SMEM_BYTES;
-constexpr int TAB_BYTES = TAB_RUN + 608 * 4;     // 8048
-
 // Philox4x32-10 (Random123); one block per (env, step). Draw contract:
 //   key = (seed lo, seed hi), ctr = (global env id lo, hi, t, 0)
 //   slot 0 (choice of 10) = mulhi(w0,10); slots 1,2,3 (choice of 4) = (w1 >> 0,2,4)&3 + lo;
@@ -149,7 +136,8 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 }  // namespace ta

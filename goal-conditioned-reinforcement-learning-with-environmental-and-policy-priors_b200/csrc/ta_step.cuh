@@ -8,43 +8,68 @@
 //                              Grid.slice :641-660, Grid.encode :749-772)
 //   MiniGridEnv.reset          gym_minigrid/minigrid.py:947-980 (autoreset tail)
 //
-// Mapping: a CTA of 2 warps owns a tile of 32 envs; 14 CTAs are resident per SM, so the 2048
-// tiles of a 65536-env batch are all on chip at once.  The tile's packed grids (2560 B) arrive
-// in shared memory with one TMA bulk copy and the 32 envs' scalar state lives in warp 0's
-// registers for the whole launch.  For each of the launch's T steps (T = 1 for ta_step, the
-// rollout length for ta_rollout) warp 0 runs the per-env transition, lane e = env e (phase A:
-// balls, patrols, agent move); both warps then build the 32 observations cooperatively and
-// stream them to HBM with 16-byte stores (phase B); warp 0 finishes the step (phase C: wall
-// blocks, patrol spawn, reward, episode end, autoreset).  After the last step the state goes
-// back (grids with one TMA bulk store).  The obs is built between A and C because the
-// reference builds it inside MiniGridEnv.step, i.e. before the wall blocks / patrol balls of
-// the same step appear (ordering fact a).
+// Mapping: ONE WARP owns a tile of 32 envs and is its own CTA, so tiles never wait for each
+// other (no __syncthreads anywhere); up to 16-19 such CTAs are resident per SM, which puts all
+// 2048 tiles of a 65536-env batch on chip in one wave.  Per tile:
+//   load    32 TMA bulk copies (80 B packed grid each) into guard-padded shared-memory slots;
+//           the scalar state (2 x 16 B per env) goes straight into the lanes' registers
+//   phase A lane e = env e: balls, patrols, agent move            (twoarmy_v4.py:82-179)
+//   obs     the tile's 32 observations are one contiguous byte block in HBM.  It is produced as
+//           "runs" of 16 view cells = one 32-bit word of 2-bit codes = 48 output bytes; lane l
+//           builds run it*32+l, expands it with byte permutes (no table), writes its 48 bytes to
+//           a shared-memory ring slot, and every 32 runs (1536 B) leave with one TMA bulk store
+//   phase C lane e = env e: wall blocks, patrol spawn, reward, episode end, autoreset
+//                                                                  (twoarmy_v4.py:180-322)
+//   store   scalars from registers, the packed grids with 32 TMA bulk stores
+// With T > 1 (ta_rollout) A/obs/C repeat T times on the resident tile.  The obs is built
+// between A and C because the reference builds it inside MiniGridEnv.step, i.e. before the wall
+// blocks / patrol balls of the same step appear (ordering fact a).
 #pragma once
 #include "ta_common.cuh"
 
 namespace ta {
 
-constexpr int STEP_THREADS = 64;
-constexpr int STEP_WARPS = STEP_THREADS / 32;
-constexpr int STEP_CTAS_PER_SM = 14;  // 14 x 148 = 2072 resident tiles >= the 2048 tiles of 65536 envs
-constexpr int G_BYTES = TILE * REC_BYTES;  // 2560
-constexpr int G_PAD_BEFORE = 48;           // bytes: the V=17 window may start 134 cells early
-constexpr int G_PAD_AFTER = 48;            // ... and end 134 cells late
-constexpr int STAGE_BYTES = 6144;          // staging for the per-cell (generic view size) obs path
-// shared memory map (bytes)
-constexpr int SM_TAB = 0;
-constexpr int SM_BARS = TAB_SMEM_BYTES;                       // 2 mbarriers
-constexpr int SM_META = SM_BARS + 16;                    // 32 x u32: agent x | y<<8
-constexpr int SM_GPAD = SM_META + 128;                   // padded grid tile
-constexpr int SM_STAGE = SM_GPAD + G_PAD_BEFORE + G_BYTES + G_PAD_AFTER;
-constexpr int STEP_SMEM = SM_STAGE + STAGE_BYTES;        // 14560
-static_assert(SM_GPAD % 16 == 0 && SM_STAGE % 16 == 0 && (SM_GPAD + G_PAD_BEFORE) % 16 == 0, "alignment");
+constexpr int STEP_THREADS = 32;
+// shared-memory grid tile: env e's 20-word record sits at word GUARD0_WORDS + e*SLOT_WORDS; every
+// other word is a guard full of wall codes, so that view columns left / right of the grid (and
+// the record's own padding cells 289..319, kept at "wall" in HBM) read as walls without a mask.
+// The furthest a view reaches is 134 cells before and 150 cells after a record.
+constexpr int SLOT_WORDS = 36;
+constexpr int GUARD0_WORDS = 12;
+constexpr int GRID_S_WORDS = GUARD0_WORDS + TILE * SLOT_WORDS;  // 1164
+constexpr uint32_t WALLS16 = 0x55555555u;                        // 16 wall codes
+constexpr int RUN_BYTES = 48;                                    // 16 cells x (type,color,state)
+constexpr int CHUNK_BYTES = 32 * RUN_BYTES;                      // one warp iteration = 1536 B
+constexpr int RING = 4;                                          // chunk buffers per warp
+
+constexpr int round16(int x) { return (x + 15) / 16 * 16; }
+
+template <int V>
+struct ObsCfg {
+    static constexpr int VV = V * V;
+    static constexpr int OBS = 3 * VV;   // bytes per env
+    static constexpr int L = 2 * VV;     // bits of one env's packed view
+    static constexpr int RUNS = 2 * VV;  // 16-cell runs in a 32-env tile (32 * VV / 16)
+    static constexpr int ITERS = (RUNS + 31) / 32;
+    static constexpr int P = (L + 31) / 32;                              // words per env view (V < 17)
+    static constexpr int EV_STRIDE = (V == 17) ? 0 : ((P + 1) | 1);      // odd: conflict-free pass 1
+    static constexpr int EV_ROWS = 34;                                   // env 32, 33: readable padding
+    // shared memory map (bytes)
+    static constexpr int SM_BAR = 0;
+    static constexpr int SM_META = 16;                                   // 32 x uint4 (V = 17)
+    static constexpr int SM_HEAD = SM_META + 512;                        // 33 words (V = 17)
+    static constexpr int SM_GRID = SM_HEAD + 144;
+    static constexpr int SM_EV = SM_GRID + GRID_S_WORDS * 4;
+    static constexpr int SM_RING = SM_EV + round16(EV_ROWS * EV_STRIDE * 4);
+    static constexpr int SMEM = SM_RING + RING * CHUNK_BYTES;
+    static_assert(SM_GRID % 16 == 0 && (SM_GRID + GUARD0_WORDS * 4) % 16 == 0 && SM_RING % 16 == 0, "alignment");
+};
 
 struct StepArgs {
     uint32_t *grid;
     uint4 *sc0;
     uint4 *sc1;
-    const uint8_t *tables;
+    const uint32_t *tmpl;  // [20] the _gen_grid record
     const void *actions;
     const uint8_t *draws;
     uint8_t *obs;
@@ -56,7 +81,7 @@ struct StepArgs {
     int ntiles;
     int T;  // env steps per launch; outputs / actions / draws are [T][n]
     int version;
-    int flags;
+    int flags;  // bit 0 autoreset, bit 1 never use bulk stores for the obs (test hook)
     int action_dtype;
     uint32_t seed_lo, seed_hi;
     unsigned long long env_id0;
@@ -116,130 +141,137 @@ __device__ __forceinline__ void move_group(uint32_t *G, uint32_t (&p)[NB], int d
 constexpr uint32_t TYPE_LUT = 0x08060201u;   // empty 1, wall 2, ball 6, goal 8
 constexpr uint32_t COLOR_LUT = 0x01040500u;  // -, grey 5, yellow 4, green 1
 
-// Per-env record the scalar warp leaves for the observation builders:
-//   bits 0..15  cellbase = pad + e*320 + (ax-8)*17 + (ay-16): where view cell k=0 of env e sits
-//               in the padded shared-memory tile, in cells
-//   bits 16..20 agent y      bits 24..28 agent x
-__device__ __forceinline__ uint32_t make_meta(int e, int ax, int ay) {
-    return (uint32_t)(G_PAD_BEFORE * 4 + e * REC_CELLS + (ax - 8) * GS + (ay - 16)) | ((uint32_t)ay << 16) |
-           ((uint32_t)ax << 24);
+// 8 two-bit codes (low 16 bits of x) -> 8 nibbles
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return x;
 }
 
-// 16 consecutive view cells k0..k0+15 of one env (V = 17) as one word of 2-bit codes.  Because
-// the view is as wide as the grid and the record is column-major, they are the 32 bits at
-// cell offset cellbase + k0 -- one funnel shift -- except (a) rows above the grid and (b)
-// columns off the grid, which become walls through two masks looked up by (ay, j0) and by
-// (column-off-grid bits, j0), and (c) the agent's own cell k = 152.  i0p1 = floor(k0/17)+1,
-// j0 = k0 mod 17; valid for k0 in [-16, 288].
-__device__ __forceinline__ uint32_t codes16_v17(const uint32_t *gpadw, const uint8_t *tab, uint32_t m, int k0, int i0p1,
-                                                int j0) {
-    const int cell = (int)(m & 0xFFFFu) + k0;
-    const int ay = (int)((m >> 16) & 31u), ax = (int)(m >> 24);
-    const int wi = cell >> 4;
-    const uint32_t win = __funnelshift_r(gpadw[wi], gpadw[wi + 1], (uint32_t)(cell & 15) * 2u);
-    int s = ax + i0p1 - 1;  // grid column of view column i0, plus 8; columns < 0 or > 16 are walls
-    s = s > 31 ? 31 : (s < 0 ? 0 : s);
-    const uint32_t colbits = ((0xFE0000FFu >> s) & 1u) | (((0xFF00007Fu >> s) & 1u) << 1);
-    const uint32_t mk = reinterpret_cast<const uint32_t *>(tab + TAB_TOP)[ay * 17 + j0] |
-                        reinterpret_cast<const uint32_t *>(tab + TAB_COL)[colbits * 17 + j0];
-    uint32_t c = (win & ~mk) | (0x55555555u & mk);
+// 4 cells (4 selector nibbles in the low 16 bits of sel) -> 12 obs bytes.  Two permutes look the
+// type / colour bytes up in the register-resident tables, three more interleave them with the
+// zero state byte (selector nibble 8 = sign-replicate a byte < 0x80 = 0x00).
+// (__byte_perm masks the selector to 3 bits per nibble, so the PTX instruction is used directly.)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ void expand4(uint32_t sel, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+    const uint32_t t = prmt(TYPE_LUT, 0u, sel), c = prmt(COLOR_LUT, 0u, sel);
+    w0 = prmt(t, c, 0x1840u);  // t0 c0 0  t1
+    w1 = prmt(t, c, 0x6285u);  // c1 0  t2 c2
+    w2 = prmt(t, c, 0x8738u);  // 0  t3 c3 0
+}
+
+// 16 packed cells -> 48 obs bytes, stored as three 16-byte vectors at dst (shared memory)
+__device__ __forceinline__ void expand16_store(uint32_t c, uint4 *dst) {
+    const uint32_t sa = spread16(c & 0xFFFFu), sb = spread16(c >> 16);
+    uint32_t w[12];
+    expand4(sa, w[0], w[1], w[2]);
+    expand4(sa >> 16, w[3], w[4], w[5]);
+    expand4(sb, w[6], w[7], w[8]);
+    expand4(sb >> 16, w[9], w[10], w[11]);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+}
+
+// V = 17.  The view is as wide as the grid and the record is column-major, so the 16 view cells
+// k0..k0+15 of an env are the 32 bits at cell offset cellbase + k0 of the guard-padded tile
+// (one funnel shift), except that rows above the grid (they alias the previous column's tail)
+// become walls -- a 34-bit periodic mask kept per env as two words -- and the agent's own cell
+// (view cell 152) is empty.  meta = (cellbase, mask lo, mask hi, -).
+__device__ __forceinline__ uint4 make_meta17(int e, int ax, int ay) {
+    const int h = 16 - ay;  // rows above the grid
+    const unsigned long long rm = (1ull << (2 * (h < 0 ? 0 : h))) - 1ull;
+    const unsigned long long r2 = rm | (rm << 34);
+    return make_uint4((uint32_t)((GUARD0_WORDS + e * SLOT_WORDS) * 16 + (ax - 8) * GS + (ay - 16)), (uint32_t)r2,
+                      (uint32_t)(r2 >> 32), 0u);
+}
+__device__ __forceinline__ uint32_t fetch17(const uint32_t *gs, uint4 m, int k0) {
+    const int j0 = k0 - GS * ((k0 * 241) >> 12);  // k0 mod 17, exact for k0 < 320
+    const int cell = (int)m.x + k0, wi = cell >> 4;
+    const uint32_t win = __funnelshift_r(gs[wi], gs[wi + 1], (uint32_t)(cell & 15) * 2u);
+    const uint32_t mk = __funnelshift_rc(m.y, m.z, (uint32_t)(2 * j0));
+    uint32_t c = (win & ~mk) | (WALLS16 & mk);
     const int d = 152 - k0;  // agent cell: view (8,16)
     if ((unsigned)d < 16u) c &= ~(3u << (2 * d));
     return c;
 }
 
-// 16 packed cells -> 48 obs bytes through the 256-entry (4 cells -> 12 bytes) table, stored as
-// three 16-byte vectors at dst (16-byte aligned)
-__device__ __forceinline__ void expand16_store(uint32_t c, const uint8_t *tab, uint4 *dst) {
-    const uint4 *lut = reinterpret_cast<const uint4 *>(tab + TAB_LUT);
-    const uint4 a = lut[c & 0xFFu], b = lut[(c >> 8) & 0xFFu], cc = lut[(c >> 16) & 0xFFu], d = lut[c >> 24];
-    dst[0] = make_uint4(a.x, a.y, a.z, b.x);
-    dst[1] = make_uint4(b.y, b.z, cc.x, cc.y);
-    dst[2] = make_uint4(cc.z, d.x, d.y, d.z);
-}
-
-// V = 17, whole tile: the obs block (32 x 867 B = 27744 B) is 578 runs of 16 cells / 48 bytes.
-// Every lane builds one run per iteration; the 30 runs that straddle two envs are skipped in
-// the main loop and rebuilt by warp 3 (which has one block fewer) from both envs.
-// XPOSE: the warp's 32 x 48 B go through a shared-memory transposer so that each global store
-// instruction writes 512 contiguous bytes; otherwise every lane stores its own 48 bytes.
-template <bool XPOSE>
-__device__ __forceinline__ void emit_run(uint32_t c, bool valid, const uint8_t *tab, uint4 *d4, int run, uint4 *xp,
-                                         int lane) {
-    if (XPOSE) {
-        if (valid) expand16_store(c, tab, xp + 3 * lane);
-        __syncwarp();
-        const int u0 = (run - lane) * 3;  // first uint4 of this warp-iteration's 1536-byte block
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int src_lane = (32 * k + lane) / 3;  // the lane whose run produced this uint4
-            const bool ok = __shfl_sync(0xFFFFFFFFu, (int)valid, src_lane) != 0;
-            if (ok) d4[u0 + 32 * k + lane] = xp[32 * k + lane];
-        }
-        __syncwarp();
-    } else {
-        if (valid) expand16_store(c, tab, d4 + 3 * run);
-    }
-}
-
-template <bool XPOSE>
-__device__ __forceinline__ void obs_tile_v17(uint8_t *dst, const uint32_t *gpadw, const uint8_t *tab,
-                                             const uint32_t *runtab, const uint32_t *meta, uint8_t *xpose, int warp,
-                                             int lane) {
-    constexpr int BLOCKS = 19;  // ceil(578 / 32)
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-    uint4 *xp = reinterpret_cast<uint4 *>(xpose);
-#pragma unroll 2
-    for (int bi = warp; bi < BLOCKS; bi += STEP_WARPS) {
-        const int run = bi * 32 + lane;
-        const uint32_t rt = __ldg(runtab + run);  // coalesced, L1-resident after the first tile
-        const int e = (int)(rt & 31u), k0 = (int)((rt >> 5) & 511u), j0 = (int)((rt >> 14) & 31u),
-                  i0p1 = (int)((rt >> 19) & 31u);
-        const uint32_t c = codes16_v17(gpadw, tab, meta[e], k0, i0p1, j0);
-        emit_run<XPOSE>(c, (rt >> 24) == 0u, tab, d4, run, xp, lane);
-    }
-    if (warp == STEP_WARPS - 1) {
-        // boundary between env cidx-1 and env cidx; env 16 starts exactly on a run boundary
-        const int cidx = lane;
-        const bool valid = lane >= 1 && lane != 16;
-        const int run = (NCELL * cidx) >> 4;
-        const int k0a = valid ? 16 * run - NCELL * (cidx - 1) : 274;  // [274,288]: column 16 of env cidx-1
-        const int k0b = k0a - NCELL;                                   // [-15,-1]: "column -1" of env cidx
-        const uint32_t ca = codes16_v17(gpadw, tab, meta[valid ? cidx - 1 : 0], k0a, 17, k0a - 272);
-        const uint32_t cb = codes16_v17(gpadw, tab, meta[valid ? cidx : 1], k0b, 0, k0b + 17);
-        const uint32_t keep = (1u << (2 * (NCELL - k0a))) - 1u;
-        if (valid) expand16_store((ca & keep) | (cb & ~keep), tab, d4 + 3 * run);
-    }
-}
-
-// Any other odd V <= 17: CE envs at a time are expanded per cell into the shared staging area
-// and copied out with coalesced 4-byte stores.
+// V < 17, pass 1: lane e packs env e's V x V view (2 bits per cell, column after column) into
+// ev[e][0..P).  Everything about the bit positions is known at compile time.
 template <int V>
-__device__ __forceinline__ void obs_tile_generic(uint8_t *dst, long long limit_bytes, const uint32_t *gw,
-                                                 const uint32_t *meta, uint8_t *stage, int tid) {
-    constexpr int VV = V * V, OBS = 3 * VV;
-    constexpr int CE = (32 * OBS <= STAGE_BYTES) ? 32 : (16 * OBS <= STAGE_BYTES) ? 16 : (8 * OBS <= STAGE_BYTES) ? 8 : 4;
-    static_assert(CE * OBS <= STAGE_BYTES, "staging too small");
-    for (int e0 = 0; e0 < TILE; e0 += CE) {
-        for (int c = tid; c < CE * VV; c += STEP_THREADS) {
-            const int e = c / VV, k = c - e * VV, i = k / V, j = k - i * V;
-            const uint32_t m = meta[e0 + e];
-            const int x = (int)(m >> 24) - V / 2 + i, y = (int)((m >> 16) & 31u) - (V - 1) + j;
-            uint32_t code = inb(x, y) ? cell_get(gw + (e0 + e) * REC_WORDS, x, y) : C_WALL;
-            if (i == V / 2 && j == V - 1) code = C_EMPTY;
-            stage[3 * c + 0] = (uint8_t)(TYPE_LUT >> (8 * code));
-            stage[3 * c + 1] = (uint8_t)(COLOR_LUT >> (8 * code));
-            stage[3 * c + 2] = 0;
+__device__ __forceinline__ void build_envview(const uint32_t *gs, uint32_t *ev, int lane, int ax, int ay) {
+    using C = ObsCfg<V>;
+    uint32_t out[C::P + 1];
+#pragma unroll
+    for (int w = 0; w <= C::P; w++) out[w] = 0u;
+    int h = V - 1 - ay;  // rows above the grid
+    h = h < 0 ? 0 : h;
+    const uint32_t mk = (1u << (2 * h)) - 1u;  // h <= 14
+    const int base = (GUARD0_WORDS + lane * SLOT_WORDS) * 16 + (ax - V / 2) * GS + (ay - (V - 1));
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+        const int cell = base + GS * i, wi = cell >> 4;
+        uint32_t bits = __funnelshift_r(gs[wi], gs[wi + 1], (uint32_t)(cell & 15) * 2u) & ((1u << (2 * V)) - 1u);
+        bits = (bits & ~mk) | (WALLS16 & mk & ((1u << (2 * V)) - 1u));
+        if (i == V / 2) bits &= ~(3u << (2 * (V - 1)));  // the agent's own cell
+        const int pos = i * 2 * V, w = pos >> 5, s = pos & 31;
+        out[w] |= bits << s;
+        if (s + 2 * V > 32) out[w + 1] |= bits >> (32 - s);
+    }
+#pragma unroll
+    for (int w = 0; w < C::P; w++) ev[lane * C::EV_STRIDE + w] = out[w];
+}
+
+// The 16 cells of run r of the tile's cell stream (env e = 16r / VV, possibly continuing into
+// env e+1, and for V = 3 into e+2) as one word of 2-bit codes.
+template <int V>
+__device__ __forceinline__ uint32_t run_codes(int r, const uint32_t *gs, const uint4 *meta, const uint32_t *head,
+                                              const uint32_t *ev) {
+    using C = ObsCfg<V>;
+    if constexpr (V == 17) {
+        const int q0 = 16 * r, e = q0 / NCELL, k0 = q0 - NCELL * e;
+        uint32_t c = fetch17(gs, meta[e], k0);
+        const int nb = 2 * (NCELL - k0);  // bits env e still has from k0 on
+        if (nb < 32) c = (c & ((1u << nb) - 1u)) | (head[e + 1] << nb);
+        return c;
+    } else {
+        constexpr int S = C::EV_STRIDE;
+        const int p = 32 * r, e = p / C::L, off = p - C::L * e, wi = off >> 5;
+        uint32_t c = __funnelshift_r(ev[e * S + wi], ev[e * S + wi + 1], (uint32_t)(off & 31));
+        const int nb = C::L - off;
+        if (nb < 32) {
+            c = (c & ((1u << nb) - 1u)) | (ev[(e + 1) * S] << nb);
+            if (V == 3 && nb + C::L < 32) c |= ev[(e + 2) * S] << (nb + C::L);
         }
-        __syncthreads();
-        const long long base = (long long)e0 * OBS;
-        for (int w = tid; w < CE * OBS / 4; w += STEP_THREADS) {
-            const long long b0 = base + 4ll * w;
-            if (b0 + 4 <= limit_bytes) *reinterpret_cast<uint32_t *>(dst + b0) = reinterpret_cast<const uint32_t *>(stage)[w];
-            else if (b0 < limit_bytes)
-                for (int b = 0; b < (int)(limit_bytes - b0); b++) dst[b0 + b] = stage[4 * w + b];
+        return c;
+    }
+}
+
+// nbytes of a ring slot -> global memory.  Bulk (TMA) when the destination is 16-byte aligned:
+// whole 16-byte units by one bulk store, a ragged tail (< 16 B, last tile of a ragged batch) by
+// byte stores.  Lane 0 commits exactly one bulk group per call either way.
+__device__ __forceinline__ void emit_chunk(uint8_t *dst, const uint8_t *src, int nbytes, bool bulk, int lane) {
+    if (bulk) {
+        const int nb16 = nbytes > 0 ? (nbytes & ~15) : 0;
+        if (lane == 0) {
+            if (nb16) bulk_s2g(dst, src, (uint32_t)nb16);
+            bulk_commit();
         }
-        __syncthreads();
+        for (int b = nb16 + lane; b < nbytes; b += 32) dst[b] = src[b];
+    } else {
+        if (lane == 0) bulk_commit();
+        if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+            const int nw = nbytes > 0 ? nbytes >> 2 : 0;
+            for (int w = lane; w < nw; w += 32) reinterpret_cast<uint32_t *>(dst)[w] = reinterpret_cast<const uint32_t *>(src)[w];
+            for (int b = 4 * nw + lane; b < nbytes; b += 32) dst[b] = src[b];
+        } else {
+            for (int b = lane; b < nbytes; b += 32) dst[b] = src[b];
+        }
     }
 }
 
@@ -250,62 +282,58 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, long 
     return a > 1000 ? 1000 : (a < -1000 ? -1000 : (int)a);
 }
 
-template <int V, bool FAST>
-__global__ void __launch_bounds__(STEP_THREADS, STEP_CTAS_PER_SM) step_obs_kernel(const StepArgs a) {
+template <int V>
+__global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a) {
+    using C = ObsCfg<V>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *tab = smem + SM_TAB;
-    uint64_t *tab_bar = reinterpret_cast<uint64_t *>(smem + SM_BARS);
-    uint64_t *bar = tab_bar + 1;
-    uint32_t *meta = reinterpret_cast<uint32_t *>(smem + SM_META);
-    uint8_t *gpad = smem + SM_GPAD;
-    uint32_t *gw = reinterpret_cast<uint32_t *>(gpad + G_PAD_BEFORE);
-    uint8_t *stage = smem + SM_STAGE;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int OBS_ENV = 3 * V * V;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::SM_BAR);
+    uint4 *meta = reinterpret_cast<uint4 *>(smem + C::SM_META);
+    uint32_t *head = reinterpret_cast<uint32_t *>(smem + C::SM_HEAD);
+    uint32_t *gs = reinterpret_cast<uint32_t *>(smem + C::SM_GRID);
+    uint32_t *ev = reinterpret_cast<uint32_t *>(smem + C::SM_EV);
+    uint8_t *ring = smem + C::SM_RING;
+    const int lane = threadIdx.x;
+    uint32_t *G = gs + GUARD0_WORDS + lane * SLOT_WORDS;  // this lane's env record
 
-    if (tid == 0) {
-        mbar_init(tab_bar, 1);
+    // one-time CTA setup: barrier, guard words, the reset template word of this lane
+    if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
-        mbar_expect_tx(tab_bar, TAB_SMEM_BYTES);
-        bulk_g2s(tab, a.tables, TAB_SMEM_BYTES, tab_bar);
     }
-    __syncthreads();
+    for (int w = lane; w < GRID_S_WORDS; w += 32) {
+        const int s = w - GUARD0_WORDS;
+        if (s < 0 || (s % SLOT_WORDS) >= REC_WORDS) gs[w] = WALLS16;
+    }
+    if constexpr (V == 17) {
+        if (lane == 0) head[32] = 0u;
+    } else {
+        for (int w = lane; w < 2 * C::EV_STRIDE; w += 32) ev[32 * C::EV_STRIDE + w] = 0u;
+    }
+    const uint32_t tmpl_word = lane < REC_WORDS ? __ldg(a.tmpl + lane) : 0u;
+    fence_proxy_async();  // generic-proxy writes above vs. the async-proxy copies below
+    __syncwarp();
     uint32_t phase = 0;
+    uint32_t gi = 0;  // obs chunks emitted so far (ring slot = gi % RING)
     const bool v4 = a.version == 4;
-    bool first = true;
-    const uint32_t *runtab = reinterpret_cast<const uint32_t *>(a.tables + TAB_RUN);
 
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        // ---- tile prologue (warp 0): state of 32 envs -> registers, packed grids -> smem -------
+        // ---- tile prologue: packed grids -> smem, state of 32 envs -> registers ------------------
         const long long env = tile * TILE + lane;
         const bool live = env < a.n;
-        int ax = 0, ay = 0, risk = 0, step_count = 0, step_move = 0;
-        uint32_t fl = 0, tcount = 0, err = 0;
-        uint32_t mid[3] = {0, 0, 0}, o1[3] = {0, 0, 0}, o2[4] = {0, 0, 0, 0};
-        uint32_t *G = gw + lane * REC_WORDS;
         long long nvalid = a.n - tile * TILE;
         nvalid = nvalid > TILE ? TILE : nvalid;
-        if (warp == 0) {
-            if (lane == 0) {
-                bulk_wait_read0();  // the previous tile's grid store has finished reading smem
-                mbar_expect_tx(bar, G_BYTES);
-                bulk_g2s(gw, a.grid + tile * (G_BYTES / 4), G_BYTES, bar);
-            }
-            const uint4 s0 = a.sc0[env], s1 = a.sc1[env];
-            ax = (int)(s0.x & 0xFFu);
-            ay = (int)((s0.x >> 8) & 0xFFu);
-            fl = (s0.x >> 16) & 0xFFu;
-            risk = (int)(s0.x >> 24);
-            step_count = (int)s0.y;
-            step_move = (int)s0.z;
-            tcount = s0.w;
-            mid[0] = ball_get(s1.x, 0); mid[1] = ball_get(s1.x, 1); mid[2] = ball_get(s1.x, 2);
-            o1[0] = ball_get(s1.y, 0); o1[1] = ball_get(s1.y, 1); o1[2] = ball_get(s1.y, 2);
-            o2[0] = ball_get(s1.z, 0); o2[1] = ball_get(s1.z, 1); o2[2] = ball_get(s1.z, 2);
-            o2[3] = ball_get(s1.w, 0);
-            err = (s1.w >> 16) & 0xFFu;
-        }
+        if (lane == 0) mbar_expect_tx(bar, TILE * REC_BYTES);
+        __syncwarp();
+        bulk_g2s(G, a.grid + env * REC_WORDS, REC_BYTES, bar);
+        const uint4 s0 = a.sc0[env], s1 = a.sc1[env];
+        int ax = (int)(s0.x & 0xFFu), ay = (int)((s0.x >> 8) & 0xFFu), risk = (int)(s0.x >> 24);
+        uint32_t fl = (s0.x >> 16) & 0xFFu;
+        int step_count = (int)s0.y, step_move = (int)s0.z;
+        uint32_t tcount = s0.w;
+        uint32_t mid[3] = {ball_get(s1.x, 0), ball_get(s1.x, 1), ball_get(s1.x, 2)};
+        uint32_t o1[3] = {ball_get(s1.y, 0), ball_get(s1.y, 1), ball_get(s1.y, 2)};
+        uint32_t o2[4] = {ball_get(s1.z, 0), ball_get(s1.z, 1), ball_get(s1.z, 2), ball_get(s1.w, 0)};
+        uint32_t err = (s1.w >> 16) & 0xFFu;
 
         // ---- T env steps on the resident tile -------------------------------------------------
         for (int t = 0; t < a.T; t++) {
@@ -314,232 +342,237 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_CTAS_PER_SM) step_obs_kerne
             DrawSrc d;
             d.rec_lo = d.rec_hi = 0xFFFFFFFFu;
             d.consumed = 0;
-            // ---- warp 0, phase A: everything up to and including the agent move -------------
-            if (warp == 0) {
-                int act = live ? load_action(a.actions, a.action_dtype, out_idx) : 6;
-                if (a.draws != nullptr) {
-                    if (live) {
-                        const uint2 r = reinterpret_cast<const uint2 *>(a.draws)[out_idx];
-                        d.rec_lo = r.x;
-                        d.rec_hi = r.y;
-                    }
-                } else {
-                    const unsigned long long gid = a.env_id0 + (unsigned long long)env;
-                    philox_record(d, (uint32_t)gid, (uint32_t)(gid >> 32), tcount, a.seed_lo, a.seed_hi);
+            // ---- phase A: everything up to and including the agent move ----------------------
+            int act = live ? load_action(a.actions, a.action_dtype, out_idx) : 6;
+            if (a.draws != nullptr) {
+                if (live) {
+                    const uint2 r = reinterpret_cast<const uint2 *>(a.draws)[out_idx];
+                    d.rec_lo = r.x;
+                    d.rec_hi = r.y;
                 }
-                // situations where the reference raises (documented divergence: the env is left
-                // untouched and an error bit is set)
-                if (act >= 7) act = 0;  // twoarmy_v4.py:84-85
-                int adx = 0, ady = 0;
-                if (act == 0) adx = -1;
-                else if (act == 1) adx = 1;
-                else if (act == 2) ady = -1;
-                else if (act == 3) ady = 1;
-                if (!(act == 0 || act == 1 || act == 2 || act == 3 || act == 6)) {
-                    err |= ERR_BAD_ACTION;
-                    skip = true;
-                } else if ((fl & F_PATROL) && (o1[0] == NOPOS || o2[0] == NOPOS)) {
-                    err |= ERR_NONE_POS;
-                    skip = true;
-                } else if (!inb(ax + adx, ay + ady)) {
-                    err |= ERR_OOB_MOVE;
-                    skip = true;
-                }
-                if (t == 0) {
-                    mbar_wait(bar, phase);
-                    phase ^= 1u;
-                }
-                if (!skip) {
-                    tcount += 1u;
-                    step_move += 1;
-                    const int m6 = step_move % 6, m4 = step_move & 3;
-                    {  // mid-row balls, twoarmy_v4.py:95-111
-                        const int dx = (m6 == 1 || m6 == 0) ? 1 : ((m6 == 2 || m6 == 3) ? -1 : 0);
-                        move_group<3>(G, mid, dx, 0, true);
-                    }
-                    if (v4) {
-                        bool mv1 = false, mv2 = false;
-                        if (fl & F_UPD_L) {  // twoarmy_v4.py:115-144 (the draw is short-circuited)
-                            fl &= ~F_UPD_H;
-                            if (m4 == 2 || m6 == 3 || m6 == 0 || draw(d, 0) == 6) mv1 = (fl & F_PATROL) != 0;
-                        }
-                        if (fl & F_UPD_H) {  // twoarmy_v4.py:147-176
-                            fl &= ~F_UPD_L;
-                            if (m6 != 1 || draw(d, 0) == 6) mv2 = (fl & F_PATROL) != 0;
-                        }
-                        if (mv1) {
-                            const bool up = (fl & F_UP1) != 0;
-                            move_group<3>(G, o1, 0, up ? -1 : 1, false);
-                            if (up) {
-                                if (pos_y(o1[0]) == 3) fl &= ~F_UP1;
-                            } else if (pos_y(o1[2]) == 7) {
-                                fl |= F_UP1;
-                            }
-                        }
-                        if (mv2) {
-                            const bool right = (fl & F_RIGHT2) != 0;
-                            move_group<4>(G, o2, right ? 1 : -1, 0, false);
-                            if (right) {
-                                if (pos_x(o2[3]) == 11) fl &= ~F_RIGHT2;
-                            } else if (pos_x(o2[0]) == 5) {
-                                fl |= F_RIGHT2;
-                            }
-                        }
-                    }
-                    // MiniGridEnv.step, minigrid.py:1333-1441
-                    step_count += 1;
-                    const int tx = ax + adx, ty = ay + ady;
-                    const uint32_t c = cell_get(G, tx, ty);
-                    if (c == C_EMPTY || c == C_GOAL) {
-                        ax = tx;
-                        ay = ty;
-                    }
-                    if (c == C_GOAL) term = true;
-                    if (step_count >= 50) trunc = true;
-                }
-                meta[lane] = make_meta(lane, ax, ay);
+            } else {
+                const unsigned long long gid = a.env_id0 + (unsigned long long)env;
+                philox_record(d, (uint32_t)gid, (uint32_t)(gid >> 32), tcount, a.seed_lo, a.seed_hi);
             }
-            if (first) {  // LUT, masks and the reset template
-                mbar_wait(tab_bar, 0);
-                first = false;
+            if (act >= 7) act = 0;  // twoarmy_v4.py:84-85
+            int adx = 0, ady = 0;
+            if (act == 0) adx = -1;
+            else if (act == 1) adx = 1;
+            else if (act == 2) ady = -1;
+            else if (act == 3) ady = 1;
+            // situations where the reference raises (documented divergence: the env is left
+            // untouched and an error bit is set)
+            if (!(act == 0 || act == 1 || act == 2 || act == 3 || act == 6)) {
+                err |= ERR_BAD_ACTION;
+                skip = true;
+            } else if ((fl & F_PATROL) && (o1[0] == NOPOS || o2[0] == NOPOS)) {
+                err |= ERR_NONE_POS;
+                skip = true;
+            } else if (!inb(ax + adx, ay + ady)) {
+                err |= ERR_OOB_MOVE;
+                skip = true;
             }
-            __syncthreads();
+            if (t == 0) {  // the packed grids have landed
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
+            if (!skip) {
+                tcount += 1u;
+                step_move += 1;
+                const int m6 = step_move % 6, m4 = step_move & 3;
+                {  // mid-row balls, twoarmy_v4.py:95-111
+                    const int dx = (m6 == 1 || m6 == 0) ? 1 : ((m6 == 2 || m6 == 3) ? -1 : 0);
+                    move_group<3>(G, mid, dx, 0, true);
+                }
+                if (v4) {
+                    bool mv1 = false, mv2 = false;
+                    if (fl & F_UPD_L) {  // twoarmy_v4.py:115-144 (the draw is short-circuited)
+                        fl &= ~F_UPD_H;
+                        if (m4 == 2 || m6 == 3 || m6 == 0 || draw(d, 0) == 6) mv1 = (fl & F_PATROL) != 0;
+                    }
+                    if (fl & F_UPD_H) {  // twoarmy_v4.py:147-176
+                        fl &= ~F_UPD_L;
+                        if (m6 != 1 || draw(d, 0) == 6) mv2 = (fl & F_PATROL) != 0;
+                    }
+                    if (mv1) {
+                        const bool up = (fl & F_UP1) != 0;
+                        move_group<3>(G, o1, 0, up ? -1 : 1, false);
+                        if (up) {
+                            if (pos_y(o1[0]) == 3) fl &= ~F_UP1;
+                        } else if (pos_y(o1[2]) == 7) {
+                            fl |= F_UP1;
+                        }
+                    }
+                    if (mv2) {
+                        const bool right = (fl & F_RIGHT2) != 0;
+                        move_group<4>(G, o2, right ? 1 : -1, 0, false);
+                        if (right) {
+                            if (pos_x(o2[3]) == 11) fl &= ~F_RIGHT2;
+                        } else if (pos_x(o2[0]) == 5) {
+                            fl |= F_RIGHT2;
+                        }
+                    }
+                }
+                // MiniGridEnv.step, minigrid.py:1333-1441
+                step_count += 1;
+                const int tx = ax + adx, ty = ay + ady;
+                const uint32_t c = cell_get(G, tx, ty);
+                if (c == C_EMPTY || c == C_GOAL) {
+                    ax = tx;
+                    ay = ty;
+                }
+                if (c == C_GOAL) term = true;
+                if (step_count >= 50) trunc = true;
+            }
 
-            // ---- phase B: observations of all 32 envs, every warp ----------------------------
+            // ---- observations of all 32 envs (gen_obs) ------------------------------------------
+            if constexpr (V == 17) {
+                const uint4 m = make_meta17(lane, ax, ay);
+                meta[lane] = m;
+                __syncwarp();  // every lane's grid edits are visible
+                head[lane] = fetch17(gs, m, 0);
+            } else {
+                __syncwarp();
+                build_envview<V>(gs, ev, lane, ax, ay);
+            }
+            __syncwarp();
             {
-                uint8_t *dst = a.obs + ((long long)t * a.n + tile * TILE) * OBS_ENV;
-                if (FAST && nvalid == TILE && (((long long)t * a.n * OBS_ENV) & 15) == 0) {
-                    if (a.flags & 2)
-                        obs_tile_v17<true>(dst, reinterpret_cast<const uint32_t *>(gpad), tab, runtab, meta,
-                                           stage + warp * 1536, warp, lane);
-                    else
-                        obs_tile_v17<false>(dst, reinterpret_cast<const uint32_t *>(gpad), tab, runtab, meta, stage, warp,
-                                            lane);
-                } else {  // other view sizes, and the ragged last tile of a batch
-                    obs_tile_generic<V>(dst, nvalid * OBS_ENV, gw, meta, stage, tid);
+                uint8_t *dst = a.obs + ((long long)t * a.n + tile * TILE) * C::OBS;
+                const bool bulk = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && !(a.flags & 2);
+                const int valid_bytes = (int)nvalid * C::OBS;
+#pragma unroll 1
+                for (int it = 0; it < C::ITERS; it++) {
+                    int r = it * 32 + lane;
+                    r = r < C::RUNS ? r : C::RUNS - 1;
+                    const uint32_t c = run_codes<V>(r, gs, meta, head, ev);
+                    uint8_t *slot = ring + (gi % RING) * CHUNK_BYTES;
+                    gi++;
+                    if (lane == 0) bulk_wait_read<RING - 1>();  // the slot's previous bulk store has read it
+                    __syncwarp();
+                    expand16_store(c, reinterpret_cast<uint4 *>(slot + lane * RUN_BYTES));
+                    fence_proxy_async();
+                    __syncwarp();
+                    int len = (C::RUNS - it * 32) * RUN_BYTES;
+                    len = len > CHUNK_BYTES ? CHUNK_BYTES : len;
+                    const int rem = valid_bytes - it * CHUNK_BYTES;
+                    emit_chunk(dst + it * CHUNK_BYTES, slot, len < rem ? len : rem, bulk, lane);
                 }
             }
-            __syncthreads();
+            __syncwarp();  // the obs pass has read the grids; phase C edits them
 
-            // ---- warp 0, phase C: rest of Twoarmy.step ----------------------------------------
-            if (warp == 0) {
-                int reward = R_STEP;  // twoarmy_v4.py:180
-                bool need_reset = false;
-                if (!skip) {
-                    if (!(fl & F_PONE) && (ax > 3 || ay < 14)) {  // twoarmy_v4.py:181-195, twoarmy_v6.py:182-198
-                        int i = v4 ? draw(d, 1) : 11;
-                        put_cell(G, 4, i, C_WALL); put_cell(G, 5, i, C_WALL);
-                        put_cell(G, 4, i + 1, C_WALL); put_cell(G, 5, i + 1, C_WALL);
-                        i = v4 ? draw(d, 2) : 8;
-                        put_cell(G, i, 11, C_WALL); put_cell(G, i, 12, C_WALL);
-                        put_cell(G, i + 1, 11, C_WALL); put_cell(G, i + 1, 12, C_WALL);
-                        fl |= F_PONE;
-                    }
-                    if (v4 && !(fl & F_PATROL) && ay <= 8) {  // twoarmy_v4.py:212-225
-                        const int i = draw(d, 3);
-                        const int bx[4] = {i, i + 1, i, i + 1}, by[4] = {4, 4, 5, 5};
+            // ---- phase C: rest of Twoarmy.step -----------------------------------------------
+            int reward = R_STEP;  // twoarmy_v4.py:180
+            bool need_reset = false;
+            if (!skip) {
+                if (!(fl & F_PONE) && (ax > 3 || ay < 14)) {  // twoarmy_v4.py:181-195, twoarmy_v6.py:182-198
+                    int i = v4 ? draw(d, 1) : 11;
+                    put_cell(G, 4, i, C_WALL); put_cell(G, 5, i, C_WALL);
+                    put_cell(G, 4, i + 1, C_WALL); put_cell(G, 5, i + 1, C_WALL);
+                    i = v4 ? draw(d, 2) : 8;
+                    put_cell(G, i, 11, C_WALL); put_cell(G, i, 12, C_WALL);
+                    put_cell(G, i + 1, 11, C_WALL); put_cell(G, i + 1, 12, C_WALL);
+                    fl |= F_PONE;
+                }
+                if (v4 && !(fl & F_PATROL) && ay <= 8) {  // twoarmy_v4.py:212-225
+                    const int i = draw(d, 3);
+                    const int bx[4] = {i, i + 1, i, i + 1}, by[4] = {4, 4, 5, 5};
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (inb(bx[k], by[k])) {
-                                cell_set(G, bx[k], by[k], C_BALL);
-                                o2[k] = pack_pos(bx[k], by[k]);
-                            }
-                        d.consumed |= 1u << 4;  // :221 choice(range(4,5)) == 4, no generator words
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            cell_set(G, 12, 4 + k, C_BALL);
-                            o1[k] = pack_pos(12, 4 + k);
+                    for (int k = 0; k < 4; k++)
+                        if (inb(bx[k], by[k])) {
+                            cell_set(G, bx[k], by[k], C_BALL);
+                            o2[k] = pack_pos(bx[k], by[k]);
                         }
-                        fl |= F_PATROL;
+                    d.consumed |= 1u << 4;  // :221 choice(range(4,5)) == 4, no generator words
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        cell_set(G, 12, 4 + k, C_BALL);
+                        o1[k] = pack_pos(12, 4 + k);
                     }
-                    const uint32_t ap = pack_pos(ax, ay);
-                    // twoarmy_v4.py:228-240
-                    if (ap == mid[0] || ap == mid[1] || ap == mid[2]) {
+                    fl |= F_PATROL;
+                }
+                const uint32_t ap = pack_pos(ax, ay);
+                // twoarmy_v4.py:228-240
+                if (ap == mid[0] || ap == mid[1] || ap == mid[2]) {
+                    reward = R_HIT;
+                    trunc = true;
+                }
+                if (ay == pos_y(mid[0]) + 1 && (ax == pos_x(mid[0]) || ax == pos_x(mid[1]) || ax == pos_x(mid[2])))
+                    reward = R_RISK;
+                if (fl & F_PATROL) {  // twoarmy_v4.py:242-280
+                    if (ay == pos_y(o2[2]) + 1 && (ax == pos_x(o2[2]) || ax == pos_x(o2[3]))) reward = R_RISK;
+                    if (ax == pos_x(o2[0]) - 1 && (ay == pos_y(o2[0]) || ay == pos_y(o2[2]))) reward = R_RISK;
+                    if (ax == pos_x(o2[1]) + 1 && (ay == pos_y(o2[1]) || ay == pos_y(o2[3]))) reward = R_RISK;
+                    if (ax == pos_x(o1[0]) - 1 && (ay == pos_y(o1[0]) || ay == pos_y(o1[1]) || ay == pos_y(o1[2])))
+                        reward = R_RISK;
+                    if (ap == o1[0] || ap == o1[1] || ap == o1[2] || ap == o2[0] || ap == o2[1] || ap == o2[2] ||
+                        ap == o2[3]) {
                         reward = R_HIT;
                         trunc = true;
                     }
-                    if (ay == pos_y(mid[0]) + 1 && (ax == pos_x(mid[0]) || ax == pos_x(mid[1]) || ax == pos_x(mid[2])))
-                        reward = R_RISK;
-                    if (fl & F_PATROL) {  // twoarmy_v4.py:242-280
-                        if (ay == pos_y(o2[2]) + 1 && (ax == pos_x(o2[2]) || ax == pos_x(o2[3]))) reward = R_RISK;
-                        if (ax == pos_x(o2[0]) - 1 && (ay == pos_y(o2[0]) || ay == pos_y(o2[2]))) reward = R_RISK;
-                        if (ax == pos_x(o2[1]) + 1 && (ay == pos_y(o2[1]) || ay == pos_y(o2[3]))) reward = R_RISK;
-                        if (ax == pos_x(o1[0]) - 1 && (ay == pos_y(o1[0]) || ay == pos_y(o1[1]) || ay == pos_y(o1[2])))
-                            reward = R_RISK;
-                        if (ap == o1[0] || ap == o1[1] || ap == o1[2] || ap == o2[0] || ap == o2[1] || ap == o2[2] ||
-                            ap == o2[3]) {
-                            reward = R_HIT;
-                            trunc = true;
-                        }
-                    }
-                    if ((fl & F_FIRST) && ay == 7) {  // twoarmy_v4.py:282-285
-                        reward = R_ROOM2;
-                        fl &= ~F_FIRST;
-                    }
-                    if (reward == R_RISK) {  // twoarmy_v4.py:287-291
-                        risk += 1;
-                        if (risk > 5) trunc = true;
-                    }
-                    if (term || trunc) {  // twoarmy_v4.py:293-315
-                        if (term) reward = R_GOAL;
-                        step_move = 0;
-                        fl &= ~(F_PONE | F_PATROL);
-                        fl |= F_FIRST;
-                        risk = 0;
-                        if (draw(d, 5) == 1) fl = (fl & ~F_UP1) | F_RIGHT2;
-                        else fl = (fl | F_UP1) & ~F_RIGHT2;
-                        if (draw(d, 6) == 1) fl = (fl & ~F_UPD_H) | F_UPD_L;
-                        else fl = (fl | F_UPD_H) & ~F_UPD_L;
-                        need_reset = (a.flags & 1) != 0;
-                    }
                 }
-                if (live) {
-                    a.reward[out_idx] = reward_value(reward);
-                    a.term[out_idx] = term ? 1 : 0;
-                    a.trunc[out_idx] = trunc ? 1 : 0;
-                    if (a.consumed) a.consumed[out_idx] = (uint8_t)d.consumed;
+                if ((fl & F_FIRST) && ay == 7) {  // twoarmy_v4.py:282-285
+                    reward = R_ROOM2;
+                    fl &= ~F_FIRST;
                 }
-                // autoreset: MiniGridEnv.reset (minigrid.py:947-980) -- grid, balls, agent, step_count
-                if (need_reset) {
-                    ax = 3; ay = 15; step_count = 0;
-                    mid[0] = ball_get(MID_INIT, 0); mid[1] = ball_get(MID_INIT, 1); mid[2] = ball_get(MID_INIT, 2);
-                    o1[0] = o1[1] = o1[2] = NOPOS;
-                    o2[0] = o2[1] = o2[2] = o2[3] = NOPOS;
+                if (reward == R_RISK) {  // twoarmy_v4.py:287-291
+                    risk += 1;
+                    if (risk > 5) trunc = true;
                 }
-                __syncwarp();
-                uint32_t rmask = __ballot_sync(0xFFFFFFFFu, need_reset);
-                while (rmask) {
-                    const int e = __ffs(rmask) - 1;
-                    rmask &= rmask - 1;
-                    if (lane < REC_WORDS)
-                        gw[e * REC_WORDS + lane] = reinterpret_cast<const uint32_t *>(tab + TAB_TEMPLATE)[lane];
+                if (term || trunc) {  // twoarmy_v4.py:293-315
+                    if (term) reward = R_GOAL;
+                    step_move = 0;
+                    fl &= ~(F_PONE | F_PATROL);
+                    fl |= F_FIRST;
+                    risk = 0;
+                    if (draw(d, 5) == 1) fl = (fl & ~F_UP1) | F_RIGHT2;
+                    else fl = (fl | F_UP1) & ~F_RIGHT2;
+                    if (draw(d, 6) == 1) fl = (fl & ~F_UPD_H) | F_UPD_L;
+                    else fl = (fl | F_UPD_H) & ~F_UPD_L;
+                    need_reset = (a.flags & 1) != 0;
                 }
-                __syncwarp();
             }
+            if (live) {
+                a.reward[out_idx] = reward_value(reward);
+                a.term[out_idx] = term ? 1 : 0;
+                a.trunc[out_idx] = trunc ? 1 : 0;
+                if (a.consumed) a.consumed[out_idx] = (uint8_t)d.consumed;
+            }
+            // autoreset: MiniGridEnv.reset (minigrid.py:947-980) -- grid, balls, agent, step_count
+            if (need_reset) {
+                ax = 3; ay = 15; step_count = 0;
+                mid[0] = ball_get(MID_INIT, 0); mid[1] = ball_get(MID_INIT, 1); mid[2] = ball_get(MID_INIT, 2);
+                o1[0] = o1[1] = o1[2] = NOPOS;
+                o2[0] = o2[1] = o2[2] = o2[3] = NOPOS;
+            }
+            __syncwarp();
+            uint32_t rmask = __ballot_sync(0xFFFFFFFFu, need_reset);
+            while (rmask) {
+                const int e = __ffs(rmask) - 1;
+                rmask &= rmask - 1;
+                if (lane < REC_WORDS) gs[GUARD0_WORDS + e * SLOT_WORDS + lane] = tmpl_word;
+            }
+            __syncwarp();
         }
 
-        // ---- tile epilogue (warp 0): registers -> state arrays, packed grids -> HBM ------------
-        if (warp == 0) {
-            uint4 s0, s1;
-            s0.x = (uint32_t)ax | ((uint32_t)ay << 8) | (fl << 16) | ((uint32_t)risk << 24);
-            s0.y = (uint32_t)step_count;
-            s0.z = (uint32_t)step_move;
-            s0.w = tcount;
-            s1.x = mid[0] | (mid[1] << 10) | (mid[2] << 20);
-            s1.y = o1[0] | (o1[1] << 10) | (o1[2] << 20);
-            s1.z = o2[0] | (o2[1] << 10) | (o2[2] << 20);
-            s1.w = o2[3] | (err << 16);
-            a.sc0[env] = s0;
-            a.sc1[env] = s1;
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(a.grid + tile * (G_BYTES / 4), gw, G_BYTES);
-                bulk_commit();
-            }
-        }
+        // ---- tile epilogue: registers -> state arrays, packed grids -> HBM -------------------------
+        uint4 o0, o1w;
+        o0.x = (uint32_t)ax | ((uint32_t)ay << 8) | (fl << 16) | ((uint32_t)risk << 24);
+        o0.y = (uint32_t)step_count;
+        o0.z = (uint32_t)step_move;
+        o0.w = tcount;
+        o1w.x = mid[0] | (mid[1] << 10) | (mid[2] << 20);
+        o1w.y = o1[0] | (o1[1] << 10) | (o1[2] << 20);
+        o1w.z = o2[0] | (o2[1] << 10) | (o2[2] << 20);
+        o1w.w = o2[3] | (err << 16);
+        a.sc0[env] = o0;
+        a.sc1[env] = o1w;
+        fence_proxy_async();
+        __syncwarp();
+        bulk_s2g(a.grid + env * REC_WORDS, G, REC_BYTES);
+        bulk_commit();
+        bulk_wait_read<0>();  // smem may be reloaded (next tile) or released (exit)
+        __syncwarp();
     }
-    if (tid == 0) bulk_wait_all0();
 }
 
 }  // namespace ta

@@ -48,9 +48,8 @@ struct ta_batch {
     uint64_t seed, env_id0;
     uint32_t *grid = nullptr;
     uint4 *sc0 = nullptr, *sc1 = nullptr;
-    int ctas_per_sm = STEP_CTAS_PER_SM;
-    int kernel_flags = 2;  // bit 1: transpose obs stores through shared memory (coalesced 512 B stores)
-    uint8_t *tables = nullptr;
+    int ctas_per_sm = 0;   // 0 = whatever fits (tuning knob: TA_CTAS_PER_SM)
+    uint32_t *tmpl = nullptr;  // [20] the _gen_grid record
     // host-call path (ta_step_host)
     cudaStream_t own_stream = nullptr;
     void *d_act = nullptr;
@@ -64,60 +63,31 @@ struct ta_batch {
 
 namespace {
 
-void build_tables(std::vector<uint8_t> &t) {
-    t.assign(TAB_BYTES, 0);
-    static const uint8_t type_of[4] = {1, 2, 6, 8}, color_of[4] = {0, 5, 4, 1};
-    for (int b = 0; b < 256; b++)  // 4 packed cells -> (type,color,0) x 4
-        for (int k = 0; k < 4; k++) {
-            int c = (b >> (2 * k)) & 3;
-            t[TAB_LUT + b * 16 + 3 * k + 0] = type_of[c];
-            t[TAB_LUT + b * 16 + 3 * k + 1] = color_of[c];
-            t[TAB_LUT + b * 16 + 3 * k + 2] = 0;
-        }
-    uint32_t *top = reinterpret_cast<uint32_t *>(t.data() + TAB_TOP);
-    for (int ay = 0; ay < 17; ay++)
-        for (int j0 = 0; j0 < 17; j0++) {
-            uint32_t m = 0;
-            for (int b = 0; b < 16; b++)
-                if ((j0 + b) % 17 < 16 - ay) m |= 3u << (2 * b);
-            top[ay * 17 + j0] = m;
-        }
-    uint32_t *col = reinterpret_cast<uint32_t *>(t.data() + TAB_COL);
-    for (int cb = 0; cb < 4; cb++)
-        for (int j0 = 0; j0 < 17; j0++) {
-            uint32_t m = 0;
-            for (int b = 0; b < 16; b++) {
-                bool second = j0 + b >= 17;
-                if (second ? (cb & 2) : (cb & 1)) m |= 3u << (2 * b);
-            }
-            col[cb * 17 + j0] = m;
-        }
-    uint32_t *rt = reinterpret_cast<uint32_t *>(t.data() + TAB_RUN);
-    for (int run = 0; run < 608; run++) {
-        if (run >= 578) {
-            rt[run] = 1u << 25;
-            continue;
-        }
-        int q0 = run * 16, e = q0 / NCELL, k0 = q0 - e * NCELL, i0 = k0 / 17, j0 = k0 - 17 * i0;
-        rt[run] = (uint32_t)e | ((uint32_t)k0 << 5) | ((uint32_t)j0 << 14) | ((uint32_t)(i0 + 1) << 19) |
-                  ((k0 > NCELL - 16) ? (1u << 24) : 0u);
-    }
-    uint32_t *tm = reinterpret_cast<uint32_t *>(t.data() + TAB_TEMPLATE);
+// the _gen_grid record (twoarmy_v4.py:38-80); padding cells 289..319 hold the wall code
+void build_template(uint32_t *tm) {
+    for (int w = 0; w < REC_WORDS; w++) tm[w] = 0x55555555u;
     for (int x = 0; x < GS; x++)
         for (int y = 0; y < GS; y++) cell_set(tm, x, y, initial_cell(x, y));
 }
 
-template <int V, bool FAST>
+template <int V>
 int launch_step_t(ta_batch *h, const StepArgs &a, cudaStream_t st) {
-    static bool attr_set[64] = {};
-    auto kern = step_obs_kernel<V, FAST>;
-    if (!attr_set[h->device & 63]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM));
-        attr_set[h->device & 63] = true;
+    static int ctas_per_sm[64] = {};
+    auto kern = step_obs_kernel<V>;
+    constexpr int SMEM = ObsCfg<V>::SMEM;
+    int &cps = ctas_per_sm[h->device & 63];
+    if (!cps) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STEP_THREADS, SMEM));
+        cps = occ > 0 ? occ : 1;
     }
-    const int max_ctas = h->sm_count * h->ctas_per_sm;
+    int per_sm = cps;
+    if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
+    const int max_ctas = h->sm_count * per_sm;
     int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
-    kern<<<grid, STEP_THREADS, STEP_SMEM, st>>>(a);
+    kern<<<grid, STEP_THREADS, SMEM, st>>>(a);
     return launch_ok("step_obs_kernel");
 }
 
@@ -125,14 +95,14 @@ int g_force_generic = 0;
 
 int launch_step(ta_batch *h, const StepArgs &a, cudaStream_t st) {
     switch (h->view) {
-        case 3: return launch_step_t<3, false>(h, a, st);
-        case 5: return launch_step_t<5, false>(h, a, st);
-        case 7: return launch_step_t<7, false>(h, a, st);
-        case 9: return launch_step_t<9, false>(h, a, st);
-        case 11: return launch_step_t<11, false>(h, a, st);
-        case 13: return launch_step_t<13, false>(h, a, st);
-        case 15: return launch_step_t<15, false>(h, a, st);
-        case 17: return g_force_generic ? launch_step_t<17, false>(h, a, st) : launch_step_t<17, true>(h, a, st);
+        case 3: return launch_step_t<3>(h, a, st);
+        case 5: return launch_step_t<5>(h, a, st);
+        case 7: return launch_step_t<7>(h, a, st);
+        case 9: return launch_step_t<9>(h, a, st);
+        case 11: return launch_step_t<11>(h, a, st);
+        case 13: return launch_step_t<13>(h, a, st);
+        case 15: return launch_step_t<15>(h, a, st);
+        case 17: return launch_step_t<17>(h, a, st);
     }
     return TA_E_UNSUPPORTED;
 }
@@ -141,7 +111,7 @@ int do_reset(ta_batch *h, const uint8_t *mask, int hard, uint8_t *obs_out, cudaS
     // padded tail envs (>= n) are reset only at creation
     const long long cnt = pad_too ? h->npad : h->n;
     reset_grid_kernel<<<blocks_for(cnt * REC_WORDS, 256), 256, 0, st>>>(
-        h->grid, reinterpret_cast<const uint32_t *>(h->tables + TAB_TEMPLATE), mask, cnt);
+        h->grid, h->tmpl, mask, cnt);
     if (int rc = launch_ok("reset_grid_kernel")) return rc;
     reset_scalar_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(h->sc0, h->sc1, mask, hard, cnt);
     if (int rc = launch_ok("reset_scalar_kernel")) return rc;
@@ -187,10 +157,9 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    if (const char *e = getenv("TA_XPOSE")) h->kernel_flags = atoi(e) ? 2 : 0;
     if (const char *e = getenv("TA_CTAS_PER_SM")) {  // tuning knob for experiments
         int v = atoi(e);
-        if (v >= 1 && v <= 16) h->ctas_per_sm = v;
+        if (v >= 1 && v <= 32) h->ctas_per_sm = v;
     }
     if (prop.major < 10) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; this library is built for sm_100a only", device,
@@ -201,12 +170,12 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
     CK(cudaMalloc(&h->grid, (size_t)h->npad * REC_BYTES));
     CK(cudaMalloc(&h->sc0, (size_t)h->npad * sizeof(uint4)));
     CK(cudaMalloc(&h->sc1, (size_t)h->npad * sizeof(uint4)));
-    CK(cudaMalloc(&h->tables, TAB_BYTES));
+    CK(cudaMalloc(&h->tmpl, REC_BYTES));
     CK(cudaMemset(h->sc0, 0, (size_t)h->npad * sizeof(uint4)));
     CK(cudaMemset(h->sc1, 0, (size_t)h->npad * sizeof(uint4)));
-    std::vector<uint8_t> t;
-    build_tables(t);
-    CK(cudaMemcpy(h->tables, t.data(), TAB_BYTES, cudaMemcpyHostToDevice));
+    uint32_t tm[REC_WORDS];
+    build_template(tm);
+    CK(cudaMemcpy(h->tmpl, tm, REC_BYTES, cudaMemcpyHostToDevice));
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
@@ -219,7 +188,7 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
 int ta_destroy(ta_handle h) {
     if (!h) return TA_E_INVALID;
     cudaSetDevice(h->device);
-    cudaFree(h->grid); cudaFree(h->sc0); cudaFree(h->sc1); cudaFree(h->tables);
+    cudaFree(h->grid); cudaFree(h->sc0); cudaFree(h->sc1); cudaFree(h->tmpl);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -246,11 +215,11 @@ static int step_launch(ta_handle h, const void *actions, int action_dtype, const
     if (((uintptr_t)obs_out & 15u) || (draws && ((uintptr_t)draws & 7u))) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
     StepArgs a;
-    a.grid = h->grid; a.sc0 = h->sc0; a.sc1 = h->sc1; a.tables = h->tables;
+    a.grid = h->grid; a.sc0 = h->sc0; a.sc1 = h->sc1; a.tmpl = h->tmpl;
     a.actions = actions; a.draws = draws;
     a.obs = obs_out; a.reward = reward_out; a.term = term_out; a.trunc = trunc_out; a.consumed = consumed_out;
     a.n = h->n; a.ntiles = (int)(h->npad / TILE); a.T = T;
-    a.version = h->version; a.flags = (flags & 1) | h->kernel_flags; a.action_dtype = action_dtype;
+    a.version = h->version; a.flags = (flags & 1) | (g_force_generic ? 2 : 0); a.action_dtype = action_dtype;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32);
     a.env_id0 = h->env_id0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -374,8 +343,8 @@ int ta_last_step_ms(ta_handle h, float *ms) {
     return TA_OK;
 }
 
-/* test hook: route V=17 through the generic per-cell observation builder (1) or the
- * windowed fast path (0, default) so the two can be compared against each other */
+/* test hook: emit the observations with per-lane stores (1) instead of TMA bulk stores
+ * (0, default) -- the path taken when an obs slice is not 16-byte aligned */
 int ta_debug_force_generic_obs(int on) {
     g_force_generic = on;
     return TA_OK;
