@@ -128,6 +128,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the rollout / 7x7-view secondary measurements")
+    ap.add_argument("--rollout-T", type=int, default=16)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -138,7 +140,9 @@ def main():
                 f"view {args.view}x{args.view}x3, random actions, Philox draws, autoreset (BASELINE configs[2])")
     config = {"workload": workload, "envs_per_gpu": args.envs, "view": args.view, "env_version": args.version,
               "parallelism": f"env-sharded x{world}, no data-path collective",
-              "l2": f"{args.batches} rotating env batches + obs ring, working set > 126 MB L2"}
+              "l2": f"{args.batches} rotating env batches, each with its own obs slot: working set "
+                    f"{args.batches * args.envs * (3 * args.view * args.view + 230) / 1e6:.0f} MB > 126 MB L2",
+              "launch": "ta_step launches replayed from a CUDA graph (one kernel node per batch)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -171,58 +175,150 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n, V, B = args.envs, args.view, args.batches
-    envs = [pkg.TwoarmyVecEnv(args.version, n, V, device=dev, seed=9981, env_id0=(rank * B + b) * n) for b in range(B)]
-    for e in envs:
-        e.reset()
-    g = torch.Generator(device=dev).manual_seed(7 + rank)
     amap = torch.tensor([0, 1, 2, 3, 6], dtype=torch.uint8, device=dev)
-    R = 16
-    actions = amap[torch.randint(0, 5, (R, n), generator=g, device=dev)].contiguous()
-    outs = [dict(obs=torch.empty((n, V, V, 3), dtype=torch.uint8, device=dev),
-                 reward=torch.empty(n, dtype=torch.float32, device=dev),
-                 terminated=torch.empty(n, dtype=torch.uint8, device=dev),
-                 truncated=torch.empty(n, dtype=torch.uint8, device=dev)) for _ in range(B)]
-
-    def run(k0, k):
-        for i in range(k0, k0 + k):
-            envs[i % B].step(actions[i % R], out=outs[i % B])
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
 
     def barrier():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    run(0, args.warmup)
+    class Workload:
+        """B independent env batches of n envs (rotated so that the timed launches miss L2), one
+        obs/reward/flag slot per batch, pre-sampled uniform actions.  step(i) = ONE fused
+        step+gen_obs launch (ta_step) on batch i % B."""
+
+        def __init__(self, view, batches, id_base):
+            self.view, self.B = view, batches
+            self.envs = [pkg.TwoarmyVecEnv(args.version, n, view, device=dev, seed=9981,
+                                           env_id0=id_base + (rank * batches + b) * n) for b in range(batches)]
+            for e in self.envs:
+                e.reset()
+            self.actions = amap[torch.randint(0, 5, (batches, n), generator=g, device=dev)].contiguous()
+            self.outs = [dict(obs=torch.empty((n, view, view, 3), dtype=torch.uint8, device=dev),
+                              reward=torch.empty(n, dtype=torch.float32, device=dev),
+                              terminated=torch.empty(n, dtype=torch.uint8, device=dev),
+                              truncated=torch.empty(n, dtype=torch.uint8, device=dev)) for _ in range(batches)]
+            self.graph = None
+
+        def step(self, i):
+            b = i % self.B
+            self.envs[b].step(self.actions[b], out=self.outs[b])
+
+        def capture(self):
+            """The launch-bound inner loop (B launches, one per batch) as one CUDA graph."""
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(self.B):
+                    self.step(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                for i in range(self.B):
+                    self.step(i)
+
+        def run(self, k):
+            """k launches: whole graph replays, the remainder as single launches. Returns the
+            number of step kernels enqueued."""
+            reps, rem = divmod(k, self.B)
+            for _ in range(reps):
+                self.graph.replay()
+            for i in range(rem):
+                self.step(i)
+            return k
+
+        def timed(self, steps, warmup):
+            self.run(warmup)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            launches = self.run(steps)
+            ev1.record()
+            barrier()
+            ms = ev0.elapsed_time(ev1)
+            if dist:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, launches
+
+        def close(self):
+            self.graph = None
+            for e in self.envs:
+                e.close()
+
+    wl = Workload(V, B, 0)
+    wl.capture()
+    wl.run(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = pkg.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    run(args.warmup, args.steps)
-    ev1.record()
-    barrier()
-    launches = pkg.launch_count() - l0
-    ms = ev0.elapsed_time(ev1)
+    ms, launches = wl.timed(args.steps, args.warmup)
     # a short run gives nvidia-smi nothing to sample: keep the GPU under the same load a bit longer
     clocks = None
     if rank == 0:
-        t_end = time.time() + max(0.0, 0.6 - ms / 1e3)
+        t_end = time.time() + max(0.0, 0.7 - ms / 1e3)
         while time.time() < t_end:
-            run(0, 200)
+            wl.run(25 * B)
             torch.cuda.synchronize()
         clocks = sampler.stop()
-    if dist:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     total_steps = args.steps * n * world
     value = total_steps / (ms / 1e3)
 
+    # ---- secondary measurements (same timing rules; reported under "extra") ----------------
+    extra = {}
+    if not args.no_extra:
+        # (a) T-step rollouts in ONE launch (ta_rollout: pre-sampled actions, state stays on chip)
+        T = args.rollout_T
+        racts = amap[torch.randint(0, 5, (T, n), generator=g, device=dev)].contiguous()
+        robs = [torch.empty((T, n, V, V, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+        rrew = torch.empty((T, n), dtype=torch.float32, device=dev)
+        rte = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        rtr = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        import ctypes as C
+        L = pkg._capi.lib()
+
+        def rollout(i):
+            e = wl.envs[i % B]
+            pkg._capi.check(L.ta_rollout(e._h, C.c_void_p(racts.data_ptr()), 1, T, C.c_void_p(robs[i % 2].data_ptr()),
+                                         C.c_void_p(rrew.data_ptr()), C.c_void_p(rte.data_ptr()), C.c_void_p(rtr.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ta_rollout")
+
+        for i in range(3):
+            rollout(i)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        R = max(4, args.steps // (4 * T))
+        ev0.record()
+        for i in range(R):
+            rollout(i)
+        ev1.record()
+        barrier()
+        rms = ev0.elapsed_time(ev1)
+        if dist:
+            t = torch.tensor([rms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rms = float(t.item())
+        extra["rollout"] = {"call": "ta_rollout", "T": T, "launches": R, "us_per_env_step_batch": rms * 1e3 / (R * T),
+                            "value": R * T * n * world / (rms / 1e3), "unit": UNIT,
+                            "hbm_bytes_per_env_step": 3 * V * V + 1 + 6 + (2 * 112) / T}
+        del robs
+        # (b) the north-star 7x7x3 view (agent_view_size=7), single-step launches
+        if V != 7:
+            wl7 = Workload(7, B, 1 << 40)
+            wl7.capture()
+            ms7, _ = wl7.timed(args.steps, args.warmup)
+            extra["view7"] = {"us_per_launch": ms7 * 1e3 / args.steps, "value": args.steps * n * world / (ms7 / 1e3),
+                              "unit": UNIT, "alg_bytes_per_env_step": alg_bytes(7),
+                              "achieved_gbs": alg_bytes(7) * n / (ms7 / args.steps / 1e3) / 1e9}
+            wl7.close()
+
     # ---- end to end through the public host-buffer call ---------------------------------
-    e2e_env = envs[0]
+    e2e_env = wl.envs[0]
+    actions = wl.actions
     h_act = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_act.copy_(actions[0].cpu())
     h_obs = torch.empty((n, V, V, 3), dtype=torch.uint8).pin_memory()
@@ -253,17 +349,29 @@ def main():
     peak, peak_src = measured_peak()
     per_launch_ms = ms / args.steps
     achieved = alg_bytes(V) * n / (per_launch_ms / 1e3) / 1e9
+    # bytes this layout really has to move per env-step (2-bit packed grid, 80 B each way)
+    layout_bytes = 1 + 2 * (80 + 32) + 3 * V * V + 6
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(f"step_obs_v{V}_n{n}")
+        except Exception:
+            traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "step_obs_kernel", "alg_bytes_per_env_step": alg_bytes(V),
-                     "peak_source": peak_src, "launch_us": per_launch_ms * 1e3},
+                     "traffic": traffic, "kernel": f"step_obs_kernel<{V}>", "alg_bytes_per_env_step": alg_bytes(V),
+                     "peak_source": peak_src, "launch_us": per_launch_ms * 1e3,
+                     "layout_bytes_per_env_step": layout_bytes,
+                     "achieved_layout_bytes": layout_bytes * n / (per_launch_ms / 1e3) / 1e9,
+                     "timing": "CUDA events on the launching stream around K graph-replayed launches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n),
                 "d2h_bytes_per_step": int(n * (3 * V * V + 4 + 1 + 1)), "steps": args.e2e_steps,
                 "call": "TwoarmyVecEnv.step_host -> ta_step_host (pinned host buffers)"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
     }
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O

@@ -111,15 +111,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    // try_wait suspends the thread for up to the hinted time (ns) instead of spinning
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(4000u)
         : "memory");
 }
 // global -> shared, completion counted on an mbarrier
@@ -135,6 +136,9 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                  "r"(bytes)
                  : "memory");
 }
+// programmatic dependent launch (PTX griddepcontrol; no-ops when the launch has no such edge)
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

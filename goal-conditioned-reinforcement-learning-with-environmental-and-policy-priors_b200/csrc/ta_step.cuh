@@ -39,8 +39,10 @@ constexpr int GUARD0_WORDS = 12;
 constexpr int GRID_S_WORDS = GUARD0_WORDS + TILE * SLOT_WORDS;  // 1164
 constexpr uint32_t WALLS16 = 0x55555555u;                        // 16 wall codes
 constexpr int RUN_BYTES = 48;                                    // 16 cells x (type,color,state)
-constexpr int CHUNK_BYTES = 32 * RUN_BYTES;                      // one warp iteration = 1536 B
-constexpr int RING = 4;                                          // chunk buffers per warp
+constexpr int ITER_BYTES = 32 * RUN_BYTES;                       // one warp iteration = 1536 B
+constexpr int CHUNK_ITERS = 2;                                   // warp iterations per bulk store
+constexpr int CHUNK_BYTES = CHUNK_ITERS * ITER_BYTES;            // 3072 B
+constexpr int RING = 2;                                          // chunk buffers per warp
 
 constexpr int round16(int x) { return (x + 15) / 16 * 16; }
 
@@ -51,6 +53,7 @@ struct ObsCfg {
     static constexpr int L = 2 * VV;     // bits of one env's packed view
     static constexpr int RUNS = 2 * VV;  // 16-cell runs in a 32-env tile (32 * VV / 16)
     static constexpr int ITERS = (RUNS + 31) / 32;
+    static constexpr int CHUNKS = (ITERS + CHUNK_ITERS - 1) / CHUNK_ITERS;
     static constexpr int P = (L + 31) / 32;                              // words per env view (V < 17)
     static constexpr int EV_STRIDE = (V == 17) ? 0 : ((P + 1) | 1);      // odd: conflict-free pass 1
     static constexpr int EV_ROWS = 34;                                   // env 32, 33: readable padding
@@ -62,6 +65,7 @@ struct ObsCfg {
     static constexpr int SM_EV = SM_GRID + GRID_S_WORDS * 4;
     static constexpr int SM_RING = SM_EV + round16(EV_ROWS * EV_STRIDE * 4);
     static constexpr int SMEM = SM_RING + RING * CHUNK_BYTES;
+    static_assert((RING & (RING - 1)) == 0, "RING must be a power of two");
     static_assert(SM_GRID % 16 == 0 && (SM_GRID + GUARD0_WORDS * 4) % 16 == 0 && SM_RING % 16 == 0, "alignment");
 };
 
@@ -69,7 +73,7 @@ struct StepArgs {
     uint32_t *grid;
     uint4 *sc0;
     uint4 *sc1;
-    const uint32_t *tmpl;  // [20] the _gen_grid record
+    const uint32_t *tmpl;  // [20] the _gen_grid record, [20..23] TYPE_LUT, COLOR_LUT twice
     const void *actions;
     const uint8_t *draws;
     uint8_t *obs;
@@ -81,7 +85,8 @@ struct StepArgs {
     int ntiles;
     int T;  // env steps per launch; outputs / actions / draws are [T][n]
     int version;
-    int flags;  // bit 0 autoreset, bit 1 never use bulk stores for the obs (test hook)
+    int flags;  // bit 0 autoreset, bit 1 never use bulk stores for the obs (test hook),
+                // bits 2,3 timing experiments only: skip the obs pass / the scalar phases
     int action_dtype;
     uint32_t seed_lo, seed_hi;
     unsigned long long env_id0;
@@ -158,21 +163,22 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
-__device__ __forceinline__ void expand4(uint32_t sel, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
-    const uint32_t t = prmt(TYPE_LUT, 0u, sel), c = prmt(COLOR_LUT, 0u, sel);
+__device__ __forceinline__ void expand4(uint32_t sel, uint32_t tl, uint32_t cl, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+    const uint32_t t = prmt(tl, 0u, sel), c = prmt(cl, 0u, sel);
     w0 = prmt(t, c, 0x1840u);  // t0 c0 0  t1
     w1 = prmt(t, c, 0x6285u);  // c1 0  t2 c2
     w2 = prmt(t, c, 0x8738u);  // 0  t3 c3 0
 }
 
 // 16 packed cells -> 48 obs bytes, stored as three 16-byte vectors at dst (shared memory)
-__device__ __forceinline__ void expand16_store(uint32_t c, uint4 *dst) {
+// (tl, cl: TYPE_LUT / COLOR_LUT held in registers by the caller)
+__device__ __forceinline__ void expand16_store(uint32_t c, uint32_t tl, uint32_t cl, uint4 *dst) {
     const uint32_t sa = spread16(c & 0xFFFFu), sb = spread16(c >> 16);
     uint32_t w[12];
-    expand4(sa, w[0], w[1], w[2]);
-    expand4(sa >> 16, w[3], w[4], w[5]);
-    expand4(sb, w[6], w[7], w[8]);
-    expand4(sb >> 16, w[9], w[10], w[11]);
+    expand4(sa, tl, cl, w[0], w[1], w[2]);
+    expand4(sa >> 16, tl, cl, w[3], w[4], w[5]);
+    expand4(sb, tl, cl, w[6], w[7], w[8]);
+    expand4(sb >> 16, tl, cl, w[9], w[10], w[11]);
     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
@@ -181,8 +187,9 @@ __device__ __forceinline__ void expand16_store(uint32_t c, uint4 *dst) {
 // V = 17.  The view is as wide as the grid and the record is column-major, so the 16 view cells
 // k0..k0+15 of an env are the 32 bits at cell offset cellbase + k0 of the guard-padded tile
 // (one funnel shift), except that rows above the grid (they alias the previous column's tail)
-// become walls -- a 34-bit periodic mask kept per env as two words -- and the agent's own cell
-// (view cell 152) is empty.  meta = (cellbase, mask lo, mask hi, -).
+// become walls -- a 34-bit periodic mask kept per env as two words.  The agent's own cell (view
+// cell 152) must read as empty: the kernel clears it in the shared-memory grid for the duration
+// of the obs pass.  meta = (cellbase, mask lo, mask hi, -).
 __device__ __forceinline__ uint4 make_meta17(int e, int ax, int ay) {
     const int h = 16 - ay;  // rows above the grid
     const unsigned long long rm = (1ull << (2 * (h < 0 ? 0 : h))) - 1ull;
@@ -195,10 +202,7 @@ __device__ __forceinline__ uint32_t fetch17(const uint32_t *gs, uint4 m, int k0)
     const int cell = (int)m.x + k0, wi = cell >> 4;
     const uint32_t win = __funnelshift_r(gs[wi], gs[wi + 1], (uint32_t)(cell & 15) * 2u);
     const uint32_t mk = __funnelshift_rc(m.y, m.z, (uint32_t)(2 * j0));
-    uint32_t c = (win & ~mk) | (WALLS16 & mk);
-    const int d = 152 - k0;  // agent cell: view (8,16)
-    if ((unsigned)d < 16u) c &= ~(3u << (2 * d));
-    return c;
+    return (win & ~mk) | (WALLS16 & mk);
 }
 
 // V < 17, pass 1: lane e packs env e's V x V view (2 bits per cell, column after column) into
@@ -252,26 +256,15 @@ __device__ __forceinline__ uint32_t run_codes(int r, const uint32_t *gs, const u
     }
 }
 
-// nbytes of a ring slot -> global memory.  Bulk (TMA) when the destination is 16-byte aligned:
-// whole 16-byte units by one bulk store, a ragged tail (< 16 B, last tile of a ragged batch) by
-// byte stores.  Lane 0 commits exactly one bulk group per call either way.
-__device__ __forceinline__ void emit_chunk(uint8_t *dst, const uint8_t *src, int nbytes, bool bulk, int lane) {
-    if (bulk) {
-        const int nb16 = nbytes > 0 ? (nbytes & ~15) : 0;
-        if (lane == 0) {
-            if (nb16) bulk_s2g(dst, src, (uint32_t)nb16);
-            bulk_commit();
-        }
-        for (int b = nb16 + lane; b < nbytes; b += 32) dst[b] = src[b];
+// slow path (obs slice not 16-byte aligned, ragged last tile, or the test hook): nbytes of a
+// staging buffer -> global memory with per-lane stores
+__device__ __forceinline__ void copy_out(uint8_t *dst, const uint8_t *src, int nbytes, int lane) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+        const int nw = nbytes > 0 ? nbytes >> 2 : 0;
+        for (int w = lane; w < nw; w += 32) reinterpret_cast<uint32_t *>(dst)[w] = reinterpret_cast<const uint32_t *>(src)[w];
+        for (int b = 4 * nw + lane; b < nbytes; b += 32) dst[b] = src[b];
     } else {
-        if (lane == 0) bulk_commit();
-        if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
-            const int nw = nbytes > 0 ? nbytes >> 2 : 0;
-            for (int w = lane; w < nw; w += 32) reinterpret_cast<uint32_t *>(dst)[w] = reinterpret_cast<const uint32_t *>(src)[w];
-            for (int b = 4 * nw + lane; b < nbytes; b += 32) dst[b] = src[b];
-        } else {
-            for (int b = lane; b < nbytes; b += 32) dst[b] = src[b];
-        }
+        for (int b = lane; b < nbytes; b += 32) dst[b] = src[b];
     }
 }
 
@@ -295,23 +288,25 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
     const int lane = threadIdx.x;
     uint32_t *G = gs + GUARD0_WORDS + lane * SLOT_WORDS;  // this lane's env record
 
-    // one-time CTA setup: barrier, guard words, the reset template word of this lane
+    // Programmatic dependent launch: the next kernel in the stream may be scheduled as soon as
+    // every CTA of this grid has got here, and this grid may have been scheduled before its
+    // predecessor finished -- nothing the predecessor may write (actions, draws, this handle's
+    // state) is read, and nothing is written to global memory, before griddep_wait() below.
+    griddep_launch_dependents();
+    // one-time CTA setup: barrier, the reset template word of this lane (guards: see below)
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
     }
-    for (int w = lane; w < GRID_S_WORDS; w += 32) {
-        const int s = w - GUARD0_WORDS;
-        if (s < 0 || (s % SLOT_WORDS) >= REC_WORDS) gs[w] = WALLS16;
-    }
-    if constexpr (V == 17) {
-        if (lane == 0) head[32] = 0u;
-    } else {
-        for (int w = lane; w < 2 * C::EV_STRIDE; w += 32) ev[32 * C::EV_STRIDE + w] = 0u;
-    }
     const uint32_t tmpl_word = lane < REC_WORDS ? __ldg(a.tmpl + lane) : 0u;
-    fence_proxy_async();  // generic-proxy writes above vs. the async-proxy copies below
     __syncwarp();
+    bool first_tile = true;
+    griddep_wait();
+    // the two look-up words live in ordinary registers: loaded through a lane-dependent address
+    // (tmpl[20..23] = TYPE, COLOR, TYPE, COLOR) so that ptxas cannot turn them back into immediates
+    // / uniform registers, which it re-materialises in front of every permute
+    const uint32_t type_lut = __ldg(a.tmpl + REC_WORDS + 2 * (lane & 1));
+    const uint32_t color_lut = __ldg(a.tmpl + REC_WORDS + 1 + 2 * (lane & 1));
     uint32_t phase = 0;
     uint32_t gi = 0;  // obs chunks emitted so far (ring slot = gi % RING)
     const bool v4 = a.version == 4;
@@ -326,6 +321,18 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
         __syncwarp();
         bulk_g2s(G, a.grid + env * REC_WORDS, REC_BYTES, bar);
         const uint4 s0 = a.sc0[env], s1 = a.sc1[env];
+        if (first_tile) {  // guard words (never written again), while the loads are in flight
+            first_tile = false;
+            const uint4 w4 = make_uint4(WALLS16, WALLS16, WALLS16, WALLS16);
+            uint4 *g4 = reinterpret_cast<uint4 *>(G + REC_WORDS);
+            g4[0] = w4; g4[1] = w4; g4[2] = w4; g4[3] = w4;
+            if (lane < GUARD0_WORDS / 4) reinterpret_cast<uint4 *>(gs)[lane] = w4;
+            if constexpr (V == 17) {
+                if (lane == 0) head[32] = 0u;
+            } else {
+                for (int w = lane; w < 2 * C::EV_STRIDE; w += 32) ev[32 * C::EV_STRIDE + w] = 0u;
+            }
+        }
         int ax = (int)(s0.x & 0xFFu), ay = (int)((s0.x >> 8) & 0xFFu), risk = (int)(s0.x >> 24);
         uint32_t fl = (s0.x >> 16) & 0xFFu;
         int step_count = (int)s0.y, step_move = (int)s0.z;
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
                 mbar_wait(bar, phase);
                 phase ^= 1u;
             }
+            if (a.flags & 8) skip = true;
             if (!skip) {
                 tcount += 1u;
                 step_move += 1;
@@ -426,7 +434,12 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
             }
 
             // ---- observations of all 32 envs (gen_obs) ------------------------------------------
+            uint32_t agent_cell = C_EMPTY;
             if constexpr (V == 17) {
+                if (inb(ax, ay)) {  // the agent's own cell reads as empty (minigrid.py:1472-1476)
+                    agent_cell = cell_get(G, ax, ay);
+                    if (agent_cell != C_EMPTY) cell_set(G, ax, ay, C_EMPTY);
+                }
                 const uint4 m = make_meta17(lane, ax, ay);
                 meta[lane] = m;
                 __syncwarp();  // every lane's grid edits are visible
@@ -436,27 +449,59 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
                 build_envview<V>(gs, ev, lane, ax, ay);
             }
             __syncwarp();
-            {
+            if (!(a.flags & 4)) {
                 uint8_t *dst = a.obs + ((long long)t * a.n + tile * TILE) * C::OBS;
-                const bool bulk = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && !(a.flags & 2);
-                const int valid_bytes = (int)nvalid * C::OBS;
+                const bool fast = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && !(a.flags & 2) && nvalid == TILE;
+                if (fast) {
+                    // whole tile, aligned: CHUNK_ITERS x 1536 B are staged, then leave with one bulk store
 #pragma unroll 1
-                for (int it = 0; it < C::ITERS; it++) {
-                    int r = it * 32 + lane;
-                    r = r < C::RUNS ? r : C::RUNS - 1;
-                    const uint32_t c = run_codes<V>(r, gs, meta, head, ev);
-                    uint8_t *slot = ring + (gi % RING) * CHUNK_BYTES;
-                    gi++;
-                    if (lane == 0) bulk_wait_read<RING - 1>();  // the slot's previous bulk store has read it
+                    for (int ch = 0; ch < C::CHUNKS; ch++) {
+                        uint8_t *slot = ring + (gi & (RING - 1)) * CHUNK_BYTES;
+                        gi++;
+                        if (lane == 0) bulk_wait_read<RING - 1>();  // the slot's previous bulk store has read it
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < CHUNK_ITERS; k++) {
+                            const int it = ch * CHUNK_ITERS + k;
+                            if (it < C::ITERS) {
+                                int r = it * 32 + lane;
+                                r = r < C::RUNS ? r : C::RUNS - 1;
+                                const uint32_t c = run_codes<V>(r, gs, meta, head, ev);
+                                expand16_store(c, type_lut, color_lut,
+                                               reinterpret_cast<uint4 *>(slot + k * ITER_BYTES + lane * RUN_BYTES));
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            int len = C::RUNS * RUN_BYTES - ch * CHUNK_BYTES;
+                            len = len > CHUNK_BYTES ? CHUNK_BYTES : len;
+                            bulk_s2g(dst + ch * CHUNK_BYTES, slot, (uint32_t)len);
+                            bulk_commit();
+                        }
+                    }
+                } else {
+                    if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
-                    expand16_store(c, reinterpret_cast<uint4 *>(slot + lane * RUN_BYTES));
-                    fence_proxy_async();
-                    __syncwarp();
-                    int len = (C::RUNS - it * 32) * RUN_BYTES;
-                    len = len > CHUNK_BYTES ? CHUNK_BYTES : len;
-                    const int rem = valid_bytes - it * CHUNK_BYTES;
-                    emit_chunk(dst + it * CHUNK_BYTES, slot, len < rem ? len : rem, bulk, lane);
+                    const int valid_bytes = (int)nvalid * C::OBS;
+#pragma unroll 1
+                    for (int it = 0; it < C::ITERS; it++) {
+                        int r = it * 32 + lane;
+                        r = r < C::RUNS ? r : C::RUNS - 1;
+                        const uint32_t c = run_codes<V>(r, gs, meta, head, ev);
+                        expand16_store(c, type_lut, color_lut, reinterpret_cast<uint4 *>(ring + lane * RUN_BYTES));
+                        __syncwarp();
+                        int len = (C::RUNS - it * 32) * RUN_BYTES;
+                        len = len > ITER_BYTES ? ITER_BYTES : len;
+                        const int rem = valid_bytes - it * ITER_BYTES;
+                        copy_out(dst + it * ITER_BYTES, ring, len < rem ? len : rem, lane);
+                        __syncwarp();
+                    }
                 }
+            }
+            if constexpr (V == 17) {
+                __syncwarp();
+                if (agent_cell != C_EMPTY) cell_set(G, ax, ay, agent_cell);
             }
             __syncwarp();  // the obs pass has read the grids; phase C edits them
 

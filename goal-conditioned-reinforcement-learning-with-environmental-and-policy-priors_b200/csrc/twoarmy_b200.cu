@@ -49,6 +49,9 @@ struct ta_batch {
     uint32_t *grid = nullptr;
     uint4 *sc0 = nullptr, *sc1 = nullptr;
     int ctas_per_sm = 0;   // 0 = whatever fits (tuning knob: TA_CTAS_PER_SM)
+    int pdl = 0;           // programmatic dependent launch of the step kernel (TA_PDL=1 turns it on;
+                           // measured slower on B200: 19.2 vs 16.8 us per 65536-env launch, so off)
+    int debug_flags = 0;   // TA_DEBUG_FLAGS: timing experiments (StepArgs::flags bits 2,3)
     uint32_t *tmpl = nullptr;  // [20] the _gen_grid record
     // host-call path (ta_step_host)
     cudaStream_t own_stream = nullptr;
@@ -87,7 +90,17 @@ int launch_step_t(ta_batch *h, const StepArgs &a, cudaStream_t st) {
     if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
     const int max_ctas = h->sm_count * per_sm;
     int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
-    kern<<<grid, STEP_THREADS, SMEM, st>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(STEP_THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, a));
     return launch_ok("step_obs_kernel");
 }
 
@@ -157,6 +170,8 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("TA_PDL")) h->pdl = atoi(e) != 0;
+    if (const char *e = getenv("TA_DEBUG_FLAGS")) h->debug_flags = atoi(e) & 3;
     if (const char *e = getenv("TA_CTAS_PER_SM")) {  // tuning knob for experiments
         int v = atoi(e);
         if (v >= 1 && v <= 32) h->ctas_per_sm = v;
@@ -170,12 +185,14 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
     CK(cudaMalloc(&h->grid, (size_t)h->npad * REC_BYTES));
     CK(cudaMalloc(&h->sc0, (size_t)h->npad * sizeof(uint4)));
     CK(cudaMalloc(&h->sc1, (size_t)h->npad * sizeof(uint4)));
-    CK(cudaMalloc(&h->tmpl, REC_BYTES));
+    CK(cudaMalloc(&h->tmpl, REC_BYTES + 16));
     CK(cudaMemset(h->sc0, 0, (size_t)h->npad * sizeof(uint4)));
     CK(cudaMemset(h->sc1, 0, (size_t)h->npad * sizeof(uint4)));
-    uint32_t tm[REC_WORDS];
+    uint32_t tm[REC_WORDS + 4];
     build_template(tm);
-    CK(cudaMemcpy(h->tmpl, tm, REC_BYTES, cudaMemcpyHostToDevice));
+    tm[REC_WORDS] = tm[REC_WORDS + 2] = TYPE_LUT;
+    tm[REC_WORDS + 1] = tm[REC_WORDS + 3] = COLOR_LUT;
+    CK(cudaMemcpy(h->tmpl, tm, REC_BYTES + 16, cudaMemcpyHostToDevice));
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
@@ -219,7 +236,7 @@ static int step_launch(ta_handle h, const void *actions, int action_dtype, const
     a.actions = actions; a.draws = draws;
     a.obs = obs_out; a.reward = reward_out; a.term = term_out; a.trunc = trunc_out; a.consumed = consumed_out;
     a.n = h->n; a.ntiles = (int)(h->npad / TILE); a.T = T;
-    a.version = h->version; a.flags = (flags & 1) | (g_force_generic ? 2 : 0); a.action_dtype = action_dtype;
+    a.version = h->version; a.flags = (flags & 1) | (g_force_generic ? 2 : 0) | (h->debug_flags << 2); a.action_dtype = action_dtype;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32);
     a.env_id0 = h->env_id0;
     cudaStream_t st = (cudaStream_t)stream;
