@@ -100,19 +100,162 @@ def cpu_reference_run(version, view, envs, steps, warmup, threads=None):
     """The CPU arm: the oracle's port of the path, all host threads, bounded sample."""
     from oracle import oracle as O
     cores = threads or os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     # size a step so that warmup+steps stay within a couple of minutes: probe first
-    probe_steps, probe_s = O.bench_rollout(version, envs, 4, view)
+    probe_steps, probe_s = O.bench_rollout(version, envs, 4, view, threads=cores)
+    cores = O.max_threads()
     rate = probe_steps / max(probe_s, 1e-9)
     per_step_T = max(1, int(rate * 0.05 / envs))  # about 50 ms of CPU work per "step"
     total = 0
     t_all = 0.0
     for i in range(warmup + steps):
-        n, s = O.bench_rollout(version, envs, per_step_T, view, seed=9981 + i)
+        n, s = O.bench_rollout(version, envs, per_step_T, view, seed=9981 + i, threads=cores)
         if i >= warmup:
             total += n
             t_all += s
     return total / t_all, cores, per_step_T, t_all
+
+
+def bench_ppo(args, rank, world, local_rank):
+    """--workload ppo (BASELINE configs[3]): full PPO rollout-update loop on Twoarmy-17x17-v4,
+    `--ppo-envs` envs GLOBAL x `--ppo-horizon` steps per update, GAE/advantages on the GPU, NCCL
+    gradient all-reduce.  A step = one rollout + one PPO.update (K_epochs x minibatches).  Metric:
+    env frames consumed per second by the whole loop."""
+    import importlib
+    metric, unit = "ppo_frames_per_sec", "frames/s"
+    n_global, T = args.ppo_envs, args.ppo_horizon
+    config = {"workload": f"PPO rollout+update loop, MiniGrid-twoarmy-17x17-v{args.version}, {n_global} envs x {T}-step horizon "
+                          f"(BASELINE configs[3])", "envs_global": n_global, "horizon": T, "K_epochs": args.ppo_epochs,
+              "minibatch_per_rank": args.ppo_minibatch, "nets": "Net_PPO_actor/critic (TINet), bf16 autocast, channels_last",
+              "parallelism": f"env-sharded dp{world}, NCCL gradient all-reduce"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # the reference's loop shape on the host cores: ONE env, select_action at B=1, buffer 2048,
+        # update K_epochs x minibatches of 128 (soa/train_ppo.py:99-160) -- env via the C port, nets
+        # via this repo's PyTorch mirror of all_net.py on the CPU (the Python reference cannot travel)
+        import numpy as np
+        import torch
+        from oracle import oracle as O
+        sys.path.insert(0, ROOT)
+        import twoarmy_b200 as pkg
+        P = importlib.import_module(pkg.__name__ + ".ppo")
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        torch.manual_seed(0)
+        agent = P.PPO(device="cpu", autocast=False)
+        cap = args.ppo_ref_frames
+        ora = O.OracleBatch(args.version, 1, 17, seed=9981)
+        ora.reset()
+        lut = np.array(P.MATRIX_LUT, np.float32)
+        t0 = time.perf_counter()
+        f = ora.matrix().astype(np.float32)
+        sm = np.repeat(f[:, None], 5, 1)
+        ss = np.tile(np.array([[15.0, 3.0]], np.float32), (1, 5, 1))
+        g = torch.tensor([[2.0, 14.0]])
+        rec = {k: [] for k in ("s", "p", "a", "r", "a_logp")}
+        amap = np.array([0, 1, 2, 3, 6], np.int32)
+        for i in range(cap):
+            a, lp = agent.select_action(torch.from_numpy(sm), torch.from_numpy(ss), g)
+            out = ora.step(amap[a.numpy()], None, autoreset=False)
+            e = ora.envs[0]
+            sm = np.concatenate([sm[:, 1:], ora.matrix().astype(np.float32)[:, None]], 1)
+            ss = np.concatenate([ss[:, 1:], np.array([[[float(e["ay"]), float(e["ax"])]]], np.float32)], 1)
+            rec["s"].append(sm[0].copy()); rec["p"].append(ss[0].copy()); rec["a"].append([int(a)])
+            rec["r"].append([float(out["reward"][0])]); rec["a_logp"].append([float(lp)])
+            if out["terminated"][0] or out["truncated"][0]:
+                ora.reset()
+                f = ora.matrix().astype(np.float32)
+                sm = np.repeat(f[:, None], 5, 1)
+                ss = np.tile(np.array([[15.0, 3.0]], np.float32), (1, 5, 1))
+        buf = {k: torch.tensor(np.array(v)) for k, v in rec.items()}
+        buf["g"] = g.repeat(cap, 1)
+        agent.update(buf)
+        secs = time.perf_counter() - t0
+        v = cap / secs
+        line = {"metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
+                                 "sample": f"one buffer of {cap} frames: single env (C port) + select_action at B=1 + "
+                                           f"PPO.update K=10 x minibatch 128 on {cores} CPU threads"},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import twoarmy_b200 as pkg
+    P = importlib.import_module(pkg.__name__ + ".ppo")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    n_local = n_global // world
+    torch.manual_seed(9981)
+    agent = P.PPO(device=dev)
+    agent.broadcast_parameters()
+    torch.manual_seed(9981 + 1000 * (rank + 1))
+    env = pkg.TwoarmyVecEnv(args.version, n_local, 17, device=dev, seed=9981, env_id0=rank * n_local, autoreset=False)
+    roll = P.VecRollout(env, agent, T)
+
+    def one_step():
+        buf = roll.collect()
+        return agent.update(buf.flat(), minibatch=args.ppo_minibatch, epochs=args.ppo_epochs)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warmup = args.ppo_steps, args.ppo_warmup
+    for _ in range(warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = pkg.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        losses = one_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = pkg.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # phase split (one more step, timed per phase)
+    t0 = time.perf_counter(); buf = roll.collect(); torch.cuda.synchronize(); t1 = time.perf_counter()
+    agent.update(buf.flat(), minibatch=args.ppo_minibatch, epochs=args.ppo_epochs); torch.cuda.synchronize(); t2 = time.perf_counter()
+    if rank == 0:
+        frames = steps * T * n_local * world
+        fwd_flop = 47.53e6  # per sample per net (SURVEY.md section 2.1)
+        upd_flop = 3 * 2 * fwd_flop * T * n_local * args.ppo_epochs + 2 * 2 * fwd_flop * T * n_local  # update + the two critic passes
+        roll_flop = fwd_flop * T * n_local  # actor forward per frame
+        tf = 1353.2
+        try:
+            tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        except Exception:
+            pass
+        achieved_tf = (upd_flop + roll_flop) / ((ms / steps) / 1e3) / 1e12
+        line = {"metric": metric, "value": frames / (ms / 1e3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": config,
+                "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tf, "unit": "TFLOP/s", "frac": achieved_tf / tf,
+                             "traffic": None, "kernel": "cuDNN/cuBLAS conv+GEMM of TINet (library calls, per north_star)",
+                             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"},
+                "phases": {"rollout_s": t1 - t0, "update_s": t2 - t1},
+                "losses": {"action": losses[0], "value": losses[1]},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
 
 
 def main():
@@ -130,12 +273,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the rollout / 7x7-view secondary measurements")
     ap.add_argument("--rollout-T", type=int, default=16)
+    ap.add_argument("--workload", default="step", choices=["step", "ppo"])
+    ap.add_argument("--ppo-envs", type=int, default=16384, help="GLOBAL env count of the PPO workload")
+    ap.add_argument("--ppo-horizon", type=int, default=128)
+    ap.add_argument("--ppo-minibatch", type=int, default=4096)
+    ap.add_argument("--ppo-epochs", type=int, default=10)
+    ap.add_argument("--ppo-steps", type=int, default=2)
+    ap.add_argument("--ppo-warmup", type=int, default=1)
+    ap.add_argument("--ppo-ref-frames", type=int, default=2048)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "ppo":
+        return bench_ppo(args, rank, world, local_rank)
     workload = (f"MiniGrid-twoarmy-17x17-v{args.version} batched step+gen_obs, {args.envs} envs per GPU, "
                 f"view {args.view}x{args.view}x3, random actions, Philox draws, autoreset (BASELINE configs[2])")
     config = {"workload": workload, "envs_per_gpu": args.envs, "view": args.view, "env_version": args.version,
@@ -376,11 +529,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
         cn = 4096
-        ps, pt = O.bench_rollout(args.version, cn, 8, V)
+        ps, pt = O.bench_rollout(args.version, cn, 8, V, threads=cores)
+        cores = O.max_threads()
         T = max(8, int(ps / pt * args.cpu_seconds / cn))
-        cs, ct = O.bench_rollout(args.version, cn, T, V)
+        cs, ct = O.bench_rollout(args.version, cn, T, V, threads=cores)
         line["cpu_baseline"] = {"value": cs / ct, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{cn} envs x {T} steps ({ct:.1f} s) of the same workload through "
                                           f"oracle/twoarmy_oracle.c (C port of the reference path, OpenMP over envs)"}

@@ -183,8 +183,17 @@ __global__ void __launch_bounds__(320) state_matrix_kernel(const uint32_t *grid,
     }
 }
 
-// Frame-stack roll fused with matrix_env: s [n][5][289], p [n][5][2].
-__global__ void __launch_bounds__(320) stack_roll_kernel(const uint32_t *grid, const uint4 *sc0, float *s, float *p,
+// Frame-stack roll fused with matrix_env: s [n][5][289], p [n][5][2].  ST = float (the LUT
+// applied) or uint8_t (the compact codes; the LUT is applied by the network's loader).
+template <typename ST>
+__device__ __forceinline__ ST stack_value(uint32_t mc);
+template <>
+__device__ __forceinline__ float stack_value<float>(uint32_t mc) { return matrix_value(mc); }
+template <>
+__device__ __forceinline__ uint8_t stack_value<uint8_t>(uint32_t mc) { return (uint8_t)mc; }
+
+template <typename ST>
+__global__ void __launch_bounds__(320) stack_roll_kernel(const uint32_t *grid, const uint4 *sc0, ST *s, float *p,
                                                         const uint8_t *init_mask, int init, long long n) {
     __shared__ uint32_t sg[SM_ENVS * REC_WORDS];
     __shared__ uint32_t sa[SM_ENVS];
@@ -201,14 +210,14 @@ __global__ void __launch_bounds__(320) stack_roll_kernel(const uint32_t *grid, c
     for (int i = threadIdx.x; i < cnt * NCELL; i += blockDim.x) {
         const int e = i / NCELL, c = i - e * NCELL, y = c / GS, x = c - y * GS;
         const uint32_t a = sa[e];
-        const float v = matrix_value(matrix_code(cell_get(sg + e * REC_WORDS, x, y), x == (int)(a & 0xFFu) && y == (int)(a >> 8)));
-        float *row = s + (e0 + e) * 5 * NCELL + c;
+        const ST v = stack_value<ST>(matrix_code(cell_get(sg + e * REC_WORDS, x, y), x == (int)(a & 0xFFu) && y == (int)(a >> 8)));
+        ST *row = s + (e0 + e) * 5 * NCELL + c;
         if (sinit[e] == 2) continue;
         if (sinit[e]) {
 #pragma unroll
             for (int f = 0; f < 5; f++) row[f * NCELL] = v;
         } else {
-            const float f1 = row[1 * NCELL], f2 = row[2 * NCELL], f3 = row[3 * NCELL], f4 = row[4 * NCELL];
+            const ST f1 = row[1 * NCELL], f2 = row[2 * NCELL], f3 = row[3 * NCELL], f4 = row[4 * NCELL];
             row[0] = f1; row[1 * NCELL] = f2; row[2 * NCELL] = f3; row[3 * NCELL] = f4; row[4 * NCELL] = v;
         }
     }

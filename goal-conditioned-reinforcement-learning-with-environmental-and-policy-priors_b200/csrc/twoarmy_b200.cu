@@ -296,9 +296,17 @@ int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *p
 int ta_stack_roll(ta_handle h, float *s_stack, float *p_stack, const uint8_t *init_mask, int init, void *stream) {
     if (!h || !s_stack) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
-    stack_roll_kernel<<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, s_stack, p_stack,
-                                                                                 init_mask, init, h->n);
+    stack_roll_kernel<float><<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, s_stack, p_stack,
+                                                                                        init_mask, init, h->n);
     return launch_ok("stack_roll_kernel");
+}
+
+int ta_stack_roll_codes(ta_handle h, uint8_t *s_codes, float *p_stack, const uint8_t *init_mask, int init, void *stream) {
+    if (!h || !s_codes) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    stack_roll_kernel<uint8_t><<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, s_codes, p_stack,
+                                                                                          init_mask, init, h->n);
+    return launch_ok("stack_roll_kernel<u8>");
 }
 
 int ta_export_state(ta_handle h, ta_env_state *out, void *stream) {

@@ -1,0 +1,406 @@
+"""Vectorised PPO for the batched Twoarmy env -- host-side mirror of the reference's agent.
+
+Mirrors (reference file:line, paths relative to the reference root)
+    soa/agent/net/all_net.py:139-247   TINet, Net_PPO_actor, Net_PPO_critic
+    soa/agent/PPO.py:41-161            PPO: hyper-parameters, select_action, update
+    soa/train_ppo.py:93-160            rollout buffer record, episode loop
+
+Same class / attribute / parameter names (`actor.bone1.cnn_base.0.weight`, ...), same
+initialisation order and the same arithmetic, so a reference checkpoint loads with
+`load_state_dict` and, under the same torch seed, the networks are bit-identical to the
+reference's (tests/test_ppo_cpu.py checks both against fixtures produced by the reference).
+What changes is the batching: select_action takes N envs at once, update can use large
+minibatches, bf16 autocast + channels_last on the GPU (cuDNN / cuBLAS tensor-core kernels: per
+BASELINE.json's north_star the policy/value GEMMs and convolutions are the only tensor-core
+work on this path and stay library calls), and gradients are all-reduced over
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) when a process group is up.
+
+The env step, observation, featuriser and advantage arithmetic all run in the CUDA library
+(include/twoarmy_b200.h); nothing here re-implements them.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.distributions import Categorical
+from torch.utils.data.sampler import BatchSampler, SubsetRandomSampler
+
+# Env_transact.matrix_env (soa/env_buffer.py:300-318) as a table over the compact codes the
+# featuriser kernel emits: 0 empty/goal 0.9, 1 wall -0.9, 2 ball -0.5, 4 agent 0.3
+MATRIX_LUT = (0.9, -0.9, -0.5, 0.0, 0.3)
+# Env_transact.env_action (soa/env_buffer.py:364-376): policy index -> env action
+POLICY_TO_ENV_ACTION = (0, 1, 2, 3, 6)
+
+
+def _weights_init(m):  # all_net.py:162-172 (identical in the three classes)
+    if isinstance(m, nn.Linear):
+        nn.init.xavier_normal_(m.weight)
+        nn.init.constant_(m.bias, 0)
+    elif isinstance(m, nn.Conv2d):
+        nn.init.xavier_uniform_(m.weight, gain=nn.init.calculate_gain("relu"))
+        nn.init.constant_(m.bias, 0.1)
+    elif isinstance(m, nn.BatchNorm2d):
+        nn.init.constant_(m.weight, 1)
+        nn.init.constant_(m.bias, 0)
+
+
+class TINet(nn.Module):
+    """all_net.py:139-189: 4 frames of 17x17 -> nearest x4 -> 4 convs -> fc0; positions+goal ->
+    positionnet; concat -> fc1 -> 512 features."""
+
+    def __init__(self, in_frames: int = 4):
+        super().__init__()
+        self.cnn_base = nn.Sequential(
+            nn.Conv2d(in_frames, 64, kernel_size=4, stride=2), nn.ReLU(),   # (64, 33, 33)
+            nn.Conv2d(64, 64, kernel_size=3, stride=2), nn.ReLU(),          # (64, 16, 16)
+            nn.Conv2d(64, 128, kernel_size=4, stride=2), nn.ReLU(),         # (128, 7, 7)
+            nn.Conv2d(128, 256, kernel_size=3, stride=2), nn.ReLU(),        # (256, 3, 3)
+            nn.Flatten(),
+        )
+        self.positionnet = nn.Linear(10, 128)
+        self.fc0 = nn.Linear(2304, 256)
+        self.fc1 = nn.Linear(256 + 128, 512)
+        self.upsamplingnearest = nn.UpsamplingNearest2d(scale_factor=4)
+        self.apply(_weights_init)
+
+    def forward(self, state_matrix, position, goal):
+        B, T, _ = state_matrix.shape
+        position = position.contiguous().view(-1, 8)
+        position_goal = torch.relu(self.positionnet(torch.cat([position, goal], 1)))
+        x = state_matrix.contiguous().view(-1, T, 17, 17)
+        x = self.upsamplingnearest(x)
+        if x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x = torch.relu(self.fc0(self.cnn_base(x)))
+        x = torch.cat([x, position_goal.to(x.dtype)], 1)
+        return torch.relu(self.fc1(x))
+
+
+class Net_PPO_actor(nn.Module):  # all_net.py:191-218
+    def __init__(self):
+        super().__init__()
+        self.bone1 = TINet()
+        self.A = nn.Linear(512, 5)
+        self.apply(_weights_init)
+
+    def forward(self, state_matrix, position, goal, model="actor"):
+        return torch.softmax(self.A(self.bone1(state_matrix, position, goal)).float(), dim=1)
+
+    def logits(self, state_matrix, position, goal):
+        return self.A(self.bone1(state_matrix, position, goal)).float()
+
+
+class Net_PPO_critic(nn.Module):  # all_net.py:222-247
+    def __init__(self):
+        super().__init__()
+        self.bone2 = TINet()
+        self.V = nn.Linear(512, 1)
+        self.apply(_weights_init)
+
+    def forward(self, state_matrix, position, goal, model="actor"):
+        return self.V(self.bone2(state_matrix, position, goal)).float()
+
+
+def decode_matrix(codes: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """uint8 featuriser codes -> the float matrix_env values (the LUT is applied here, in the
+    network's loader, so the rollout buffer keeps 1 byte per cell)."""
+    lut = torch.tensor(MATRIX_LUT, dtype=dtype, device=codes.device)
+    return lut[codes.long()]
+
+
+class RolloutBuffer:
+    """Device-resident, time-major form of Buffer_gridworld's record (train_ppo.py:93-97):
+    s uint8 codes [T,N,5,289] (decoded on load), a int64 [T,N], p float32 [T,N,5,2],
+    g float32 [N,2] (constant goal), r, d, a_logp float32 [T,N]."""
+
+    def __init__(self, T: int, N: int, device):
+        self.T, self.N, self.device = T, N, device
+        self.s = torch.empty((T, N, 5, 289), dtype=torch.uint8, device=device)
+        self.p = torch.empty((T, N, 5, 2), dtype=torch.float32, device=device)
+        self.a = torch.empty((T, N), dtype=torch.int64, device=device)
+        self.r = torch.empty((T, N), dtype=torch.float32, device=device)
+        self.d = torch.empty((T, N), dtype=torch.float32, device=device)
+        self.a_logp = torch.empty((T, N), dtype=torch.float32, device=device)
+        self.g = torch.empty((N, 2), dtype=torch.float32, device=device)
+        self.counter = 0
+
+    @property
+    def full(self):
+        return self.counter >= self.T
+
+    def store(self, s_codes, a, p, r, d, a_logp):
+        t = self.counter
+        self.s[t].copy_(s_codes); self.a[t].copy_(a); self.p[t].copy_(p)
+        self.r[t].copy_(r); self.d[t].copy_(d); self.a_logp[t].copy_(a_logp)
+        self.counter += 1
+
+    def flat(self):
+        """Sample-major views ([T*N, ...]) in the field names the reference uses."""
+        B = self.counter * self.N
+        T = self.counter
+        return {"s": self.s[:T].reshape(B, 5, 289), "p": self.p[:T].reshape(B, 5, 2), "a": self.a[:T].reshape(B, 1),
+                "g": self.g.unsqueeze(0).expand(T, self.N, 2).reshape(B, 2), "r": self.r[:T].reshape(B, 1),
+                "d": self.d[:T].reshape(B, 1), "a_logp": self.a_logp[:T].reshape(B, 1)}
+
+
+class PPO:
+    """soa/agent/PPO.py:41-161 with the same defaults.  Differences, all opt-in or structural:
+    no TensorBoard writer / heat-map side effects (out of scope), `select_action` is batched,
+    `update` accepts a dict of device tensors, an optional `minibatch` override, bf16 autocast
+    and a distributed gradient all-reduce."""
+
+    def __init__(self, device="cpu", autocast: Optional[bool] = None, flat_grads: bool = True):
+        self.device = torch.device(device)
+        self.actor = Net_PPO_actor().to(self.device)    # PPO.py:46-47
+        self.critic = Net_PPO_critic().to(self.device)
+        self.gamma = 0.99
+        self.lr = 0.0001
+        self.weight_decay = 0.0001
+        self.lr_step_size = 200
+        self.lr_gamma = 0.8
+        self.batch_size = 128
+        self.clip_param = 0.1
+        self.K_epochs = 10
+        self.entropy_coef = 0.01
+        self.use_grad_clip = False
+        self.use_lr_decay = False
+        self.update_count = 0
+        self.max_steps = 0
+        self.name = None
+        self.autocast = (self.device.type == "cuda") if autocast is None else bool(autocast)
+        if self.device.type == "cuda":
+            self.actor.to(memory_format=torch.channels_last)
+            self.critic.to(memory_format=torch.channels_last)
+        # one contiguous gradient buffer per network: a single all-reduce per optimiser step
+        self._flat = {}
+        if flat_grads:
+            for name, net in (("actor", self.actor), ("critic", self.critic)):
+                self._flat[name] = self._flatten_grads(net)
+        fused = {"fused": True} if self.device.type == "cuda" else {}   # one multi-tensor kernel per step on the GPU
+        self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=self.lr, eps=1e-5, **fused)    # PPO.py:57-58
+        self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=self.lr, eps=1e-5, **fused)
+        self.scheduler_actor = torch.optim.lr_scheduler.StepLR(self.optimizer_actor, self.lr_step_size, self.lr_gamma)
+        self.scheduler_critic = torch.optim.lr_scheduler.StepLR(self.optimizer_critic, self.lr_step_size, self.lr_gamma)
+        self.last_action_loss = float("nan")
+        self.last_value_loss = float("nan")
+
+    @staticmethod
+    def _flatten_grads(net):
+        params = [p for p in net.parameters()]
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+        off = 0
+        for p in params:
+            n = p.numel()
+            g = flat[off:off + n].view(p.shape)
+            if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+                g = flat[off:off + n].view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
+            p.grad = g
+            off += n
+        return flat
+
+    # ------------------------------------------------------------------ acting
+    def _amp(self):
+        return torch.autocast(device_type=self.device.type, dtype=torch.bfloat16, enabled=self.autocast)
+
+    @torch.no_grad()
+    def select_action(self, state_matrix, states_stack, goal, device=None):
+        """PPO.py:73-92 for N envs: state_matrix [N,5,289] (float, or uint8 codes), states_stack
+        [N,5,2], goal [N,2] -> (action index int64 [N], log-prob float32 [N]).  Uses frames
+        1..4 (the newest four) like the reference."""
+        if state_matrix.dtype == torch.uint8:
+            state_matrix = decode_matrix(state_matrix[:, 1:5])
+        else:
+            state_matrix = state_matrix[:, 1:5]
+        self.actor.eval()
+        self.critic.eval()
+        with self._amp():
+            a_prob = self.actor(state_matrix.float(), states_stack[:, 1:5].float(), goal.float())
+        dist = Categorical(probs=a_prob)
+        a = dist.sample()
+        return a, dist.log_prob(a)
+
+    # ------------------------------------------------------------------ learning
+    @torch.no_grad()
+    def values(self, s, p, g, chunk: int = 16384):
+        """(V(s[:,0:4]), V(s[:,1:5])) in chunks: the two critic passes of PPO.py:113-114."""
+        outs0, outs1 = [], []
+        self.critic.eval()
+        for i in range(0, s.shape[0], chunk):
+            sc = s[i:i + chunk]
+            sc = decode_matrix(sc) if sc.dtype == torch.uint8 else sc
+            pc, gc = p[i:i + chunk], g[i:i + chunk]
+            with self._amp():
+                outs0.append(self.critic(sc[:, 0:4], pc[:, 0:4], gc))
+                outs1.append(self.critic(sc[:, 1:5], pc[:, 1:5], gc))
+        return torch.cat(outs0), torch.cat(outs1)
+
+    def advantages(self, r, v, v_next):
+        """PPO.py:112-115: target_v = r + gamma*V(s'), adv = target_v - V(s).  On a GPU this is
+        the ta_gae kernel in reference mode; on the CPU (tests, the reference arm) the two
+        torch ops the reference uses."""
+        if r.is_cuda:
+            from . import advantage
+            adv, target_v = advantage.reference_mode(r, v, v_next, self.gamma)
+            return target_v, adv
+        target_v = r + self.gamma * v_next
+        return target_v, target_v - v
+
+    def _allreduce(self, name, net, group):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        ws = dist.get_world_size(group)
+        if name in self._flat:
+            dist.all_reduce(self._flat[name], group=group)
+            self._flat[name].div_(ws)
+        else:
+            for p in net.parameters():
+                dist.all_reduce(p.grad, group=group)
+                p.grad.div_(ws)
+
+    def update(self, buffer, device=None, i_ep: int = 0, minibatch: Optional[int] = None, epochs: Optional[int] = None,
+               group=None, sampler_generator=None):
+        """PPO.py:103-158.  `buffer` is a dict of tensors with the reference's field names
+        (s [B,5,289] float or uint8 codes, p [B,5,2], a [B,1], g [B,2], r [B,1], a_logp [B,1]) or
+        a numpy structured array like Buffer_gridworld.buffer."""
+        if not isinstance(buffer, dict):
+            buffer = {k: torch.as_tensor(buffer[k]) for k in ("s", "p", "a", "g", "r", "a_logp")}
+        dev = self.device
+        s = buffer["s"].to(dev)
+        p = buffer["p"].to(dev, torch.float32)
+        a = buffer["a"].to(dev, torch.int64)
+        g = buffer["g"].to(dev, torch.float32)
+        r = buffer["r"].to(dev, torch.float32).view(-1, 1)
+        old_a_logp = buffer["a_logp"].to(dev, torch.float32).view(-1, 1)
+        if s.dtype != torch.uint8:
+            s = s.to(torch.float32)
+        B = s.shape[0]
+        v, v_next = self.values(s, p, g)
+        target_v, adv = self.advantages(r, v, v_next)
+        bs = minibatch or self.batch_size
+        self.actor.train()
+        self.critic.train()
+
+        def minibatches():
+            # PPO.py:122: BatchSampler(SubsetRandomSampler(range(len(buffer))), batch_size, drop_last=False).
+            # On the CPU that exact sampler (same torch RNG stream as the reference); on the GPU the
+            # same thing -- a fresh random permutation per epoch cut into batches -- drawn on the device
+            # (a Python-level sampler over millions of indices would cost more than the update itself).
+            if dev.type != "cuda" or sampler_generator is not None:
+                for sample_index in BatchSampler(SubsetRandomSampler(range(B), generator=sampler_generator), batch_size=bs,
+                                                 drop_last=False):
+                    yield torch.as_tensor(sample_index, device=dev)
+            else:
+                perm = torch.randperm(B, device=dev)
+                for i in range(0, B, bs):
+                    yield perm[i:i + bs]
+
+        for _ in range(epochs or self.K_epochs):
+            for idx in minibatches():
+                sb = s[idx]
+                sb = decode_matrix(sb[:, 0:4]) if sb.dtype == torch.uint8 else sb[:, 0:4]
+                pb, gb = p[idx][:, 0:4], g[idx]
+                with self._amp():
+                    probs = self.actor(sb, pb, gb)
+                    vpred = self.critic(sb, pb, gb)
+                dist = Categorical(probs=probs)
+                dist_entropy = dist.entropy().view(-1, 1)
+                a_logp = dist.log_prob(a[idx].squeeze(-1)).view(-1, 1)
+                ratio = torch.exp(a_logp - old_a_logp[idx])
+                surr1 = ratio * adv[idx]
+                surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv[idx]
+                action_loss = (-torch.min(surr1, surr2) - self.entropy_coef * dist_entropy).mean()
+                value_loss = F.smooth_l1_loss(vpred, target_v[idx])
+                for name in self._flat:
+                    self._flat[name].zero_()
+                if not self._flat:
+                    self.optimizer_actor.zero_grad()
+                    self.optimizer_critic.zero_grad()
+                action_loss.backward()
+                value_loss.backward()
+                self._allreduce("actor", self.actor, group)
+                self._allreduce("critic", self.critic, group)
+                if self.use_grad_clip:
+                    torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
+                    torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
+                self.optimizer_actor.step()
+                self.optimizer_critic.step()
+                self.update_count += 1
+                self._last = (action_loss.detach(), value_loss.detach())
+        self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)
+        if self.use_lr_decay:
+            self.scheduler_actor.step()
+            self.scheduler_critic.step()
+        return self.last_action_loss, self.last_value_loss
+
+    # ------------------------------------------------------------------ checkpoints (PPO.py:94-101)
+    def state_dict(self, i_ep: int = 0):
+        return {"model_actor": self.actor.state_dict(), "model_critic": self.critic.state_dict(),
+                "optimizer_actor": self.optimizer_actor.state_dict(), "optimizer_critic": self.optimizer_critic.state_dict(),
+                "epoch": i_ep}
+
+    def load_state_dict(self, state):
+        self.actor.load_state_dict(state["model_actor"])
+        self.critic.load_state_dict(state["model_critic"])
+        if "optimizer_actor" in state:
+            self.optimizer_actor.load_state_dict(state["optimizer_actor"])
+            self.optimizer_critic.load_state_dict(state["optimizer_critic"])
+
+    def save_param(self, path, i_ep: int = 0):
+        torch.save(self.state_dict(i_ep), path)
+
+    def broadcast_parameters(self, group=None, src: int = 0):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for net in (self.actor, self.critic):
+                for t in list(net.parameters()) + list(net.buffers()):
+                    dist.broadcast(t.data, src, group=group)
+
+
+class VecRollout:
+    """soa/train_ppo.py:99-160 for N envs at once: Env_transact.reset / env_action / step,
+    frame-stack roll and Buffer_gridworld.store, all on the device.  One collect() fills a
+    [T, N] RolloutBuffer; episodes end / restart independently per env (autoreset), and a new
+    episode's stack is tiled with its first frame exactly like Env_transact.reset
+    (env_buffer.py:420-423)."""
+
+    def __init__(self, env, agent: PPO, horizon: int):
+        self.env, self.agent, self.T = env, agent, int(horizon)
+        N, dev = env.num_envs, env.device
+        self.buffer = RolloutBuffer(self.T, N, dev)
+        self.buffer.g[:] = torch.tensor([float(env.goal_pos[1]), float(env.goal_pos[0])], device=dev)  # data_env: (y, x)
+        self.s_codes = torch.empty((N, 5, 289), dtype=torch.uint8, device=dev)
+        self.p_stack = torch.empty((N, 5, 2), dtype=torch.float32, device=dev)
+        self.amap = torch.tensor(POLICY_TO_ENV_ACTION, dtype=torch.uint8, device=dev)
+        self.ep_return = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.finished_returns = []
+        env.reset()
+        env.stack_roll_codes(self.s_codes, self.p_stack, init=True)
+        self._out = {}
+
+    @torch.no_grad()
+    def collect(self):
+        """T steps of the reference's inner loop (train_ppo.py:108-123) for every env: select
+        action, env.step (no autoreset), featurise the post-step state, store, then
+        MiniGridEnv.reset + stack re-tiling for the envs whose episode ended (what the
+        reference does at the top of its next episode, train_ppo.py:104-105)."""
+        env, buf = self.env, self.buffer
+        assert not env.autoreset, "VecRollout drives the resets itself (the terminal frame is part of the record)"
+        buf.counter = 0
+        for _ in range(self.T):
+            a_idx, a_logp = self.agent.select_action(self.s_codes, self.p_stack, buf.g)
+            obs, rew, term, trunc, _ = env.step(self.amap[a_idx], out=self._out)
+            self._out = {"obs": obs, "reward": rew, "terminated": term.view(torch.uint8), "truncated": trunc.view(torch.uint8)}
+            done = (term | trunc).view(torch.uint8)
+            env.stack_roll_codes(self.s_codes, self.p_stack)
+            buf.store(self.s_codes, a_idx, self.p_stack, rew, term.float(), a_logp)
+            self.ep_return += rew
+            self.last_done, self.last_return = done, self.ep_return.clone()
+            self.ep_return.masked_fill_(done.bool(), 0.0)
+            env.reset_masked(done)
+            env.stack_roll_codes(self.s_codes, self.p_stack, init_mask=done, init=True)
+        return buf

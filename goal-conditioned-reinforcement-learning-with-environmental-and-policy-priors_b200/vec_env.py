@@ -23,6 +23,7 @@ MISSION = "get to the green goal square"  # twoarmy_v4.py:25-27,80
 GOAL_POS = (14, 2)                        # twoarmy_v4.py:9
 MAX_STEPS = 50                            # twoarmy_v4.py:32
 NUM_ACTIONS = 7                           # MiniGridEnv.Actions, minigrid.py:849-864
+POLICY_TO_ENV_ACTION = (0, 1, 2, 3, 6)    # Env_transact.env_action, soa/env_buffer.py:364-376
 
 # numpy mirror of `ta_env_state`
 STATE_DTYPE = np.dtype(
@@ -96,6 +97,11 @@ class TwoarmyVecEnv:
         obs = self._new_obs()
         _capi.check(self._L.ta_reset(self._h, _ptr(mask), int(hard), _ptr(obs), self._stream()), "ta_reset")
         return obs
+
+    def reset_masked(self, mask: torch.Tensor) -> None:
+        """MiniGridEnv.reset on the masked envs without producing observations."""
+        mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _capi.check(self._L.ta_reset(self._h, _ptr(mask), 0, None, self._stream()), "ta_reset")
 
     def observe(self) -> torch.Tensor:
         """gen_obs() of the current state (no transition)."""
@@ -193,6 +199,17 @@ class TwoarmyVecEnv:
             init_mask = init_mask.to(device=self.device, dtype=torch.uint8).contiguous()
         _capi.check(self._L.ta_stack_roll(self._h, _ptr(s_stack), _ptr(p_stack), _ptr(init_mask), int(init),
                                           self._stream()), "ta_stack_roll")
+
+    def stack_roll_codes(self, s_codes: torch.Tensor, p_stack: torch.Tensor, init_mask: Optional[torch.Tensor] = None,
+                         init: bool = False):
+        """stack_roll on uint8 codes [N,5,289] (what the device rollout buffer stores)."""
+        assert s_codes.is_contiguous() and p_stack.is_contiguous()
+        assert s_codes.shape == (self.num_envs, 5, 289) and p_stack.shape == (self.num_envs, 5, 2)
+        assert s_codes.dtype == torch.uint8 and p_stack.dtype == torch.float32
+        if init_mask is not None:
+            init_mask = init_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _capi.check(self._L.ta_stack_roll_codes(self._h, _ptr(s_codes), _ptr(p_stack), _ptr(init_mask), int(init),
+                                                self._stream()), "ta_stack_roll_codes")
 
     # ------------------------------------------------------------------ state access
     def export_state(self) -> np.ndarray:

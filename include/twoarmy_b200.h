@@ -143,6 +143,11 @@ int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *p
  * for envs whose mask byte is non-zero (mask NULL = all). */
 int ta_stack_roll(ta_handle h, float *s_stack, float *p_stack, const uint8_t *init_mask, int init,
                   void *stream);
+/* Same roll on the compact codes (uint8 [n][5][289], the codes of ta_state_matrix): the form
+ * the device rollout buffer stores (1 byte per cell instead of Buffer_gridworld's float32,
+ * soa/train_ppo.py:93-97); the float LUT of matrix_env is applied when a minibatch is loaded. */
+int ta_stack_roll_codes(ta_handle h, uint8_t *s_codes, float *p_stack, const uint8_t *init_mask, int init,
+                        void *stream);
 
 /* Export / import the full env state (device buffers of n ta_env_state records). */
 int ta_export_state(ta_handle h, ta_env_state *out, void *stream);

@@ -197,11 +197,15 @@ def gae(r, v, done, gamma, lam, use_mask=True, v_next=None, last_v=None):
     return adv, ret
 
 
+def max_threads() -> int:
+    return int(lib().ora_max_threads())
+
+
 def bench_rollout(version, n, T, view, seed=9981, threads=None):
     """Timed CPU baseline: returns (env_steps, seconds, threads_used)."""
     import time
     if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+        lib().ora_set_threads(C.c_int(int(threads)))
     b = OracleBatch(version, n, view, seed)
     obs = np.empty((n, view, view, 3), np.uint8)
     rew = np.empty(n, np.float32); te = np.empty(n, np.uint8); tr = np.empty(n, np.uint8)

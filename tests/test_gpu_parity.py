@@ -276,3 +276,61 @@ def test_matrix_env_and_stack_roll_match_reference(golden):
                 ref_s[mm] = np.repeat(cur[0].cpu().numpy()[mm][:, None], 5, 1)
                 ref_p[mm] = np.repeat(cur[1].cpu().numpy()[mm][:, None], 5, 1)
                 assert np.array_equal(s.cpu().numpy(), ref_s)
+
+
+def test_stack_roll_codes_equals_float_stack_roll(golden):
+    """ta_stack_roll_codes decoded with the matrix_env LUT == ta_stack_roll (float)."""
+    import importlib
+    pkg = _pkg()
+    P = importlib.import_module(pkg.__name__ + ".ppo")
+    n = 300
+    env = pkg.TwoarmyVecEnv(4, n, 17, seed=3, autoreset=False)
+    env.reset()
+    sf = torch.empty((n, 5, 289), device=env.device); pf = torch.empty((n, 5, 2), device=env.device)
+    sc = torch.empty((n, 5, 289), dtype=torch.uint8, device=env.device); pc = torch.empty((n, 5, 2), device=env.device)
+    env.stack_roll(sf, pf, init=True); env.stack_roll_codes(sc, pc, init=True)
+    g = torch.Generator().manual_seed(1)
+    amap = torch.tensor([0, 1, 2, 3, 6], dtype=torch.int32)
+    for t in range(70):
+        _, _, te, tr, _ = env.step(amap[torch.randint(0, 5, (n,), generator=g)])
+        env.stack_roll(sf, pf); env.stack_roll_codes(sc, pc)
+        assert torch.equal(P.decode_matrix(sc), sf) and torch.equal(pc, pf)
+        done = (te | tr)
+        env.reset_masked(done)
+        env.stack_roll(sf, pf, init_mask=done, init=True); env.stack_roll_codes(sc, pc, init_mask=done, init=True)
+        assert torch.equal(P.decode_matrix(sc), sf) and torch.equal(pc, pf)
+
+
+def test_vec_rollout_records_follow_reference_loop():
+    """VecRollout.collect == the reference loop (train_ppo.py:108-123) replayed on the oracle with
+    the actions the policy sampled: rewards, done, and the 5-frame records (terminal frame kept,
+    new episode tiled)."""
+    import importlib
+    pkg, O = _pkg(), _oracle()
+    P = importlib.import_module(pkg.__name__ + ".ppo")
+    n, T = 64, 60
+    torch.manual_seed(0)
+    agent = P.PPO(device="cuda:0")
+    env = pkg.TwoarmyVecEnv(6, n, 17, seed=5, autoreset=False)
+    roll = P.VecRollout(env, agent, T)
+    buf = roll.collect()
+    ora = O.OracleBatch(6, n, 17, seed=5)
+    ora.reset()
+    lut = np.array([0.9, -0.9, -0.5, 0.0, 0.3], np.float32)
+    def feat():
+        m = ora.matrix().astype(np.float32)           # [n,289] float matrix_env
+        return m
+    stack = np.repeat(feat()[:, None, :], 5, 1)
+    amap = np.array([0, 1, 2, 3, 6], np.int32)
+    a = buf.a.cpu().numpy()
+    for t in range(T):
+        out = ora.step(amap[a[t]], None, autoreset=False)
+        stack = np.concatenate([stack[:, 1:], feat()[:, None, :]], 1)
+        np.testing.assert_array_equal(buf.r[t].cpu().numpy(), out["reward"])
+        np.testing.assert_array_equal(buf.d[t].cpu().numpy(), out["terminated"].astype(np.float32))
+        np.testing.assert_array_equal(lut[buf.s[t].cpu().numpy()], stack)
+        done = (out["terminated"] | out["truncated"]).astype(bool)
+        if done.any():
+            ora.reset(done.astype(np.uint8))
+            f = feat()
+            stack[done] = np.repeat(f[done][:, None, :], 5, 1)

@@ -1,0 +1,142 @@
+"""CPU: the PPO host layer (twoarmy_b200.ppo) against fixtures produced by the REFERENCE's own
+networks and PPO.update (tests/golden/make_golden_ppo.py -> ppo_ref.npz), plus the 2-rank gloo
+test of the gradient all-reduce path."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+
+def _ppo():
+    import twoarmy_b200
+    return importlib.import_module(twoarmy_b200.__name__ + ".ppo")
+
+
+def _sums(net):
+    return np.array([p.detach().double().sum().item() for p in net.parameters()])
+
+
+def test_networks_match_reference_under_same_seed(golden):
+    """Same construction / init order as all_net.py: under torch.manual_seed(0) every parameter
+    tensor and the outputs equal the reference's."""
+    P = _ppo()
+    fx = golden("ppo_ref.npz")
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    actor, critic = P.Net_PPO_actor(), P.Net_PPO_critic()
+    np.testing.assert_allclose(_sums(actor), fx["actor_sums"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(_sums(critic), fx["critic_sums"], rtol=0, atol=1e-9)
+    s, p, g = (torch.from_numpy(fx[k]) for k in ("x_s", "x_p", "x_g"))
+    with torch.no_grad():
+        prob = actor(s, p, g).numpy()
+        val = critic(s, p, g).numpy()
+    np.testing.assert_allclose(prob, fx["actor_prob"], rtol=1e-6, atol=1e-7)   # fp32, tolerance 1e-6 relative
+    np.testing.assert_allclose(val, fx["critic_v"], rtol=1e-5, atol=1e-6)
+    # parameter names are the reference's (checkpoints interchange)
+    names = [n for n, _ in actor.named_parameters()]
+    assert names[0] == "bone1.cnn_base.0.weight" and names[-1] == "A.bias" and "bone1.positionnet.weight" in names
+
+
+def test_update_matches_reference(golden):
+    """PPO.update (PPO.py:103-158) on the reference's record layout: same sampler stream, same
+    losses, same Adam steps -> same parameters (fp32, 1e-5 relative on the per-tensor sums)."""
+    P = _ppo()
+    fx = golden("ppo_ref.npz")
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    agent = P.PPO(device="cpu", autocast=False)
+    agent.K_epochs, agent.batch_size = 2, 32
+    buf = {k: torch.from_numpy(fx[f"buf_{k}"]) for k in ("s", "a", "p", "g", "r", "a_logp")}
+    torch.manual_seed(1)
+    agent.update(buf)
+    np.testing.assert_allclose(_sums(agent.actor), fx["upd_actor_sums"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(_sums(agent.critic), fx["upd_critic_sums"], rtol=1e-5, atol=1e-5)
+    assert agent.update_count == 2 * 3
+
+
+def test_codes_decode_to_matrix_env_values():
+    P = _ppo()
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)
+    assert P.decode_matrix(codes).tolist() == pytest.approx([0.9, -0.9, -0.5, 0.3])
+
+
+def test_select_action_is_batched_and_uses_newest_four_frames():
+    P = _ppo()
+    torch.manual_seed(0)
+    agent = P.PPO(device="cpu", autocast=False)
+    N = 5
+    s = torch.randint(0, 3, (N, 5, 289), dtype=torch.uint8)
+    p = torch.randint(1, 16, (N, 5, 2)).float()
+    g = torch.tensor([[2.0, 14.0]]).repeat(N, 1)
+    torch.manual_seed(5)
+    a, lp = agent.select_action(s, p, g)
+    assert a.shape == (N,) and lp.shape == (N,) and a.dtype == torch.int64
+    s2 = s.clone()
+    s2[:, 0] = 1  # the oldest frame is not an input of the policy (PPO.py:74-77)
+    torch.manual_seed(5)
+    a2, lp2 = agent.select_action(s2, p, g)
+    assert torch.equal(a, a2) and torch.equal(lp, lp2)
+    with torch.no_grad():
+        prob = agent.actor(P.decode_matrix(s[:, 1:5]), p[:, 1:5], g)
+    assert torch.allclose(lp, torch.log(prob[torch.arange(N), a]), atol=1e-6)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _ddp_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    P = _ppo()
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    agent = P.PPO(device="cpu", autocast=False)
+    agent.broadcast_parameters()
+    agent.K_epochs = 1
+    g = torch.Generator().manual_seed(11)
+    n = 32
+    full = {"s": torch.randint(0, 3, (n, 5, 289), generator=g, dtype=torch.uint8), "p": torch.randint(1, 16, (n, 5, 2), generator=g).float(),
+            "a": torch.randint(0, 5, (n, 1), generator=g), "g": torch.tensor([[2.0, 14.0]]).repeat(n, 1),
+            "r": torch.rand(n, 1, generator=g) - 0.5, "a_logp": torch.log(torch.rand(n, 1, generator=g) * 0.3 + 0.1)}
+    half = n // world
+    shard = {k: v[rank * half:(rank + 1) * half] for k, v in full.items()}
+    agent.update(shard, minibatch=half)  # one optimiser step; gradients averaged over ranks
+    ret[rank] = _sums(agent.actor).tolist() + _sums(agent.critic).tolist()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_equals_single_rank_full_batch():
+    """world_size 2 (gloo, CPU): each rank updates on half the batch with the gradient
+    all-reduce; the result equals one rank updating on the whole batch, and both ranks agree."""
+    import torch.multiprocessing as mp
+    P = _ppo()
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ddp_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] == pytest.approx(ret[1], rel=0, abs=0)
+    # single-rank reference on the full batch
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    agent = P.PPO(device="cpu", autocast=False)
+    agent.K_epochs = 1
+    g = torch.Generator().manual_seed(11)
+    n = 32
+    full = {"s": torch.randint(0, 3, (n, 5, 289), generator=g, dtype=torch.uint8), "p": torch.randint(1, 16, (n, 5, 2), generator=g).float(),
+            "a": torch.randint(0, 5, (n, 1), generator=g), "g": torch.tensor([[2.0, 14.0]]).repeat(n, 1),
+            "r": torch.rand(n, 1, generator=g) - 0.5, "a_logp": torch.log(torch.rand(n, 1, generator=g) * 0.3 + 0.1)}
+    agent.update(full, minibatch=n)
+    want = _sums(agent.actor).tolist() + _sums(agent.critic).tolist()
+    np.testing.assert_allclose(np.array(ret[0]), np.array(want), rtol=1e-5, atol=1e-5)
