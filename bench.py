@@ -358,8 +358,10 @@ def main():
             b = i % self.B
             self.envs[b].step(self.actions[b], out=self.outs[b])
 
-        def capture(self):
-            """The launch-bound inner loop (B launches, one per batch) as one CUDA graph."""
+        def capture(self, streams=1):
+            """The launch-bound inner loop (B launches, one per batch) as one CUDA graph.  With
+            streams=2 the batches alternate between two captured branches, so launches on
+            independent batches may overlap (secondary measurement only)."""
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -369,8 +371,17 @@ def main():
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                for i in range(self.B):
-                    self.step(i)
+                if streams == 1:
+                    for i in range(self.B):
+                        self.step(i)
+                else:
+                    main = torch.cuda.current_stream()
+                    branch = torch.cuda.Stream(device=dev)
+                    branch.wait_stream(main)
+                    for i in range(self.B):
+                        with torch.cuda.stream(branch if i % 2 else main):
+                            self.step(i)
+                    main.wait_stream(branch)
 
         def run(self, k):
             """k launches: whole graph replays, the remainder as single launches. Returns the
@@ -459,6 +470,13 @@ def main():
                             "value": R * T * n * world / (rms / 1e3), "unit": UNIT,
                             "hbm_bytes_per_env_step": 3 * V * V + 1 + 6 + (2 * 112) / T}
         del robs
+        # (a2) single-step launches again, independent batches alternating between two streams
+        wl.capture(streams=2)
+        ms2, _ = wl.timed(args.steps, args.warmup)
+        extra["two_streams"] = {"us_per_launch": ms2 * 1e3 / args.steps, "value": args.steps * n * world / (ms2 / 1e3), "unit": UNIT,
+                                "note": "same launches, the 8 independent batches alternate between 2 streams so the serial "
+                                        "head/tail of one launch overlaps the observation stores of the other"}
+        wl.capture(streams=1)
         # (b) the north-star 7x7x3 view (agent_view_size=7), single-step launches
         if V != 7:
             wl7 = Workload(7, B, 1 << 40)

@@ -29,7 +29,7 @@
 
 namespace ta {
 
-constexpr int STEP_THREADS = 32;
+constexpr int STEP_MAX_WARPS = 8;  // independent warps (tiles) per CTA; they share nothing but the launch
 // shared-memory grid tile: env e's 20-word record sits at word GUARD0_WORDS + e*SLOT_WORDS; every
 // other word is a guard full of wall codes, so that view columns left / right of the grid (and
 // the record's own padding cells 289..319, kept at "wall" in HBM) read as walls without a mask.
@@ -64,7 +64,7 @@ struct ObsCfg {
     static constexpr int SM_GRID = SM_HEAD + 144;
     static constexpr int SM_EV = SM_GRID + GRID_S_WORDS * 4;
     static constexpr int SM_RING = SM_EV + round16(EV_ROWS * EV_STRIDE * 4);
-    static constexpr int SMEM = SM_RING + RING * CHUNK_BYTES;
+    static constexpr int SMEM = (SM_RING + RING * CHUNK_BYTES + 127) / 128 * 128;  // per warp
     static_assert((RING & (RING - 1)) == 0, "RING must be a power of two");
     static_assert(SM_GRID % 16 == 0 && (SM_GRID + GUARD0_WORDS * 4) % 16 == 0 && SM_RING % 16 == 0, "alignment");
 };
@@ -86,7 +86,8 @@ struct StepArgs {
     int T;  // env steps per launch; outputs / actions / draws are [T][n]
     int version;
     int flags;  // bit 0 autoreset, bit 1 never use bulk stores for the obs (test hook),
-                // bits 2,3 timing experiments only: skip the obs pass / the scalar phases
+                // bits 2,3 timing experiments only: skip the obs pass / the scalar phases,
+                // bit 4 observe only: gen_obs() of the current state, nothing else read or written
     int action_dtype;
     uint32_t seed_lo, seed_hi;
     unsigned long long env_id0;
@@ -276,16 +277,18 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, long 
 }
 
 template <int V>
-__global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const StepArgs a) {
     using C = ObsCfg<V>;
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    const int warps_per_cta = (int)(blockDim.x >> 5), warp = (int)(threadIdx.x >> 5);
+    uint8_t *smem = smem_all + warp * C::SMEM;  // every warp has its own slice (and its own mbarrier)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::SM_BAR);
     uint4 *meta = reinterpret_cast<uint4 *>(smem + C::SM_META);
     uint32_t *head = reinterpret_cast<uint32_t *>(smem + C::SM_HEAD);
     uint32_t *gs = reinterpret_cast<uint32_t *>(smem + C::SM_GRID);
     uint32_t *ev = reinterpret_cast<uint32_t *>(smem + C::SM_EV);
     uint8_t *ring = smem + C::SM_RING;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     uint32_t *G = gs + GUARD0_WORDS + lane * SLOT_WORDS;  // this lane's env record
 
     // Programmatic dependent launch: the next kernel in the stream may be scheduled as soon as
@@ -311,7 +314,8 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
     uint32_t gi = 0;  // obs chunks emitted so far (ring slot = gi % RING)
     const bool v4 = a.version == 4;
 
-    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (long long tile = (long long)blockIdx.x * warps_per_cta + warp; tile < a.ntiles;
+         tile += (long long)gridDim.x * warps_per_cta) {
         // ---- tile prologue: packed grids -> smem, state of 32 envs -> registers ------------------
         const long long env = tile * TILE + lane;
         const bool live = env < a.n;
@@ -350,8 +354,10 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
             d.rec_lo = d.rec_hi = 0xFFFFFFFFu;
             d.consumed = 0;
             // ---- phase A: everything up to and including the agent move ----------------------
-            int act = live ? load_action(a.actions, a.action_dtype, out_idx) : 6;
-            if (a.draws != nullptr) {
+            const bool observe_only = (a.flags & 16) != 0;
+            int act = (live && !observe_only) ? load_action(a.actions, a.action_dtype, out_idx) : 6;
+            if (observe_only) {
+            } else if (a.draws != nullptr) {
                 if (live) {
                     const uint2 r = reinterpret_cast<const uint2 *>(a.draws)[out_idx];
                     d.rec_lo = r.x;
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
                 mbar_wait(bar, phase);
                 phase ^= 1u;
             }
-            if (a.flags & 8) skip = true;
+            if (a.flags & (8 | 16)) skip = true;
             if (!skip) {
                 tcount += 1u;
                 step_move += 1;
@@ -576,7 +582,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
                     need_reset = (a.flags & 1) != 0;
                 }
             }
-            if (live) {
+            if (live && !observe_only) {
                 a.reward[out_idx] = reward_value(reward);
                 a.term[out_idx] = term ? 1 : 0;
                 a.trunc[out_idx] = trunc ? 1 : 0;
@@ -600,6 +606,11 @@ __global__ void __launch_bounds__(STEP_THREADS) step_obs_kernel(const StepArgs a
         }
 
         // ---- tile epilogue: registers -> state arrays, packed grids -> HBM -------------------------
+        if (a.flags & 16) {  // observe only: the state is unchanged
+            bulk_wait_read<0>();
+            __syncwarp();
+            continue;
+        }
         uint4 o0, o1w;
         o0.x = (uint32_t)ax | ((uint32_t)ay << 8) | (fl << 16) | ((uint32_t)risk << 24);
         o0.y = (uint32_t)step_count;

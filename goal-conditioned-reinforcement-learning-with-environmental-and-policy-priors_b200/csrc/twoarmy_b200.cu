@@ -51,6 +51,7 @@ struct ta_batch {
     int ctas_per_sm = 0;   // 0 = whatever fits (tuning knob: TA_CTAS_PER_SM)
     int pdl = 0;           // programmatic dependent launch of the step kernel (TA_PDL=1 turns it on;
                            // measured slower on B200: 19.2 vs 16.8 us per 65536-env launch, so off)
+    int warps_per_cta = 0; // independent tiles per CTA; 0 = chosen per launch (TA_WARPS_PER_CTA, 1..8)
     int debug_flags = 0;   // TA_DEBUG_FLAGS: timing experiments (StepArgs::flags bits 2,3)
     uint32_t *tmpl = nullptr;  // [20] the _gen_grid record
     // host-call path (ta_step_host)
@@ -75,25 +76,37 @@ void build_template(uint32_t *tm) {
 
 template <int V>
 int launch_step_t(ta_batch *h, const StepArgs &a, cudaStream_t st) {
-    static int ctas_per_sm[64] = {};
+    static int ctas_per_sm[64][STEP_MAX_WARPS + 1] = {};
     auto kern = step_obs_kernel<V>;
-    constexpr int SMEM = ObsCfg<V>::SMEM;
-    int &cps = ctas_per_sm[h->device & 63];
+    // warps (= independent 32-env tiles) per CTA: whatever spreads the tiles most evenly over the
+    // SMs, the larger count on a tie (fewer CTAs to dispatch; measured equal or slightly better)
+    int W = h->warps_per_cta;
+    if (W <= 0) {
+        long long best = -1;
+        for (int w = 1; w <= STEP_MAX_WARPS; w++) {
+            const long long ctas = (a.ntiles + w - 1) / w;
+            const long long worst = (ctas + h->sm_count - 1) / h->sm_count * w;  // tiles on the fullest SM
+            if (best < 0 || worst <= best) { best = worst; W = w; }
+        }
+    }
+    const int smem = ObsCfg<V>::SMEM * W;
+    int &cps = ctas_per_sm[h->device & 63][W];
     if (!cps) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ObsCfg<V>::SMEM * STEP_MAX_WARPS));
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STEP_THREADS, SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
         cps = occ > 0 ? occ : 1;
     }
     int per_sm = cps;
     if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
     const int max_ctas = h->sm_count * per_sm;
-    int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
+    const int want = (a.ntiles + W - 1) / W;
+    int grid = want < max_ctas ? want : max_ctas;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(STEP_THREADS);
-    cfg.dynamicSmemBytes = SMEM;
+    cfg.blockDim = dim3(32 * W);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -120,6 +133,21 @@ int launch_step(ta_batch *h, const StepArgs &a, cudaStream_t st) {
     return TA_E_UNSUPPORTED;
 }
 
+// gen_obs() of the current state: the step kernel's obs pass alone (flags bit 4)
+int launch_observe(ta_batch *h, uint8_t *obs_out, cudaStream_t st) {
+    if ((uintptr_t)obs_out & 15u) {  // unaligned caller buffer: the simple per-cell kernel
+        observe_kernel<<<blocks_for(h->n * h->view * h->view, 256), 256, 0, st>>>(h->grid, h->sc0, obs_out, h->view, h->n);
+        return launch_ok("observe_kernel");
+    }
+    StepArgs a = {};
+    a.grid = h->grid; a.sc0 = h->sc0; a.sc1 = h->sc1; a.tmpl = h->tmpl;
+    a.obs = obs_out;
+    a.n = h->n; a.ntiles = (int)(h->npad / TILE); a.T = 1;
+    a.version = h->version; a.flags = 16 | (g_force_generic ? 2 : 0);
+    a.env_id0 = h->env_id0;
+    return launch_step(h, a, st);
+}
+
 int do_reset(ta_batch *h, const uint8_t *mask, int hard, uint8_t *obs_out, cudaStream_t st, bool pad_too) {
     // padded tail envs (>= n) are reset only at creation
     const long long cnt = pad_too ? h->npad : h->n;
@@ -128,10 +156,7 @@ int do_reset(ta_batch *h, const uint8_t *mask, int hard, uint8_t *obs_out, cudaS
     if (int rc = launch_ok("reset_grid_kernel")) return rc;
     reset_scalar_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(h->sc0, h->sc1, mask, hard, cnt);
     if (int rc = launch_ok("reset_scalar_kernel")) return rc;
-    if (obs_out) {
-        observe_kernel<<<blocks_for(h->n * h->view * h->view, 256), 256, 0, st>>>(h->grid, h->sc0, obs_out, h->view, h->n);
-        if (int rc = launch_ok("observe_kernel")) return rc;
-    }
+    if (obs_out) return launch_observe(h, obs_out, st);
     return TA_OK;
 }
 
@@ -170,6 +195,10 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("TA_WARPS_PER_CTA")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= STEP_MAX_WARPS) h->warps_per_cta = v;
+    }
     if (const char *e = getenv("TA_PDL")) h->pdl = atoi(e) != 0;
     if (const char *e = getenv("TA_DEBUG_FLAGS")) h->debug_flags = atoi(e) & 3;
     if (const char *e = getenv("TA_CTAS_PER_SM")) {  // tuning knob for experiments
