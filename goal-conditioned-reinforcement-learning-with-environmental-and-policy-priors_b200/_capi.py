@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     L.ta_state_matrix.argtypes = [vp, vp, vp, vp, vp]
     L.ta_stack_roll.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ta_stack_roll_codes.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ta_stack_push.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.ta_export_state.argtypes = [vp, vp, vp]
     L.ta_import_state.argtypes = [vp, vp, vp]
     L.ta_gae.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp]

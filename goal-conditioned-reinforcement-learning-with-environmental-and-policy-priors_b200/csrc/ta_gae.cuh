@@ -86,11 +86,145 @@ gae_kernel(const float *__restrict__ r, const float *__restrict__ v, const float
     }
 }
 
+// Vectorised form (n % 4 == 0, 16-byte aligned arrays): a thread owns FOUR adjacent envs (one
+// float4 column) and GV_L consecutive steps, a CTA 128 envs x (GV_L x blockDim.y) steps.  Per
+// element it keeps only tv_t = r_t + gamma*nd_t*V_{t+1} and delta_t = tv_t - V_t (+ the nd bits);
+// pass 1 reduces the chunk to (prod c, A with A_in = 0), the chunk summaries are chained through
+// shared memory, pass 2 re-runs the recurrence A_t = delta_t + c_t*A_{t+1} from the true A_in and
+// writes adv_t = A_t, ret_t = tv_t + c_t*A_{t+1} as 16-byte stores.  V_{t+1} comes from the row
+// already in registers, so every input byte is read once.
+constexpr int GV_MAX_THREADS = 1024;
+
+__device__ __forceinline__ float f4get(const float4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+template <int GV_L, int GV_CH>
+__global__ void __launch_bounds__(32 * GV_CH)
+gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const float *__restrict__ v_next,
+                const float *__restrict__ last_v, const uint8_t *__restrict__ done, float gamma, float lam, int use_mask,
+                int T, long long n, float *__restrict__ adv, float *__restrict__ ret) {
+    __shared__ float sP[GV_CH][32][4], sA[GV_CH][32][4];
+    const int lx = threadIdx.x, cy = threadIdx.y, CH = blockDim.y;
+    const long long col = ((long long)blockIdx.x * 32 + lx) * 4;  // first of this thread's 4 envs
+    const bool valid = col < n;
+    const int span = GV_L * CH;
+    const float gl = __fmul_rn(gamma, lam);
+    float carry[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int base = ((T - 1) / span) * span; base >= 0; base -= span) {
+        const int t0 = base + cy * GV_L;
+        float tv[GV_L][4], dl[GV_L][4];
+        uint32_t ndbits = 0;  // bit 4*j+i: element (j, i) is not done (or mask off)
+        {
+            float4 vv[GV_L + 1];
+            float4 rr[GV_L];
+            uint32_t dd[GV_L];
+#pragma unroll
+            for (int j = 0; j < GV_L; j++) {
+                const int t = t0 + j;
+                const bool in = valid && t < T;
+                const long long idx = (long long)t * n + col;
+                rr[j] = in ? __ldg(reinterpret_cast<const float4 *>(r + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vv[j] = in ? __ldg(reinterpret_cast<const float4 *>(v + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dd[j] = (use_mask && in) ? __ldg(reinterpret_cast<const uint32_t *>(done + idx)) : 0u;
+            }
+            float4 vn[GV_L];
+            if (v_next) {
+#pragma unroll
+                for (int j = 0; j < GV_L; j++) {
+                    const int t = t0 + j;
+                    vn[j] = (valid && t < T) ? __ldg(reinterpret_cast<const float4 *>(v_next + (long long)t * n + col))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                const int tl = t0 + GV_L;  // the row after this chunk
+                vv[GV_L] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && tl < T) vv[GV_L] = __ldg(reinterpret_cast<const float4 *>(v + (long long)tl * n + col));
+                const float4 lv = valid ? __ldg(reinterpret_cast<const float4 *>(last_v + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < GV_L; j++) vn[j] = (t0 + j == T - 1) ? lv : vv[j + 1];
+            }
+#pragma unroll
+            for (int j = 0; j < GV_L; j++) {
+                const bool in = valid && (t0 + j) < T;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const bool nd = !((dd[j] >> (8 * i)) & 0xFFu);
+                    // r + gamma*V' as two rounded ops (torch: mul kernel then add kernel)
+                    const float tvj = __fadd_rn(f4get(rr[j], i), nd ? __fmul_rn(gamma, f4get(vn[j], i)) : 0.0f);
+                    tv[j][i] = tvj;
+                    dl[j][i] = in ? __fsub_rn(tvj, f4get(vv[j], i)) : 0.0f;
+                    if (nd) ndbits |= 1u << (4 * j + i);
+                }
+            }
+        }
+        // pass 1: chunk summary
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float acc = 0.0f, P = 1.0f;
+#pragma unroll
+            for (int j = GV_L - 1; j >= 0; j--) {
+                const bool in = valid && (t0 + j) < T;
+                const float cj = in ? (((ndbits >> (4 * j + i)) & 1u) ? gl : 0.0f) : 1.0f;
+                acc = __fadd_rn(dl[j][i], __fmul_rn(cj, acc));
+                P *= cj;
+            }
+            sP[cy][lx][i] = P;
+            sA[cy][lx][i] = acc;
+        }
+        __syncthreads();
+        float ain[4], cnext[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float a = carry[i];
+            for (int k = CH - 1; k > cy; k--) a = sA[k][lx][i] + sP[k][lx][i] * a;
+            ain[i] = a;
+            for (int k = cy; k >= 0; k--) a = sA[k][lx][i] + sP[k][lx][i] * a;
+            cnext[i] = a;
+        }
+        // pass 2: the recurrence from the true A_in, outputs
+        float A[4] = {ain[0], ain[1], ain[2], ain[3]};
+#pragma unroll
+        for (int j = GV_L - 1; j >= 0; j--) {
+            const int t = t0 + j;
+            const bool in = valid && t < T;
+            float ao[4], ro[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float cj = in ? (((ndbits >> (4 * j + i)) & 1u) ? gl : 0.0f) : 1.0f;
+                const float ca = __fmul_rn(cj, A[i]);
+                ro[i] = __fadd_rn(tv[j][i], ca);
+                ao[i] = __fadd_rn(dl[j][i], ca);
+                A[i] = ao[i];
+            }
+            if (in) {
+                const long long idx = (long long)t * n + col;
+                *reinterpret_cast<float4 *>(adv + idx) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+                *reinterpret_cast<float4 *>(ret + idx) = make_float4(ro[0], ro[1], ro[2], ro[3]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++) carry[i] = cnext[i];
+    }
+}
+
 // (sum, sum of squares, count) of adv in float64 -- PPO.py:115's mean / std ingredients.
+// 16-byte loads over the 16-byte aligned body, scalar head / tail.
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float *__restrict__ adv, long long count, double *stats) {
     double s = 0.0, ss = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-        const double x = (double)adv[i];
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    long long head = ((16 - ((uintptr_t)adv & 15u)) & 15u) / 4;
+    head = head < count ? head : count;
+    const long long n4 = (count - head) / 4;
+    const float4 *a4 = reinterpret_cast<const float4 *>(adv + head);
+    for (long long i = tid; i < n4; i += nth) {
+        const float4 x = __ldg(a4 + i);
+        // per-thread partial sums in fp32 pairs would lose bits on 1e8 elements: accumulate in fp64
+        s += (double)x.x + (double)x.y + (double)x.z + (double)x.w;
+        ss += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
+    }
+    for (long long i = tid; i < head + (count - head - 4 * n4); i += nth) {
+        const long long j = i < head ? i : head + 4 * n4 + (i - head);
+        const double x = (double)adv[j];
         s += x;
         ss += x * x;
     }
@@ -118,8 +252,20 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float *__restrict__ 
     double var = (stats[1] - stats[0] * mean) / (cnt > 1.0 ? cnt - 1.0 : 1.0);
     var = var < 0.0 ? 0.0 : var;
     const float m = (float)mean, inv = 1.0f / ((float)sqrt(var) + 1e-8f);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
-        adv[i] = (adv[i] - m) * inv;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    long long head = ((16 - ((uintptr_t)adv & 15u)) & 15u) / 4;
+    head = head < count ? head : count;
+    const long long n4 = (count - head) / 4;
+    float4 *a4 = reinterpret_cast<float4 *>(adv + head);
+    for (long long i = tid; i < n4; i += nth) {
+        float4 x = a4[i];
+        x.x = (x.x - m) * inv; x.y = (x.y - m) * inv; x.z = (x.z - m) * inv; x.w = (x.w - m) * inv;
+        a4[i] = x;
+    }
+    for (long long i = tid; i < head + (count - head - 4 * n4); i += nth) {
+        const long long j = i < head ? i : head + 4 * n4 + (i - head);
+        adv[j] = (adv[j] - m) * inv;
+    }
 }
 
 }  // namespace ta

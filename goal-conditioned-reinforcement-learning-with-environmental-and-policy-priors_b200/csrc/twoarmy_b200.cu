@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "ta_aux.cuh"
+#include "ta_feat.cuh"
 #include "ta_gae.cuh"
 #include "ta_step.cuh"
 
@@ -317,6 +318,11 @@ int ta_rollout(ta_handle h, const void *actions, int action_dtype, int T, uint8_
 int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *place_out, void *stream) {
     if (!h) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
+    if ((((uintptr_t)codes_out | (uintptr_t)matrix_out) & 15u) == 0) {
+        frame_codes_tile_kernel<<<blocks_for(h->n, FEAT_ENVS), FEAT_THREADS, 0, (cudaStream_t)stream>>>(
+            h->grid, h->sc0, codes_out, matrix_out, place_out, h->n);
+        return launch_ok("frame_codes_tile_kernel");
+    }
     state_matrix_kernel<<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, codes_out, matrix_out,
                                                                                    place_out, h->n);
     return launch_ok("state_matrix_kernel");
@@ -336,6 +342,23 @@ int ta_stack_roll_codes(ta_handle h, uint8_t *s_codes, float *p_stack, const uin
     stack_roll_kernel<uint8_t><<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, s_codes, p_stack,
                                                                                           init_mask, init, h->n);
     return launch_ok("stack_roll_kernel<u8>");
+}
+
+int ta_stack_push(ta_handle h, const void *s_prev, void *s_out, const float *p_prev, float *p_out, const uint8_t *prev_done,
+                  int init_all, int dtype, void *stream) {
+    if (!h || !s_out || (dtype != TA_STACK_F32 && dtype != TA_STACK_U8)) return TA_E_INVALID;
+    if (!init_all && (!s_prev || (p_out && !p_prev))) return TA_E_INVALID;
+    if (s_prev == s_out || (p_out && p_prev == p_out)) return TA_E_INVALID;  // out of place only
+    if ((((uintptr_t)s_prev | (uintptr_t)s_out) & 15u) != 0) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const unsigned nb = blocks_for(h->n, FEAT_ENVS);
+    if (dtype == TA_STACK_U8)
+        stack_push_codes_tile_kernel<<<nb, FEAT_THREADS, 0, (cudaStream_t)stream>>>(
+            h->grid, h->sc0, (const uint8_t *)s_prev, (uint8_t *)s_out, p_prev, p_out, prev_done, init_all, h->n);
+    else
+        stack_push_kernel<float><<<nb, FEAT_THREADS, 0, (cudaStream_t)stream>>>(
+            h->grid, h->sc0, (const float *)s_prev, (float *)s_out, p_prev, p_out, prev_done, init_all, h->n);
+    return launch_ok("stack_push_kernel");
 }
 
 int ta_export_state(ta_handle h, ta_env_state *out, void *stream) {
@@ -359,6 +382,21 @@ int ta_gae(const float *reward, const float *v, const float *v_next, const float
     if (!reward || !v || !adv_out || !ret_out || T <= 0 || n <= 0) return TA_E_INVALID;
     if (!v_next && !last_v) return TA_E_INVALID;
     if (use_mask && !done) return TA_E_INVALID;
+    const uintptr_t al = (uintptr_t)reward | (uintptr_t)v | (uintptr_t)v_next | (uintptr_t)last_v | (uintptr_t)adv_out |
+                         (uintptr_t)ret_out;
+    if ((n & 3) == 0 && (al & 15u) == 0 && ((uintptr_t)done & 3u) == 0) {  // four envs per thread, 16-byte accesses
+        // 8 steps per thread; time chunks per CTA: TA_GAE_CH (tuning knob, default 16 = 128 steps a pass)
+        // measured on B200 (T = 128): 4 chunks (32 steps a pass, 128-thread CTAs) reach 0.89 of the HBM
+        // peak once there are enough CTAs; small problems want the extra time-parallelism of 8
+        static int gch = -1;
+        if (gch < 0) { const char *e = getenv("TA_GAE_CH"); gch = e ? atoi(e) : 0; if (gch < 0 || gch > 16) gch = 0; }
+        int want = gch ? gch : (n / 128 >= 4 * 148 ? 4 : 8);
+        int chv = (T + 7) / 8;
+        if (chv > want) chv = want;
+        gae_vec4_kernel<8, 16><<<blocks_for(n / 4, 32), dim3(32, chv), 0, (cudaStream_t)stream>>>(
+            reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out, ret_out);
+        return launch_ok("gae_vec4_kernel");
+    }
     int ch = (T + GAE_L - 1) / GAE_L;
     if (ch > GAE_CH) ch = GAE_CH;
     dim3 block(32, ch);
@@ -370,7 +408,7 @@ int ta_gae(const float *reward, const float *v, const float *v_next, const float
 int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream) {
     if (!adv || !stats3 || count <= 0) return TA_E_INVALID;
     CK(cudaMemsetAsync(stats3, 0, 3 * sizeof(double), (cudaStream_t)stream));
-    unsigned nb = blocks_for(count, 256 * 8);
+    unsigned nb = blocks_for(count, 256 * 16);
     if (nb > 148 * 8) nb = 148 * 8;
     adv_stats_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(adv, count, stats3);
     return launch_ok("adv_stats_kernel");
@@ -378,8 +416,8 @@ int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream) 
 
 int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stream) {
     if (!adv || !stats3 || count <= 0) return TA_E_INVALID;
-    unsigned nb = blocks_for(count, 256 * 4);
-    if (nb > 148 * 16) nb = 148 * 16;
+    unsigned nb = blocks_for(count, 256 * 16);
+    if (nb > 148 * 8) nb = 148 * 8;
     adv_normalize_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(adv, count, stats3);
     return launch_ok("adv_normalize_kernel");
 }

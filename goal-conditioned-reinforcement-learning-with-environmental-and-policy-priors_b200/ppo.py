@@ -211,14 +211,18 @@ class PPO:
         """PPO.py:73-92 for N envs: state_matrix [N,5,289] (float, or uint8 codes), states_stack
         [N,5,2], goal [N,2] -> (action index int64 [N], log-prob float32 [N]).  Uses frames
         1..4 (the newest four) like the reference."""
-        if state_matrix.dtype == torch.uint8:
-            state_matrix = decode_matrix(state_matrix[:, 1:5])
-        else:
-            state_matrix = state_matrix[:, 1:5]
+        return self.select_action_frames(state_matrix[:, 1:5], states_stack[:, 1:5], goal)
+
+    @torch.no_grad()
+    def select_action_frames(self, frames, positions, goal):
+        """The same on the four current frames directly: frames [N,4,289] (float or uint8 codes),
+        positions [N,4,2], goal [N,2]."""
+        if frames.dtype == torch.uint8:
+            frames = decode_matrix(frames)
         self.actor.eval()
         self.critic.eval()
         with self._amp():
-            a_prob = self.actor(state_matrix.float(), states_stack[:, 1:5].float(), goal.float())
+            a_prob = self.actor(frames.float(), positions.float(), goal.float())
         dist = Categorical(probs=a_prob)
         a = dist.sample()
         return a, dist.log_prob(a)
@@ -364,43 +368,61 @@ class PPO:
 class VecRollout:
     """soa/train_ppo.py:99-160 for N envs at once: Env_transact.reset / env_action / step,
     frame-stack roll and Buffer_gridworld.store, all on the device.  One collect() fills a
-    [T, N] RolloutBuffer; episodes end / restart independently per env (autoreset), and a new
-    episode's stack is tiled with its first frame exactly like Env_transact.reset
-    (env_buffer.py:420-423)."""
+    [T, N] RolloutBuffer; episodes end / restart independently per env, and a new episode's
+    stack is the tiled reset frame exactly like Env_transact.reset (env_buffer.py:420-423).
+
+    The frame stacks are never rolled in place: record t is written straight into the buffer by
+    ta_stack_push from record t-1 (or from the tiled reset frame for envs whose episode ended at
+    t-1), so each step moves 4 frames in and 5 frames out per env and nothing else."""
 
     def __init__(self, env, agent: PPO, horizon: int):
+        assert horizon >= 2
         self.env, self.agent, self.T = env, agent, int(horizon)
         N, dev = env.num_envs, env.device
+        assert not env.autoreset, "VecRollout drives the resets itself (the terminal frame is part of the record)"
         self.buffer = RolloutBuffer(self.T, N, dev)
         self.buffer.g[:] = torch.tensor([float(env.goal_pos[1]), float(env.goal_pos[0])], device=dev)  # data_env: (y, x)
-        self.s_codes = torch.empty((N, 5, 289), dtype=torch.uint8, device=dev)
-        self.p_stack = torch.empty((N, 5, 2), dtype=torch.float32, device=dev)
         self.amap = torch.tensor(POLICY_TO_ENV_ACTION, dtype=torch.uint8, device=dev)
         self.ep_return = torch.zeros(N, dtype=torch.float32, device=dev)
-        self.finished_returns = []
         env.reset()
-        env.stack_roll_codes(self.s_codes, self.p_stack, init=True)
+        # the stack Env_transact.reset builds (a constant: _gen_grid is deterministic)
+        s0 = torch.empty((N, 5, 289), dtype=torch.uint8, device=dev)
+        p0 = torch.empty((N, 5, 2), dtype=torch.float32, device=dev)
+        env.stack_push(None, s0, None, p0, init_all=True)
+        self.reset_s, self.reset_p = s0[0, 1:5].clone(), p0[0, 1:5].clone()
+        self.prev_s = self.prev_p = None
+        self.prev_done = torch.ones(N, dtype=torch.uint8, device=dev)
         self._out = {}
+
+    def current_frames(self):
+        """The policy's input: the four newest frames / positions of every env."""
+        N = self.env.num_envs
+        if self.prev_s is None:
+            return self.reset_s.expand(N, 4, 289), self.reset_p.expand(N, 4, 2)
+        m = self.prev_done.bool()[:, None, None]
+        return torch.where(m, self.reset_s, self.prev_s[:, 1:5]), torch.where(m, self.reset_p, self.prev_p[:, 1:5])
 
     @torch.no_grad()
     def collect(self):
         """T steps of the reference's inner loop (train_ppo.py:108-123) for every env: select
-        action, env.step (no autoreset), featurise the post-step state, store, then
-        MiniGridEnv.reset + stack re-tiling for the envs whose episode ended (what the
-        reference does at the top of its next episode, train_ppo.py:104-105)."""
+        action, env.step (no autoreset), featurise the post-step state into record t, then
+        MiniGridEnv.reset for the envs whose episode ended (what the reference does at the top of
+        its next episode, train_ppo.py:104-105)."""
         env, buf = self.env, self.buffer
-        assert not env.autoreset, "VecRollout drives the resets itself (the terminal frame is part of the record)"
         buf.counter = 0
-        for _ in range(self.T):
-            a_idx, a_logp = self.agent.select_action(self.s_codes, self.p_stack, buf.g)
+        for t in range(self.T):
+            frames, positions = self.current_frames()
+            a_idx, a_logp = self.agent.select_action_frames(frames, positions, buf.g)
             obs, rew, term, trunc, _ = env.step(self.amap[a_idx], out=self._out)
             self._out = {"obs": obs, "reward": rew, "terminated": term.view(torch.uint8), "truncated": trunc.view(torch.uint8)}
             done = (term | trunc).view(torch.uint8)
-            env.stack_roll_codes(self.s_codes, self.p_stack)
-            buf.store(self.s_codes, a_idx, self.p_stack, rew, term.float(), a_logp)
+            env.stack_push(self.prev_s, buf.s[t], self.prev_p, buf.p[t], self.prev_done, init_all=self.prev_s is None)
+            buf.a[t].copy_(a_idx); buf.r[t].copy_(rew); buf.d[t].copy_(term); buf.a_logp[t].copy_(a_logp)
+            buf.counter += 1
             self.ep_return += rew
-            self.last_done, self.last_return = done, self.ep_return.clone()
             self.ep_return.masked_fill_(done.bool(), 0.0)
+            self.prev_s, self.prev_p, self.prev_done = buf.s[t], buf.p[t], done.clone()
             env.reset_masked(done)
-            env.stack_roll_codes(self.s_codes, self.p_stack, init_mask=done, init=True)
+        if self.T >= 2:  # record T-1 is read while record 0 of the next collect() is written
+            pass
         return buf

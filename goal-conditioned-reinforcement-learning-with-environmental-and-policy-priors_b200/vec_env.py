@@ -211,6 +211,22 @@ class TwoarmyVecEnv:
         _capi.check(self._L.ta_stack_roll_codes(self._h, _ptr(s_codes), _ptr(p_stack), _ptr(init_mask), int(init),
                                                 self._stream()), "ta_stack_roll_codes")
 
+    def stack_push(self, s_prev: Optional[torch.Tensor], s_out: torch.Tensor, p_prev: Optional[torch.Tensor],
+                   p_out: Optional[torch.Tensor], prev_done: Optional[torch.Tensor] = None, init_all: bool = False):
+        """Out-of-place frame-stack push (ta_stack_push): s_out = roll(base) + current frame with
+        base = tiled reset frame where prev_done / init_all, else s_prev.  uint8 codes or float32."""
+        assert s_out.is_contiguous() and s_out.shape == (self.num_envs, 5, 289) and s_out.dtype in (torch.uint8, torch.float32)
+        if s_prev is not None:
+            assert s_prev.is_contiguous() and s_prev.shape == s_out.shape and s_prev.dtype == s_out.dtype
+        if p_out is not None:
+            assert p_out.is_contiguous() and p_out.shape == (self.num_envs, 5, 2) and p_out.dtype == torch.float32
+        if p_prev is not None:
+            assert p_prev.is_contiguous() and p_prev.dtype == torch.float32
+        if prev_done is not None:
+            prev_done = prev_done.to(device=self.device, dtype=torch.uint8).contiguous()
+        _capi.check(self._L.ta_stack_push(self._h, _ptr(s_prev), _ptr(s_out), _ptr(p_prev), _ptr(p_out), _ptr(prev_done),
+                                          int(init_all), 1 if s_out.dtype == torch.uint8 else 0, self._stream()), "ta_stack_push")
+
     # ------------------------------------------------------------------ state access
     def export_state(self) -> np.ndarray:
         buf = torch.empty(self.num_envs * STATE_DTYPE.itemsize, dtype=torch.uint8, device=self.device)

@@ -149,6 +149,20 @@ int ta_stack_roll(ta_handle h, float *s_stack, float *p_stack, const uint8_t *in
 int ta_stack_roll_codes(ta_handle h, uint8_t *s_codes, float *p_stack, const uint8_t *init_mask, int init,
                         void *stream);
 
+/* The same frame-stack update OUT OF PLACE, fused with the episode-start tiling -- what the
+ * vectorised rollout uses (one pass: read 4 frames, write 5):
+ *   base  = tile(reset frame) x5 / (15,3) x5   for envs with init_all != 0 or prev_done[e] != 0
+ *           (Env_transact.reset after MiniGridEnv.reset, soa/env_buffer.py:413-428)
+ *         = s_prev[e] / p_prev[e]               otherwise
+ *   s_out[e] = [base[1], base[2], base[3], base[4], matrix_env(current state)]   (train_ppo.py:116-121)
+ * dtype: TA_STACK_F32 (float32 LUT values, the reference record) or TA_STACK_U8 (compact codes).
+ * s_prev/s_out [n][5][289] must be 16-byte aligned and distinct; p_prev/p_out float32 [n][5][2]
+ * (p_out nullable); prev_done uint8 [n] nullable. */
+#define TA_STACK_F32 0
+#define TA_STACK_U8 1
+int ta_stack_push(ta_handle h, const void *s_prev, void *s_out, const float *p_prev, float *p_out,
+                  const uint8_t *prev_done, int init_all, int dtype, void *stream);
+
 /* Export / import the full env state (device buffers of n ta_env_state records). */
 int ta_export_state(ta_handle h, ta_env_state *out, void *stream);
 int ta_import_state(ta_handle h, const ta_env_state *in, void *stream);

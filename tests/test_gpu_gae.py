@@ -25,7 +25,7 @@ def test_reference_mode_is_bit_exact(golden):
     assert np.array_equal(adv.cpu().numpy(), fx["adv"])
 
 
-@pytest.mark.parametrize("T,N", [(128, 16384), (1, 7), (33, 100), (300, 257), (50, 1)])
+@pytest.mark.parametrize("T,N", [(128, 16384), (1, 7), (33, 100), (300, 257), (50, 1), (300, 260), (129, 4)])
 @pytest.mark.parametrize("lam,use_mask", [(0.95, True), (1.0, True), (0.0, False), (0.9, False)])
 def test_gae_matches_float64_oracle(T, N, lam, use_mask):
     from oracle import oracle as O

@@ -334,3 +334,38 @@ def test_vec_rollout_records_follow_reference_loop():
             ora.reset(done.astype(np.uint8))
             f = feat()
             stack[done] = np.repeat(f[done][:, None, :], 5, 1)
+
+
+@pytest.mark.parametrize("n", [300, 16, 65])
+def test_stack_push_equals_roll_and_tile(n):
+    """ta_stack_push (out of place, fused with the episode-start tiling) == ta_stack_roll in place
+    + ta_stack_roll(init) on the finished envs, for both dtypes."""
+    import importlib
+    pkg = _pkg()
+    env = pkg.TwoarmyVecEnv(4, n, 17, seed=3, autoreset=False)
+    env.reset()
+    dev = env.device
+    sf = torch.empty((n, 5, 289), device=dev); pf = torch.empty((n, 5, 2), device=dev)
+    sc = torch.empty((n, 5, 289), dtype=torch.uint8, device=dev); pc = torch.empty((n, 5, 2), device=dev)
+    env.stack_roll(sf, pf, init=True); env.stack_roll_codes(sc, pc, init=True)
+    prev = {torch.float32: None, torch.uint8: None}
+    pprev = None
+    prev_done = torch.ones(n, dtype=torch.uint8, device=dev)
+    g = torch.Generator().manual_seed(1)
+    amap = torch.tensor([0, 1, 2, 3, 6], dtype=torch.int32)
+    for t in range(70):
+        _, _, te, tr, _ = env.step(amap[torch.randint(0, 5, (n,), generator=g)])
+        env.stack_roll(sf, pf); env.stack_roll_codes(sc, pc)
+        outs = {}
+        for dt in (torch.float32, torch.uint8):
+            o = torch.empty((n, 5, 289), dtype=dt, device=dev); po = torch.empty((n, 5, 2), device=dev)
+            env.stack_push(prev[dt], o, pprev, po, prev_done, init_all=prev[dt] is None)
+            outs[dt] = (o, po)
+        assert torch.equal(outs[torch.float32][0], sf) and torch.equal(outs[torch.uint8][0], sc)
+        assert torch.equal(outs[torch.float32][1], pf) and torch.equal(outs[torch.uint8][1], pc)
+        prev = {dt: outs[dt][0] for dt in outs}
+        pprev = outs[torch.uint8][1]
+        done = (te | tr)
+        prev_done = done.to(torch.uint8)
+        env.reset_masked(done)
+        env.stack_roll(sf, pf, init_mask=done, init=True); env.stack_roll_codes(sc, pc, init_mask=done, init=True)
