@@ -273,7 +273,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the rollout / 7x7-view secondary measurements")
     ap.add_argument("--rollout-T", type=int, default=16)
-    ap.add_argument("--workload", default="step", choices=["step", "ppo"])
+    ap.add_argument("--workload", default="step", choices=["step", "ppo", "aux"])
     ap.add_argument("--ppo-envs", type=int, default=16384, help="GLOBAL env count of the PPO workload")
     ap.add_argument("--ppo-horizon", type=int, default=128)
     ap.add_argument("--ppo-minibatch", type=int, default=4096)
@@ -289,6 +289,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "ppo":
         return bench_ppo(args, rank, world, local_rank)
+    if args.workload == "aux":  # featuriser / advantage kernels against the HBM roofline (rank 0, one GPU)
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import aux_kernels_bench
+            aux_kernels_bench.main()
+        return
     workload = (f"MiniGrid-twoarmy-17x17-v{args.version} batched step+gen_obs, {args.envs} envs per GPU, "
                 f"view {args.view}x{args.view}x3, random actions, Philox draws, autoreset (BASELINE configs[2])")
     config = {"workload": workload, "envs_per_gpu": args.envs, "view": args.view, "env_version": args.version,

@@ -235,16 +235,18 @@ __global__ void __launch_bounds__(FEAT_THREADS) stack_push_codes_tile_kernel(con
     for (int e = 0; e < cnt; e++)
         if (sdone[e])
             for (int j = threadIdx.x; j < SHIFT_ELEMS; j += FEAT_THREADS) tile[e * STACK_ELEMS + j] = sreset[j % NCELL];
-    // 3. out
-    tile_out(s_out + e0 * STACK_ELEMS, tile, total);
-    if (p_out && threadIdx.x < cnt * 10) {  // data_env: (y, x) rows; reset position (15, 3)
+    // 3. out (in place is fine: every read of s_prev / p_prev that matters happened before the
+    //    barrier inside tile_out; reads beyond this CTA's slice only feed positions overwritten in 2)
+    float pv = 0.0f;
+    const bool pact = p_out && threadIdx.x < cnt * 10;
+    if (pact) {  // data_env: (y, x) rows; reset position (15, 3)
         const int e = threadIdx.x / 10, r = threadIdx.x - 10 * e, f = r >> 1, comp = r & 1;
-        float v;
-        if (f == 4) v = comp ? (float)(sa[e] & 0xFFu) : (float)(sa[e] >> 8);
-        else if (sdone[e]) v = comp ? 3.0f : 15.0f;
-        else v = p_prev[(e0 + e) * 10 + r + 2];
-        p_out[(e0 + e) * 10 + r] = v;
+        if (f == 4) pv = comp ? (float)(sa[e] & 0xFFu) : (float)(sa[e] >> 8);
+        else if (sdone[e]) pv = comp ? 3.0f : 15.0f;
+        else pv = p_prev[e0 * 10 + threadIdx.x + 2];
     }
+    tile_out(s_out + e0 * STACK_ELEMS, tile, total);
+    if (pact) p_out[e0 * 10 + threadIdx.x] = pv;
 }
 
 }  // namespace ta

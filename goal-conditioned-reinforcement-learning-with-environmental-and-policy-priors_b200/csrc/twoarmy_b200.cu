@@ -11,6 +11,7 @@
 #include "ta_aux.cuh"
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
+#include "ta_her.cuh"
 #include "ta_step.cuh"
 
 using namespace ta;
@@ -339,6 +340,11 @@ int ta_stack_roll(ta_handle h, float *s_stack, float *p_stack, const uint8_t *in
 int ta_stack_roll_codes(ta_handle h, uint8_t *s_codes, float *p_stack, const uint8_t *init_mask, int init, void *stream) {
     if (!h || !s_codes) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
+    if (!init && ((uintptr_t)s_codes & 15u) == 0) {  // the roll itself: the tile kernel, in place
+        stack_push_codes_tile_kernel<<<blocks_for(h->n, FEAT_ENVS), FEAT_THREADS, 0, (cudaStream_t)stream>>>(
+            h->grid, h->sc0, s_codes, s_codes, p_stack, p_stack, nullptr, 0, h->n);
+        return launch_ok("stack_push_codes_tile_kernel");
+    }
     stack_roll_kernel<uint8_t><<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, s_codes, p_stack,
                                                                                           init_mask, init, h->n);
     return launch_ok("stack_roll_kernel<u8>");
@@ -420,6 +426,17 @@ int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stre
     if (nb > 148 * 8) nb = 148 * 8;
     adv_normalize_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(adv, count, stats3);
     return launch_ok("adv_normalize_kernel");
+}
+
+int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, uint64_t seed, uint64_t env_id0,
+                const uint8_t *chosen_in, uint8_t *uniq_out, uint8_t *m_out, uint16_t *plan_out, void *stream) {
+    if (!p || !done || !plan_out || T <= 0 || n <= 0) return TA_E_INVALID;
+    CK(cudaMemsetAsync(plan_out, 0xFF, (size_t)T * n * 4 * sizeof(uint16_t), (cudaStream_t)stream));
+    if (uniq_out) CK(cudaMemsetAsync(uniq_out, 0xFF, (size_t)T * n * HER_MAXLEN, (cudaStream_t)stream));
+    if (m_out) CK(cudaMemsetAsync(m_out, 0, (size_t)T * n, (cudaStream_t)stream));
+    her_plan_kernel<<<blocks_for(n, HER_WARPS), 32 * HER_WARPS, 0, (cudaStream_t)stream>>>(
+        p, done, T, n, (uint32_t)seed, (uint32_t)(seed >> 32), env_id0, chosen_in, uniq_out, m_out, plan_out);
+    return launch_ok("her_plan_kernel");
 }
 
 int ta_set_timing(ta_handle h, int on) {

@@ -126,6 +126,7 @@ class RolloutBuffer:
         self.d = torch.empty((T, N), dtype=torch.float32, device=device)
         self.a_logp = torch.empty((T, N), dtype=torch.float32, device=device)
         self.g = torch.empty((N, 2), dtype=torch.float32, device=device)
+        self.ended = torch.zeros((T, N), dtype=torch.uint8, device=device)   # terminated | truncated
         self.counter = 0
 
     @property
@@ -145,6 +146,22 @@ class RolloutBuffer:
         return {"s": self.s[:T].reshape(B, 5, 289), "p": self.p[:T].reshape(B, 5, 2), "a": self.a[:T].reshape(B, 1),
                 "g": self.g.unsqueeze(0).expand(T, self.N, 2).reshape(B, 2), "r": self.r[:T].reshape(B, 1),
                 "d": self.d[:T].reshape(B, 1), "a_logp": self.a_logp[:T].reshape(B, 1)}
+
+
+def with_her(buf: "RolloutBuffer", seed: int = 9981, env_id0: int = 0):
+    """The rollout's samples followed by their hindsight relabels (train_ppo.py:128-134 with
+    args.her on): a dict for PPO.update in which `src` maps every sample to the record it copies."""
+    from . import her
+    flat = buf.flat()
+    T, N = buf.counter, buf.N
+    extra = her.relabel(buf.p[:T], buf.r[:T], buf.ended[:T], seed, env_id0)
+    base = torch.arange(T * N, device=buf.device)
+    out = dict(flat)
+    out["src"] = torch.cat([base, extra["src"]])
+    out["g"] = torch.cat([flat["g"], extra["g"]])
+    out["r"] = torch.cat([flat["r"], extra["r"].view(-1, 1)])
+    out["d"] = torch.cat([flat["d"], extra["d"].view(-1, 1)])
+    return out
 
 
 class PPO:
@@ -229,14 +246,16 @@ class PPO:
 
     # ------------------------------------------------------------------ learning
     @torch.no_grad()
-    def values(self, s, p, g, chunk: int = 16384):
+    def values(self, s, p, g, chunk: int = 16384, src=None):
         """(V(s[:,0:4]), V(s[:,1:5])) in chunks: the two critic passes of PPO.py:113-114."""
         outs0, outs1 = [], []
         self.critic.eval()
-        for i in range(0, s.shape[0], chunk):
-            sc = s[i:i + chunk]
+        B = s.shape[0] if src is None else src.shape[0]
+        for i in range(0, B, chunk):
+            rows = slice(i, i + chunk) if src is None else src[i:i + chunk]
+            sc = s[rows]
             sc = decode_matrix(sc) if sc.dtype == torch.uint8 else sc
-            pc, gc = p[i:i + chunk], g[i:i + chunk]
+            pc, gc = p[rows], g[i:i + chunk]
             with self._amp():
                 outs0.append(self.critic(sc[:, 0:4], pc[:, 0:4], gc))
                 outs1.append(self.critic(sc[:, 1:5], pc[:, 1:5], gc))
@@ -282,8 +301,15 @@ class PPO:
         old_a_logp = buffer["a_logp"].to(dev, torch.float32).view(-1, 1)
         if s.dtype != torch.uint8:
             s = s.to(torch.float32)
-        B = s.shape[0]
-        v, v_next = self.values(s, p, g)
+        # hindsight-relabelled samples (her.relabel): record i copies s, p, a, a_logp of record src[i]
+        # and carries its own g, r -- the fields her_func overrides (env_buffer.py:118-127)
+        src = buffer.get("src")
+        if src is not None:
+            src = src.to(dev)
+            assert g.shape[0] == src.shape[0] and r.shape[0] == src.shape[0]
+            old_a_logp, a = old_a_logp[src], a[src]
+        B = s.shape[0] if src is None else src.shape[0]
+        v, v_next = self.values(s, p, g, src=src)
         target_v, adv = self.advantages(r, v, v_next)
         bs = minibatch or self.batch_size
         self.actor.train()
@@ -305,9 +331,10 @@ class PPO:
 
         for _ in range(epochs or self.K_epochs):
             for idx in minibatches():
-                sb = s[idx]
+                rows = idx if src is None else src[idx]
+                sb = s[rows]
                 sb = decode_matrix(sb[:, 0:4]) if sb.dtype == torch.uint8 else sb[:, 0:4]
-                pb, gb = p[idx][:, 0:4], g[idx]
+                pb, gb = p[rows][:, 0:4], g[idx]
                 with self._amp():
                     probs = self.actor(sb, pb, gb)
                     vpred = self.critic(sb, pb, gb)
@@ -418,6 +445,7 @@ class VecRollout:
             done = (term | trunc).view(torch.uint8)
             env.stack_push(self.prev_s, buf.s[t], self.prev_p, buf.p[t], self.prev_done, init_all=self.prev_s is None)
             buf.a[t].copy_(a_idx); buf.r[t].copy_(rew); buf.d[t].copy_(term); buf.a_logp[t].copy_(a_logp)
+            buf.ended[t].copy_(done)
             buf.counter += 1
             self.ep_return += rew
             self.ep_return.masked_fill_(done.bool(), 0.0)

@@ -183,6 +183,23 @@ int ta_gae(const float *reward, const float *v, const float *v_next, const float
 int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream);
 int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stream);
 
+/* Hindsight relabelling of a [T][n] rollout: Buffer_gridworld.her_func (soa/env_buffer.py:101-143)
+ * for every episode that ends inside the window, without materialising the copies.
+ *   p         float32 [T][n][5][2], the record's p field; [4] = (y, x) reached by the step
+ *   done      uint8 [T][n], the episode ended with this record (terminated | truncated)
+ *   chosen_in nullable uint8 [T][n][4].  NULL: the up-to-4 relabel indices are drawn with Philox
+ *             keyed by (seed, global env id, t).  Non-NULL (verification): read at each
+ *             episode-end record, the record indices np.random.choice(indices, k, replace=False)
+ *             returned (env_buffer.py:115), 0xFF = none
+ *   uniq_out  nullable uint8 [T][n][64], m_out nullable uint8 [T][n]: at each episode-end record the
+ *             `indices` np.unique returns (env_buffer.py:108; first occurrence of every distinct
+ *             position in sorted (y,x) order) and their count -- what the host feeds np.random.choice
+ *   plan_out  uint16 [T][n][4]: 0xFFFF = the record is not part of relabel slot c; otherwise the
+ *             new goal y<<5|x, with bit 15 set on the prefix's last record (r = 0.9, d = 1 there,
+ *             env_buffer.py:126-127).  Prefixes with index 0 are dropped like line 121. */
+int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, uint64_t seed, uint64_t env_id0,
+                const uint8_t *chosen_in, uint8_t *uniq_out, uint8_t *m_out, uint16_t *plan_out, void *stream);
+
 /* introspection */
 int ta_abi_version(void);
 const char *ta_strerror(int code);

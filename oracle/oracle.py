@@ -216,3 +216,77 @@ def bench_rollout(version, n, T, view, seed=9981, threads=None):
     steps = L.ora_bench_rollout(_p(b.envs), C.c_int64(n), C.c_int(T), C.c_int(view), C.c_uint64(seed),
                                 _p(obs), _p(rew), _p(te), _p(tr))
     return int(steps), time.perf_counter() - t0
+
+
+# ---- hindsight relabelling (soa/env_buffer.py:101-143) ------------------------------------------
+def her_select(p4, newgoal_size_in=4, choice=None):
+    """The selection half of Buffer_gridworld.her_func for ONE episode (env_buffer.py:108-117):
+    p4 [L,2] = buffer['p'][:,4,0:2] of the episode's records.  Returns (indices, episode_idxs):
+    `indices` = first-occurrence record index of every distinct position, in np.unique's (sorted
+    lexicographic) order; `episode_idxs` = np.random.choice(indices, size=min(4, len), replace=False)
+    drawn from the GLOBAL legacy numpy stream like the reference (or from `choice` if given)."""
+    p4 = np.asarray(p4)
+    _, indices, _ = np.unique(p4[:, 0:2], return_index=True, return_counts=True, axis=0)
+    k = min(newgoal_size_in, indices.size)
+    if p4.shape[0] <= 0:
+        return indices, np.zeros(0, np.int64)
+    chooser = choice or (lambda a, size: np.random.choice(a, size=size, replace=False))
+    return indices, np.asarray(chooser(indices, k), dtype=np.int64)
+
+
+def her_func(p4, r, counter_start, capacity=2048, newgoal_size_in=4, choice=None):
+    """Buffer_gridworld.her_func (env_buffer.py:101-143) for an episode whose L records sit at
+    buffer positions counter_start .. counter_start+L-1 (no wrap inside the episode, as the
+    reference's slice requires).  Returns dict(src, g, r, d, counter, full): the appended records in
+    order (src = index of the copied episode record, g = relabelled goal, r / d after the
+    overrides of lines 126-127), the new buffer counter and whether the ring wrapped."""
+    p4 = np.asarray(p4, np.float32)
+    r = np.asarray(r, np.float32)
+    L = p4.shape[0]
+    end = counter_start + L - 1           # epo_counter_end = self.counter - 1
+    src, g, rr, dd = [], [], [], []
+    full = False
+    if L > 0:
+        _, idxs = her_select(p4, newgoal_size_in, choice)
+        for index in idxs:
+            index = int(index)
+            if index > 0 and index < capacity:
+                n = index + 1
+                goal = p4[index, 0:2]
+                rn = r[:n].copy(); rn[index] = np.float32(0.9)
+                dn = np.zeros(n, np.float32); dn[index] = 1
+                src += list(range(n)); g += [goal] * n; rr += list(rn); dd += list(dn)
+                if end + 1 + n <= capacity:
+                    end = end + 1 + index
+                else:
+                    end = end + 1 + n - capacity - 1
+                    full = True
+    return dict(src=np.array(src, np.int64), g=np.array(g, np.float32).reshape(-1, 2), r=np.array(rr, np.float32),
+                d=np.array(dd, np.float32), counter=end + 1, full=full)
+
+
+def her_plan(pos_y, pos_x, done, choose):
+    """The vectorised form the CUDA kernel computes: pos_y/pos_x/done [T,N]; every episode segment
+    that ENDS inside the window (segments start at t=0 or after a done) is relabelled like her_func;
+    choose(indices, k, t_end, env) -> the k chosen record indices.  Returns plan uint16 [T,N,4]:
+    0xFFFF = record not in relabel slot c, else goal y*32+x | 0x8000 on the prefix's last record."""
+    T, N = done.shape
+    plan = np.full((T, N, 4), 0xFFFF, np.uint16)
+    for e in range(N):
+        t0 = 0
+        for t1 in range(T):
+            if not done[t1, e]:
+                continue
+            L = t1 - t0 + 1
+            p4 = np.stack([pos_y[t0:t1 + 1, e], pos_x[t0:t1 + 1, e]], 1)
+            _, indices, _ = np.unique(p4, return_index=True, return_counts=True, axis=0)
+            k = min(4, indices.size)
+            chosen = choose(indices, k, t1, e)
+            for c, index in enumerate(chosen):
+                index = int(index)
+                if index > 0:
+                    goal = int(p4[index, 0]) * 32 + int(p4[index, 1])
+                    plan[t0:t0 + index + 1, e, c] = goal
+                    plan[t0 + index, e, c] = goal | 0x8000
+            t0 = t1 + 1
+    return plan

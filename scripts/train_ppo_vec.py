@@ -8,8 +8,8 @@
 Reference flow (soa/train_ppo.py:99-160): select_action -> env_action -> env.step -> matrix_env /
 data_env -> frame-stack roll -> buffer.store -> update when the buffer is full.  Here every env of
 the shard advances together, the buffer is [horizon, envs] on the device, and gradients are
-all-reduced over NCCL (the only collective).  HER relabelling (train_ppo.py:128-134) is not part
-of this loop yet."""
+all-reduced over NCCL (the only collective).  --her appends the hindsight relabels of every episode
+that ended in the rollout (train_ppo.py:128-134 with args.her on), computed on the device."""
 import argparse
 import importlib
 import json
@@ -35,6 +35,7 @@ def main(argv=None):
     ap.add_argument("--updates", type=int, default=10)
     ap.add_argument("--view", type=int, default=17)
     ap.add_argument("--fp32", action="store_true", help="no bf16 autocast")
+    ap.add_argument("--her", action="store_true", help="append hindsight relabels (Buffer_gridworld.her_func) to every update")
     ap.add_argument("--save", default="")
     args = ap.parse_args(argv)
 
@@ -62,7 +63,8 @@ def main(argv=None):
         buf = roll.collect()
         torch.cuda.synchronize()
         t1 = time.time()
-        al, vl = agent.update(buf.flat(), minibatch=args.minibatch, epochs=args.epochs)
+        data = P.with_her(buf, seed=args.seed + u, env_id0=rank * n_local) if args.her else buf.flat()
+        al, vl = agent.update(data, minibatch=args.minibatch, epochs=args.epochs)
         torch.cuda.synchronize()
         t2 = time.time()
         if rank == 0:

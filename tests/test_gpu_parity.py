@@ -369,3 +369,87 @@ def test_stack_push_equals_roll_and_tile(n):
         prev_done = done.to(torch.uint8)
         env.reset_masked(done)
         env.stack_roll(sf, pf, init_mask=done, init=True); env.stack_roll_codes(sc, pc, init_mask=done, init=True)
+
+
+def _np_choice(indices, k, *_):
+    return np.random.choice(indices, size=k, replace=False)
+
+
+def test_her_plan_matches_her_func_oracle():
+    """ta_her_plan against oracle.her_plan (her_func per finished episode, pinned to the reference by
+    tests/golden/her_ref.npz): first pass returns np.unique's `indices`; the relabel indices are then
+    drawn with np.random.choice from the legacy stream exactly like env_buffer.py:115 and replayed."""
+    import importlib
+    pkg, O = _pkg(), _oracle()
+    H = importlib.import_module(pkg.__name__ + ".her")
+    rng = np.random.RandomState(5)
+    T, N = 131, 37
+    # agent tracks with revisits; episode ends every <= 50 records at random places
+    pos = np.zeros((T, N, 2), np.int64)
+    done = np.zeros((T, N), np.uint8)
+    for e in range(N):
+        y, x, age = 15, 3, 0
+        for t in range(T):
+            dy, dx = [(0, -1), (0, 1), (-1, 0), (1, 0), (0, 0)][rng.randint(5)]
+            if rng.rand() < 0.3:
+                dy = dx = 0
+            y, x = min(15, max(1, y + dy)), min(15, max(1, x + dx))
+            pos[t, e] = (y, x)
+            age += 1
+            if age >= 50 or rng.rand() < 0.03:
+                done[t, e] = 1
+                y, x, age = 15, 3, 0
+    p = np.zeros((T, N, 5, 2), np.float32)
+    p[:, :, 4] = pos
+    p[:, :, :4] = rng.randint(1, 16, size=(T, N, 4, 2))
+    dev = "cuda:0"
+    pt, dt = torch.tensor(p, device=dev), torch.tensor(done, device=dev)
+    _, uniq, m = H.plan(pt, dt, want_unique=True)
+    uniq, m = uniq.cpu().numpy(), m.cpu().numpy()
+    # np.unique's indices per finished episode, and the reference's choice from them
+    np.random.seed(77)
+    chosen = np.full((T, N, 4), 0xFF, np.uint8)
+    picks = {}
+
+    def choose(indices, k, t1, e):
+        assert m[t1, e] == len(indices) and list(uniq[t1, e, :len(indices)]) == list(indices), (t1, e)
+        c = _np_choice(indices, k)
+        chosen[t1, e, :k] = c
+        picks[(t1, e)] = c
+        return c
+
+    want = O.her_plan(pos[:, :, 0], pos[:, :, 1], done, choose)
+    got = H.plan(pt, dt, chosen=torch.tensor(chosen)).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    assert (want != 0xFFFF).sum() > 1000
+    # the relabelled triples: goal/r/d exactly as her_func writes them
+    r = rng.choice(np.array([-0.01, -0.1, 0.2], np.float32), size=(T, N))
+    rel = H.relabel(pt, torch.tensor(r, device=dev), dt, chosen=torch.tensor(chosen))
+    src, g, rr, dd = (rel[k].cpu().numpy() for k in ("src", "g", "r", "d"))
+    t_idx, e_idx = src // N, src % N
+    assert np.all(dd[rr == np.float32(0.9)] >= 0) and np.all(rr[dd == 1] == np.float32(0.9))
+    assert np.array_equal(rr[dd == 0], r[t_idx, e_idx][dd == 0])
+    assert np.array_equal(g[dd == 1], pos[t_idx, e_idx][dd == 1].astype(np.float32))  # the goal is the position reached
+
+
+def test_her_plan_philox_is_valid_and_sharding_invariant():
+    import importlib
+    pkg = _pkg()
+    H = importlib.import_module(pkg.__name__ + ".her")
+    g = torch.Generator().manual_seed(3)
+    T, N = 128, 256
+    p = torch.zeros((T, N, 5, 2))
+    p[:, :, 4] = torch.randint(1, 5, (T, N, 2), generator=g).float()
+    done = (torch.rand((T, N), generator=g) < 0.04)
+    dev = "cuda:0"
+    full, uniq, m = H.plan(p.to(dev), done.to(dev), seed=5, want_unique=True)
+    a = H.plan(p[:, :100].contiguous().to(dev), done[:, :100].contiguous().to(dev), seed=5)
+    b = H.plan(p[:, 100:].contiguous().to(dev), done[:, 100:].contiguous().to(dev), seed=5, env_id0=100)
+    assert torch.equal(torch.cat([a, b], 1), full)
+    full = full.cpu().numpy().astype(np.int64)
+    # every slot's prefix starts at its episode's first record, ends on a flagged record whose position is the goal
+    lastmask = (full != 0xFFFF) & ((full & 0x8000) != 0)
+    tt, ee, cc = np.nonzero(lastmask)
+    pos = p[:, :, 4].numpy().astype(np.int64)
+    assert len(tt) > 100
+    assert np.array_equal(full[tt, ee, cc] & 0x7FFF, pos[tt, ee, 0] * 32 + pos[tt, ee, 1])

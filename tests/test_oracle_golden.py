@@ -140,3 +140,27 @@ def test_td_advantage(golden):
     a64, r64 = O.gae(fx["r"].reshape(1, -1), fx["v"].reshape(1, -1), np.zeros((1, 2048), np.uint8),
                      0.99, 0.0, use_mask=False, v_next=fx["v_next"].reshape(1, -1))
     np.testing.assert_allclose(a64[0], fx["adv"][:, 0], rtol=1e-5, atol=1e-6)
+
+
+def test_her_func_matches_reference(golden):
+    """oracle.her_func (restating soa/env_buffer.py:101-143) against what the reference's own
+    her_func appended to its buffer (tests/golden/her_ref.npz), same global numpy seed."""
+    from oracle import oracle as O
+    fx = golden("her_ref.npz")
+    cases = sorted({k.split("_")[0] for k in fx})
+    assert len(cases) >= 10
+    n_nonempty = 0
+    for c in cases:
+        L, start, seed, cnt_before, counter, full = (int(v) for v in fx[f"{c}_meta"])
+        if cnt_before != start + L:      # the episode itself wrapped the ring: the reference's slice is empty
+            assert len(fx[f"{c}_new_src"]) == 0
+            continue
+        np.random.seed(seed)
+        got = O.her_func(fx[f"{c}_p4"], fx[f"{c}_r"], start)
+        np.testing.assert_array_equal(got["src"], fx[f"{c}_new_src"])
+        np.testing.assert_array_equal(got["g"], fx[f"{c}_new_g"].reshape(-1, 2))
+        np.testing.assert_array_equal(got["r"], fx[f"{c}_new_r"])
+        np.testing.assert_array_equal(got["d"], fx[f"{c}_new_d"])
+        assert got["counter"] % 2048 == counter % 2048 and got["full"] == bool(full)
+        n_nonempty += len(got["src"]) > 0
+    assert n_nonempty >= 6

@@ -86,6 +86,35 @@ def test_select_action_is_batched_and_uses_newest_four_frames():
     assert torch.allclose(lp, torch.log(prob[torch.arange(N), a]), atol=1e-6)
 
 
+def test_update_with_virtual_her_samples_equals_materialised_copies():
+    """`src` indirection (her.relabel's virtual samples) == the same records physically copied with
+    their g / r overridden, which is what her_func appends (env_buffer.py:118-139)."""
+    P = _ppo()
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(4)
+    n, m = 24, 10
+    base = {"s": torch.randint(0, 3, (n, 5, 289), generator=g, dtype=torch.uint8), "p": torch.randint(1, 16, (n, 5, 2), generator=g).float(),
+            "a": torch.randint(0, 5, (n, 1), generator=g), "r": torch.rand(n, 1, generator=g) - 0.5,
+            "a_logp": torch.log(torch.rand(n, 1, generator=g) * 0.3 + 0.1)}
+    src = torch.cat([torch.arange(n), torch.randint(0, n, (m,), generator=g)])
+    gg = torch.cat([torch.tensor([[2.0, 14.0]]).repeat(n, 1), torch.randint(1, 16, (m, 2), generator=g).float()])
+    rr = torch.cat([base["r"], torch.full((m, 1), 0.9)])
+    out = []
+    for mode in ("virtual", "copied"):
+        torch.manual_seed(0)
+        agent = P.PPO(device="cpu", autocast=False)
+        agent.K_epochs = 1
+        if mode == "virtual":
+            buf = dict(base, src=src, g=gg, r=rr)
+        else:
+            buf = {k: v[src] for k, v in base.items()}
+            buf.update(g=gg, r=rr)
+        torch.manual_seed(9)
+        agent.update(buf, minibatch=17)
+        out.append(_sums(agent.actor).tolist() + _sums(agent.critic).tolist())
+    np.testing.assert_allclose(out[0], out[1], rtol=0, atol=0)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
