@@ -67,15 +67,59 @@ class TINet(nn.Module):
         self.upsamplingnearest = nn.UpsamplingNearest2d(scale_factor=4)
         self.apply(_weights_init)
 
+    # Sel[p][d][k]: which of the 4 kernel taps k of one axis land on input offset d for output phase p
+    # (even outputs see one input pixel through all 4 taps, odd outputs two pixels through 2 taps each)
+    _SEL = ((( 1., 1., 1., 1.), (0., 0., 0., 0.)), ((1., 1., 0., 0.), (0., 0., 1., 1.)))
+    # Off by default: built from torch ops (cat / GEMM / interleaving copy) the folded layer measured
+    # 22.0 ms per optimiser step against 19.9 ms for upsample + cuDNN (B = 4096, two nets); it only
+    # pays once the interleave is fused into the GEMM epilogue.
+    fold_conv1 = False
+
+    def _conv1_folded(self, x):
+        """UpsamplingNearest2d(4) + Conv2d(4, 64, k=4, s=2) + ReLU (all_net.py:142-143,157,180-181) folded
+        exactly: output pixel (2m+py, 2n+px) only sees input pixels
+        (m+dy, n+dx), dy, dx in {0,1}, through sums of kernel taps.  So the layer is one GEMM over 2x2
+        patches of the 17x17 frame (K = 16) producing the four phases of 64 channels, interleaved by
+        a single copy -- no 68x68 tensor, no channel-padded cuDNN kernel.  x [B,4,17,17] ->
+        [B,64,33,33] channels_last."""
+        conv1 = self.cnn_base[0]
+        B = x.shape[0]
+        sel = torch.tensor(self._SEL, dtype=conv1.weight.dtype, device=x.device)           # [p, d, k]
+        w = torch.einsum("ocyx,pdy,qex->pqodec", conv1.weight, sel, sel).reshape(256, 16)  # rows (py,px,o), cols (dy,dx,c)
+        xn = F.pad(x.permute(0, 2, 3, 1), (0, 0, 0, 1, 0, 1))                              # [B,18,18,4]
+        cols = torch.cat([xn[:, dy:dy + 17, dx:dx + 17, :] for dy in range(2) for dx in range(2)], dim=3)  # [B,17,17,16]
+        if torch.is_autocast_enabled():
+            cols, w = cols.to(torch.bfloat16), w.to(torch.bfloat16)
+        y = F.linear(cols.reshape(B * 289, 16), w.to(cols.dtype), conv1.bias.repeat(4).to(cols.dtype))   # [B*289, 256]
+        y = y.view(B, 17, 17, 2, 2, 64).permute(0, 1, 3, 2, 4, 5).reshape(B, 34, 34, 64)[:, :33, :33, :]
+        return torch.relu(y.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last))
+
     def forward(self, state_matrix, position, goal):
         B, T, _ = state_matrix.shape
         position = position.contiguous().view(-1, 8)
         position_goal = torch.relu(self.positionnet(torch.cat([position, goal], 1)))
         x = state_matrix.contiguous().view(-1, T, 17, 17)
-        x = self.upsamplingnearest(x)
         if x.is_cuda:
-            x = x.contiguous(memory_format=torch.channels_last)
-        x = torch.relu(self.fc0(self.cnn_base(x)))
+            if self.fold_conv1:
+                x = self._conv1_folded(x)
+            else:
+                x = self.upsamplingnearest(x).contiguous(memory_format=torch.channels_last)
+                x = self.cnn_base[:2](x)
+            # The last conv (128 -> 256, 3x3 stride 2 on 7x7) as an explicit im2col + cuBLAS GEMM: for
+            # this shape cuDNN picks a kernel that takes 1.8 ms fwd+bwd at B = 4096, the GEMM 0.2 ms
+            # (scripts/conv_gemm_probe.py).  Same arithmetic, same parameters.
+            x = self.cnn_base[2:6](x)
+            conv4 = self.cnn_base[6]
+            B = x.shape[0]
+            xn = x.permute(0, 2, 3, 1)                                        # [B, 7, 7, 128], a view (channels_last)
+            # im2col by nine strided slices (torch's unfold loops over the batch): rows (ky, kx, c)
+            cols = torch.cat([xn[:, ky:ky + 5:2, kx:kx + 5:2, :] for ky in range(3) for kx in range(3)], dim=3)
+            w = conv4.weight.permute(0, 2, 3, 1).reshape(256, -1).to(cols.dtype)
+            y = F.linear(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype))   # [B*9, 256]
+            x = torch.relu(y).view(B, 9, 256).transpose(1, 2).reshape(B, 2304)     # Flatten of [B, 256, 3, 3]
+            x = torch.relu(self.fc0(x))
+        else:
+            x = torch.relu(self.fc0(self.cnn_base(self.upsamplingnearest(x))))
         x = torch.cat([x, position_goal.to(x.dtype)], 1)
         return torch.relu(self.fc1(x))
 

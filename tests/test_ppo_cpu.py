@@ -115,6 +115,18 @@ def test_update_with_virtual_her_samples_equals_materialised_copies():
     np.testing.assert_allclose(out[0], out[1], rtol=0, atol=0)
 
 
+def test_folded_conv1_is_exact():
+    """Upsample(4)+Conv2d(4,64,4,2)+ReLU == the 2x2-patch GEMM with phase-summed taps (fp32 round-off)."""
+    P = _ppo()
+    torch.manual_seed(0)
+    net = P.TINet()
+    x = torch.randn(3, 4, 17, 17)
+    with torch.no_grad():
+        want = torch.relu(net.cnn_base[0](net.upsamplingnearest(x)))
+        got = net._conv1_folded(x)
+    assert got.shape == want.shape and float((got - want).abs().max()) < 1e-5
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
