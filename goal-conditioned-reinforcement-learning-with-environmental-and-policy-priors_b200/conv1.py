@@ -1,0 +1,66 @@
+"""TINet's first layer through the fused CUDA kernels (ta_conv1_fwd / ta_conv1_bwd).
+
+UpsamplingNearest2d(4) + Conv2d(4, 64, kernel 4, stride 2) + ReLU (soa/agent/net/all_net.py:142-143,
+157,180-181) applied to 17x17 frames is folded exactly: output pixel (2m+py, 2n+px) sees input pixels
+(m+dy, n+dx) through phase-dependent sums of kernel taps.  `fold` builds that [256,16] weight with an
+einsum (differentiable, so the conv's own parameters receive the gradient), the kernels do the K = 16
+products, bias, ReLU and the bf16 channels-last store, straight from the rollout buffer's uint8 codes or
+from float frames.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+
+# Sel[p][d][k]: kernel tap k of one axis lands on input offset d for output phase p
+_SEL = (((1., 1., 1., 1.), (0., 0., 0., 0.)), ((1., 1., 0., 0.), (0., 0., 1., 1.)))
+
+
+def fold(weight: torch.Tensor, bias: torch.Tensor):
+    """conv weight [64,4,4,4], bias [64] -> (w4 [256,16] rows (py,px,o) cols (dy,dx,c), b4 [256]), float32."""
+    sel = torch.tensor(_SEL, dtype=torch.float32, device=weight.device)
+    w4 = torch.einsum("ocyx,pdy,qex->pqodec", weight.float(), sel, sel).reshape(256, 16)
+    return w4.contiguous(), bias.float().repeat(4).contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class _Conv1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w4, b4):
+        # x [B, >=4, 289] uint8 codes or float32; only frames 0..3 of each sample are read
+        assert x.is_cuda and x.dim() == 3 and x.shape[2] == 289 and x.shape[1] >= 4
+        if x.dtype not in (torch.uint8, torch.float32):
+            x = x.float()
+        if x.stride(2) != 1 or x.stride(1) != 289 or x.stride(0) < 4 * 289:  # e.g. an expanded constant stack
+            x = x.contiguous()
+        B = x.shape[0]
+        y = torch.empty((B, 33, 33, 64), dtype=torch.bfloat16, device=x.device)
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        w4, b4 = w4.detach().float().contiguous(), b4.detach().float().contiguous()
+        _capi.check(_capi.lib().ta_conv1_fwd(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(w4), _ptr(b4), B,
+                                             _ptr(y), st), "ta_conv1_fwd")
+        ctx.save_for_backward(x, y)
+        return y.permute(0, 3, 1, 2)  # logical [B,64,33,33] in channels-last memory
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dy = dy.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        dw4 = torch.empty((256, 16), dtype=torch.float32, device=x.device)
+        db4 = torch.empty((256,), dtype=torch.float32, device=x.device)
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _capi.check(_capi.lib().ta_conv1_bwd(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(y), _ptr(dy),
+                                             x.shape[0], _ptr(dw4), _ptr(db4), st), "ta_conv1_bwd")
+        return None, dw4, db4
+
+
+def conv1_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """relu(conv(upsample4(decode(x)))) as bf16 [B,64,33,33] (channels-last)."""
+    w4, b4 = fold(conv.weight, conv.bias)
+    return _Conv1.apply(x, w4, b4)

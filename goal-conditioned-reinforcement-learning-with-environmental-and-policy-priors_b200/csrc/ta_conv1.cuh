@@ -1,0 +1,166 @@
+// ta_conv1.cuh -- TINet's first layer, fused: LUT decode + UpsamplingNearest2d(4) + Conv2d(4, 64, k=4, s=2)
+// + bias + ReLU (soa/agent/net/all_net.py:142-143, 157, 180-181; soa/env_buffer.py:300-318 for the LUT).
+//
+// The layer is folded exactly: on a x4 nearest-upsampled 17x17 frame a
+// 4x4 stride-2 kernel at output (2m+py, 2n+px) only ever sees the four input pixels (m+dy, n+dx),
+// dy, dx in {0,1} -- through sums of kernel taps that depend on the output phase (py, px).  So
+//     y[b, 2m+py, 2n+px, o] = relu( b4[(py,px,o)] + sum_{dy,dx,c} w4[(py,px,o)][(dy,dx,c)] * x[b, c, m+dy, n+dx] )
+// with K = 16.  The host folds the 64x4x4x4 conv weight into w4 [256][16] (an einsum, differentiable),
+// these kernels do the rest: no 68x68 tensor, no separate bias / ReLU / layout passes.  The layer is
+// HBM-bound on its 139 KB (bf16, NHWC) of output per sample; the 1.1 MFLOP per sample run on the FMA pipe.
+//
+// Thread roles: role = (phase, channel group of 4) -- 64 roles, weights of a role live in 64 registers;
+// a 256-thread CTA is 4 pixel lanes x 64 roles and walks the samples of its share of the batch.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ta_common.cuh"
+
+namespace ta {
+
+constexpr int C1_THREADS = 256;
+constexpr int C1_OUT = 33;    // output height = width
+constexpr int C1_CH = 64;
+
+// matrix_env LUT over the featuriser's codes (ppo.MATRIX_LUT): 0 -> 0.9, 1 -> -0.9, 2 -> -0.5, 4 -> 0.3
+__device__ __forceinline__ float c1_decode(uint32_t code) {
+    return code == 0u ? 0.9f : (code == 1u ? -0.9f : (code == 2u ? -0.5f : (code == 4u ? 0.3f : 0.0f)));
+}
+
+// one sample's four frames -> shared memory as [18][18] float4 (c = frame), zero row / column 17
+template <typename XT>
+__device__ __forceinline__ void c1_stage_input(const XT *x, float4 *sx) {
+    for (int i = threadIdx.x; i < 18 * 18; i += C1_THREADS) {
+        const int m = i / 18, n = i - 18 * m;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < 17 && n < 17) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if constexpr (sizeof(XT) == 1) v[c] = c1_decode((uint32_t)x[c * NCELL + m * GS + n]);
+                else v[c] = (float)x[c * NCELL + m * GS + n];
+            }
+        }
+        sx[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__device__ __forceinline__ void c1_patch(const float4 *sx, int m, int n, float (&p)[16]) {
+    const float4 a = sx[m * 18 + n], b = sx[m * 18 + n + 1], c = sx[(m + 1) * 18 + n], d = sx[(m + 1) * 18 + n + 1];
+    p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;      // (dy,dx) = (0,0), c = 0..3
+    p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;      // (0,1)
+    p[8] = c.x; p[9] = c.y; p[10] = c.z; p[11] = c.w;    // (1,0)
+    p[12] = d.x; p[13] = d.y; p[14] = d.z; p[15] = d.w;  // (1,1)
+}
+
+// x: XT [B] samples of 4 frames x 289, `xstride` elements apart; w4 float [256][16], b4 float [256]
+// (row = (py*2+px)*64 + o); y: bf16 [B][33][33][64].
+template <typename XT>
+__global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const XT *__restrict__ x, long long xstride,
+                                                              const float *__restrict__ w4, const float *__restrict__ b4,
+                                                              long long B, __nv_bfloat16 *__restrict__ y) {
+    __shared__ float4 sx[2][18 * 18];
+    const int role = threadIdx.x & 63, plane = threadIdx.x >> 6;
+    const int phase = role >> 4, cg = role & 15, py = phase >> 1, px = phase & 1;
+    float w[4][16], bias[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int row = phase * 64 + cg * 4 + i;
+        bias[i] = __ldg(b4 + row);
+#pragma unroll
+        for (int k = 0; k < 16; k++) w[i][k] = __ldg(w4 + row * 16 + k);
+    }
+    const int M = 17 - py, N = 17 - px, npix = M * N;
+    int buf = 0;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
+        c1_stage_input<XT>(x + b * xstride, sx[buf]);
+        __syncthreads();  // (the other buffer is still being read by slower threads: double buffered)
+        __nv_bfloat16 *yb = y + b * (long long)(C1_OUT * C1_OUT * C1_CH);
+        for (int idx = plane; idx < npix; idx += 4) {
+            const int m = idx / N, n = idx - N * m;
+            float p[16];
+            c1_patch(sx[buf], m, n, p);
+            float acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a = bias[i];
+#pragma unroll
+                for (int k = 0; k < 16; k++) a = fmaf(w[i][k], p[k], a);
+                acc[i] = a > 0.f ? a : 0.f;
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[0], acc[1]), hi = __floats2bfloat162_rn(acc[2], acc[3]);
+            uint2 out;
+            out.x = *reinterpret_cast<const uint32_t *>(&lo);
+            out.y = *reinterpret_cast<const uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(yb + ((2 * m + py) * C1_OUT + (2 * n + px)) * C1_CH + cg * 4) = out;
+        }
+    }
+}
+
+// dw4 [256][16] += sum over the batch of dz (x) patch, db4 [256] += sum dz, dz = dy where y > 0.
+template <typename XT>
+__global__ void __launch_bounds__(C1_THREADS) conv1_bwd_kernel(const XT *__restrict__ x, long long xstride,
+                                                              const __nv_bfloat16 *__restrict__ y,
+                                                              const __nv_bfloat16 *__restrict__ dy, long long B,
+                                                              float *__restrict__ dw4, float *__restrict__ db4) {
+    __shared__ float4 sx[2][18 * 18];
+    __shared__ float sacc[64][17 * 4 + 1];
+    const int role = threadIdx.x & 63, plane = threadIdx.x >> 6;
+    const int phase = role >> 4, cg = role & 15, py = phase >> 1, px = phase & 1;
+    float dw[4][16], db[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) dw[i][k] = 0.f;
+    const int M = 17 - py, N = 17 - px, npix = M * N;
+    int buf = 0;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
+        c1_stage_input<XT>(x + b * xstride, sx[buf]);
+        __syncthreads();
+        const long long base = b * (long long)(C1_OUT * C1_OUT * C1_CH);
+        for (int idx = plane; idx < npix; idx += 4) {
+            const int m = idx / N, n = idx - N * m;
+            const long long off = base + ((2 * m + py) * C1_OUT + (2 * n + px)) * C1_CH + cg * 4;
+            const uint2 yv = __ldg(reinterpret_cast<const uint2 *>(y + off)), gv = __ldg(reinterpret_cast<const uint2 *>(dy + off));
+            const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&yv.x));
+            const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&yv.y));
+            const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gv.x));
+            const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gv.y));
+            const float dz[4] = {y01.x > 0.f ? g01.x : 0.f, y01.y > 0.f ? g01.y : 0.f, y23.x > 0.f ? g23.x : 0.f,
+                                 y23.y > 0.f ? g23.y : 0.f};
+            float p[16];
+            c1_patch(sx[buf], m, n, p);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                db[i] += dz[i];
+#pragma unroll
+                for (int k = 0; k < 16; k++) dw[i][k] = fmaf(dz[i], p[k], dw[i][k]);
+            }
+        }
+    }
+    // the four pixel lanes of a role -> shared memory -> one atomicAdd per value and CTA
+    for (int pl = 0; pl < 4; pl++) {
+        __syncthreads();
+        if (plane == pl) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    float *s = &sacc[role][i * 17 + k];
+                    *s = pl == 0 ? dw[i][k] : *s + dw[i][k];
+                }
+                float *s = &sacc[role][i * 17 + 16];
+                *s = pl == 0 ? db[i] : *s + db[i];
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 64 * 68; j += C1_THREADS) {
+        const int r = j / 68, q = j - 68 * r, i = q / 17, k = q - 17 * i;
+        const int ph = r >> 4, g = r & 15, row = ph * 64 + g * 4 + i;
+        const float v = sacc[r][q];
+        if (k < 16) atomicAdd(dw4 + row * 16 + k, v);
+        else atomicAdd(db4 + row, v);
+    }
+}
+
+}  // namespace ta

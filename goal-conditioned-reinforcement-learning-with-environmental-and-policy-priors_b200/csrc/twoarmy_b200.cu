@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "ta_aux.cuh"
+#include "ta_conv1.cuh"
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
 #include "ta_her.cuh"
@@ -439,6 +440,62 @@ int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, uint64_t 
     return launch_ok("her_plan_kernel");
 }
 
+}  // extern "C"
+
+namespace {
+template <typename K>
+int conv1_grid(K kern, long long batch, int *grid) {
+    int dev = 0, sms = 0, occ = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C1_THREADS, 0));
+    long long g = (long long)sms * (occ > 0 ? occ : 1);
+    *grid = (int)(batch < g ? batch : g);
+    return TA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch, void *y_bf16,
+                 void *stream) {
+    if (!x || !w4 || !b4 || !y_bf16 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
+        return TA_E_INVALID;
+    if ((uintptr_t)y_bf16 & 7u) return TA_E_INVALID;
+    int grid = 1;
+    if (x_dtype == TA_X_U8) {
+        if (int rc = conv1_grid(conv1_fwd_kernel<uint8_t>, batch, &grid)) return rc;
+        conv1_fwd_kernel<uint8_t><<<grid, C1_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)x, x_stride, w4, b4, batch,
+                                                                                (__nv_bfloat16 *)y_bf16);
+    } else {
+        if (int rc = conv1_grid(conv1_fwd_kernel<float>, batch, &grid)) return rc;
+        conv1_fwd_kernel<float><<<grid, C1_THREADS, 0, (cudaStream_t)stream>>>((const float *)x, x_stride, w4, b4, batch,
+                                                                              (__nv_bfloat16 *)y_bf16);
+    }
+    return launch_ok("conv1_fwd_kernel");
+}
+
+int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, int64_t batch,
+                 float *dw4, float *db4, void *stream) {
+    if (!x || !y_bf16 || !dy_bf16 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL ||
+        (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
+        return TA_E_INVALID;
+    if (((uintptr_t)y_bf16 | (uintptr_t)dy_bf16) & 7u) return TA_E_INVALID;
+    CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), (cudaStream_t)stream));
+    CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
+    int grid = 1;
+    if (x_dtype == TA_X_U8) {
+        if (int rc = conv1_grid(conv1_bwd_kernel<uint8_t>, batch, &grid)) return rc;
+        conv1_bwd_kernel<uint8_t><<<grid, C1_THREADS, 0, (cudaStream_t)stream>>>(
+            (const uint8_t *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4);
+    } else {
+        if (int rc = conv1_grid(conv1_bwd_kernel<float>, batch, &grid)) return rc;
+        conv1_bwd_kernel<float><<<grid, C1_THREADS, 0, (cudaStream_t)stream>>>(
+            (const float *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4);
+    }
+    return launch_ok("conv1_bwd_kernel");
+}
+
 int ta_set_timing(ta_handle h, int on) {
     if (!h) return TA_E_INVALID;
     h->timing = on;
@@ -450,6 +507,34 @@ int ta_last_step_ms(ta_handle h, float *ms) {
     CK(cudaEventSynchronize(h->ev1));
     CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return TA_OK;
+}
+
+/* measurement probe (not part of the ABI): what does this GPU sustain for a pure WRITE stream?
+ * mode 0: 16-byte stores, one grid-stride pass; mode 1: 3 KB TMA bulk stores from shared memory
+ * (the pattern of the step kernel's obs pass).  Used by scripts/write_bw.py. */
+__global__ void __launch_bounds__(256) write_probe_stg(uint4 *dst, long long n16) {
+    const uint4 v = make_uint4(0x01020304u, 0x05060708u, 0x090a0b0cu, 0x0d0e0f10u);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = v;
+}
+__global__ void __launch_bounds__(32) write_probe_bulk(uint8_t *dst, long long nchunks) {
+    __shared__ __align__(128) uint8_t buf[3072];
+    for (int i = threadIdx.x; i < 3072 / 4; i += 32) reinterpret_cast<uint32_t *>(buf)[i] = 0x01020304u * (i + 1);
+    fence_proxy_async();
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            bulk_s2g(dst + c * 3072, buf, 3072);
+            bulk_commit();
+            bulk_wait_read<8>();
+        }
+        bulk_wait_read<0>();
+    }
+}
+int ta_debug_write_probe(void *dst, int64_t bytes, int mode, void *stream) {
+    if (!dst || bytes <= 0) return TA_E_INVALID;
+    if (mode == 0) write_probe_stg<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((uint4 *)dst, bytes / 16);
+    else write_probe_bulk<<<148 * 16, 32, 0, (cudaStream_t)stream>>>((uint8_t *)dst, bytes / 3072);
+    return launch_ok("write_probe");
 }
 
 /* test hook: emit the observations with per-lane stores (1) instead of TMA bulk stores

@@ -74,6 +74,8 @@ class TINet(nn.Module):
     # 22.0 ms per optimiser step against 19.9 ms for upsample + cuDNN (B = 4096, two nets); it only
     # pays once the interleave is fused into the GEMM epilogue.
     fold_conv1 = False
+    # the hand-written kernel pair for this layer (csrc/ta_conv1.cuh), used on the GPU under bf16 autocast
+    fused_conv1 = True
 
     def _conv1_folded(self, x):
         """UpsamplingNearest2d(4) + Conv2d(4, 64, k=4, s=2) + ReLU (all_net.py:142-143,157,180-181) folded
@@ -95,22 +97,35 @@ class TINet(nn.Module):
         return torch.relu(y.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last))
 
     def forward(self, state_matrix, position, goal):
+        """state_matrix [B,4,289]: float matrix_env values, or (GPU) the uint8 featuriser codes."""
         B, T, _ = state_matrix.shape
         position = position.contiguous().view(-1, 8)
         position_goal = torch.relu(self.positionnet(torch.cat([position, goal], 1)))
-        x = state_matrix.contiguous().view(-1, T, 17, 17)
-        if x.is_cuda:
-            if self.fold_conv1:
-                x = self._conv1_folded(x)
+        if not state_matrix.is_cuda:  # the reference's layer sequence, verbatim
+            if state_matrix.dtype == torch.uint8:
+                state_matrix = decode_matrix(state_matrix)
+            x = self.upsamplingnearest(state_matrix.contiguous().view(-1, T, 17, 17))
+            x = torch.relu(self.fc0(self.cnn_base(x)))
+        else:
+            if self.fused_conv1 and torch.is_autocast_enabled() and T == 4:
+                # LUT decode + upsample + conv1 + bias + ReLU in one kernel, straight from codes or floats
+                from . import conv1 as _c1
+                ok = state_matrix.stride(2) == 1 and state_matrix.stride(1) == 289
+                x = _c1.conv1_relu(state_matrix if ok else state_matrix.contiguous(), self.cnn_base[0])
             else:
-                x = self.upsamplingnearest(x).contiguous(memory_format=torch.channels_last)
-                x = self.cnn_base[:2](x)
+                if state_matrix.dtype == torch.uint8:
+                    state_matrix = decode_matrix(state_matrix)
+                x = state_matrix.contiguous().view(-1, T, 17, 17)
+                if self.fold_conv1:
+                    x = self._conv1_folded(x)
+                else:
+                    x = self.upsamplingnearest(x).contiguous(memory_format=torch.channels_last)
+                    x = self.cnn_base[:2](x)
+            x = self.cnn_base[2:6](x)
             # The last conv (128 -> 256, 3x3 stride 2 on 7x7) as an explicit im2col + cuBLAS GEMM: for
             # this shape cuDNN picks a kernel that takes 1.8 ms fwd+bwd at B = 4096, the GEMM 0.2 ms
             # (scripts/conv_gemm_probe.py).  Same arithmetic, same parameters.
-            x = self.cnn_base[2:6](x)
             conv4 = self.cnn_base[6]
-            B = x.shape[0]
             xn = x.permute(0, 2, 3, 1)                                        # [B, 7, 7, 128], a view (channels_last)
             # im2col by nine strided slices (torch's unfold loops over the batch): rows (ky, kx, c)
             cols = torch.cat([xn[:, ky:ky + 5:2, kx:kx + 5:2, :] for ky in range(3) for kx in range(3)], dim=3)
@@ -118,8 +133,6 @@ class TINet(nn.Module):
             y = F.linear(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype))   # [B*9, 256]
             x = torch.relu(y).view(B, 9, 256).transpose(1, 2).reshape(B, 2304)     # Flatten of [B, 256, 3, 3]
             x = torch.relu(self.fc0(x))
-        else:
-            x = torch.relu(self.fc0(self.cnn_base(self.upsamplingnearest(x))))
         x = torch.cat([x, position_goal.to(x.dtype)], 1)
         return torch.relu(self.fc1(x))
 
@@ -278,12 +291,12 @@ class PPO:
     def select_action_frames(self, frames, positions, goal):
         """The same on the four current frames directly: frames [N,4,289] (float or uint8 codes),
         positions [N,4,2], goal [N,2]."""
-        if frames.dtype == torch.uint8:
+        if frames.dtype == torch.uint8 and not (frames.is_cuda and self.autocast):
             frames = decode_matrix(frames)
         self.actor.eval()
         self.critic.eval()
         with self._amp():
-            a_prob = self.actor(frames.float(), positions.float(), goal.float())
+            a_prob = self.actor(frames if frames.dtype == torch.uint8 else frames.float(), positions.float(), goal.float())
         dist = Categorical(probs=a_prob)
         a = dist.sample()
         return a, dist.log_prob(a)
@@ -298,7 +311,8 @@ class PPO:
         for i in range(0, B, chunk):
             rows = slice(i, i + chunk) if src is None else src[i:i + chunk]
             sc = s[rows]
-            sc = decode_matrix(sc) if sc.dtype == torch.uint8 else sc
+            if sc.dtype == torch.uint8 and not (sc.is_cuda and self.autocast):
+                sc = decode_matrix(sc)
             pc, gc = p[rows], g[i:i + chunk]
             with self._amp():
                 outs0.append(self.critic(sc[:, 0:4], pc[:, 0:4], gc))
@@ -377,7 +391,9 @@ class PPO:
             for idx in minibatches():
                 rows = idx if src is None else src[idx]
                 sb = s[rows]
-                sb = decode_matrix(sb[:, 0:4]) if sb.dtype == torch.uint8 else sb[:, 0:4]
+                if sb.dtype == torch.uint8 and not (sb.is_cuda and self.autocast):
+                    sb = decode_matrix(sb)
+                sb = sb[:, 0:4]
                 pb, gb = p[rows][:, 0:4], g[idx]
                 with self._amp():
                     probs = self.actor(sb, pb, gb)

@@ -200,6 +200,22 @@ int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stre
 int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, uint64_t seed, uint64_t env_id0,
                 const uint8_t *chosen_in, uint8_t *uniq_out, uint8_t *m_out, uint16_t *plan_out, void *stream);
 
+/* First layer of TINet fused for the device rollout buffer: matrix_env LUT decode + UpsamplingNearest2d(4)
+ * + Conv2d(4, 64, kernel 4, stride 2) + bias + ReLU (soa/agent/net/all_net.py:142-143,157,180-181),
+ * folded exactly into a K = 16 product over 2x2 patches of the 17x17 frames (see csrc/ta_conv1.cuh).
+ *   x        4 frames x 289 per sample, samples x_stride ELEMENTS apart: TA_X_F32 float32 matrix_env
+ *            values, or TA_X_U8 the compact codes (decoded on the fly)
+ *   w4, b4   float32 [256][16] / [256]: the conv weight / bias folded per output phase by the host
+ *            (row (py*2+px)*64 + o, column (dy*2+dx)*4 + c)
+ *   y_bf16   bfloat16 [batch][33][33][64] (channels-last), = relu(conv + bias)
+ * ta_conv1_bwd: gradients of w4 / b4 (overwritten) given y and dL/dy; x needs no gradient. */
+#define TA_X_F32 0
+#define TA_X_U8 1
+int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch,
+                 void *y_bf16, void *stream);
+int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16,
+                 int64_t batch, float *dw4, float *db4, void *stream);
+
 /* introspection */
 int ta_abi_version(void);
 const char *ta_strerror(int code);

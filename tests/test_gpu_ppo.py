@@ -47,3 +47,32 @@ def test_rollout_and_update_run_and_learn_signal_is_finite():
     assert np.isfinite(al) and np.isfinite(vl)
     assert any(not torch.equal(a, b) for a, b in zip(before, agent.actor.parameters()))
     assert buf.ended[:64].sum() > 0 and float(buf.r[:64].mean()) < 0
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_fused_conv1_matches_cudnn_layer(dtype):
+    """ta_conv1_fwd / ta_conv1_bwd == decode + UpsamplingNearest2d(4) + Conv2d(4,64,4,2) + ReLU in
+    fp32 (forward to bf16 rounding, weight / bias gradients to 1e-2 relative of their scale)."""
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    C1 = importlib.import_module(pkg.__name__ + ".conv1")
+    torch.manual_seed(0)
+    net = P.TINet().cuda()
+    conv = net.cnn_base[0]
+    g = torch.Generator().manual_seed(2)
+    B = 37
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)[torch.randint(0, 4, (B, 5, 289), generator=g)].cuda()
+    x_in = codes[:, 1:5] if dtype == "u8" else P.decode_matrix(codes[:, 1:5]).contiguous()
+    xf = P.decode_matrix(codes[:, 1:5]).view(B, 4, 17, 17)
+    want = torch.relu(conv(net.upsamplingnearest(xf)))
+    gy = torch.randn(want.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    (want * gy).sum().backward()
+    gw, gb = conv.weight.grad.clone(), conv.bias.grad.clone()
+    conv.weight.grad = None; conv.bias.grad = None
+    got = C1.conv1_relu(x_in, conv)
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    assert float((got.float() - want).abs().max()) < 2e-2 * float(want.abs().max())
+    # gradients: same upstream gradient, ReLU mask taken from the kernel's own (bf16) output
+    (got.float() * gy).sum().backward()
+    assert float((conv.weight.grad - gw).abs().max()) < 1e-2 * float(gw.abs().max())
+    assert float((conv.bias.grad - gb).abs().max()) < 1e-2 * float(gb.abs().max())
