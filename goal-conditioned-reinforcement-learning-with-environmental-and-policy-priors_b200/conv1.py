@@ -64,3 +64,37 @@ def conv1_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
     """relu(conv(upsample4(decode(x)))) as bf16 [B,64,33,33] (channels-last)."""
     w4, b4 = fold(conv.weight, conv.bias)
     return _Conv1.apply(x, w4, b4)
+
+
+class _ConvS2(torch.autograd.Function):
+    """Conv2d(stride 2, no padding) on channels-last bf16: forward and weight / bias gradients stay with
+    cuDNN; the DATA gradient, for which cuDNN's strided-dgrad kernels take 1-1.7 ms at B = 4096, is a plain
+    cuBLAS GEMM (dY x W) followed by the col2im gather kernel (ta_col2im_s2)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.ops.aten.convolution(x, w, b, [2, 2], [0, 0], [1, 1], False, [0, 0], 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        cout, cin, k, _ = w.shape
+        _, gw, gb = torch.ops.aten.convolution_backward(dy, x, w, [cout], [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
+                                                        [False, True, True])
+        gx = None
+        if ctx.needs_input_grad[0]:
+            B, _, H, W = x.shape
+            dcols = dy.permute(0, 2, 3, 1).reshape(-1, cout) @ w.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+            gx_nhwc = torch.empty((B, H, W, cin), dtype=torch.bfloat16, device=x.device)
+            st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            _capi.check(_capi.lib().ta_col2im_s2(_ptr(dcols), _ptr(gx_nhwc), B, H, W, cin, k, st), "ta_col2im_s2")
+            gx = gx_nhwc.permute(0, 3, 1, 2)
+        return gx, gw, gb
+
+
+def conv_s2(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """conv(x) for a stride-2 unpadded Conv2d, x bf16 channels-last, with the GEMM + col2im data gradient."""
+    return _ConvS2.apply(x, conv.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+                         conv.bias.to(torch.bfloat16))

@@ -163,4 +163,50 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_bwd_kernel(const XT *__restr
     }
 }
 
+// ---- data gradient of a stride-2, unpadded convolution in channels-last bf16: col2im ---------------
+// dcols bf16 [B*OH*OW][KS*KS*C] (one row per output pixel, columns (ky,kx,c)) is the GEMM dY x W; every
+// input element gathers the <= ceil(KS/2)^2 patch entries that cover it (no atomics, each dcols byte is
+// read exactly once, 16-byte loads / stores over 8 channels).  dx bf16 [B][H][W][C].
+template <int KS>
+__global__ void __launch_bounds__(256) col2im_s2_kernel(const __nv_bfloat16 *__restrict__ dcols, __nv_bfloat16 *__restrict__ dx,
+                                                       long long total8, int H, int W, int C, int OH, int OW) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 channels of one input pixel
+    if (i >= total8) return;
+    const int c8n = C >> 3;
+    const int c8 = (int)(i % c8n);
+    long long pix = i / c8n;
+    const int xx = (int)(pix % W);
+    pix /= W;
+    const int yy = (int)(pix % H);
+    const long long b = pix / H;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long rowlen = (long long)KS * KS * C;
+#pragma unroll
+    for (int ky = 0; ky < KS; ky++) {
+        const int ty = yy - ky;
+        if (ty < 0 || (ty & 1) || (ty >> 1) >= OH) continue;
+#pragma unroll
+        for (int kx = 0; kx < KS; kx++) {
+            const int tx = xx - kx;
+            if (tx < 0 || (tx & 1) || (tx >> 1) >= OW) continue;
+            const long long row = (b * OH + (ty >> 1)) * OW + (tx >> 1);
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(dcols + row * rowlen + (ky * KS + kx) * C + c8 * 8));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[q]));
+                acc[2 * q] += f.x;
+                acc[2 * q + 1] += f.y;
+            }
+        }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+        o[q] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(dx + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace ta

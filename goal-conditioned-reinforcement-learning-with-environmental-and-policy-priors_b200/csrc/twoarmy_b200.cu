@@ -496,6 +496,22 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
     return launch_ok("conv1_bwd_kernel");
 }
 
+int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream) {
+    if (!dcols_bf16 || !dx_bf16 || batch <= 0 || H < ksize || W < ksize || C <= 0 || (C & 7) || (ksize != 3 && ksize != 4))
+        return TA_E_INVALID;
+    if (((uintptr_t)dcols_bf16 | (uintptr_t)dx_bf16) & 15u) return TA_E_INVALID;
+    const int OH = (H - ksize) / 2 + 1, OW = (W - ksize) / 2 + 1;
+    const long long total8 = batch * H * W * (C / 8);
+    const unsigned nb = blocks_for(total8, 256);
+    if (ksize == 3)
+        col2im_s2_kernel<3><<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dcols_bf16, (__nv_bfloat16 *)dx_bf16, total8,
+                                                                H, W, C, OH, OW);
+    else
+        col2im_s2_kernel<4><<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dcols_bf16, (__nv_bfloat16 *)dx_bf16, total8,
+                                                                H, W, C, OH, OW);
+    return launch_ok("col2im_s2_kernel");
+}
+
 int ta_set_timing(ta_handle h, int on) {
     if (!h) return TA_E_INVALID;
     h->timing = on;

@@ -76,6 +76,8 @@ class TINet(nn.Module):
     fold_conv1 = False
     # the hand-written kernel pair for this layer (csrc/ta_conv1.cuh), used on the GPU under bf16 autocast
     fused_conv1 = True
+    # data gradients of conv2 / conv3 as GEMM + col2im (csrc/ta_conv1.cuh) instead of cuDNN's strided dgrad
+    gemm_dgrad = True
 
     def _conv1_folded(self, x):
         """UpsamplingNearest2d(4) + Conv2d(4, 64, k=4, s=2) + ReLU (all_net.py:142-143,157,180-181) folded
@@ -95,6 +97,16 @@ class TINet(nn.Module):
         y = F.linear(cols.reshape(B * 289, 16), w.to(cols.dtype), conv1.bias.repeat(4).to(cols.dtype))   # [B*289, 256]
         y = y.view(B, 17, 17, 2, 2, 64).permute(0, 1, 3, 2, 4, 5).reshape(B, 34, 34, 64)[:, :33, :33, :]
         return torch.relu(y.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last))
+
+    _c4_idx = {}
+
+    @classmethod
+    def _conv4_index(cls, device):
+        key = str(device)
+        if key not in cls._c4_idx:
+            idx = [(2 * oy + ky) * 7 + (2 * ox + kx) for oy in range(3) for ox in range(3) for ky in range(3) for kx in range(3)]
+            cls._c4_idx[key] = torch.tensor(idx, dtype=torch.int64, device=device)
+        return cls._c4_idx[key]
 
     def forward(self, state_matrix, position, goal):
         """state_matrix [B,4,289]: float matrix_env values, or (GPU) the uint8 featuriser codes."""
@@ -121,14 +133,20 @@ class TINet(nn.Module):
                 else:
                     x = self.upsamplingnearest(x).contiguous(memory_format=torch.channels_last)
                     x = self.cnn_base[:2](x)
-            x = self.cnn_base[2:6](x)
+            if self.gemm_dgrad and x.dtype == torch.bfloat16 and torch.is_grad_enabled():
+                from . import conv1 as _c1
+                x = torch.relu(_c1.conv_s2(x, self.cnn_base[2]))
+                x = torch.relu(_c1.conv_s2(x, self.cnn_base[4]))
+            else:
+                x = self.cnn_base[2:6](x)
             # The last conv (128 -> 256, 3x3 stride 2 on 7x7) as an explicit im2col + cuBLAS GEMM: for
             # this shape cuDNN picks a kernel that takes 1.8 ms fwd+bwd at B = 4096, the GEMM 0.2 ms
             # (scripts/conv_gemm_probe.py).  Same arithmetic, same parameters.
             conv4 = self.cnn_base[6]
-            xn = x.permute(0, 2, 3, 1)                                        # [B, 7, 7, 128], a view (channels_last)
-            # im2col by nine strided slices (torch's unfold loops over the batch): rows (ky, kx, c)
-            cols = torch.cat([xn[:, ky:ky + 5:2, kx:kx + 5:2, :] for ky in range(3) for kx in range(3)], dim=3)
+            xn = x.permute(0, 2, 3, 1).reshape(B, 49, 128)                    # NHWC pixels (channels_last memory)
+            # im2col as ONE gather (torch's unfold loops over the batch; slices cost 27 kernels in backward):
+            # row (o, k) of the index = input pixel (2*oy+ky, 2*ox+kx); columns end up ordered (ky, kx, c)
+            cols = xn.index_select(1, self._conv4_index(x.device))
             w = conv4.weight.permute(0, 2, 3, 1).reshape(256, -1).to(cols.dtype)
             y = F.linear(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype))   # [B*9, 256]
             x = torch.relu(y).view(B, 9, 256).transpose(1, 2).reshape(B, 2304)     # Flatten of [B, 256, 3, 3]

@@ -216,6 +216,11 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16,
                  int64_t batch, float *dw4, float *db4, void *stream);
 
+/* Data gradient helper for TINet's stride-2 unpadded convolutions (all_net.py:144-149) in channels-last
+ * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].
+ * k in {3, 4}, C a multiple of 8, OH = (H-k)/2+1. */
+int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
+
 /* introspection */
 int ta_abi_version(void);
 const char *ta_strerror(int code);

@@ -76,3 +76,30 @@ def test_fused_conv1_matches_cudnn_layer(dtype):
     (got.float() * gy).sum().backward()
     assert float((conv.weight.grad - gw).abs().max()) < 1e-2 * float(gw.abs().max())
     assert float((conv.bias.grad - gb).abs().max()) < 1e-2 * float(gb.abs().max())
+
+
+@pytest.mark.parametrize("layer", [2, 4])
+def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
+    """conv_s2 (cuDNN forward / wgrad, GEMM + ta_col2im_s2 data gradient) == nn.Conv2d autograd in bf16."""
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    C1 = importlib.import_module(pkg.__name__ + ".conv1")
+    torch.manual_seed(0)
+    conv = P.TINet().cuda().cnn_base[layer]
+    cin, hin = (64, 33) if layer == 2 else (64, 16)
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(19, cin, hin, hin, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    outs = []
+    for mode in ("ref", "gemm"):
+        x = x0.clone().requires_grad_(True)
+        conv.weight.grad = None; conv.bias.grad = None
+        if mode == "ref":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = conv(x)
+        else:
+            y = C1.conv_s2(x, conv)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6)).cuda().to(y.dtype)
+        (y.float() * gy.float()).sum().backward()
+        outs.append((y.float(), x.grad.float(), conv.weight.grad.clone(), conv.bias.grad.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert float((a - b).abs().max()) <= 2e-2 * float(a.abs().max()) + 1e-6
