@@ -98,3 +98,27 @@ def conv_s2(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
     """conv(x) for a stride-2 unpadded Conv2d, x bf16 channels-last, with the GEMM + col2im data gradient."""
     return _ConvS2.apply(x, conv.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
                          conv.bias.to(torch.bfloat16))
+
+
+class _Im2colS2(torch.autograd.Function):
+    """Patches of a channels-last bf16 map for a stride-2 unpadded k x k conv: forward one gather
+    (index_select over pixels), backward the col2im kernel (instead of index_add_ with atomics)."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, index, k):
+        B, H, W, Cc = x_nhwc.shape
+        ctx.shape, ctx.k = (B, H, W, Cc), k
+        return x_nhwc.reshape(B, H * W, Cc).index_select(1, index)        # [B, OH*OW*k*k, C]
+
+    @staticmethod
+    def backward(ctx, dcols):
+        B, H, W, Cc = ctx.shape
+        dcols = dcols.to(torch.bfloat16).contiguous()
+        gx = torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=dcols.device)
+        st = C.c_void_p(torch.cuda.current_stream(dcols.device).cuda_stream)
+        _capi.check(_capi.lib().ta_col2im_s2(_ptr(dcols), _ptr(gx), B, H, W, Cc, ctx.k, st), "ta_col2im_s2")
+        return gx, None, None
+
+
+def im2col_s2(x_nhwc: torch.Tensor, index: torch.Tensor, k: int) -> torch.Tensor:
+    return _Im2colS2.apply(x_nhwc, index, k)

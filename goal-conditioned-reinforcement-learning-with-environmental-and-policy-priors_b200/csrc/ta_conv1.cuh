@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const XT *__restr
 
 // dw4 [256][16] += sum over the batch of dz (x) patch, db4 [256] += sum dz, dz = dy where y > 0.
 template <typename XT>
-__global__ void __launch_bounds__(C1_THREADS) conv1_bwd_kernel(const XT *__restrict__ x, long long xstride,
+__global__ void __launch_bounds__(C1_THREADS, 2) conv1_bwd_kernel(const XT *__restrict__ x, long long xstride,
                                                               const __nv_bfloat16 *__restrict__ y,
                                                               const __nv_bfloat16 *__restrict__ dy, long long B,
                                                               float *__restrict__ dw4, float *__restrict__ db4) {
@@ -117,23 +117,36 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_bwd_kernel(const XT *__restr
         c1_stage_input<XT>(x + b * xstride, sx[buf]);
         __syncthreads();
         const long long base = b * (long long)(C1_OUT * C1_OUT * C1_CH);
-        for (int idx = plane; idx < npix; idx += 4) {
-            const int m = idx / N, n = idx - N * m;
-            const long long off = base + ((2 * m + py) * C1_OUT + (2 * n + px)) * C1_CH + cg * 4;
-            const uint2 yv = __ldg(reinterpret_cast<const uint2 *>(y + off)), gv = __ldg(reinterpret_cast<const uint2 *>(dy + off));
-            const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&yv.x));
-            const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&yv.y));
-            const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gv.x));
-            const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gv.y));
-            const float dz[4] = {y01.x > 0.f ? g01.x : 0.f, y01.y > 0.f ? g01.y : 0.f, y23.x > 0.f ? g23.x : 0.f,
-                                 y23.y > 0.f ? g23.y : 0.f};
-            float p[16];
-            c1_patch(sx[buf], m, n, p);
+        // four pixels per trip, their eight 8-byte loads in flight together (the loop is latency-bound otherwise)
+        for (int idx0 = plane; idx0 < npix; idx0 += 16) {
+            uint2 yv[4], gv[4];
+            int mm[4], nn[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                db[i] += dz[i];
+            for (int u = 0; u < 4; u++) {
+                const int idx = idx0 + 4 * u;
+                const bool ok = idx < npix;
+                mm[u] = ok ? idx / N : 0;
+                nn[u] = ok ? idx - N * mm[u] : 0;
+                const long long off = base + ((2 * mm[u] + py) * C1_OUT + (2 * nn[u] + px)) * C1_CH + cg * 4;
+                yv[u] = ok ? __ldg(reinterpret_cast<const uint2 *>(y + off)) : make_uint2(0u, 0u);
+                gv[u] = ok ? __ldg(reinterpret_cast<const uint2 *>(dy + off)) : make_uint2(0u, 0u);
+            }
 #pragma unroll
-                for (int k = 0; k < 16; k++) dw[i][k] = fmaf(dz[i], p[k], dw[i][k]);
+            for (int u = 0; u < 4; u++) {
+                const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&yv[u].x));
+                const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&yv[u].y));
+                const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gv[u].x));
+                const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gv[u].y));
+                const float dz[4] = {y01.x > 0.f ? g01.x : 0.f, y01.y > 0.f ? g01.y : 0.f, y23.x > 0.f ? g23.x : 0.f,
+                                     y23.y > 0.f ? g23.y : 0.f};  // (a pixel past the end contributes zeros)
+                float p[16];
+                c1_patch(sx[buf], mm[u], nn[u], p);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    db[i] += dz[i];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) dw[i][k] = fmaf(dz[i], p[k], dw[i][k]);
+                }
             }
         }
     }
@@ -169,18 +182,16 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_bwd_kernel(const XT *__restr
 // read exactly once, 16-byte loads / stores over 8 channels).  dx bf16 [B][H][W][C].
 template <int KS>
 __global__ void __launch_bounds__(256) col2im_s2_kernel(const __nv_bfloat16 *__restrict__ dcols, __nv_bfloat16 *__restrict__ dx,
-                                                       long long total8, int H, int W, int C, int OH, int OW) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 channels of one input pixel
-    if (i >= total8) return;
+                                                       int H, int W, int C, int OH, int OW) {
+    // one CTA per input row (b, y); a thread = 8 channels of one pixel of that row
     const int c8n = C >> 3;
-    const int c8 = (int)(i % c8n);
-    long long pix = i / c8n;
-    const int xx = (int)(pix % W);
-    pix /= W;
-    const int yy = (int)(pix % H);
-    const long long b = pix / H;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long b = blockIdx.x / H;
+    const int yy = blockIdx.x - (int)b * H;
     const long long rowlen = (long long)KS * KS * C;
+    for (int t = threadIdx.x; t < W * c8n; t += blockDim.x) {
+    const int xx = t / c8n, c8 = t - xx * c8n;
+    const long long i = ((long long)blockIdx.x * W + xx) * c8n + c8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < KS; ky++) {
         const int ty = yy - ky;
@@ -207,6 +218,7 @@ __global__ void __launch_bounds__(256) col2im_s2_kernel(const __nv_bfloat16 *__r
         o[q] = *reinterpret_cast<const uint32_t *>(&h);
     }
     *reinterpret_cast<uint4 *>(dx + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 }  // namespace ta

@@ -501,14 +501,14 @@ int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, in
         return TA_E_INVALID;
     if (((uintptr_t)dcols_bf16 | (uintptr_t)dx_bf16) & 15u) return TA_E_INVALID;
     const int OH = (H - ksize) / 2 + 1, OW = (W - ksize) / 2 + 1;
-    const long long total8 = batch * H * W * (C / 8);
-    const unsigned nb = blocks_for(total8, 256);
+    if (batch * H > 0x7FFFFFFFll) return TA_E_INVALID;
+    const unsigned nb = (unsigned)(batch * H);
     if (ksize == 3)
-        col2im_s2_kernel<3><<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dcols_bf16, (__nv_bfloat16 *)dx_bf16, total8,
-                                                                H, W, C, OH, OW);
+        col2im_s2_kernel<3><<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dcols_bf16, (__nv_bfloat16 *)dx_bf16, H, W, C,
+                                                                OH, OW);
     else
-        col2im_s2_kernel<4><<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dcols_bf16, (__nv_bfloat16 *)dx_bf16, total8,
-                                                                H, W, C, OH, OW);
+        col2im_s2_kernel<4><<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dcols_bf16, (__nv_bfloat16 *)dx_bf16, H, W, C,
+                                                                OH, OW);
     return launch_ok("col2im_s2_kernel");
 }
 

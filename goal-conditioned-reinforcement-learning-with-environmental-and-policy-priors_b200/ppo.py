@@ -143,10 +143,14 @@ class TINet(nn.Module):
             # this shape cuDNN picks a kernel that takes 1.8 ms fwd+bwd at B = 4096, the GEMM 0.2 ms
             # (scripts/conv_gemm_probe.py).  Same arithmetic, same parameters.
             conv4 = self.cnn_base[6]
-            xn = x.permute(0, 2, 3, 1).reshape(B, 49, 128)                    # NHWC pixels (channels_last memory)
-            # im2col as ONE gather (torch's unfold loops over the batch; slices cost 27 kernels in backward):
-            # row (o, k) of the index = input pixel (2*oy+ky, 2*ox+kx); columns end up ordered (ky, kx, c)
-            cols = xn.index_select(1, self._conv4_index(x.device))
+            # im2col as ONE gather (torch's unfold loops over the batch): row (o, k) of the index = input pixel
+            # (2*oy+ky, 2*ox+kx), so the columns end up ordered (ky, kx, c); its backward is the col2im kernel
+            xn = x.permute(0, 2, 3, 1)                                        # [B,7,7,128], a view (channels_last)
+            if x.dtype == torch.bfloat16:
+                from . import conv1 as _c1
+                cols = _c1.im2col_s2(xn, self._conv4_index(x.device), 3)
+            else:
+                cols = xn.reshape(B, 49, 128).index_select(1, self._conv4_index(x.device))
             w = conv4.weight.permute(0, 2, 3, 1).reshape(256, -1).to(cols.dtype)
             y = F.linear(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype))   # [B*9, 256]
             x = torch.relu(y).view(B, 9, 256).transpose(1, 2).reshape(B, 2304)     # Flatten of [B, 256, 3, 3]
