@@ -11,8 +11,11 @@
 // Mapping: ONE WARP owns a tile of 32 envs and is its own CTA, so tiles never wait for each
 // other (no __syncthreads anywhere); up to 16-19 such CTAs are resident per SM, which puts all
 // 2048 tiles of a 65536-env batch on chip in one wave.  Per tile:
-//   load    32 TMA bulk copies (80 B packed grid each) into guard-padded shared-memory slots;
-//           the scalar state (2 x 16 B per env) goes straight into the lanes' registers
+//   load    the tile's 2560 B of packed grids as five perfectly coalesced 16-byte loads per lane, scattered
+//           into guard-padded shared-memory slots; the scalar state (2 x 16 B per env) goes straight
+//           into the lanes' registers.  (Per-lane TMA bulk copies were tried first: a bulk copy with
+//           lane-dependent addresses is issued by a 32-trip serial loop, ~290 instructions each way,
+//           and the mbarrier wait spins; plain vector loads cost 15 instructions and stall silently.)
 //   phase A lane e = env e: balls, patrols, agent move            (twoarmy_v4.py:82-179)
 //   obs     the tile's 32 observations are one contiguous byte block in HBM.  It is produced as
 //           "runs" of 16 view cells = one 32-bit word of 2-bit codes = 48 output bytes; lane l
@@ -20,7 +23,7 @@
 //           a shared-memory ring slot, and every 32 runs (1536 B) leave with one TMA bulk store
 //   phase C lane e = env e: wall blocks, patrol spawn, reward, episode end, autoreset
 //                                                                  (twoarmy_v4.py:180-322)
-//   store   scalars from registers, the packed grids with 32 TMA bulk stores
+//   store   scalars from registers, the packed grids with five coalesced 16-byte stores per lane
 // With T > 1 (ta_rollout) A/obs/C repeat T times on the resident tile.  The obs is built
 // between A and C because the reference builds it inside MiniGridEnv.step, i.e. before the wall
 // blocks / patrol balls of the same step appear (ordering fact a).
@@ -58,7 +61,6 @@ struct ObsCfg {
     static constexpr int EV_STRIDE = (V == 17) ? 0 : ((P + 1) | 1);      // odd: conflict-free pass 1
     static constexpr int EV_ROWS = 34;                                   // env 32, 33: readable padding
     // shared memory map (bytes)
-    static constexpr int SM_BAR = 0;
     static constexpr int SM_META = 16;                                   // 32 x uint4 (V = 17)
     static constexpr int SM_HEAD = SM_META + 512;                        // 33 words (V = 17)
     static constexpr int SM_GRID = SM_HEAD + 144;
@@ -281,8 +283,7 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
     using C = ObsCfg<V>;
     extern __shared__ __align__(128) uint8_t smem_all[];
     const int warps_per_cta = (int)(blockDim.x >> 5), warp = (int)(threadIdx.x >> 5);
-    uint8_t *smem = smem_all + warp * C::SMEM;  // every warp has its own slice (and its own mbarrier)
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::SM_BAR);
+    uint8_t *smem = smem_all + warp * C::SMEM;  // every warp has its own slice
     uint4 *meta = reinterpret_cast<uint4 *>(smem + C::SM_META);
     uint32_t *head = reinterpret_cast<uint32_t *>(smem + C::SM_HEAD);
     uint32_t *gs = reinterpret_cast<uint32_t *>(smem + C::SM_GRID);
@@ -296,11 +297,7 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
     // predecessor finished -- nothing the predecessor may write (actions, draws, this handle's
     // state) is read, and nothing is written to global memory, before griddep_wait() below.
     griddep_launch_dependents();
-    // one-time CTA setup: barrier, the reset template word of this lane (guards: see below)
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
+    // one-time setup: the reset template word of this lane (guards: see below)
     const uint32_t tmpl_word = lane < REC_WORDS ? __ldg(a.tmpl + lane) : 0u;
     __syncwarp();
     bool first_tile = true;
@@ -310,7 +307,6 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
     // / uniform registers, which it re-materialises in front of every permute
     const uint32_t type_lut = __ldg(a.tmpl + REC_WORDS + 2 * (lane & 1));
     const uint32_t color_lut = __ldg(a.tmpl + REC_WORDS + 1 + 2 * (lane & 1));
-    uint32_t phase = 0;
     uint32_t gi = 0;  // obs chunks emitted so far (ring slot = gi % RING)
     const bool v4 = a.version == 4;
 
@@ -321,9 +317,11 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
         const bool live = env < a.n;
         long long nvalid = a.n - tile * TILE;
         nvalid = nvalid > TILE ? TILE : nvalid;
-        if (lane == 0) mbar_expect_tx(bar, TILE * REC_BYTES);
-        __syncwarp();
-        bulk_g2s(G, a.grid + env * REC_WORDS, REC_BYTES, bar);
+        // the tile's 32 records are 160 contiguous 16-byte pieces: piece q = lane + 32k belongs to env q / 5
+        const uint4 *gsrc = reinterpret_cast<const uint4 *>(a.grid + tile * (TILE * REC_WORDS));
+        uint4 piece[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) piece[k] = gsrc[lane + 32 * k];
         const uint4 s0 = a.sc0[env], s1 = a.sc1[env];
         if (first_tile) {  // guard words (never written again), while the loads are in flight
             first_tile = false;
@@ -385,9 +383,13 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
                 err |= ERR_OOB_MOVE;
                 skip = true;
             }
-            if (t == 0) {  // the packed grids have landed
-                mbar_wait(bar, phase);
-                phase ^= 1u;
+            if (t == 0) {  // the packed grids have landed: scatter the pieces into the padded slots
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const int q = lane + 32 * k, e = (q * 205) >> 10, part = q - 5 * e;  // q / 5 exact for q < 1024
+                    *reinterpret_cast<uint4 *>(gs + GUARD0_WORDS + e * SLOT_WORDS + 4 * part) = piece[k];
+                }
+                __syncwarp();
             }
             if (a.flags & (8 | 16)) skip = true;
             if (!skip) {
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
 
         // ---- tile epilogue: registers -> state arrays, packed grids -> HBM -------------------------
         if (a.flags & 16) {  // observe only: the state is unchanged
-            bulk_wait_read<0>();
+            if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
             continue;
         }
@@ -622,11 +624,14 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
         o1w.w = o2[3] | (err << 16);
         a.sc0[env] = o0;
         a.sc1[env] = o1w;
-        fence_proxy_async();
         __syncwarp();
-        bulk_s2g(a.grid + env * REC_WORDS, G, REC_BYTES);
-        bulk_commit();
-        bulk_wait_read<0>();  // smem may be reloaded (next tile) or released (exit)
+        uint4 *gdst = reinterpret_cast<uint4 *>(a.grid + tile * (TILE * REC_WORDS));
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int q = lane + 32 * k, e = (q * 205) >> 10, part = q - 5 * e;
+            gdst[q] = *reinterpret_cast<const uint4 *>(gs + GUARD0_WORDS + e * SLOT_WORDS + 4 * part);
+        }
+        if (lane == 0) bulk_wait_read<0>();  // the obs ring may be rewritten (next tile) or released (exit)
         __syncwarp();
     }
 }
