@@ -194,7 +194,12 @@ def bench_ppo(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     n_local = n_global // world
     torch.manual_seed(9981)
-    agent = P.PPO(device=dev)
+    if args.ppo_predictor:
+        agent = importlib.import_module(pkg.__name__ + ".predictor").ppo_predictor(device=dev)
+        config["workload"] = config["workload"].replace("PPO rollout+update loop", "PPO + frame-predictor rollout+update loop").replace("configs[3]", "configs[4]")
+        config["nets"] = "Net_PPO_Predictor_actor/critic (8-channel TINet) + frozen Net_Encoder / LSTM(1024x3) / Net_Decoder, bf16 autocast"
+    else:
+        agent = P.PPO(device=dev)
     agent.broadcast_parameters()
     torch.manual_seed(9981 + 1000 * (rank + 1))
     env = pkg.TwoarmyVecEnv(args.version, n_local, 17, device=dev, seed=9981, env_id0=rank * n_local, autoreset=False)
@@ -281,6 +286,8 @@ def main():
     ap.add_argument("--ppo-steps", type=int, default=2)
     ap.add_argument("--ppo-warmup", type=int, default=1)
     ap.add_argument("--ppo-ref-frames", type=int, default=2048)
+    ap.add_argument("--ppo-predictor", action="store_true",
+                    help="BASELINE configs[4]: actor / critic also see 4 frames predicted by the frozen Encoder-LSTM-Decoder")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -249,10 +249,12 @@ class PPO:
     `update` accepts a dict of device tensors, an optional `minibatch` override, bf16 autocast
     and a distributed gradient all-reduce."""
 
-    def __init__(self, device="cpu", autocast: Optional[bool] = None, flat_grads: bool = True):
+    def __init__(self, device="cpu", autocast: Optional[bool] = None, flat_grads: bool = True, _nets=None):
         self.device = torch.device(device)
-        self.actor = Net_PPO_actor().to(self.device)    # PPO.py:46-47
-        self.critic = Net_PPO_critic().to(self.device)
+        if _nets is None:
+            _nets = (Net_PPO_actor(), Net_PPO_critic())   # PPO.py:46-47
+        self.actor = _nets[0].to(self.device)
+        self.critic = _nets[1].to(self.device)
         self.gamma = 0.99
         self.lr = 0.0001
         self.weight_decay = 0.0001
@@ -299,6 +301,10 @@ class PPO:
         return flat
 
     # ------------------------------------------------------------------ acting
+    def _net_in(self, frames):
+        """What the actor / critic receive for 4 frames [B,4,289] (subclasses add predicted frames)."""
+        return frames
+
     def _amp(self):
         return torch.autocast(device_type=self.device.type, dtype=torch.bfloat16, enabled=self.autocast)
 
@@ -317,8 +323,9 @@ class PPO:
             frames = decode_matrix(frames)
         self.actor.eval()
         self.critic.eval()
+        x = self._net_in(frames if frames.dtype == torch.uint8 else frames.float())
         with self._amp():
-            a_prob = self.actor(frames if frames.dtype == torch.uint8 else frames.float(), positions.float(), goal.float())
+            a_prob = self.actor(x, positions.float(), goal.float())
         dist = Categorical(probs=a_prob)
         a = dist.sample()
         return a, dist.log_prob(a)
@@ -336,9 +343,10 @@ class PPO:
             if sc.dtype == torch.uint8 and not (sc.is_cuda and self.autocast):
                 sc = decode_matrix(sc)
             pc, gc = p[rows], g[i:i + chunk]
+            x0, x1 = self._net_in(sc[:, 0:4]), self._net_in(sc[:, 1:5])
             with self._amp():
-                outs0.append(self.critic(sc[:, 0:4], pc[:, 0:4], gc))
-                outs1.append(self.critic(sc[:, 1:5], pc[:, 1:5], gc))
+                outs0.append(self.critic(x0, pc[:, 0:4], gc))
+                outs1.append(self.critic(x1, pc[:, 1:5], gc))
         return torch.cat(outs0), torch.cat(outs1)
 
     def advantages(self, r, v, v_next):
@@ -415,7 +423,7 @@ class PPO:
                 sb = s[rows]
                 if sb.dtype == torch.uint8 and not (sb.is_cuda and self.autocast):
                     sb = decode_matrix(sb)
-                sb = sb[:, 0:4]
+                sb = self._net_in(sb[:, 0:4])
                 pb, gb = p[rows][:, 0:4], g[idx]
                 with self._amp():
                     probs = self.actor(sb, pb, gb)

@@ -36,6 +36,8 @@ def main(argv=None):
     ap.add_argument("--view", type=int, default=17)
     ap.add_argument("--fp32", action="store_true", help="no bf16 autocast")
     ap.add_argument("--her", action="store_true", help="append hindsight relabels (Buffer_gridworld.her_func) to every update")
+    ap.add_argument("--predictor", default=None, nargs="?", const="",
+                    help="soa/train_ppo_predictor.py: PPO + frozen frame predictor; optional checkpoint with model_encoder / model_decoder / model_predictor")
     ap.add_argument("--save", default="")
     args = ap.parse_args(argv)
 
@@ -52,7 +54,12 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=dev)
     n_local = args.num_envs // world
     torch.manual_seed(args.seed)            # same initial weights on every rank (train_ppo.py:49-56)
-    agent = P.PPO(device=dev, autocast=not args.fp32)
+    if args.predictor is not None:
+        agent = importlib.import_module(pkg.__name__ + ".predictor").ppo_predictor(device=dev, autocast=not args.fp32)
+        if args.predictor:
+            agent.load_predictor(torch.load(args.predictor, map_location=dev))
+    else:
+        agent = P.PPO(device=dev, autocast=not args.fp32)
     agent.gamma, agent.lr = args.gamma, args.lr
     agent.broadcast_parameters()
     torch.manual_seed(args.seed + 1000 * (rank + 1))   # action sampling differs per shard

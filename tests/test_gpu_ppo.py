@@ -103,3 +103,28 @@ def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
         outs.append((y.float(), x.grad.float(), conv.weight.grad.clone(), conv.bias.grad.clone()))
     for a, b in zip(outs[0], outs[1]):
         assert float((a - b).abs().max()) <= 2e-2 * float(a.abs().max()) + 1e-6
+
+
+def test_predictor_agent_rollout_and_update_on_gpu():
+    """BASELINE configs[4] plumbing: ppo_predictor drives VecRollout and updates on the device."""
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    M = importlib.import_module(pkg.__name__ + ".predictor")
+    torch.manual_seed(0)
+    agent = M.ppo_predictor(device="cuda:0")
+    env = pkg.TwoarmyVecEnv(4, 128, 17, seed=2, autoreset=False)
+    roll = P.VecRollout(env, agent, 16)
+    buf = roll.collect()
+    before = [p.detach().clone() for p in agent.critic.parameters()]
+    al, vl = agent.update(buf.flat(), minibatch=1024, epochs=1)
+    assert np.isfinite(al) and np.isfinite(vl)
+    assert any(not torch.equal(a, b) for a, b in zip(before, agent.critic.parameters()))
+    # GPU (bf16) prediction stays close to the fp32 CPU one for the same weights
+    x = P.decode_matrix(buf.s[3, :8, 0:4]).float()
+    got = agent.pred_states(x)[0].cpu()
+    cpu = M.ppo_predictor(device="cpu", autocast=False)
+    cpu.load_predictor(agent.state_dict())
+    want = cpu.pred_states(x.cpu())[0]
+    assert float((got - want).abs().max()) < 0.05 * max(1.0, float(want.abs().max()))
+    idx, e = M.pre_transition_records(buf.ended[:16])
+    assert idx.shape[1] == 9 and idx.shape[0] == e.shape[0]
