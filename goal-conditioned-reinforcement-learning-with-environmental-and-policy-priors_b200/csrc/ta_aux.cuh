@@ -145,6 +145,30 @@ __global__ void import_kernel(uint32_t *grid, uint4 *sc0, uint4 *sc1, const EnvS
     }
 }
 
+// get_full_render (minigrid.py:1514-1563 -> Grid.render :712-747): every cell is one of 16 cached tile
+// images (cell code | agent here << 2 | highlighted << 3) of ts x ts x 3 bytes; the frame is a blit.
+// One thread per output byte (a frame row is 51*ts bytes, rarely a multiple of 4).  env_ids selects the
+// envs to draw (NULL = the first m).  Highlighted = inside the agent's view window, if `highlight`.
+__global__ void __launch_bounds__(256) render_kernel(const uint32_t *grid, const uint4 *sc0, const uint8_t *atlas,
+                                                    const long long *env_ids, long long m, int ts, int highlight, int V,
+                                                    uint8_t *out) {
+    const int side = GS * ts;
+    const long long per_env = (long long)side * side * 3, total = m * per_env;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long k = i / per_env;
+        const int r = (int)(i - k * per_env);
+        const int Y = r / (side * 3), q = r - Y * side * 3, X = q / 3, c = q - 3 * X;
+        const int y = Y / ts, x = X / ts, ry = Y - y * ts, rx = X - x * ts;
+        const long long e = env_ids ? env_ids[k] : k;
+        const uint32_t a = sc0[e].x;
+        const int ax = (int)(a & 0xFFu), ay = (int)((a >> 8) & 0xFFu);
+        uint32_t idx = cell_get(grid + e * REC_WORDS, x, y);
+        if (x == ax && y == ay) idx |= 4u;
+        if (highlight && x >= ax - V / 2 && x <= ax + V / 2 && y >= ay - (V - 1) && y <= ay) idx |= 8u;
+        out[i] = atlas[((idx * ts + ry) * ts + rx) * 3 + c];
+    }
+}
+
 // matrix_env (env_buffer.py:300-318): None 0.9, wall -0.9, ball -0.5, goal 0.9, then the
 // agent's cell 0.3; index y*17 + x.  The float64 LUT is cast to float32 exactly as
 // train_ppo.py:122 does on store.  Compact code: 0 -> 0.9, 1 -> -0.9, 2 -> -0.5, 4 -> 0.3.

@@ -368,6 +368,19 @@ int ta_stack_push(ta_handle h, const void *s_prev, void *s_out, const float *p_p
     return launch_ok("stack_push_kernel");
 }
 
+int ta_render(ta_handle h, const uint8_t *atlas, int tile_size, int highlight, const int64_t *env_ids, int64_t m,
+              uint8_t *rgb_out, void *stream) {
+    if (!h || !atlas || !rgb_out || tile_size < 1 || tile_size > 64 || m <= 0) return TA_E_INVALID;
+    if (!env_ids && m > h->n) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const long long total = (long long)m * GS * tile_size * GS * tile_size * 3;
+    unsigned nb = blocks_for(total, 256 * 4);
+    if (nb > 148u * 32u) nb = 148u * 32u;
+    render_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, atlas, (const long long *)env_ids, m, tile_size,
+                                                      highlight, h->view, rgb_out);
+    return launch_ok("render_kernel");
+}
+
 int ta_export_state(ta_handle h, ta_env_state *out, void *stream) {
     if (!h || !out) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));

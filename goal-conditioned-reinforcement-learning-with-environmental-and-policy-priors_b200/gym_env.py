@@ -223,18 +223,12 @@ class TwoarmyEnv(_EnvBase):
 
     # ---- rendering (host side; not part of the accelerated path) -----------------------------
     def get_full_render(self, highlight=None, tile_size=None):
-        """RGB picture of the whole grid (the reference's software rasteriser, minigrid.py:1514-
-        1563, is out of scope for the GPU path; this is a flat-colour stand-in with the same
-        shape: (17*tile, 17*tile, 3) uint8)."""
+        """minigrid.py:1514-1563: the RGB picture of the whole grid, (17*tile, 17*tile, 3) uint8,
+        pixel-identical to the reference's software rasteriser (ta_render blits the cached tiles)."""
+        from . import render as _render
         ts = int(tile_size or self.tile_size)
-        colors = {0: (0, 0, 0), 1: (100, 100, 100), 2: (255, 255, 0), 3: (0, 255, 0)}
-        codes = self._state["grid"].reshape(17, 17)
-        img = np.zeros((17, 17, 3), np.uint8)
-        for c, rgb in colors.items():
-            img[codes == c] = rgb
-        ax, ay = self.agent_pos
-        img[ay, ax] = (255, 0, 0)
-        return np.kron(img, np.ones((ts, ts, 1), np.uint8))
+        hl = self.highlight if highlight is None else highlight
+        return _render.render(self._vec, None, ts, bool(hl))[0].cpu().numpy()
 
     def render(self, *a, **k):
         return self.get_full_render()

@@ -227,6 +227,11 @@ class TwoarmyVecEnv:
         _capi.check(self._L.ta_stack_push(self._h, _ptr(s_prev), _ptr(s_out), _ptr(p_prev), _ptr(p_out), _ptr(prev_done),
                                           int(init_all), 1 if s_out.dtype == torch.uint8 else 0, self._stream()), "ta_stack_push")
 
+    def render(self, env_ids: Optional[torch.Tensor] = None, tile_size: int = 32, highlight: bool = False) -> torch.Tensor:
+        """get_full_render() of the selected envs: uint8 [M, 17*tile_size, 17*tile_size, 3]."""
+        from . import render as _render
+        return _render.render(self, env_ids, tile_size, highlight)
+
     # ------------------------------------------------------------------ state access
     def export_state(self) -> np.ndarray:
         buf = torch.empty(self.num_envs * STATE_DTYPE.itemsize, dtype=torch.uint8, device=self.device)

@@ -163,6 +163,14 @@ int ta_stack_roll_codes(ta_handle h, uint8_t *s_codes, float *p_stack, const uin
 int ta_stack_push(ta_handle h, const void *s_prev, void *s_out, const float *p_prev, float *p_out,
                   const uint8_t *prev_done, int init_all, int dtype, void *stream);
 
+/* Replaces MiniGridEnv.get_full_render (gym_minigrid/minigrid.py:1514-1563, Grid.render :712-747) for the
+ * envs env_ids[0..m) (NULL = envs 0..m-1): rgb_out uint8 [m][17*ts][17*ts][3].
+ *   atlas  uint8 [16][ts][ts][3] on the device: the tile images render_tile (:662-710) caches, index =
+ *          cell code | agent here << 2 | highlighted << 3 (built on the host, render.tile_atlas)
+ *   highlight != 0: cells inside the agent's view window use the highlighted tiles (env.highlight) */
+int ta_render(ta_handle h, const uint8_t *atlas, int tile_size, int highlight, const int64_t *env_ids, int64_t m,
+              uint8_t *rgb_out, void *stream);
+
 /* Export / import the full env state (device buffers of n ta_env_state records). */
 int ta_export_state(ta_handle h, ta_env_state *out, void *stream);
 int ta_import_state(ta_handle h, const ta_env_state *in, void *stream);

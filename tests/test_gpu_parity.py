@@ -453,3 +453,21 @@ def test_her_plan_philox_is_valid_and_sharding_invariant():
     pos = p[:, :, 4].numpy().astype(np.int64)
     assert len(tt) > 100
     assert np.array_equal(full[tt, ee, cc] & 0x7FFF, pos[tt, ee, 0] * 32 + pos[tt, ee, 1])
+
+
+def test_render_kernel_matches_reference_frames(golden):
+    """ta_render on imported states == the reference's get_full_render (tests/golden/render_ref.npz)."""
+    pkg = _pkg()
+    fx = golden("render_ref.npz")
+    n = len([k for k in fx if k.endswith("_meta")])
+    for k in range(n):
+        ts, hl, view, ax, ay = (int(v) for v in fx[f"r{k}_meta"])
+        env = pkg.TwoarmyVecEnv(4, 3, view, seed=1, autoreset=False)
+        env.reset()
+        st = env.export_state()
+        st["grid"][1] = fx[f"r{k}_grid"]; st["agent_x"][1] = ax; st["agent_y"][1] = ay
+        env.import_state(st)
+        img = env.render(torch.tensor([1, 0]), tile_size=ts, highlight=bool(hl))
+        assert img.shape == (2, 17 * ts, 17 * ts, 3)
+        assert np.array_equal(img[0].cpu().numpy(), fx[f"r{k}_img"]), k
+        env.close()

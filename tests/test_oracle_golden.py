@@ -164,3 +164,18 @@ def test_her_func_matches_reference(golden):
         assert got["counter"] % 2048 == counter % 2048 and got["full"] == bool(full)
         n_nonempty += len(got["src"]) > 0
     assert n_nonempty >= 6
+
+
+def test_render_tiles_compose_to_reference_frames(golden):
+    """Host tile atlas (render.tile_atlas: my restatement of render_tile / rendering.py) composed per cell ==
+    the reference's get_full_render, pixel for pixel, for tile sizes 5/8/17, highlight on/off, views 17/7."""
+    import importlib
+    import twoarmy_b200 as pkg
+    R = importlib.import_module(pkg.__name__ + ".render")
+    fx = golden("render_ref.npz")
+    n = len([k for k in fx if k.endswith("_meta")])
+    assert n >= 20
+    for k in range(n):
+        ts, hl, view, ax, ay = (int(v) for v in fx[f"r{k}_meta"])
+        got = R.compose(fx[f"r{k}_grid"], (ax, ay), ts, bool(hl), view)
+        assert np.array_equal(got, fx[f"r{k}_img"]), k
