@@ -471,3 +471,32 @@ def test_render_kernel_matches_reference_frames(golden):
         assert img.shape == (2, 17 * ts, 17 * ts, 3)
         assert np.array_equal(img[0].cpu().numpy(), fx[f"r{k}_img"]), k
         env.close()
+
+
+@pytest.mark.parametrize("view", [17, 7])
+def test_persistent_tile_loop_matches_oracle(view, monkeypatch):
+    """More tiles than resident warps (forced with the tuning knobs: 1 warp per CTA, 1 CTA per SM, so
+    every warp walks ~5 tiles): shared-memory slots, the obs ring and the guards are reused across
+    tiles.  Bit-exact against the oracle, single steps and a T-step rollout."""
+    monkeypatch.setenv("TA_WARPS_PER_CTA", "1")
+    monkeypatch.setenv("TA_CTAS_PER_SM", "1")
+    pkg, O = _pkg(), _oracle()
+    n = 32 * 148 * 4 + 19
+    env = pkg.TwoarmyVecEnv(4, n, view, seed=11)
+    ora = O.OracleBatch(4, n, view, seed=11)
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset())
+    rng = np.random.default_rng(1)
+    amap = np.array([0, 1, 2, 2, 3, 6], np.int32)
+    for t in range(12):
+        a = amap[rng.integers(0, len(amap), size=n)]
+        obs, rew, te, tr, _ = env.step(torch.as_tensor(a))
+        want = ora.step(a, None, autoreset=True)
+        assert np.array_equal(obs.cpu().numpy(), want["obs"]), t
+        assert np.array_equal(rew.cpu().numpy(), want["reward"]), t
+    acts = amap[rng.integers(0, len(amap), size=(9, n))]
+    obs, rew, te, tr = env.rollout(torch.as_tensor(acts))
+    for t in range(9):
+        want = ora.step(acts[t], None, autoreset=True)
+        assert np.array_equal(obs[t].cpu().numpy(), want["obs"]), t
+        assert np.array_equal(te[t].cpu().numpy().astype(np.uint8), want["terminated"]), t
+    env.close()
