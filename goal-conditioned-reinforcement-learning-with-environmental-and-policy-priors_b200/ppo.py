@@ -283,6 +283,8 @@ class PPO:
         self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=self.lr, eps=1e-5, **fused)
         self.scheduler_actor = torch.optim.lr_scheduler.StepLR(self.optimizer_actor, self.lr_step_size, self.lr_gamma)
         self.scheduler_critic = torch.optim.lr_scheduler.StepLR(self.optimizer_critic, self.lr_step_size, self.lr_gamma)
+        self.two_streams = self.device.type == "cuda"   # actor / critic passes of update() on two CUDA streams
+        self._streams = None
         self.last_action_loss = float("nan")
         self.last_value_loss = float("nan")
 
@@ -417,6 +419,11 @@ class PPO:
                 for i in range(0, B, bs):
                     yield perm[i:i + bs]
 
+        streams = None
+        if dev.type == "cuda" and self.two_streams:
+            if self._streams is None:
+                self._streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            streams = self._streams
         for _ in range(epochs or self.K_epochs):
             for idx in minibatches():
                 rows = idx if src is None else src[idx]
@@ -425,24 +432,47 @@ class PPO:
                     sb = decode_matrix(sb)
                 sb = self._net_in(sb[:, 0:4])
                 pb, gb = p[rows][:, 0:4], g[idx]
-                with self._amp():
-                    probs = self.actor(sb, pb, gb)
-                    vpred = self.critic(sb, pb, gb)
-                dist = Categorical(probs=probs)
-                dist_entropy = dist.entropy().view(-1, 1)
-                a_logp = dist.log_prob(a[idx].squeeze(-1)).view(-1, 1)
-                ratio = torch.exp(a_logp - old_a_logp[idx])
-                surr1 = ratio * adv[idx]
-                surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv[idx]
-                action_loss = (-torch.min(surr1, surr2) - self.entropy_coef * dist_entropy).mean()
-                value_loss = F.smooth_l1_loss(vpred, target_v[idx])
                 for name in self._flat:
                     self._flat[name].zero_()
                 if not self._flat:
                     self.optimizer_actor.zero_grad()
                     self.optimizer_critic.zero_grad()
-                action_loss.backward()
-                value_loss.backward()
+
+                def actor_part():
+                    with self._amp():
+                        probs = self.actor(sb, pb, gb)
+                    dist = Categorical(probs=probs)
+                    dist_entropy = dist.entropy().view(-1, 1)
+                    a_logp = dist.log_prob(a[idx].squeeze(-1)).view(-1, 1)
+                    ratio = torch.exp(a_logp - old_a_logp[idx])
+                    surr1 = ratio * adv[idx]
+                    surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv[idx]
+                    loss = (-torch.min(surr1, surr2) - self.entropy_coef * dist_entropy).mean()
+                    loss.backward()
+                    return loss.detach()
+
+                def critic_part():
+                    with self._amp():
+                        vpred = self.critic(sb, pb, gb)
+                    loss = F.smooth_l1_loss(vpred, target_v[idx])
+                    loss.backward()
+                    return loss.detach()
+
+                if streams is None:
+                    action_loss, value_loss = actor_part(), critic_part()
+                else:
+                    # the two networks are independent: their forward / backward run on two streams so
+                    # that one net's small kernels fill the gaps of the other's (the reference's order
+                    # of operations inside each network is unchanged)
+                    cur = torch.cuda.current_stream(dev)
+                    for st in streams:
+                        st.wait_stream(cur)
+                    with torch.cuda.stream(streams[0]):
+                        action_loss = actor_part()
+                    with torch.cuda.stream(streams[1]):
+                        value_loss = critic_part()
+                    for st in streams:
+                        cur.wait_stream(st)
                 self._allreduce("actor", self.actor, group)
                 self._allreduce("critic", self.critic, group)
                 if self.use_grad_clip:
@@ -451,7 +481,7 @@ class PPO:
                 self.optimizer_actor.step()
                 self.optimizer_critic.step()
                 self.update_count += 1
-                self._last = (action_loss.detach(), value_loss.detach())
+                self._last = (action_loss, value_loss)
         self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)
         if self.use_lr_decay:
             self.scheduler_actor.step()
