@@ -67,36 +67,43 @@ def conv1_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
 
 
 class _ConvS2(torch.autograd.Function):
-    """Conv2d(stride 2, no padding) on channels-last bf16: forward and weight / bias gradients stay with
-    cuDNN; the DATA gradient, for which cuDNN's strided-dgrad kernels take 1-1.7 ms at B = 4096, is a plain
-    cuBLAS GEMM (dY x W) followed by the col2im gather kernel (ta_col2im_s2)."""
+    """relu(Conv2d(stride 2, no padding)) on channels-last bf16.  Forward: cuDNN's fused conv + bias + ReLU
+    (111 us instead of 314 us for conv2 at B = 4096: no separate bias-add / ReLU passes).  Backward: weight
+    gradient from cuDNN; bias gradient from the channel-sum kernel (29 us instead of aten::sum's 112 us);
+    DATA gradient, for which cuDNN's strided-dgrad kernels take 1-1.7 ms, as a plain cuBLAS GEMM (dZ x W)
+    followed by the col2im gather kernel (ta_col2im_s2)."""
 
     @staticmethod
     def forward(ctx, x, w, b):
-        ctx.save_for_backward(x, w)
-        return torch.ops.aten.convolution(x, w, b, [2, 2], [0, 0], [1, 1], False, [0, 0], 1)
+        y = torch.cudnn_convolution_relu(x, w, b, [2, 2], [0, 0], [1, 1], 1)
+        ctx.save_for_backward(x, w, y)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
-        dy = dy.contiguous(memory_format=torch.channels_last)
+        x, w, y = ctx.saved_tensors
+        dz = torch.ops.aten.threshold_backward(dy, y, 0).contiguous(memory_format=torch.channels_last)
         cout, cin, k, _ = w.shape
-        _, gw, gb = torch.ops.aten.convolution_backward(dy, x, w, [cout], [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
-                                                        [False, True, True])
+        lib, st = _capi.lib(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _, gw, _ = torch.ops.aten.convolution_backward(dz, x, w, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
+                                                       [False, True, False])
+        dz_rows = dz.permute(0, 2, 3, 1).reshape(-1, cout)            # [B*OH*OW, cout], a view of channels-last memory
+        gb32 = torch.empty((cout,), dtype=torch.float32, device=x.device)
+        _capi.check(lib.ta_channel_sum_bf16(_ptr(dz_rows), dz_rows.shape[0], cout, _ptr(gb32), st), "ta_channel_sum_bf16")
         gx = None
         if ctx.needs_input_grad[0]:
             B, _, H, W = x.shape
-            dcols = dy.permute(0, 2, 3, 1).reshape(-1, cout) @ w.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+            dcols = dz_rows @ w.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
             gx_nhwc = torch.empty((B, H, W, cin), dtype=torch.bfloat16, device=x.device)
-            st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-            _capi.check(_capi.lib().ta_col2im_s2(_ptr(dcols), _ptr(gx_nhwc), B, H, W, cin, k, st), "ta_col2im_s2")
+            _capi.check(lib.ta_col2im_s2(_ptr(dcols), _ptr(gx_nhwc), B, H, W, cin, k, st), "ta_col2im_s2")
             gx = gx_nhwc.permute(0, 3, 1, 2)
-        return gx, gw, gb
+        return gx, gw, gb32.to(w.dtype)
 
 
-def conv_s2(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
-    """conv(x) for a stride-2 unpadded Conv2d, x bf16 channels-last, with the GEMM + col2im data gradient."""
-    return _ConvS2.apply(x, conv.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+def conv_s2_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """relu(conv(x)) for a stride-2 unpadded Conv2d, x bf16 channels-last (see _ConvS2)."""
+    return _ConvS2.apply(x.contiguous(memory_format=torch.channels_last),
+                         conv.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
                          conv.bias.to(torch.bfloat16))
 
 

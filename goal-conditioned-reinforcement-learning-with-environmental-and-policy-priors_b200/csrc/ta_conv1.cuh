@@ -221,4 +221,34 @@ __global__ void __launch_bounds__(256) col2im_s2_kernel(const __nv_bfloat16 *__r
     }
 }
 
+// ---- per-channel sum of a channels-last bf16 tensor (the bias gradient of a convolution) -------------
+// x bf16 [rows][C], C in {64, 128, 256}: a thread owns 8 channels (16-byte loads) and strides over the
+// rows of its CTA's slab; row lanes are combined through shared memory, one atomicAdd per channel and CTA.
+// (aten::sum over (N,H,W) of a channels-last tensor runs far below the HBM rate; this is one streaming pass.)
+__global__ void __launch_bounds__(256) channel_sum_bf16_kernel(const __nv_bfloat16 *__restrict__ x, long long rows, int C,
+                                                              float *__restrict__ out) {
+    __shared__ float sacc[256][9];
+    const int c8n = C >> 3, c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, nrl = 256 / c8n;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long r = (long long)blockIdx.x * nrl + rl; r < rows; r += (long long)gridDim.x * nrl) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(x + r * C + c8 * 8));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[q]));
+            acc[2 * q] += f.x;
+            acc[2 * q + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) sacc[threadIdx.x][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < C) {  // channel threadIdx.x: sum over the row lanes
+        const int g = threadIdx.x >> 3, q = threadIdx.x & 7;
+        float s = 0.f;
+        for (int l = 0; l < nrl; l++) s += sacc[l * c8n + g][q];
+        atomicAdd(out + threadIdx.x, s);
+    }
+}
+
 }  // namespace ta

@@ -525,6 +525,16 @@ int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, in
     return launch_ok("col2im_s2_kernel");
 }
 
+int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, void *stream) {
+    if (!x_bf16 || !out || rows <= 0 || (C != 64 && C != 128 && C != 256) || ((uintptr_t)x_bf16 & 15u)) return TA_E_INVALID;
+    CK(cudaMemsetAsync(out, 0, C * sizeof(float), (cudaStream_t)stream));
+    const int nrl = 256 / (C / 8);
+    unsigned nb = blocks_for(rows, (long long)nrl * 16);
+    if (nb > 148u * 8u) nb = 148u * 8u;
+    channel_sum_bf16_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x_bf16, rows, C, out);
+    return launch_ok("channel_sum_bf16_kernel");
+}
+
 int ta_set_timing(ta_handle h, int on) {
     if (!h) return TA_E_INVALID;
     h->timing = on;

@@ -135,8 +135,8 @@ class TINet(nn.Module):
                     x = self.cnn_base[:2](x)
             if self.gemm_dgrad and x.dtype == torch.bfloat16 and torch.is_grad_enabled():
                 from . import conv1 as _c1
-                x = torch.relu(_c1.conv_s2(x, self.cnn_base[2]))
-                x = torch.relu(_c1.conv_s2(x, self.cnn_base[4]))
+                x = _c1.conv_s2_relu(x, self.cnn_base[2])
+                x = _c1.conv_s2_relu(x, self.cnn_base[4])
             else:
                 x = self.cnn_base[2:6](x)
             # The last conv (128 -> 256, 3x3 stride 2 on 7x7) as an explicit im2col + cuBLAS GEMM: for

@@ -7,7 +7,7 @@ P = importlib.import_module(pkg.__name__ + ".ppo")
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 agent = P.PPO(device=dev)
-B = int(os.environ.get("B", "32768")); mb = int(os.environ.get("MB", "4096"))
+B = int(os.environ.get("B", "16384")); mb = int(os.environ.get("MB", "4096"))
 g = torch.Generator(device=dev).manual_seed(1)
 buf = {"s": torch.randint(0, 3, (B, 5, 289), generator=g, device=dev, dtype=torch.uint8),
        "p": torch.randint(1, 16, (B, 5, 2), generator=g, device=dev).float(),

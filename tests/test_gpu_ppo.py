@@ -80,7 +80,8 @@ def test_fused_conv1_matches_cudnn_layer(dtype):
 
 @pytest.mark.parametrize("layer", [2, 4])
 def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
-    """conv_s2 (cuDNN forward / wgrad, GEMM + ta_col2im_s2 data gradient) == nn.Conv2d autograd in bf16."""
+    """conv_s2_relu (cuDNN fused forward, cuDNN wgrad, channel-sum bias gradient, GEMM + ta_col2im_s2 data
+    gradient) == relu(nn.Conv2d) autograd in bf16."""
     import twoarmy_b200 as pkg
     P = _ppo()
     C1 = importlib.import_module(pkg.__name__ + ".conv1")
@@ -95,14 +96,19 @@ def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
         conv.weight.grad = None; conv.bias.grad = None
         if mode == "ref":
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                y = conv(x)
+                y = torch.relu(conv(x))
         else:
-            y = C1.conv_s2(x, conv)
+            y = C1.conv_s2_relu(x, conv)
         gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6)).cuda().to(y.dtype)
         (y.float() * gy.float()).sum().backward()
         outs.append((y.float(), x.grad.float(), conv.weight.grad.clone(), conv.bias.grad.clone()))
-    for a, b in zip(outs[0], outs[1]):
-        assert float((a - b).abs().max()) <= 2e-2 * float(a.abs().max()) + 1e-6
+    # the fused forward rounds conv + bias once, the unfused one twice: activations within one bf16 ulp of
+    # zero can land on either side of the ReLU, so single gradient entries may differ by one term; compare
+    # y elementwise to rounding and the gradients in the Frobenius norm
+    y0, y1 = outs[0][0], outs[1][0]
+    assert float((y0 - y1).abs().max()) <= 2e-2 * float(y0.abs().max())
+    for name, a, b in zip(("dx", "dw", "db"), outs[0][1:], outs[1][1:]):
+        assert float((a - b).norm()) <= 2e-2 * float(a.norm()), name
 
 
 def test_predictor_agent_rollout_and_update_on_gpu():
