@@ -133,7 +133,7 @@ class TINet(nn.Module):
                 else:
                     x = self.upsamplingnearest(x).contiguous(memory_format=torch.channels_last)
                     x = self.cnn_base[:2](x)
-            if self.gemm_dgrad and x.dtype == torch.bfloat16 and torch.is_grad_enabled():
+            if self.gemm_dgrad and x.dtype == torch.bfloat16:
                 from . import conv1 as _c1
                 x = _c1.conv_s2_relu(x, self.cnn_base[2])
                 x = _c1.conv_s2_relu(x, self.cnn_base[4])
