@@ -19,9 +19,15 @@ from . import _capi
 _SEL = (((1., 1., 1., 1.), (0., 0., 0., 0.)), ((1., 1., 0., 0.), (0., 0., 1., 1.)))
 
 
+_sel_cache = {}
+
+
 def fold(weight: torch.Tensor, bias: torch.Tensor):
     """conv weight [64,4,4,4], bias [64] -> (w4 [256,16] rows (py,px,o) cols (dy,dx,c), b4 [256]), float32."""
-    sel = torch.tensor(_SEL, dtype=torch.float32, device=weight.device)
+    key = str(weight.device)
+    if key not in _sel_cache:  # built once per device (a host-to-device copy is not capturable in a CUDA graph)
+        _sel_cache[key] = torch.tensor(_SEL, dtype=torch.float32, device=weight.device)
+    sel = _sel_cache[key]
     w4 = torch.einsum("ocyx,pdy,qex->pqodec", weight.float(), sel, sel).reshape(256, 16)
     return w4.contiguous(), bias.float().repeat(4).contiguous()
 

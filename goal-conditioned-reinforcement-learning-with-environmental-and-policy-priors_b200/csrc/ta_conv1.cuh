@@ -75,16 +75,20 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const XT *__restr
         c1_stage_input<XT>(x + b * xstride, sx[buf]);
         __syncthreads();  // (the other buffer is still being read by slower threads: double buffered)
         __nv_bfloat16 *yb = y + b * (long long)(C1_OUT * C1_OUT * C1_CH);
-        for (int idx = plane; idx < npix; idx += 4) {
-            const int m = idx / N, n = idx - N * m;
+        int m = 0, n = plane;  // pixel idx = plane + 4j of this phase's M x N grid, walked without divisions (N >= 16)
+        for (int idx = plane; idx < npix; idx += 4, n += 4) {
+            if (n >= N) { n -= N; m++; }
             float p[16];
             c1_patch(sx[buf], m, n, p);
+            // Blackwell's packed fp32 FMA (FFMA2): even / odd k accumulate in the two halves of a float2
             float acc[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                float a = bias[i];
+                float2 a2 = make_float2(bias[i], 0.f);
 #pragma unroll
-                for (int k = 0; k < 16; k++) a = fmaf(w[i][k], p[k], a);
+                for (int k = 0; k < 16; k += 2)
+                    a2 = __ffma2_rn(make_float2(w[i][k], w[i][k + 1]), make_float2(p[k], p[k + 1]), a2);
+                const float a = a2.x + a2.y;
                 acc[i] = a > 0.f ? a : 0.f;
             }
             const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[0], acc[1]), hi = __floats2bfloat162_rn(acc[2], acc[3]);
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_bwd_kernel(const XT *__re
         __syncthreads();
         const long long base = b * (long long)(C1_OUT * C1_OUT * C1_CH);
         // four pixels per trip, their eight 8-byte loads in flight together (the loop is latency-bound otherwise)
+        int m = 0, n = plane;
         for (int idx0 = plane; idx0 < npix; idx0 += 16) {
             uint2 yv[4], gv[4];
             int mm[4], nn[4];
@@ -125,8 +130,10 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_bwd_kernel(const XT *__re
             for (int u = 0; u < 4; u++) {
                 const int idx = idx0 + 4 * u;
                 const bool ok = idx < npix;
-                mm[u] = ok ? idx / N : 0;
-                nn[u] = ok ? idx - N * mm[u] : 0;
+                if (n >= N) { n -= N; m++; }
+                mm[u] = ok ? m : 0;
+                nn[u] = ok ? n : 0;
+                n += 4;
                 const long long off = base + ((2 * mm[u] + py) * C1_OUT + (2 * nn[u] + px)) * C1_CH + cg * 4;
                 yv[u] = ok ? __ldg(reinterpret_cast<const uint2 *>(y + off)) : make_uint2(0u, 0u);
                 gv[u] = ok ? __ldg(reinterpret_cast<const uint2 *>(dy + off)) : make_uint2(0u, 0u);
@@ -144,8 +151,13 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_bwd_kernel(const XT *__re
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     db[i] += dz[i];
+                    const float2 d2 = make_float2(dz[i], dz[i]);
 #pragma unroll
-                    for (int k = 0; k < 16; k++) dw[i][k] = fmaf(dz[i], p[k], dw[i][k]);
+                    for (int k = 0; k < 16; k += 2) {
+                        const float2 r = __ffma2_rn(d2, make_float2(p[k], p[k + 1]), make_float2(dw[i][k], dw[i][k + 1]));
+                        dw[i][k] = r.x;
+                        dw[i][k + 1] = r.y;
+                    }
                 }
             }
         }

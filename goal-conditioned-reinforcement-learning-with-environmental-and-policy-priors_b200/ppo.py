@@ -184,11 +184,16 @@ class Net_PPO_critic(nn.Module):  # all_net.py:222-247
         return self.V(self.bone2(state_matrix, position, goal)).float()
 
 
+_lut_cache = {}
+
+
 def decode_matrix(codes: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     """uint8 featuriser codes -> the float matrix_env values (the LUT is applied here, in the
     network's loader, so the rollout buffer keeps 1 byte per cell)."""
-    lut = torch.tensor(MATRIX_LUT, dtype=dtype, device=codes.device)
-    return lut[codes.long()]
+    key = (str(codes.device), dtype)
+    if key not in _lut_cache:  # built once per device (a host-to-device copy is not capturable in a CUDA graph)
+        _lut_cache[key] = torch.tensor(MATRIX_LUT, dtype=dtype, device=codes.device)
+    return _lut_cache[key][codes.long()]
 
 
 class RolloutBuffer:
@@ -278,12 +283,14 @@ class PPO:
         if flat_grads:
             for name, net in (("actor", self.actor), ("critic", self.critic)):
                 self._flat[name] = self._flatten_grads(net)
-        fused = {"fused": True} if self.device.type == "cuda" else {}   # one multi-tensor kernel per step on the GPU
+        # one multi-tensor kernel per step on the GPU; capturable: the step counter lives on the device
+        fused = {"fused": True, "capturable": True} if self.device.type == "cuda" else {}
         self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=self.lr, eps=1e-5, **fused)    # PPO.py:57-58
         self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=self.lr, eps=1e-5, **fused)
         self.scheduler_actor = torch.optim.lr_scheduler.StepLR(self.optimizer_actor, self.lr_step_size, self.lr_gamma)
         self.scheduler_critic = torch.optim.lr_scheduler.StepLR(self.optimizer_critic, self.lr_step_size, self.lr_gamma)
         self.two_streams = self.device.type == "cuda"   # actor / critic passes of update() on two CUDA streams
+        self.use_graph = self.device.type == "cuda"     # replay the optimiser step from a CUDA graph (one GPU)
         self._streams = None
         self.last_action_loss = float("nan")
         self.last_value_loss = float("nan")
@@ -424,64 +431,106 @@ class PPO:
             if self._streams is None:
                 self._streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
             streams = self._streams
+
+        def step(idx):
+            """One optimiser step on the minibatch `idx` (PPO.py:124-144); returns the two losses."""
+            rows = idx if src is None else src[idx]
+            sb = s[rows]
+            if sb.dtype == torch.uint8 and not (sb.is_cuda and self.autocast):
+                sb = decode_matrix(sb)
+            sb = self._net_in(sb[:, 0:4])
+            pb, gb = p[rows][:, 0:4], g[idx]
+            for name in self._flat:
+                self._flat[name].zero_()
+            if not self._flat:
+                self.optimizer_actor.zero_grad()
+                self.optimizer_critic.zero_grad()
+
+            def actor_part():
+                with self._amp():
+                    probs = self.actor(sb, pb, gb)
+                # (argument validation reads the probabilities back on the host: not capturable, off on the GPU)
+                dist = Categorical(probs=probs, validate_args=None if dev.type != "cuda" else False)
+                dist_entropy = dist.entropy().view(-1, 1)
+                a_logp = dist.log_prob(a[idx].squeeze(-1)).view(-1, 1)
+                ratio = torch.exp(a_logp - old_a_logp[idx])
+                surr1 = ratio * adv[idx]
+                surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv[idx]
+                loss = (-torch.min(surr1, surr2) - self.entropy_coef * dist_entropy).mean()
+                loss.backward()
+                return loss.detach()
+
+            def critic_part():
+                with self._amp():
+                    vpred = self.critic(sb, pb, gb)
+                loss = F.smooth_l1_loss(vpred, target_v[idx])
+                loss.backward()
+                return loss.detach()
+
+            if streams is None:
+                action_loss, value_loss = actor_part(), critic_part()
+            else:
+                # the two networks are independent: their forward / backward run on two streams so
+                # that one net's small kernels fill the gaps of the other's (the reference's order
+                # of operations inside each network is unchanged)
+                cur = torch.cuda.current_stream(dev)
+                for st in streams:
+                    st.wait_stream(cur)
+                with torch.cuda.stream(streams[0]):
+                    action_loss = actor_part()
+                with torch.cuda.stream(streams[1]):
+                    value_loss = critic_part()
+                for st in streams:
+                    cur.wait_stream(st)
+            self._allreduce("actor", self.actor, group)
+            self._allreduce("critic", self.critic, group)
+            if self.use_grad_clip:
+                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
+                torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
+            self.optimizer_actor.step()
+            self.optimizer_critic.step()
+            return action_loss, value_loss
+
+        # The step is ~300 small launches; driven from Python the update is CPU-bound.  On one GPU the
+        # whole step (gather, both nets forward / backward, Adam) is captured ONCE per update() into a
+        # CUDA graph over a static index buffer and replayed for every full minibatch (same steps,
+        # same order as the eager loop).
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size(group)
+        want_graph = (dev.type == "cuda" and self.use_graph and world == 1 and bool(self._flat) and sampler_generator is None)
+        graph, idx_static, loss_static, eager_full = None, None, None, 0
+        side = torch.cuda.Stream(device=dev) if want_graph else None
+
+        self._last = None
         for _ in range(epochs or self.K_epochs):
             for idx in minibatches():
-                rows = idx if src is None else src[idx]
-                sb = s[rows]
-                if sb.dtype == torch.uint8 and not (sb.is_cuda and self.autocast):
-                    sb = decode_matrix(sb)
-                sb = self._net_in(sb[:, 0:4])
-                pb, gb = p[rows][:, 0:4], g[idx]
-                for name in self._flat:
-                    self._flat[name].zero_()
-                if not self._flat:
-                    self.optimizer_actor.zero_grad()
-                    self.optimizer_critic.zero_grad()
-
-                def actor_part():
-                    with self._amp():
-                        probs = self.actor(sb, pb, gb)
-                    dist = Categorical(probs=probs)
-                    dist_entropy = dist.entropy().view(-1, 1)
-                    a_logp = dist.log_prob(a[idx].squeeze(-1)).view(-1, 1)
-                    ratio = torch.exp(a_logp - old_a_logp[idx])
-                    surr1 = ratio * adv[idx]
-                    surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv[idx]
-                    loss = (-torch.min(surr1, surr2) - self.entropy_coef * dist_entropy).mean()
-                    loss.backward()
-                    return loss.detach()
-
-                def critic_part():
-                    with self._amp():
-                        vpred = self.critic(sb, pb, gb)
-                    loss = F.smooth_l1_loss(vpred, target_v[idx])
-                    loss.backward()
-                    return loss.detach()
-
-                if streams is None:
-                    action_loss, value_loss = actor_part(), critic_part()
+                full = idx.numel() == bs
+                if want_graph and full and graph is None and eager_full >= 2:
+                    # two eager steps have warmed the allocator and the cuDNN / cuBLAS plans up: capture the
+                    # step once (capture records, it does not execute) and replay it from here on
+                    idx_static = idx.clone()
+                    torch.cuda.synchronize(dev)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        loss_static = step(idx_static)
+                if graph is not None and full:
+                    idx_static.copy_(idx)
+                    graph.replay()
+                    self._last = loss_static
+                elif want_graph and full:
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):   # warm-up steps run on a side stream, as capture will
+                        self._last = step(idx)
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    eager_full += 1
                 else:
-                    # the two networks are independent: their forward / backward run on two streams so
-                    # that one net's small kernels fill the gaps of the other's (the reference's order
-                    # of operations inside each network is unchanged)
-                    cur = torch.cuda.current_stream(dev)
-                    for st in streams:
-                        st.wait_stream(cur)
-                    with torch.cuda.stream(streams[0]):
-                        action_loss = actor_part()
-                    with torch.cuda.stream(streams[1]):
-                        value_loss = critic_part()
-                    for st in streams:
-                        cur.wait_stream(st)
-                self._allreduce("actor", self.actor, group)
-                self._allreduce("critic", self.critic, group)
-                if self.use_grad_clip:
-                    torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
-                    torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
-                self.optimizer_actor.step()
-                self.optimizer_critic.step()
+                    self._last = step(idx)
                 self.update_count += 1
-                self._last = (action_loss, value_loss)
+        if graph is not None:
+            torch.cuda.synchronize(dev)
+            self._last = tuple(x.clone() for x in self._last)
+            del graph
         self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)
         if self.use_lr_decay:
             self.scheduler_actor.step()
