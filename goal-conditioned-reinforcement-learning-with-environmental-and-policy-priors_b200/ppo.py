@@ -21,6 +21,7 @@ The env step, observation, featuriser and advantage arithmetic all run in the CU
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -290,7 +291,8 @@ class PPO:
         self.scheduler_actor = torch.optim.lr_scheduler.StepLR(self.optimizer_actor, self.lr_step_size, self.lr_gamma)
         self.scheduler_critic = torch.optim.lr_scheduler.StepLR(self.optimizer_critic, self.lr_step_size, self.lr_gamma)
         self.two_streams = self.device.type == "cuda"   # actor / critic passes of update() on two CUDA streams
-        self.use_graph = self.device.type == "cuda"     # replay the optimiser step from a CUDA graph (one GPU)
+        self.use_graph = self.device.type == "cuda"     # replay the optimiser step from a CUDA graph
+        self.graph_with_nccl = os.environ.get("TA_PPO_GRAPH_NCCL", "0") == "1"   # measured slower at 2 GPUs: off
         self._streams = None
         self.last_action_loss = float("nan")
         self.last_value_loss = float("nan")
@@ -498,7 +500,9 @@ class PPO:
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(group)
-        want_graph = (dev.type == "cuda" and self.use_graph and world == 1 and bool(self._flat) and sampler_generator is None)
+        # (with several ranks the gradient all-reduce is captured too: every rank replays the same graph)
+        want_graph = (dev.type == "cuda" and self.use_graph and (world == 1 or self.graph_with_nccl) and bool(self._flat)
+                      and sampler_generator is None)
         graph, idx_static, loss_static, eager_full = None, None, None, 0
         side = torch.cuda.Stream(device=dev) if want_graph else None
 
