@@ -500,3 +500,48 @@ def test_persistent_tile_loop_matches_oracle(view, monkeypatch):
         assert np.array_equal(obs[t].cpu().numpy(), want["obs"]), t
         assert np.array_equal(te[t].cpu().numpy().astype(np.uint8), want["terminated"]), t
     env.close()
+
+
+def test_long_run_invariants_at_full_size():
+    """BASELINE configs[2] size (v4, 65536 envs), 1500 steps in T=50 rollouts with Philox draws and
+    autoreset: size-independent properties of the reference's dynamics -- rewards / observation bytes
+    stay in the reference's value sets, no episode is longer than max_steps = 50, a terminated step pays
+    0.9, the agent never sits on a wall, no error bits, and the final state equals the oracle's after the
+    same 1500 steps on a 2048-env slice (sharding invariance makes the slice independent of the rest)."""
+    pkg, O = _pkg(), _oracle()
+    n, T, R = 65536, 50, 30
+    env = pkg.TwoarmyVecEnv(4, n, 17, seed=77)
+    env.reset()
+    sl = 2048
+    ora = O.OracleBatch(4, sl, 17, seed=77)
+    ora.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    amap = torch.tensor([0, 1, 2, 2, 3, 6], dtype=torch.uint8, device="cuda")
+    allowed_r = torch.tensor([-0.01, -0.1, -0.9, 0.2, 0.9], device="cuda")
+    run_len = torch.zeros(n, dtype=torch.int32, device="cuda")
+    n_term = 0
+    for _ in range(R):
+        acts = amap[torch.randint(0, len(amap), (T, n), generator=g, device="cuda")]
+        obs, rew, te, tr = env.rollout(acts)
+        assert bool(torch.isin(rew, allowed_r).all())
+        assert bool((rew[te] == allowed_r[4]).all())
+        assert int(obs[..., 2].max()) == 0 and bool(torch.isin(obs[..., 0], torch.tensor([1, 2, 6, 8], device="cuda", dtype=torch.uint8)).all())
+        done = te | tr
+        for t in range(T):
+            run_len += 1
+            assert int(run_len.max()) <= 50
+            run_len[done[t]] = 0
+        n_term += int(te.sum())
+        a_np = acts[:, :sl].cpu().numpy().astype(np.int32)
+        for t in range(T):
+            ora.step(a_np[t], None, autoreset=True)
+    st = env.export_state()
+    assert int(st["error"].max()) == 0
+    ax, ay = st["agent_x"].astype(int), st["agent_y"].astype(int)
+    assert np.all(st["grid"][np.arange(n), ay * 17 + ax] != 1)
+    got = state_to_fixture(st[:sl])
+    assert np.array_equal(got["grid"], ora.envs["grid"])
+    assert np.array_equal(got["agent"][:, 0], ora.envs["ax"]) and np.array_equal(got["agent"][:, 1], ora.envs["ay"])
+    assert np.array_equal(st["step_count"][:sl], ora.envs["step_count"]) and np.array_equal(st["t"][:sl], ora.envs["t"])
+    assert n_term >= 0
+    env.close()
