@@ -1,0 +1,227 @@
+// ta_conv1_tc.cuh -- TINet's fused first layer (see ta_conv1.cuh) on the 5th-generation tensor cores.
+//
+// The folded layer is a GEMM with a tiny reduction: D[position, (phase, channel)] = P[position, 16] x W4^T[16, 256].
+// tcgen05.mma (M = 128 positions, N = 64 = one output phase, K = 16, bf16 inputs, fp32 accumulators in TMEM)
+// covers 128 input positions x 64 channels; the FP32-FMA version of the same work is bound by
+// the FMA pipe (4.6 GFMA per 4096 samples), this one by its 570 MB of output.
+//
+//   CTA = 128 threads = 4 warps; thread r owns row r of the tile = one input position (sample b, m, n):
+//     build   the tile's 128 + 18 input positions are loaded / LUT-decoded once (4 frames each) into shared
+//             memory; row r then gathers its 2x2 patch (positions r, r+1, r+17, r+18) -> two 16-byte chunks of
+//             the A tile, canonical K-major no-swizzle layout (8-row x 16-byte core matrices)
+//     mma     thread 0: tcgen05.mma [tmem], descA, descB, idesc; tcgen05.commit -> mbarrier
+//     epilog  warp w reads TMEM lanes 32w..32w+31 (tcgen05.ld 32x32b.x32): thread r gets row r, 32 channels at
+//             a time; + bias, ReLU, bf16 pack -> a swizzled 32 x 64-byte staging block in shared memory (warp
+//             private, __syncwarp only) -> read back transposed so that one store instruction covers 8 output
+//             pixels x 64 contiguous bytes (per-thread rows would touch 32 cache lines per instruction)
+//   W4 (bf16 hi/lo, canonical layout, 2 x 8 KB) and the bias stay in shared memory for the CTA's lifetime.
+//   TMEM: 64 columns per CTA (one output phase at a time), so 8 CTAs share an SM's 512 columns.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ta_conv1.cuh"
+
+namespace ta {
+
+constexpr int TC_THREADS = 128;
+constexpr int TC_M = 128, TC_N = 256;
+constexpr int TC_HALO = GS + 1;  // a row's patch reaches 18 positions ahead
+constexpr int TC_NT = 64;  // columns per MMA = TMEM columns per CTA: one output phase; 8 CTAs fit an SM's 512 columns
+// shared-memory descriptor of a K-major, no-swizzle operand with K = 16 bf16 (two 16-byte chunks per row):
+// element (row r, chunk c) at byte (r / 8) * 256 + c * 128 + (r % 8) * 16, i.e. LBO = 128 B, SBO = 256 B
+__device__ __forceinline__ uint64_t tc_smem_desc(const void *smem) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem) >> 4) & 0x3FFFu;
+    return addr | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);  // version = 1, layout = none
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = TC_NT, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ uint32_t tc_operand_offset(int row, int chunk) { return (row >> 3) * 256 + chunk * 128 + (row & 7) * 16; }
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// bounded wait: a descriptor mistake must not turn into a hung GPU
+__device__ __forceinline__ bool tc_mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); spin++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// (v0, v1) -> packed bf16 pairs hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void tc_split(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __low2float(h), v1 - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// D[tmem] (+)= A[smem] x B[smem]^T, M = 128, N = TC_NT, K = 16; issued by one thread
+__device__ __forceinline__ void tc_mma(uint32_t tmem, uint64_t descA, uint64_t descB, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
+                 "l"(descA), "l"(descB), "r"(TC_IDESC), "r"(accumulate)
+                 : "memory");
+}
+
+template <typename XT>
+__device__ __forceinline__ float tc_value(XT v) {
+    if constexpr (sizeof(XT) == 1) return c1_decode((uint32_t)v);
+    else return (float)v;
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__restrict__ x, long long xstride,
+                                                                 const float *__restrict__ w4, const float *__restrict__ b4,
+                                                                 long long B, __nv_bfloat16 *__restrict__ y, int *fail) {
+    // every operand is kept as a bf16 (hi, lo) pair, v = hi + lo to 2^-17: three MMAs (hi*hi + lo*hi + hi*lo) give
+    // fp32-grade products, so the layer matches the FP32 kernel / cuDNN fp32 to rounding of the bf16 output
+    __shared__ __align__(1024) uint8_t sA[2][TC_M * 32];   // 2 x 4 KB
+    __shared__ __align__(1024) uint8_t sB[2][TC_N * 32];   // 2 x 8 KB
+    __shared__ float sbias[TC_N];
+    __shared__ __align__(16) uint8_t sOut[TC_M * 64];      // epilogue staging: 32 channels (64 B) per row
+    __shared__ uint4 sDec[TC_M + TC_HALO];                 // decoded inputs of the tile's positions + halo
+    __shared__ long long rowinfo[TC_M];                    // (output pixel of phase 0) * 4 | (m == 16) * 2 | (n == 16); -1 = no row
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *wout = sOut + warp * 2048;
+
+    // one-time setup: W4 -> bf16 canonical layout, bias, barrier, TMEM
+    for (int i = tid; i < TC_N * 2; i += TC_THREADS) {
+        const int n = i >> 1, c = i & 1;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) tc_split(__ldg(w4 + n * 16 + c * 8 + 2 * q), __ldg(w4 + n * 16 + c * 8 + 2 * q + 1), hi[q], lo[q]);
+        *reinterpret_cast<uint4 *>(sB[0] + tc_operand_offset(n, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(sB[1] + tc_operand_offset(n, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    for (int i = tid; i < TC_N; i += TC_THREADS) sbias[i] = __ldg(b4 + i);
+    if (tid == 0) tc_mbar_init(&bar);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TC_NT));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint64_t descA_hi = tc_smem_desc(sA[0]), descA_lo = tc_smem_desc(sA[1]);
+    const uint64_t descB_hi = tc_smem_desc(sB[0]), descB_lo = tc_smem_desc(sB[1]);
+    const long long npos = B * NCELL, ntiles = (npos + TC_M - 1) / TC_M;
+    uint32_t parity = 0;
+    bool dead = false;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long P = tile * TC_M + tid;
+        const bool valid = P < npos;
+        const long long b = valid ? P / NCELL : 0;
+        const int pos = valid ? (int)(P - b * NCELL) : 0, m = pos / GS, n = pos - GS * m;
+        // ---- A tile, k = (dy*2+dx)*4 + c -------------------------------------------------------------------
+        // stage 1: positions tile*128 .. +127+18 -> decoded (hi, lo) bf16 of the 4 frames, 16 bytes per position
+        // (each input cell feeds up to four rows of the tile, so it is loaded and decoded once)
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            const int slot = tid + rep * TC_M;
+            if (slot < TC_M + TC_HALO) {
+                const long long Q = tile * TC_M + slot;
+                uint32_t hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
+                if (Q < npos) {
+                    const long long qb = Q / NCELL;
+                    const XT *xq = x + qb * xstride + (int)(Q - qb * NCELL);
+                    tc_split(tc_value<XT>(xq[0]), tc_value<XT>(xq[NCELL]), hi0, lo0);
+                    tc_split(tc_value<XT>(xq[2 * NCELL]), tc_value<XT>(xq[3 * NCELL]), hi1, lo1);
+                }
+                sDec[slot] = make_uint4(hi0, hi1, lo0, lo1);
+            }
+        }
+        __syncthreads();
+        // stage 2: row r = the 2x2 patch at positions r, r+1, r+17, r+18 (zero past the right / bottom edge)
+        {
+            const bool rgt = valid && n < 16, bot = valid && m < 16;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 d00 = valid ? sDec[tid] : z, d01 = rgt ? sDec[tid + 1] : z;
+            const uint4 d10 = bot ? sDec[tid + GS] : z, d11 = (rgt && bot) ? sDec[tid + GS + 1] : z;
+            *reinterpret_cast<uint4 *>(sA[0] + tc_operand_offset(tid, 0)) = make_uint4(d00.x, d00.y, d01.x, d01.y);
+            *reinterpret_cast<uint4 *>(sA[0] + tc_operand_offset(tid, 1)) = make_uint4(d10.x, d10.y, d11.x, d11.y);
+            *reinterpret_cast<uint4 *>(sA[1] + tc_operand_offset(tid, 0)) = make_uint4(d00.z, d00.w, d01.z, d01.w);
+            *reinterpret_cast<uint4 *>(sA[1] + tc_operand_offset(tid, 1)) = make_uint4(d10.z, d10.w, d11.z, d11.w);
+        }
+        rowinfo[tid] = valid ? (((b * (C1_OUT * C1_OUT) + 2 * m * C1_OUT + 2 * n) << 2) | (m == 16 ? 2 : 0) | (n == 16 ? 1 : 0)) : -1ll;
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's (async proxy) reads
+        __syncthreads();
+        long long info[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) info[it] = dead ? -1ll : rowinfo[warp * 32 + it * 8 + (lane >> 2)];
+        // ---- one MMA per output phase (TC_NT = 64 columns), epilogue straight out of TMEM -------------------
+#pragma unroll 1
+        for (int phase = 0; phase < TC_N / TC_NT; phase++) {
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t boff = (uint64_t)((phase * TC_NT / 8 * 256) >> 4);  // rows phase*64.. of W4
+                tc_mma(tmem_base, descA_hi, descB_hi + boff, 0u);
+                tc_mma(tmem_base, descA_lo, descB_hi + boff, 1u);
+                tc_mma(tmem_base, descA_hi, descB_lo + boff, 1u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            if (!dead && !tc_mbar_wait(&bar, parity)) dead = true;
+            parity ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int py = phase >> 1, px = phase & 1;
+#pragma unroll
+            for (int half = 0; half < TC_NT / 32; half++) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int c0 = half * 32;
+                // row `lane` of the warp's 32 x 64-byte staging block, 16-byte chunks XOR-swizzled by (row / 2) % 4
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        float a0 = __uint_as_float(r[8 * j + 2 * q]) + sbias[phase * 64 + c0 + 8 * j + 2 * q];
+                        float a1 = __uint_as_float(r[8 * j + 2 * q + 1]) + sbias[phase * 64 + c0 + 8 * j + 2 * q + 1];
+                        a0 = a0 > 0.f ? a0 : 0.f;
+                        a1 = a1 > 0.f ? a1 : 0.f;
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+                        o[q] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    *reinterpret_cast<uint4 *>(wout + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                __syncwarp();
+                // transposed read-out: 4 lanes per row -> a store instruction covers 8 rows x 64 contiguous bytes
+#pragma unroll
+                for (int it = 0; it < 4; it++) {
+                    const int row = it * 8 + (lane >> 2), j = lane & 3;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(wout + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+                    const long long inf = info[it];
+                    if (inf >= 0 && !(py && (inf & 2)) && !(px && (inf & 1)))
+                        *reinterpret_cast<uint4 *>(y + ((inf >> 2) + py * C1_OUT + px) * C1_CH + c0 + j * 8) = v;
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();  // TMEM is free for the next phase's MMA
+        }
+    }
+    if (dead && fail) atomicExch(fail, 1);
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_NT));
+}
+
+}  // namespace ta

@@ -10,6 +10,7 @@
 
 #include "ta_aux.cuh"
 #include "ta_conv1.cuh"
+#include "ta_conv1_tc.cuh"
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
 #include "ta_her.cuh"
@@ -456,6 +457,9 @@ int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, uint64_t 
 }  // extern "C"
 
 namespace {
+int *g_tc_fail = nullptr;  // set by conv1_fwd_tc_kernel if its MMA-completion barrier never arrived
+int g_use_tc = -1;         // -1: read TA_CONV1_TC on first use (default 1)
+
 template <typename K>
 int conv1_grid(K kern, long long batch, int *grid) {
     int dev = 0, sms = 0, occ = 0;
@@ -475,6 +479,50 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
     if (!x || !w4 || !b4 || !y_bf16 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
     if ((uintptr_t)y_bf16 & 7u) return TA_E_INVALID;
+    if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) != 0 : 1; }
+    if (g_use_tc) {  // tcgen05 version of the layer (TA_CONV1_TC=0 / ta_debug_conv1_tc(0) select the FP32-FMA kernel)
+        // resident CTAs per SM from the kernel's own footprint (the occupancy API answers 1 for a kernel that
+        // allocates TMEM): registers, shared memory with the large carve-out, and 512 TMEM columns per SM
+        static int per_sm_u8 = 0, per_sm_f32 = 0, sms = 0;
+        if (!sms) {
+            int dev = 0, regs_sm = 0, smem_sm = 0, smem_rsv = 0;
+            CK(cudaGetDevice(&dev));
+            CK(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+            CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+            CK(cudaDeviceGetAttribute(&smem_rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev));
+            auto fit = [&](const void *kern, int *out) -> cudaError_t {
+                cudaFuncAttributes fa;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
+                if (e != cudaSuccess) return e;
+                const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * TC_THREADS;
+                int n = 512 / TC_NT;
+                if (regs_sm / regs_cta < n) n = regs_sm / regs_cta;
+                if (smem_sm / ((int)fa.sharedSizeBytes + smem_rsv) < n) n = smem_sm / ((int)fa.sharedSizeBytes + smem_rsv);
+                *out = n > 0 ? n : 1;
+                return cudaSuccess;
+            };
+            CK(fit((const void *)conv1_fwd_tc_kernel<uint8_t>, &per_sm_u8));
+            CK(fit((const void *)conv1_fwd_tc_kernel<float>, &per_sm_f32));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm_u8, per_sm_f32, sms);
+        }
+        if (!g_tc_fail) {
+            CK(cudaMalloc(&g_tc_fail, sizeof(int)));
+            CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
+        }
+        const int per_sm = x_dtype == TA_X_U8 ? per_sm_u8 : per_sm_f32;
+        const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
+        const long long cap = (long long)sms * per_sm;
+        const int g = (int)(ntiles < cap ? ntiles : cap);
+        if (x_dtype == TA_X_U8)
+            conv1_fwd_tc_kernel<uint8_t><<<g, TC_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)x, x_stride, w4, b4, batch,
+                                                                                (__nv_bfloat16 *)y_bf16, g_tc_fail);
+        else
+            conv1_fwd_tc_kernel<float><<<g, TC_THREADS, 0, (cudaStream_t)stream>>>((const float *)x, x_stride, w4, b4, batch,
+                                                                              (__nv_bfloat16 *)y_bf16, g_tc_fail);
+        return launch_ok("conv1_fwd_tc_kernel");
+    }
     int grid = 1;
     if (x_dtype == TA_X_U8) {
         if (int rc = conv1_grid(conv1_fwd_kernel<uint8_t>, batch, &grid)) return rc;
@@ -574,6 +622,22 @@ int ta_debug_write_probe(void *dst, int64_t bytes, int mode, void *stream) {
     if (mode == 0) write_probe_stg<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((uint4 *)dst, bytes / 16);
     else write_probe_bulk<<<148 * 16, 32, 0, (cudaStream_t)stream>>>((uint8_t *)dst, bytes / 3072);
     return launch_ok("write_probe");
+}
+
+/* test hook: route ta_conv1_fwd through the tcgen05 kernel (1, default) or the FP32-FMA kernel (0); returns the
+ * previous setting (-1 = not decided yet) */
+int ta_debug_conv1_tc(int on) {
+    const int prev = g_use_tc;
+    g_use_tc = on != 0;
+    return prev;
+}
+
+/* check for the tcgen05 conv1 kernel: 1 if any launch gave up waiting for its MMA (synchronises) */
+int ta_debug_conv1_tc_failed(void) {
+    if (!g_tc_fail) return 0;
+    int v = 0;
+    if (cudaMemcpy(&v, g_tc_fail, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
 }
 
 /* test hook: emit the observations with per-lane stores (1) instead of TMA bulk stores

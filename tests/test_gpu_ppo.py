@@ -49,10 +49,22 @@ def test_rollout_and_update_run_and_learn_signal_is_finite():
     assert buf.ended[:64].sum() > 0 and float(buf.r[:64].mean()) < 0
 
 
+@pytest.fixture(params=["tcgen05", "fma"])
+def conv1_kernel(request):
+    """Run the test once through each forward kernel of the fused first layer."""
+    import twoarmy_b200 as pkg
+    L = pkg._capi.lib()
+    prev = L.ta_debug_conv1_tc(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    assert L.ta_debug_conv1_tc_failed() == 0          # no tcgen05 launch gave up on its MMA barrier
+    L.ta_debug_conv1_tc(1 if prev != 0 else 0)
+
+
 @pytest.mark.parametrize("dtype", ["u8", "f32"])
-def test_fused_conv1_matches_cudnn_layer(dtype):
-    """ta_conv1_fwd / ta_conv1_bwd == decode + UpsamplingNearest2d(4) + Conv2d(4,64,4,2) + ReLU in
-    fp32 (forward to bf16 rounding, weight / bias gradients to 1e-2 relative of their scale)."""
+def test_fused_conv1_matches_cudnn_layer(dtype, conv1_kernel):
+    """ta_conv1_fwd (tcgen05 kernel with bf16 hi/lo split operands, and the FP32-FMA kernel) / ta_conv1_bwd ==
+    decode + UpsamplingNearest2d(4) + Conv2d(4,64,4,2) + ReLU in fp32 (forward to bf16 rounding of the
+    output, weight / bias gradients to 1e-2 relative of their scale)."""
     import twoarmy_b200 as pkg
     P = _ppo()
     C1 = importlib.import_module(pkg.__name__ + ".conv1")
@@ -60,7 +72,7 @@ def test_fused_conv1_matches_cudnn_layer(dtype):
     net = P.TINet().cuda()
     conv = net.cnn_base[0]
     g = torch.Generator().manual_seed(2)
-    B = 37
+    B = 37 if dtype == "u8" else 700        # 700 x 289 positions: more 128-row tiles than resident CTAs
     codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)[torch.randint(0, 4, (B, 5, 289), generator=g)].cuda()
     x_in = codes[:, 1:5] if dtype == "u8" else P.decode_matrix(codes[:, 1:5]).contiguous()
     xf = P.decode_matrix(codes[:, 1:5]).view(B, 4, 17, 17)
