@@ -6,6 +6,10 @@
 //   :115     episode_idxs = np.random.choice(indices, size=min(4, len(indices)), replace=False)
 //   :118-127 for each chosen index > 0: the episode prefix 0..index is copied with g = the position
 //            reached at `index`, r[index] = 0.9, d[index] = 1
+// Buffer_gridworld.pre_her_func (soa/env_buffer.py:145-210) is the same selection over the 9-frame records of
+// train_ppo_predictor.py, which exist from the episode's 5th step on: record j there is step j + 4 here, so it
+// is this kernel with first_rec = 4 (candidates = steps >= 4, `index > 0` = step > 4); the four shifted pad
+// records it appends are the 5-frame records of the prefix's last four steps (see her.py).
 // The copies are not materialised: the kernel emits, for every record and each of the 4 relabel
 // slots, whether the record belongs to that slot's prefix and with which goal ("plan"); the host
 // turns the non-empty entries into (source record, goal, reward) triples.
@@ -23,7 +27,7 @@ constexpr int HER_MAXLEN = 64;
 constexpr uint32_t HER_NONE = 0xFFFFu;
 
 __global__ void __launch_bounds__(32 * HER_WARPS)
-her_plan_kernel(const float *__restrict__ p, const uint8_t *__restrict__ done, int T, long long n, uint32_t seed_lo,
+her_plan_kernel(const float *__restrict__ p, const uint8_t *__restrict__ done, int T, long long n, int first_rec, uint32_t seed_lo,
                 uint32_t seed_hi, unsigned long long env_id0, const uint8_t *__restrict__ chosen_in, uint8_t *uniq_out,
                 uint8_t *m_out, uint16_t *plan) {
     __shared__ uint8_t s_sorted[HER_WARPS][HER_MAXLEN];
@@ -53,8 +57,9 @@ her_plan_kernel(const float *__restrict__ p, const uint8_t *__restrict__ done, i
                     }
                 }
                 // first occurrence of each distinct position
-                bool first[2] = {lane < L, lane + 32 < L};
-                for (int j = 0; j < L; j++) {
+                // (records before first_rec are no candidates: pre_her_func only sees records from the 5th step on)
+                bool first[2] = {lane >= first_rec && lane < L, lane + 32 >= first_rec && lane + 32 < L};
+                for (int j = first_rec; j < L; j++) {
                     const uint32_t kj = j < 32 ? __shfl_sync(0xFFFFFFFFu, key[0], j) : __shfl_sync(0xFFFFFFFFu, key[1], j - 32);
                     if (j < lane && kj == key[0]) first[0] = false;
                     if (j < lane + 32 && kj == key[1]) first[1] = false;
@@ -107,7 +112,7 @@ her_plan_kernel(const float *__restrict__ p, const uint8_t *__restrict__ done, i
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int idx = s_chosen[warp][c];
-                    if (idx == 0xFF || idx <= 0 || idx >= L) continue;  // :121 `if index > 0`
+                    if (idx == 0xFF || idx <= first_rec || idx >= L) continue;  // :121 `if index > 0`
                     const uint32_t goal = idx < 32 ? __shfl_sync(0xFFFFFFFFu, key[0], idx) : __shfl_sync(0xFFFFFFFFu, key[1], idx - 32);
 #pragma unroll
                     for (int h = 0; h < 2; h++) {

@@ -443,14 +443,14 @@ int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stre
     return launch_ok("adv_normalize_kernel");
 }
 
-int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, uint64_t seed, uint64_t env_id0,
+int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, int first_record, uint64_t seed, uint64_t env_id0,
                 const uint8_t *chosen_in, uint8_t *uniq_out, uint8_t *m_out, uint16_t *plan_out, void *stream) {
-    if (!p || !done || !plan_out || T <= 0 || n <= 0) return TA_E_INVALID;
+    if (!p || !done || !plan_out || T <= 0 || n <= 0 || first_record < 0 || first_record >= HER_MAXLEN) return TA_E_INVALID;
     CK(cudaMemsetAsync(plan_out, 0xFF, (size_t)T * n * 4 * sizeof(uint16_t), (cudaStream_t)stream));
     if (uniq_out) CK(cudaMemsetAsync(uniq_out, 0xFF, (size_t)T * n * HER_MAXLEN, (cudaStream_t)stream));
     if (m_out) CK(cudaMemsetAsync(m_out, 0, (size_t)T * n, (cudaStream_t)stream));
     her_plan_kernel<<<blocks_for(n, HER_WARPS), 32 * HER_WARPS, 0, (cudaStream_t)stream>>>(
-        p, done, T, n, (uint32_t)seed, (uint32_t)(seed >> 32), env_id0, chosen_in, uniq_out, m_out, plan_out);
+        p, done, T, n, first_record, (uint32_t)seed, (uint32_t)(seed >> 32), env_id0, chosen_in, uniq_out, m_out, plan_out);
     return launch_ok("her_plan_kernel");
 }
 

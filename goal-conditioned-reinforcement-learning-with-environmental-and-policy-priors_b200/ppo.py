@@ -233,13 +233,14 @@ class RolloutBuffer:
                 "d": self.d[:T].reshape(B, 1), "a_logp": self.a_logp[:T].reshape(B, 1)}
 
 
-def with_her(buf: "RolloutBuffer", seed: int = 9981, env_id0: int = 0):
+def with_her(buf: "RolloutBuffer", seed: int = 9981, env_id0: int = 0, first: int = 0):
     """The rollout's samples followed by their hindsight relabels (train_ppo.py:128-134 with
-    args.her on): a dict for PPO.update in which `src` maps every sample to the record it copies."""
+    args.her on): a dict for PPO.update in which `src` maps every sample to the record it copies.
+    first = 4 gives pre_her_func's selection for the PPO + predictor loop (train_ppo_predictor.py:174-180)."""
     from . import her
     flat = buf.flat()
     T, N = buf.counter, buf.N
-    extra = her.relabel(buf.p[:T], buf.r[:T], buf.ended[:T], seed, env_id0)
+    extra = her.relabel(buf.p[:T], buf.r[:T], buf.ended[:T], seed, env_id0, first=first)
     base = torch.arange(T * N, device=buf.device)
     out = dict(flat)
     out["src"] = torch.cat([base, extra["src"]])

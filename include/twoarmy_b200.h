@@ -193,6 +193,10 @@ int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stre
 
 /* Hindsight relabelling of a [T][n] rollout: Buffer_gridworld.her_func (soa/env_buffer.py:101-143)
  * for every episode that ends inside the window, without materialising the copies.
+ *   first_record  0 for her_func.  4 = Buffer_gridworld.pre_her_func (soa/env_buffer.py:145-210): its 9-frame
+ *             records exist from an episode's 5th step on (train_ppo_predictor.py:140-142), so only records
+ *             >= first_record of an episode are candidates, indices are still counted from the episode start,
+ *             and a prefix is kept if index > first_record (its `index > 0`)
  *   p         float32 [T][n][5][2], the record's p field; [4] = (y, x) reached by the step
  *   done      uint8 [T][n], the episode ended with this record (terminated | truncated)
  *   chosen_in nullable uint8 [T][n][4].  NULL: the up-to-4 relabel indices are drawn with Philox
@@ -205,7 +209,7 @@ int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stre
  *   plan_out  uint16 [T][n][4]: 0xFFFF = the record is not part of relabel slot c; otherwise the
  *             new goal y<<5|x, with bit 15 set on the prefix's last record (r = 0.9, d = 1 there,
  *             env_buffer.py:126-127).  Prefixes with index 0 are dropped like line 121. */
-int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, uint64_t seed, uint64_t env_id0,
+int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, int first_record, uint64_t seed, uint64_t env_id0,
                 const uint8_t *chosen_in, uint8_t *uniq_out, uint8_t *m_out, uint16_t *plan_out, void *stream);
 
 /* First layer of TINet fused for the device rollout buffer: matrix_env LUT decode + UpsamplingNearest2d(4)

@@ -265,8 +265,33 @@ def her_func(p4, r, counter_start, capacity=2048, newgoal_size_in=4, choice=None
                 d=np.array(dd, np.float32), counter=end + 1, full=full)
 
 
-def her_plan(pos_y, pos_x, done, choose):
-    """The vectorised form the CUDA kernel computes: pos_y/pos_x/done [T,N]; every episode segment
+def pre_her_func(p8, r_step, newgoal_size_in=4, choice=None):
+    """Buffer_gridworld.pre_her_func (env_buffer.py:145-210) for ONE episode of the PPO + predictor loop, stated
+    over the episode's STEPS.  The reference's 9-frame record j (stored from the 5th step on, then four closing
+    pads, train_ppo_predictor.py:140-171) holds step j + 4 in its newest slot; p8 [J,2] = pre_buffer['p'][:,8,0:2]
+    of the episode's J records, r_step [L] the per-step rewards (L = J).  Returns the appended records as
+    (step, g, r0) -- `step` = the step whose 5-frame record sits in frames 0..4 (what PPO_Predictor.update reads,
+    PPO_Predictor.py:124-163), g the relabelled goal, r0 = r[:,0] after the override of line 170 has been
+    shifted into slot 0 by the four pad records (:173-196)."""
+    p8 = np.asarray(p8, np.float32)
+    J = p8.shape[0]
+    steps, g, r0 = [], [], []
+    if J > 0:
+        _, idxs = her_select(p8, newgoal_size_in, choice)
+        for index in idxs:
+            index = int(index)
+            if index > 0:
+                n = index + 1 + 4                              # records 0..index, then the 4 pads
+                rn = np.asarray(r_step[:n], np.float32).copy()
+                rn[n - 1] = np.float32(0.9)
+                steps += list(range(n)); g += [p8[index, 0:2]] * n; r0 += list(rn)
+    return dict(step=np.array(steps, np.int64), g=np.array(g, np.float32).reshape(-1, 2), r0=np.array(r0, np.float32))
+
+
+def her_plan(pos_y, pos_x, done, choose, first=0):
+    """first = 0: her_func; first = 4: pre_her_func (candidates are the records from the episode's 5th step on,
+    indices stay relative to the episode start).
+    The vectorised form the CUDA kernel computes: pos_y/pos_x/done [T,N]; every episode segment
     that ENDS inside the window (segments start at t=0 or after a done) is relabelled like her_func;
     choose(indices, k, t_end, env) -> the k chosen record indices.  Returns plan uint16 [T,N,4]:
     0xFFFF = record not in relabel slot c, else goal y*32+x | 0x8000 on the prefix's last record."""
@@ -279,12 +304,16 @@ def her_plan(pos_y, pos_x, done, choose):
                 continue
             L = t1 - t0 + 1
             p4 = np.stack([pos_y[t0:t1 + 1, e], pos_x[t0:t1 + 1, e]], 1)
-            _, indices, _ = np.unique(p4, return_index=True, return_counts=True, axis=0)
+            if L <= first:
+                t0 = t1 + 1
+                continue
+            _, indices, _ = np.unique(p4[first:], return_index=True, return_counts=True, axis=0)
+            indices = indices + first
             k = min(4, indices.size)
             chosen = choose(indices, k, t1, e)
             for c, index in enumerate(chosen):
                 index = int(index)
-                if index > 0:
+                if index > first:
                     goal = int(p4[index, 0]) * 32 + int(p4[index, 1])
                     plan[t0:t0 + index + 1, e, c] = goal
                     plan[t0 + index, e, c] = goal | 0x8000

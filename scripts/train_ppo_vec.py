@@ -70,7 +70,7 @@ def main(argv=None):
         buf = roll.collect()
         torch.cuda.synchronize()
         t1 = time.time()
-        data = P.with_her(buf, seed=args.seed + u, env_id0=rank * n_local) if args.her else buf.flat()
+        data = P.with_her(buf, seed=args.seed + u, env_id0=rank * n_local, first=4 if args.predictor is not None else 0) if args.her else buf.flat()
         al, vl = agent.update(data, minibatch=args.minibatch, epochs=args.epochs)
         torch.cuda.synchronize()
         t2 = time.time()

@@ -375,10 +375,12 @@ def _np_choice(indices, k, *_):
     return np.random.choice(indices, size=k, replace=False)
 
 
-def test_her_plan_matches_her_func_oracle():
-    """ta_her_plan against oracle.her_plan (her_func per finished episode, pinned to the reference by
-    tests/golden/her_ref.npz): first pass returns np.unique's `indices`; the relabel indices are then
-    drawn with np.random.choice from the legacy stream exactly like env_buffer.py:115 and replayed."""
+@pytest.mark.parametrize("first", [0, 4])
+def test_her_plan_matches_her_func_oracle(first):
+    """ta_her_plan against oracle.her_plan (her_func per finished episode for first = 0, pre_her_func for
+    first = 4; pinned to the reference by tests/golden/her_ref.npz / pre_her_ref.npz): first pass returns
+    np.unique's `indices`; the relabel indices are then drawn with np.random.choice from the legacy stream
+    exactly like env_buffer.py:115 / :159 and replayed."""
     import importlib
     pkg, O = _pkg(), _oracle()
     H = importlib.import_module(pkg.__name__ + ".her")
@@ -404,7 +406,7 @@ def test_her_plan_matches_her_func_oracle():
     p[:, :, :4] = rng.randint(1, 16, size=(T, N, 4, 2))
     dev = "cuda:0"
     pt, dt = torch.tensor(p, device=dev), torch.tensor(done, device=dev)
-    _, uniq, m = H.plan(pt, dt, want_unique=True)
+    _, uniq, m = H.plan(pt, dt, want_unique=True, first=first)
     uniq, m = uniq.cpu().numpy(), m.cpu().numpy()
     # np.unique's indices per finished episode, and the reference's choice from them
     np.random.seed(77)
@@ -418,13 +420,13 @@ def test_her_plan_matches_her_func_oracle():
         picks[(t1, e)] = c
         return c
 
-    want = O.her_plan(pos[:, :, 0], pos[:, :, 1], done, choose)
-    got = H.plan(pt, dt, chosen=torch.tensor(chosen)).cpu().numpy()
+    want = O.her_plan(pos[:, :, 0], pos[:, :, 1], done, choose, first=first)
+    got = H.plan(pt, dt, chosen=torch.tensor(chosen), first=first).cpu().numpy()
     np.testing.assert_array_equal(got, want)
     assert (want != 0xFFFF).sum() > 1000
     # the relabelled triples: goal/r/d exactly as her_func writes them
     r = rng.choice(np.array([-0.01, -0.1, 0.2], np.float32), size=(T, N))
-    rel = H.relabel(pt, torch.tensor(r, device=dev), dt, chosen=torch.tensor(chosen))
+    rel = H.relabel(pt, torch.tensor(r, device=dev), dt, chosen=torch.tensor(chosen), first=first)
     src, g, rr, dd = (rel[k].cpu().numpy() for k in ("src", "g", "r", "d"))
     t_idx, e_idx = src // N, src % N
     assert np.all(dd[rr == np.float32(0.9)] >= 0) and np.all(rr[dd == 1] == np.float32(0.9))

@@ -166,6 +166,51 @@ def test_her_func_matches_reference(golden):
     assert n_nonempty >= 6
 
 
+def test_pre_her_func_matches_reference(golden):
+    """oracle.pre_her_func and oracle.her_plan(first=4) (restating soa/env_buffer.py:145-210 over the episode's
+    steps) against what the reference's own pre_her_func appended to its 9-frame buffer
+    (tests/golden/pre_her_ref.npz, produced through the record loop of train_ppo_predictor.py:105-171): for every
+    appended record, the step whose 5-frame record sits in frames 0..4, the goal and a[0] / r[0] / a_logp[0]."""
+    from oracle import oracle as O
+    fx = golden("pre_her_ref.npz")
+    cases = sorted({k.split("_")[0] for k in fx})
+    assert len(cases) >= 10
+    n_nonempty = 0
+    for c in cases:
+        L, start, seed, J, n_new = (int(v) for v in fx[f"{c}_meta"])
+        pos, rew, act, alp, tags = fx[f"{c}_pos"], fx[f"{c}_rew"], fx[f"{c}_act"], fx[f"{c}_alp"], fx[f"{c}_new_tags"]
+        np.random.seed(seed)
+        got = O.pre_her_func(fx[f"{c}_p8"], rew)
+        assert len(got["step"]) == n_new
+        if L >= 4:                       # record j <-> step j + 4; the 4 closing pads repeat the last position
+            np.testing.assert_array_equal(fx[f"{c}_p8"], np.concatenate([pos[4:], np.repeat(pos[-1:], 4, 0)]))
+        if n_new == 0:
+            continue
+        n_nonempty += 1
+        step = got["step"]
+        np.testing.assert_array_equal(tags[:, 4], step)
+        for f in range(4):                # frames 0..3 = the four steps before (the reset frame before step 0)
+            np.testing.assert_array_equal(tags[:, f], np.maximum(step - 4 + f, -1))
+        np.testing.assert_array_equal(got["g"], fx[f"{c}_new_g"])
+        np.testing.assert_array_equal(got["r0"], fx[f"{c}_new_r0"])
+        np.testing.assert_array_equal(act[step], fx[f"{c}_new_a0"])
+        np.testing.assert_array_equal(alp[step], fx[f"{c}_new_alp0"])
+        # the vectorised form the device computes: same draws, plan -> (step, goal, r) per relabel slot
+        np.random.seed(seed)
+        done = np.zeros((L, 1), np.uint8); done[-1] = 1
+        plan = O.her_plan(pos[:, 0:1], pos[:, 1:2], done, lambda ind, k, t1, e: np.random.choice(ind, size=k, replace=False), first=4)
+        ps, pg, pr = [], [], []
+        for slot in range(4):
+            tt = np.nonzero(plan[:, 0, slot] != 0xFFFF)[0]
+            v = plan[tt, 0, slot].astype(np.int64)
+            ps += list(tt); pg += [((x >> 5) & 31, x & 31) for x in v]
+            pr += [np.float32(0.9) if x & 0x8000 else rew[t] for t, x in zip(tt, v)]
+        np.testing.assert_array_equal(np.array(ps), step)
+        np.testing.assert_array_equal(np.array(pg, np.float32), got["g"])
+        np.testing.assert_array_equal(np.array(pr, np.float32), got["r0"])
+    assert n_nonempty >= 6
+
+
 def test_render_tiles_compose_to_reference_frames(golden):
     """Host tile atlas (render.tile_atlas: my restatement of render_tile / rendering.py) composed per cell ==
     the reference's get_full_render, pixel for pixel, for tile sizes 5/8/17, highlight on/off, views 17/7."""
