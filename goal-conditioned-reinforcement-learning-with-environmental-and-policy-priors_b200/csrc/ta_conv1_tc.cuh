@@ -224,4 +224,193 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_NT));
 }
 
+// ---- weight / bias gradient of the same layer on the tensor cores -------------------------------------------
+// dW4[(phase, o), k] = sum over positions of dz[position, (phase, o)] * P[position, k], db4 = the same with P = 1:
+// a GEMM whose reduction runs over the positions.  Both operands are therefore "MN-major" in shared memory
+// (8 consecutive channels / taps of one position form a 16-byte chunk, consecutive positions follow at 16 bytes,
+// 8 positions = one core matrix of 128 bytes):
+//   A (dz)  half a tile at a time = 2 output phases x 64 channels = 128 rows, K = 128 positions; chunk (group g of
+//           8 rows, position p) at g * TCB_SBO + (p / 8) * 128 + (p % 8) * 16
+//   B (P)   N = 32 columns: 16 taps (bf16 hi / lo pair, as in the forward kernel), column 16 = 1 for the bias
+//           gradient, 15 zero columns; same chunk rule
+// dz = dy where y > 0 is formed on the way from global to shared memory (8 lanes read the 128 contiguous bytes of a
+// pixel).  The two fp32 accumulators (128 lanes x 32 columns each) stay in TMEM for the CTA's whole lifetime: no
+// per-tile epilogue, one atomicAdd per value and CTA at the end.
+constexpr int TCB_SBO = 128 * 16 + 16;                 // + 16: the 8 lanes of a quarter warp hit 8 different bank groups
+constexpr int TCB_A_BYTES = 16 * TCB_SBO, TCB_B_BYTES = 4 * TCB_SBO;
+constexpr int TCB_N = 32, TCB_COLS = 64, TCB_BATCH = 4;
+constexpr uint32_t TCB_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TCB_N >> 3) << 17) |
+                               ((uint32_t)(TC_M >> 4) << 24);  // D f32, A/B bf16, both MN-major, N = 32, M = 128
+
+__device__ __forceinline__ uint64_t tcb_smem_desc(const void *smem, uint32_t lbo, uint32_t sbo) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem) >> 4) & 0x3FFFu;
+    return addr | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tcb_mma(uint32_t tmem, uint64_t descA, uint64_t descB, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
+                 "l"(descA), "l"(descB), "r"(TCB_IDESC), "r"(accumulate)
+                 : "memory");
+}
+// 16-byte read-only load as a volatile asm: stays above the compiler barrier that separates a batch's loads from its stores
+__device__ __forceinline__ uint4 tcb_ldg(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// 8 bf16 of dy kept where the matching bf16 of y (a ReLU output, so >= +0) is non-zero
+__device__ __forceinline__ uint4 tcb_mask(uint4 g, uint4 yv) {
+    auto m = [](uint32_t gw, uint32_t yw) { return gw & (((yw & 0xFFFFu) ? 0xFFFFu : 0u) | ((yw >> 16) ? 0xFFFF0000u : 0u)); };
+    return make_uint4(m(g.x, yv.x), m(g.y, yv.y), m(g.z, yv.z), m(g.w, yv.w));
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__restrict__ x, long long xstride,
+                                                                 const __nv_bfloat16 *__restrict__ y,
+                                                                 const __nv_bfloat16 *__restrict__ dy, long long B,
+                                                                 float *__restrict__ dw4, float *__restrict__ db4, int swap_lbo_sbo,
+                                                                 uint32_t zero, int *fail) {
+    extern __shared__ __align__(128) uint8_t tcb_smem[];
+    uint8_t *sG = tcb_smem;                               // A: TCB_A_BYTES
+    uint8_t *sP = tcb_smem + TCB_A_BYTES;                 // B hi, B lo: 2 x TCB_B_BYTES
+    __shared__ uint4 sDec[TC_M + TC_HALO];
+    __shared__ long long rowinfo[TC_M];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) tc_mbar_init(&bar);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TCB_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = tid; i < 2 * TCB_B_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    // K-direction (positions) core-matrix stride 128 B, MN-direction group stride TCB_SBO
+    const uint32_t lbo = swap_lbo_sbo ? TCB_SBO : 128u, sbo = swap_lbo_sbo ? 128u : TCB_SBO;
+    const uint64_t descA = tcb_smem_desc(sG, lbo, sbo), descBh = tcb_smem_desc(sP, lbo, sbo),
+                   descBl = tcb_smem_desc(sP + TCB_B_BYTES, lbo, sbo);
+    const long long npos = B * NCELL, ntiles = (npos + TC_M - 1) / TC_M;
+    uint32_t parity = 0;
+    bool dead = false, any = false;
+    const int g8 = tid & 7, psub = tid >> 3;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- B tile: decoded inputs (as in the forward kernel), then the 2x2 patch of every position ----------
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            const int slot = tid + rep * TC_M;
+            if (slot < TC_M + TC_HALO) {
+                const long long Q = tile * TC_M + slot;
+                uint32_t hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
+                if (Q < npos) {
+                    const long long qb = Q / NCELL;
+                    const XT *xq = x + qb * xstride + (int)(Q - qb * NCELL);
+                    tc_split(tc_value<XT>(xq[0]), tc_value<XT>(xq[NCELL]), hi0, lo0);
+                    tc_split(tc_value<XT>(xq[2 * NCELL]), tc_value<XT>(xq[3 * NCELL]), hi1, lo1);
+                }
+                sDec[slot] = make_uint4(hi0, hi1, lo0, lo1);
+            }
+        }
+        const long long P = tile * TC_M + tid;
+        const bool valid = P < npos;
+        const long long b = valid ? P / NCELL : 0;
+        const int pos = valid ? (int)(P - b * NCELL) : 0, m = pos / GS, n = pos - GS * m;
+        rowinfo[tid] = valid ? (((b * (C1_OUT * C1_OUT) + 2 * m * C1_OUT + 2 * n) << 2) | (m == 16 ? 2 : 0) | (n == 16 ? 1 : 0)) : -1ll;
+        __syncthreads();
+        {
+            const bool rgt = valid && n < 16, bot = valid && m < 16;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 d00 = valid ? sDec[tid] : z, d01 = rgt ? sDec[tid + 1] : z;
+            const uint4 d10 = bot ? sDec[tid + GS] : z, d11 = (rgt && bot) ? sDec[tid + GS + 1] : z;
+            const uint32_t off = (tid >> 3) * 128 + (tid & 7) * 16;
+            *reinterpret_cast<uint4 *>(sP + off) = make_uint4(d00.x, d00.y, d01.x, d01.y);
+            *reinterpret_cast<uint4 *>(sP + TCB_SBO + off) = make_uint4(d10.x, d10.y, d11.x, d11.y);
+            *reinterpret_cast<uint4 *>(sP + 2 * TCB_SBO + off) = make_uint4(valid ? 0x3F80u : 0u, 0u, 0u, 0u);  // bf16 1.0: bias column
+            *reinterpret_cast<uint4 *>(sP + TCB_B_BYTES + off) = make_uint4(d00.z, d00.w, d01.z, d01.w);
+            *reinterpret_cast<uint4 *>(sP + TCB_B_BYTES + TCB_SBO + off) = make_uint4(d10.z, d10.w, d11.z, d11.w);
+        }
+        // ---- two halves: output phases (py = h, px = 0 / 1) ---------------------------------------------------
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            // dz chunks: lane group of 8 = the 128 bytes of one pixel; 16 positions per pass
+#pragma unroll 1
+            for (int it0 = 0; it0 < 8; it0 += TCB_BATCH) {  // TCB_BATCH x 4 16-byte loads in flight per thread
+                uint4 gv[TCB_BATCH][2], yv[TCB_BATCH][2];
+#pragma unroll
+                for (int u = 0; u < TCB_BATCH; u++) {
+                    const long long inf = rowinfo[(it0 + u) * 16 + psub];
+#pragma unroll
+                    for (int px = 0; px < 2; px++) {
+                        // a pixel that does not exist reads pixel 0 and is zeroed through its y (unconditional loads
+                        // keep all of the batch in flight)
+                        const bool ok = inf >= 0 && !(h && (inf & 2)) && !(px && (inf & 1));
+                        const long long e = ok ? ((inf >> 2) + h * C1_OUT + px) * C1_CH + g8 * 8 : 0ll;
+                        gv[u][px] = tcb_ldg(dy + e);
+                        yv[u][px] = tcb_ldg(y + e);
+                        if (!ok) yv[u][px] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                // every store's address depends on every load of the batch, so all of them are in flight together
+                // (ptxas otherwise interleaves loads and stores to save registers: 3 dependent round trips per batch)
+                uint32_t live = 0;
+#pragma unroll
+                for (int u = 0; u < TCB_BATCH; u++) live |= gv[u][0].x | yv[u][0].x | gv[u][1].x | yv[u][1].x;
+                const uint32_t nudge = live & zero;  // zero == 0 at run time
+#pragma unroll
+                for (int u = 0; u < TCB_BATCH; u++) {
+                    const int p = (it0 + u) * 16 + psub;
+#pragma unroll
+                    for (int px = 0; px < 2; px++)
+                        *reinterpret_cast<uint4 *>(sG + (px * 8 + g8) * TCB_SBO + (p >> 3) * 128 + (p & 7) * 16 + nudge) = tcb_mask(gv[u][px], yv[u][px]);
+                }
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + (uint32_t)(h * TCB_N);
+#pragma unroll
+                for (int ks = 0; ks < TC_M / 16; ks++) {  // 16 positions = 2 core matrices of 128 bytes per step
+                    const uint64_t koff = (uint64_t)((ks * 256) >> 4);
+                    tcb_mma(d, descA + koff, descBh + koff, (any || ks) ? 1u : 0u);
+                    tcb_mma(d, descA + koff, descBl + koff, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            if (!dead && !tc_mbar_wait(&bar, parity)) dead = true;   // sG / sP are free again
+            parity ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        any = true;
+        __syncthreads();
+    }
+    // ---- accumulators -> global: lane = row (phase pair member * 64 + channel), columns = 16 taps + bias -------
+    if (any && !dead) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * TCB_N);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int row = (2 * h + (tid >> 6)) * C1_CH + (tid & 63);
+#pragma unroll
+            for (int k = 0; k < 16; k++) atomicAdd(dw4 + row * 16 + k, __uint_as_float(r[k]));
+            atomicAdd(db4 + row, __uint_as_float(r[16]));
+        }
+    }
+    if (dead && fail) atomicExch(fail, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCB_COLS));
+}
+
 }  // namespace ta

@@ -460,6 +460,29 @@ namespace {
 int *g_tc_fail = nullptr;  // set by conv1_fwd_tc_kernel if its MMA-completion barrier never arrived
 int g_use_tc = -1;         // -1: read TA_CONV1_TC on first use (default 1)
 
+int g_bwd_tc = -1;         // conv1 weight gradient on tcgen05: -1 = read TA_CONV1_BWD_TC on first use
+int g_bwd_swap = 0;        // probe: exchange the LBO / SBO fields of the MN-major descriptors
+
+// Resident CTAs per SM of a TMEM-allocating kernel from its own footprint (the occupancy API answers 1 for such
+// kernels): registers, shared memory with the large carve-out, and 512 TMEM columns per SM.
+int tc_ctas_per_sm(const void *kern, int threads, int dyn_smem, int tmem_cols, int *out) {
+    int dev = 0, regs_sm = 0, smem_sm = 0, smem_rsv = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+    CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    CK(cudaDeviceGetAttribute(&smem_rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev));
+    cudaFuncAttributes fa;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (dyn_smem > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+    CK(cudaFuncGetAttributes(&fa, kern));
+    const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * threads, smem_cta = (int)fa.sharedSizeBytes + dyn_smem + smem_rsv;
+    int n = 512 / tmem_cols;
+    if (regs_sm / regs_cta < n) n = regs_sm / regs_cta;
+    if (smem_sm / smem_cta < n) n = smem_sm / smem_cta;
+    *out = n > 0 ? n : 1;
+    return TA_OK;
+}
+
 template <typename K>
 int conv1_grid(K kern, long long batch, int *grid) {
     int dev = 0, sms = 0, occ = 0;
@@ -481,29 +504,12 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
     if ((uintptr_t)y_bf16 & 7u) return TA_E_INVALID;
     if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) != 0 : 1; }
     if (g_use_tc) {  // tcgen05 version of the layer (TA_CONV1_TC=0 / ta_debug_conv1_tc(0) select the FP32-FMA kernel)
-        // resident CTAs per SM from the kernel's own footprint (the occupancy API answers 1 for a kernel that
-        // allocates TMEM): registers, shared memory with the large carve-out, and 512 TMEM columns per SM
         static int per_sm_u8 = 0, per_sm_f32 = 0, sms = 0;
         if (!sms) {
-            int dev = 0, regs_sm = 0, smem_sm = 0, smem_rsv = 0;
+            int dev = 0;
             CK(cudaGetDevice(&dev));
-            CK(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
-            CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-            CK(cudaDeviceGetAttribute(&smem_rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev));
-            auto fit = [&](const void *kern, int *out) -> cudaError_t {
-                cudaFuncAttributes fa;
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
-                if (e != cudaSuccess) return e;
-                const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * TC_THREADS;
-                int n = 512 / TC_NT;
-                if (regs_sm / regs_cta < n) n = regs_sm / regs_cta;
-                if (smem_sm / ((int)fa.sharedSizeBytes + smem_rsv) < n) n = smem_sm / ((int)fa.sharedSizeBytes + smem_rsv);
-                *out = n > 0 ? n : 1;
-                return cudaSuccess;
-            };
-            CK(fit((const void *)conv1_fwd_tc_kernel<uint8_t>, &per_sm_u8));
-            CK(fit((const void *)conv1_fwd_tc_kernel<float>, &per_sm_f32));
+            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<uint8_t>, TC_THREADS, 0, TC_NT, &per_sm_u8)) return rc;
+            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<float>, TC_THREADS, 0, TC_NT, &per_sm_f32)) return rc;
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm_u8, per_sm_f32, sms);
         }
@@ -544,6 +550,33 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
     if (((uintptr_t)y_bf16 | (uintptr_t)dy_bf16) & 7u) return TA_E_INVALID;
     CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), (cudaStream_t)stream));
     CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
+    if (g_bwd_tc < 0) { const char *e = getenv("TA_CONV1_BWD_TC"); g_bwd_tc = e ? atoi(e) != 0 : 1; }
+    if (g_bwd_tc && !(((uintptr_t)y_bf16 | (uintptr_t)dy_bf16) & 15u)) {
+        static int per_sm_u8 = 0, per_sm_f32 = 0, sms = 0;
+        const int dyn = TCB_A_BYTES + 2 * TCB_B_BYTES;
+        if (!sms) {
+            int dev = 0;
+            CK(cudaGetDevice(&dev));
+            if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t>, TC_THREADS, dyn, TCB_COLS, &per_sm_u8)) return rc;
+            if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float>, TC_THREADS, dyn, TCB_COLS, &per_sm_f32)) return rc;
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_bwd_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm_u8, per_sm_f32, sms);
+        }
+        if (!g_tc_fail) {
+            CK(cudaMalloc(&g_tc_fail, sizeof(int)));
+            CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
+        }
+        const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
+        const long long cap = (long long)sms * (x_dtype == TA_X_U8 ? per_sm_u8 : per_sm_f32);
+        const int g = (int)(ntiles < cap ? ntiles : cap);
+        if (x_dtype == TA_X_U8)
+            conv1_bwd_tc_kernel<uint8_t><<<g, TC_THREADS, dyn, (cudaStream_t)stream>>>(
+                (const uint8_t *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail);
+        else
+            conv1_bwd_tc_kernel<float><<<g, TC_THREADS, dyn, (cudaStream_t)stream>>>(
+                (const float *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail);
+        return launch_ok("conv1_bwd_tc_kernel");
+    }
     int grid = 1;
     if (x_dtype == TA_X_U8) {
         if (int rc = conv1_grid(conv1_bwd_kernel<uint8_t>, batch, &grid)) return rc;
@@ -630,6 +663,17 @@ int ta_debug_conv1_tc(int on) {
     const int prev = g_use_tc;
     g_use_tc = on != 0;
     return prev;
+}
+
+/* test hooks for the tcgen05 weight-gradient kernel: on/off (returns the previous setting), descriptor probe */
+int ta_debug_conv1_bwd_tc(int on) {
+    const int prev = g_bwd_tc;
+    g_bwd_tc = on != 0;
+    return prev;
+}
+int ta_debug_conv1_bwd_swap(int on) {
+    g_bwd_swap = on != 0;
+    return 0;
 }
 
 /* check for the tcgen05 conv1 kernel: 1 if any launch gave up waiting for its MMA (synchronises) */

@@ -51,18 +51,20 @@ def test_rollout_and_update_run_and_learn_signal_is_finite():
 
 @pytest.fixture(params=["tcgen05", "fma"])
 def conv1_kernel(request):
-    """Run the test once through each forward kernel of the fused first layer."""
+    """Run the test once through each kernel pair of the fused first layer (forward + weight gradient)."""
     import twoarmy_b200 as pkg
     L = pkg._capi.lib()
-    prev = L.ta_debug_conv1_tc(1 if request.param == "tcgen05" else 0)
+    on = 1 if request.param == "tcgen05" else 0
+    prev, prev_bwd = L.ta_debug_conv1_tc(on), L.ta_debug_conv1_bwd_tc(on)
     yield request.param
     assert L.ta_debug_conv1_tc_failed() == 0          # no tcgen05 launch gave up on its MMA barrier
     L.ta_debug_conv1_tc(1 if prev != 0 else 0)
+    L.ta_debug_conv1_bwd_tc(1 if prev_bwd != 0 else 0)
 
 
 @pytest.mark.parametrize("dtype", ["u8", "f32"])
 def test_fused_conv1_matches_cudnn_layer(dtype, conv1_kernel):
-    """ta_conv1_fwd (tcgen05 kernel with bf16 hi/lo split operands, and the FP32-FMA kernel) / ta_conv1_bwd ==
+    """ta_conv1_fwd / ta_conv1_bwd (tcgen05 kernels with bf16 hi/lo split inputs, and the FP32-FMA kernels) ==
     decode + UpsamplingNearest2d(4) + Conv2d(4,64,4,2) + ReLU in fp32 (forward to bf16 rounding of the
     output, weight / bias gradients to 1e-2 relative of their scale)."""
     import twoarmy_b200 as pkg
