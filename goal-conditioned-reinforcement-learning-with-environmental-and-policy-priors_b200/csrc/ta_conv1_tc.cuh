@@ -63,6 +63,12 @@ __device__ __forceinline__ void tc_split(float v0, float v1, uint32_t &hi, uint3
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+// (max(a, 0), max(b, 0)) -> packed bf16 pair in one instruction
+__device__ __forceinline__ uint32_t tc_relu_pack(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 // D[tmem] (+)= A[smem] x B[smem]^T, M = 128, N = TC_NT, K = 16; issued by one thread
 __device__ __forceinline__ void tc_mma(uint32_t tmem, uint64_t descA, uint64_t descB, uint32_t accumulate) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
     // fp32-grade products, so the layer matches the FP32 kernel / cuDNN fp32 to rounding of the bf16 output
     __shared__ __align__(1024) uint8_t sA[2][TC_M * 32];   // 2 x 4 KB
     __shared__ __align__(1024) uint8_t sB[2][TC_N * 32];   // 2 x 8 KB
-    __shared__ float sbias[TC_N];
+    __shared__ __align__(16) float sbias[TC_N];
     __shared__ __align__(16) uint8_t sOut[TC_M * 64];      // epilogue staging: 32 channels (64 B) per row
     __shared__ uint4 sDec[TC_M + TC_HALO];                 // decoded inputs of the tile's positions + halo
     __shared__ long long rowinfo[TC_M];                    // (output pixel of phase 0) * 4 | (m == 16) * 2 | (n == 16); -1 = no row
@@ -156,9 +162,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
         rowinfo[tid] = valid ? (((b * (C1_OUT * C1_OUT) + 2 * m * C1_OUT + 2 * n) << 2) | (m == 16 ? 2 : 0) | (n == 16 ? 1 : 0)) : -1ll;
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's (async proxy) reads
         __syncthreads();
-        long long info[4];
+        // the 4 rows this lane stores in the transposed read-out: address of its 16 bytes in the phase-0 pixel, edge flags
+        __nv_bfloat16 *ybase[4];
+        uint32_t edge = 0;
 #pragma unroll
-        for (int it = 0; it < 4; it++) info[it] = dead ? -1ll : rowinfo[warp * 32 + it * 8 + (lane >> 2)];
+        for (int it = 0; it < 4; it++) {
+            const long long inf = dead ? -1ll : rowinfo[warp * 32 + it * 8 + (lane >> 2)];
+            ybase[it] = inf >= 0 ? y + (inf >> 2) * C1_CH + (lane & 3) * 8 : nullptr;
+            edge |= (uint32_t)(inf & 3) << (2 * it);
+        }
         // ---- one MMA per output phase (TC_NT = 64 columns), epilogue straight out of TMEM -------------------
 #pragma unroll 1
         for (int phase = 0; phase < TC_N / TC_NT; phase++) {
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
             if (!dead && !tc_mbar_wait(&bar, parity)) dead = true;
             parity ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int py = phase >> 1, px = phase & 1;
+            const int py = phase >> 1, px = phase & 1, poff = (py * C1_OUT + px) * C1_CH;
 #pragma unroll
             for (int half = 0; half < TC_NT / 32; half++) {
                 uint32_t r[32];
@@ -191,17 +203,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
                 // row `lane` of the warp's 32 x 64-byte staging block, 16-byte chunks XOR-swizzled by (row / 2) % 4
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        float a0 = __uint_as_float(r[8 * j + 2 * q]) + sbias[phase * 64 + c0 + 8 * j + 2 * q];
-                        float a1 = __uint_as_float(r[8 * j + 2 * q + 1]) + sbias[phase * 64 + c0 + 8 * j + 2 * q + 1];
-                        a0 = a0 > 0.f ? a0 : 0.f;
-                        a1 = a1 > 0.f ? a1 : 0.f;
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-                        o[q] = *reinterpret_cast<const uint32_t *>(&h);
-                    }
-                    *reinterpret_cast<uint4 *>(wout + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    const float4 b0 = *reinterpret_cast<const float4 *>(sbias + phase * 64 + c0 + 8 * j);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(sbias + phase * 64 + c0 + 8 * j + 4);
+                    const uint32_t o0 = tc_relu_pack(__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
+                    const uint32_t o1 = tc_relu_pack(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
+                    const uint32_t o2 = tc_relu_pack(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
+                    const uint32_t o3 = tc_relu_pack(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
+                    *reinterpret_cast<uint4 *>(wout + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(o0, o1, o2, o3);
                 }
                 __syncwarp();
                 // transposed read-out: 4 lanes per row -> a store instruction covers 8 rows x 64 contiguous bytes
@@ -209,9 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
                 for (int it = 0; it < 4; it++) {
                     const int row = it * 8 + (lane >> 2), j = lane & 3;
                     const uint4 v = *reinterpret_cast<const uint4 *>(wout + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
-                    const long long inf = info[it];
-                    if (inf >= 0 && !(py && (inf & 2)) && !(px && (inf & 1)))
-                        *reinterpret_cast<uint4 *>(y + ((inf >> 2) + py * C1_OUT + px) * C1_CH + c0 + j * 8) = v;
+                    if (ybase[it] && !(py && (edge >> (2 * it + 1) & 1)) && !(px && (edge >> (2 * it) & 1))) *reinterpret_cast<uint4 *>(ybase[it] + poff + c0) = v;
                 }
                 __syncwarp();
             }

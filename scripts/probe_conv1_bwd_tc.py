@@ -53,3 +53,14 @@ for tc in (0, 1):
     for _ in range(20): L.ta_conv1_bwd(vp(x), 1, x.stride(0), vp(y), vp(dyb), B, vp(dw4), vp(db4), st)
     e1.record(); torch.cuda.synchronize()
     print(f"tc={tc}: ta_conv1_bwd B={B}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call  (dy + y = {2 * dyb.numel() * 2 / 1e6:.0f} MB)")
+w4, b4 = C1.fold(conv.weight.detach(), conv.bias.detach())
+w4 = w4.float().contiguous(); b4 = b4.float().contiguous()
+yo = torch.empty((B, 33, 33, 64), device="cuda", dtype=torch.bfloat16)
+for tc in (0, 1):
+    L.ta_debug_conv1_tc(tc)
+    for _ in range(3): L.ta_conv1_fwd(vp(x), 1, x.stride(0), vp(w4), vp(b4), B, vp(yo), st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): L.ta_conv1_fwd(vp(x), 1, x.stride(0), vp(w4), vp(b4), B, vp(yo), st)
+    e1.record(); torch.cuda.synchronize()
+    print(f"tc={tc}: ta_conv1_fwd B={B}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call  (y = {yo.numel() * 2 / 1e6:.0f} MB)")
