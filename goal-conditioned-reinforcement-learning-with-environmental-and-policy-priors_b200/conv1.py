@@ -114,14 +114,20 @@ def conv_s2_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
 
 
 class _Im2colS2(torch.autograd.Function):
-    """Patches of a channels-last bf16 map for a stride-2 unpadded k x k conv: forward one gather
-    (index_select over pixels), backward the col2im kernel (instead of index_add_ with atomics)."""
+    """Patches of a channels-last bf16 map for a stride-2 unpadded k x k conv: forward the im2col kernel
+    (ta_im2col_s2; index_select over pixels ran at a quarter of the HBM rate), backward the col2im kernel
+    (instead of index_add_ with atomics).  `index` only documents the patch order (tests compare with it)."""
 
     @staticmethod
     def forward(ctx, x_nhwc, index, k):
         B, H, W, Cc = x_nhwc.shape
         ctx.shape, ctx.k = (B, H, W, Cc), k
-        return x_nhwc.reshape(B, H * W, Cc).index_select(1, index)        # [B, OH*OW*k*k, C]
+        x_nhwc = x_nhwc.contiguous()
+        OH, OW = (H - k) // 2 + 1, (W - k) // 2 + 1
+        cols = torch.empty((B, OH * OW * k * k, Cc), dtype=torch.bfloat16, device=x_nhwc.device)
+        st = C.c_void_p(torch.cuda.current_stream(x_nhwc.device).cuda_stream)
+        _capi.check(_capi.lib().ta_im2col_s2(_ptr(x_nhwc), _ptr(cols), B, H, W, Cc, k, st), "ta_im2col_s2")
+        return cols                                                        # [B, OH*OW*k*k, C]
 
     @staticmethod
     def backward(ctx, dcols):

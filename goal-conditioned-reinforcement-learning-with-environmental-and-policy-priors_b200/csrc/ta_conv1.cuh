@@ -233,6 +233,21 @@ __global__ void __launch_bounds__(256) col2im_s2_kernel(const __nv_bfloat16 *__r
     }
 }
 
+// ---- patches of a stride-2, unpadded convolution in channels-last bf16: im2col (col2im's forward) -----------
+// x bf16 [B][H][W][C] -> cols bf16 [B*OH*OW][KS*KS*C], columns (ky,kx,c): one 16-byte chunk (8 channels) per
+// thread and trip, grid-strided; consecutive threads write consecutive chunks.
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ cols, unsigned total,
+                                                       int H, int W, int c8n, int OH, int OW, int KS) {
+    const unsigned row_chunks = (unsigned)(KS * c8n), patch_chunks = (unsigned)KS * row_chunks;  // one patch row (kx, c) is contiguous in x
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pix = i / patch_chunks, in_patch = i - pix * patch_chunks;   // output pixel (b, oy, ox)
+        const unsigned ky = in_patch / row_chunks, in_row = in_patch - ky * row_chunks;
+        const unsigned bo = pix / (unsigned)OW, ox = pix - bo * (unsigned)OW;
+        const unsigned b = bo / (unsigned)OH, oy = bo - b * (unsigned)OH;
+        cols[i] = __ldg(x + ((size_t)(b * H + 2 * oy + ky) * W + 2 * ox) * c8n + in_row);
+    }
+}
+
 // ---- per-channel sum of a channels-last bf16 tensor (the bias gradient of a convolution) -------------
 // x bf16 [rows][C], C in {64, 128, 256}: a thread owns 8 channels (16-byte loads) and strides over the
 // rows of its CTA's slab; row lanes are combined through shared memory, one atomicAdd per channel and CTA.

@@ -44,6 +44,7 @@ inline int launch_ok(const char *what) {
 
 inline unsigned blocks_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
+
 }  // namespace
 
 struct ta_batch {
@@ -588,6 +589,19 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
             (const float *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4);
     }
     return launch_ok("conv1_bwd_kernel");
+}
+
+int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream) {
+    if (!x_bf16 || !cols_bf16 || batch <= 0 || H < ksize || W < ksize || C <= 0 || (C & 7) || ksize < 1 || ksize > 8) return TA_E_INVALID;
+    if (((uintptr_t)x_bf16 | (uintptr_t)cols_bf16) & 15u) return TA_E_INVALID;
+    const int OH = (H - ksize) / 2 + 1, OW = (W - ksize) / 2 + 1;
+    const long long total = (long long)batch * OH * OW * ksize * ksize * (C >> 3);
+    if (total >= (1ll << 31)) return TA_E_INVALID;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    im2col_s2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4 *)x_bf16, (uint4 *)cols_bf16, (unsigned)total, H, W, C >> 3,
+                                                                      OH, OW, ksize);
+    return launch_ok("im2col_s2_kernel");
 }
 
 int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream) {

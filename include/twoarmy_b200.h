@@ -232,6 +232,9 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].
  * k in {3, 4}, C a multiple of 8, OH = (H-k)/2+1. */
 int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
+/* Its forward: x [batch][H][W][C] -> cols [batch*OH*OW][k*k*C] (columns (ky,kx,c)), the operand of the plain GEMM
+ * TINet's last convolution (all_net.py:150, 128 -> 256, 3x3 stride 2 on 7x7) runs as. */
+int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
 /* Bias gradient of those convolutions: out[c] = sum over rows of x [rows][C] (channels-last bf16, C in
  * {64, 128, 256}); out float32 [C] is overwritten. */
 int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, void *stream);

@@ -125,6 +125,28 @@ def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
         assert float((a - b).norm()) <= 2e-2 * float(a.norm()), name
 
 
+@pytest.mark.parametrize("shape", [(5, 7, 7, 128, 3), (3, 33, 33, 64, 3), (2, 16, 16, 64, 4), (1, 9, 8, 8, 3)])
+def test_im2col_s2_kernel_is_the_unfold_and_col2im_its_adjoint(shape):
+    """ta_im2col_s2 == F.unfold(kernel k, stride 2) with columns ordered (ky, kx, c), bit for bit (it only moves
+    bf16 values); ta_col2im_s2 is its adjoint: <im2col(x), d> == <x, col2im(d)> in fp32 up to bf16 rounding."""
+    import twoarmy_b200 as pkg
+    import torch.nn.functional as F
+    C1 = importlib.import_module(pkg.__name__ + ".conv1")
+    B, H, W, Cc, k = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((B, H, W, Cc), generator=g).cuda().to(torch.bfloat16).requires_grad_(True)
+    cols = C1.im2col_s2(x, None, k)                                       # [B, OH*OW*k*k, C]
+    OH, OW = (H - k) // 2 + 1, (W - k) // 2 + 1
+    want = F.unfold(x.detach().float().permute(0, 3, 1, 2), k, stride=2)  # [B, C*k*k, OH*OW], rows (c, ky, kx)
+    want = want.view(B, Cc, k * k, OH * OW).permute(0, 3, 2, 1).reshape(B, OH * OW * k * k, Cc)
+    assert torch.equal(cols.detach().float(), want)
+    d = torch.randn(cols.shape, generator=g).cuda().to(torch.bfloat16)
+    (cols.float() * d.float()).sum().backward()
+    want_dx = F.fold(d.float().view(B, OH * OW, k * k, Cc).permute(0, 3, 2, 1).reshape(B, Cc * k * k, OH * OW), (H, W), k, stride=2)
+    got_dx = x.grad.float().permute(0, 3, 1, 2)
+    assert float((got_dx - want_dx).abs().max()) <= 2e-2 * float(want_dx.abs().max())
+
+
 def test_predictor_agent_rollout_and_update_on_gpu():
     """BASELINE configs[4] plumbing: ppo_predictor drives VecRollout and updates on the device."""
     import twoarmy_b200 as pkg
