@@ -1,10 +1,10 @@
 """Summarise an .ncu-rep: key metrics + per-source-line instruction/stall aggregation.
-usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [top_n]"""
+usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [top_n] [launch index in the report, default 0]"""
 import collections, csv, subprocess, sys, io
-rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40; which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); h = rows[0]
-def g(k): return rows[2][h.index(k)] if k in h else None
+def g(k): return rows[2 + which][h.index(k)] if k in h else None
 keys = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'sm__cycles_active.avg', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__warps_eligible.avg.per_cycle_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -21,7 +21,8 @@ for r in csv.reader(io.StringIO(src)):
     if not r: continue
     if r[0] == 'Kernel Name':
         inst += 1
-        if inst > 1: break
+        if inst > which + 1: break
+        agg.clear(); hdr = None
     if r[0] == 'File Path': cur = r[1].split('/')[-1]; continue
     if r[0] == 'Line No':
         hdr = r; iI = hdr.index('Instructions Executed'); iW = hdr.index('Warp Stall Sampling (All Samples)'); continue
