@@ -354,8 +354,8 @@ def main():
         obs/reward/flag slot per batch, pre-sampled uniform actions.  step(i) = ONE fused
         step+gen_obs launch (ta_step) on batch i % B."""
 
-        def __init__(self, view, batches, id_base):
-            self.view, self.B = view, batches
+        def __init__(self, view, batches, id_base, n=n):
+            self.view, self.B, self.n = view, batches, n
             self.envs = [pkg.TwoarmyVecEnv(args.version, n, view, device=dev, seed=9981,
                                            env_id0=id_base + (rank * batches + b) * n) for b in range(batches)]
             for e in self.envs:
@@ -499,6 +499,19 @@ def main():
                               "unit": UNIT, "alg_bytes_per_env_step": alg_bytes(7),
                               "achieved_gbs": alg_bytes(7) * n / (ms7 / args.steps / 1e3) / 1e9}
             wl7.close()
+        # (c) the same single-step launches at larger launch sizes: the 65536-env launch of configs[2] is 15 us of
+        #     which several are the serial head / tail of one wave; more envs per launch amortise it
+        sweep = []
+        for view_s, mult in ((V, 4), (7, 16)):
+            wls = Workload(view_s, 2, 1 << 41, n=n * mult)
+            wls.capture()
+            k = max(16, args.steps // (2 * mult))
+            mss, _ = wls.timed(k, max(3, args.warmup // mult))
+            sweep.append({"view": view_s, "envs_per_launch": n * mult, "us_per_launch": mss * 1e3 / k,
+                          "value": k * n * mult * world / (mss / 1e3), "unit": UNIT,
+                          "achieved_gbs": alg_bytes(view_s) * n * mult / (mss / k / 1e3) / 1e9})
+            wls.close()
+        extra["launch_size"] = sweep
 
     # ---- end to end through the public host-buffer call ---------------------------------
     e2e_env = wl.envs[0]
