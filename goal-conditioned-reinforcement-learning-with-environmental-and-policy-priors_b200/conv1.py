@@ -113,6 +113,75 @@ def conv_s2_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
                          conv.bias.to(torch.bfloat16))
 
 
+def parity_class_weights(w: torch.Tensor):
+    """conv weight [cout, cin, 3, 3] (stride 2, no padding) -> the four conv2d weights [cin, cout, kh, kw] of its data
+    gradient split by the parity (pa, pb) of the input pixel: dx[2i+pa, 2j+pb] only receives taps ky = pa (mod 2),
+    kx = pb (mod 2), from dz[i - ky // 2, j - kx // 2] -- a STRIDE-1 convolution of dz with a 2x2 / 2x1 / 1x2 / 1x1
+    kernel and padding (1 - pa, 1 - pb).  Order: (0,0), (0,1), (1,0), (1,1)."""
+    out = []
+    for pa in (0, 1):
+        for pb in (0, 1):
+            k = w[:, :, pa::2][:, :, :, pb::2]                            # taps {0, 2} for parity 0, {1} for parity 1
+            out.append(k.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last))
+    return out
+
+
+class _Stem(torch.autograd.Function):
+    """conv1 (fused kernel) + conv2 (cuDNN fused conv + bias + ReLU) as ONE autograd node, so that conv2's data
+    gradient can stay in the form it is cheapest to produce: four stride-1 cuDNN convolutions of dz, one per parity
+    class of the 33x33 pixel (308 us at B = 4096; the plain GEMM + col2im path 780 us, cuDNN's strided dgrad 790 us;
+    scripts/probe_dgrad_classes.py).  The four planes are exactly the four output phases of the folded conv1, whose
+    tcgen05 weight-gradient kernel reads them in place (ta_conv1_bwd_planes) -- no interleaving pass, and the
+    33x33x64 gradient tensor is never materialised."""
+
+    @staticmethod
+    def forward(ctx, x, w4, b4, w2, b2):
+        assert x.is_cuda and x.dim() == 3 and x.shape[2] == 289 and x.shape[1] >= 4
+        if x.dtype not in (torch.uint8, torch.float32):
+            x = x.float()
+        if x.stride(2) != 1 or x.stride(1) != 289 or x.stride(0) < 4 * 289:
+            x = x.contiguous()
+        B = x.shape[0]
+        y1 = torch.empty((B, 33, 33, 64), dtype=torch.bfloat16, device=x.device)
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        w4d, b4d = w4.detach().float().contiguous(), b4.detach().float().contiguous()
+        _capi.check(_capi.lib().ta_conv1_fwd(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(w4d), _ptr(b4d), B,
+                                             _ptr(y1), st), "ta_conv1_fwd")
+        y2 = torch.cudnn_convolution_relu(y1.permute(0, 3, 1, 2), w2, b2, [2, 2], [0, 0], [1, 1], 1)
+        ctx.save_for_backward(x, y1, w2, y2)
+        return y2
+
+    @staticmethod
+    def backward(ctx, dy2):
+        x, y1, w2, y2 = ctx.saved_tensors
+        lib, st = _capi.lib(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        dz = torch.ops.aten.threshold_backward(dy2, y2, 0).contiguous(memory_format=torch.channels_last)
+        cout = w2.shape[0]
+        _, gw2, _ = torch.ops.aten.convolution_backward(dz, y1.permute(0, 3, 1, 2), w2, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
+                                                        [False, True, False])
+        dz_rows = dz.permute(0, 2, 3, 1).reshape(-1, cout)
+        gb2 = torch.empty((cout,), dtype=torch.float32, device=x.device)
+        _capi.check(lib.ta_channel_sum_bf16(_ptr(dz_rows), dz_rows.shape[0], cout, _ptr(gb2), st), "ta_channel_sum_bf16")
+        planes = []
+        for idx, wk in enumerate(parity_class_weights(w2)):
+            pa, pb = idx >> 1, idx & 1
+            pl = torch.nn.functional.conv2d(dz, wk, padding=(1 - pa, 1 - pb))        # [B, 64, 17 - pa, 17 - pb], channels-last
+            planes.append(pl.permute(0, 2, 3, 1).contiguous())
+        dw4 = torch.empty((256, 16), dtype=torch.float32, device=x.device)
+        db4 = torch.empty((256,), dtype=torch.float32, device=x.device)
+        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(y1), _ptr(planes[0]),
+                                            _ptr(planes[1]), _ptr(planes[2]), _ptr(planes[3]), x.shape[0], _ptr(dw4), _ptr(db4), st),
+                    "ta_conv1_bwd_planes")
+        return None, dw4, db4, gw2, gb2.to(w2.dtype)
+
+
+def stem_relu(x: torch.Tensor, conv1: torch.nn.Conv2d, conv2: torch.nn.Conv2d) -> torch.Tensor:
+    """relu(conv2(relu(conv1(upsample4(decode(x)))))) as bf16 [B,128,16,16] (channels-last); see _Stem."""
+    w4, b4 = fold(conv1.weight, conv1.bias)
+    return _Stem.apply(x, w4, b4, conv2.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+                       conv2.bias.to(torch.bfloat16))
+
+
 class _Im2colS2(torch.autograd.Function):
     """Patches of a channels-last bf16 map for a stride-2 unpadded k x k conv: forward the im2col kernel
     (ta_im2col_s2; index_select over pixels ran at a quarter of the HBM rate), backward the col2im kernel

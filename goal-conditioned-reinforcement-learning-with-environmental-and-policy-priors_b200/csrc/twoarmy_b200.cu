@@ -543,6 +543,62 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
     return launch_ok("conv1_fwd_kernel");
 }
 
+}  // extern "C"
+
+namespace {
+// the tcgen05 weight-gradient kernel; planes == nullptr: dy is one channels-last tensor
+int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, const void *const *planes,
+                        int64_t batch, float *dw4, float *db4, void *stream) {
+    static int per_sm[4] = {0, 0, 0, 0}, sms = 0;
+    const int dyn = TCB_A_BYTES + 2 * TCB_B_BYTES;
+    if (!sms) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[0])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[1])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t, true>, TC_THREADS, dyn, TCB_COLS, &per_sm[2])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float, true>, TC_THREADS, dyn, TCB_COLS, &per_sm[3])) return rc;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_bwd_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm[0], per_sm[1], sms);
+    }
+    if (!g_tc_fail) {
+        CK(cudaMalloc(&g_tc_fail, sizeof(int)));
+        CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
+    }
+    if (batch * NCELL >= (1ll << 31)) return TA_E_INVALID;
+    const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
+    const int variant = (planes ? 2 : 0) + (x_dtype == TA_X_U8 ? 0 : 1);
+    const long long cap = (long long)sms * per_sm[variant];
+    const int g = (int)(ntiles < cap ? ntiles : cap);
+    C1Planes pl = {{nullptr, nullptr, nullptr, nullptr}};
+    if (planes)
+        for (int i = 0; i < 4; i++) pl.p[i] = (const __nv_bfloat16 *)planes[i];
+    const __nv_bfloat16 *yb = (const __nv_bfloat16 *)y_bf16, *dyb = (const __nv_bfloat16 *)dy_bf16;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (variant) {
+        case 0: conv1_bwd_tc_kernel<uint8_t, false><<<g, TC_THREADS, dyn, st>>>((const uint8_t *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
+        case 1: conv1_bwd_tc_kernel<float, false><<<g, TC_THREADS, dyn, st>>>((const float *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
+        case 2: conv1_bwd_tc_kernel<uint8_t, true><<<g, TC_THREADS, dyn, st>>>((const uint8_t *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
+        default: conv1_bwd_tc_kernel<float, true><<<g, TC_THREADS, dyn, st>>>((const float *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
+    }
+    return launch_ok("conv1_bwd_tc_kernel");
+}
+}  // namespace
+
+extern "C" {
+
+int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy00, const void *dy01,
+                        const void *dy10, const void *dy11, int64_t batch, float *dw4, float *db4, void *stream) {
+    if (!x || !y_bf16 || !dy00 || !dy01 || !dy10 || !dy11 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL ||
+        (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
+        return TA_E_INVALID;
+    if (((uintptr_t)y_bf16 | (uintptr_t)dy00 | (uintptr_t)dy01 | (uintptr_t)dy10 | (uintptr_t)dy11) & 15u) return TA_E_INVALID;
+    CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), (cudaStream_t)stream));
+    CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
+    const void *planes[4] = {dy00, dy01, dy10, dy11};
+    return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, nullptr, planes, batch, dw4, db4, stream);
+}
+
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, int64_t batch,
                  float *dw4, float *db4, void *stream) {
     if (!x || !y_bf16 || !dy_bf16 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL ||
@@ -552,32 +608,8 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
     CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), (cudaStream_t)stream));
     CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
     if (g_bwd_tc < 0) { const char *e = getenv("TA_CONV1_BWD_TC"); g_bwd_tc = e ? atoi(e) != 0 : 1; }
-    if (g_bwd_tc && !(((uintptr_t)y_bf16 | (uintptr_t)dy_bf16) & 15u)) {
-        static int per_sm_u8 = 0, per_sm_f32 = 0, sms = 0;
-        const int dyn = TCB_A_BYTES + 2 * TCB_B_BYTES;
-        if (!sms) {
-            int dev = 0;
-            CK(cudaGetDevice(&dev));
-            if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t>, TC_THREADS, dyn, TCB_COLS, &per_sm_u8)) return rc;
-            if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float>, TC_THREADS, dyn, TCB_COLS, &per_sm_f32)) return rc;
-            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_bwd_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm_u8, per_sm_f32, sms);
-        }
-        if (!g_tc_fail) {
-            CK(cudaMalloc(&g_tc_fail, sizeof(int)));
-            CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
-        }
-        const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
-        const long long cap = (long long)sms * (x_dtype == TA_X_U8 ? per_sm_u8 : per_sm_f32);
-        const int g = (int)(ntiles < cap ? ntiles : cap);
-        if (x_dtype == TA_X_U8)
-            conv1_bwd_tc_kernel<uint8_t><<<g, TC_THREADS, dyn, (cudaStream_t)stream>>>(
-                (const uint8_t *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail);
-        else
-            conv1_bwd_tc_kernel<float><<<g, TC_THREADS, dyn, (cudaStream_t)stream>>>(
-                (const float *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail);
-        return launch_ok("conv1_bwd_tc_kernel");
-    }
+    if (g_bwd_tc && !(((uintptr_t)y_bf16 | (uintptr_t)dy_bf16) & 15u) && batch * NCELL < (1ll << 31))
+        return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, dy_bf16, nullptr, batch, dw4, db4, stream);
     int grid = 1;
     if (x_dtype == TA_X_U8) {
         if (int rc = conv1_grid(conv1_bwd_kernel<uint8_t>, batch, &grid)) return rc;

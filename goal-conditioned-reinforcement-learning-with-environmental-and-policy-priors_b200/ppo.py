@@ -77,6 +77,9 @@ class TINet(nn.Module):
     fold_conv1 = False
     # the hand-written kernel pair for this layer (csrc/ta_conv1.cuh), used on the GPU under bf16 autocast
     fused_conv1 = True
+    # conv1 + conv2 in one autograd node (conv2's data gradient as four parity-class convolutions feeding the conv1
+    # weight-gradient kernel directly)
+    fused_stem = True
     # data gradients of conv2 / conv3 as GEMM + col2im (csrc/ta_conv1.cuh) instead of cuDNN's strided dgrad
     gemm_dgrad = True
 
@@ -120,11 +123,15 @@ class TINet(nn.Module):
             x = self.upsamplingnearest(state_matrix.contiguous().view(-1, T, 17, 17))
             x = torch.relu(self.fc0(self.cnn_base(x)))
         else:
+            stem = False
             if self.fused_conv1 and torch.is_autocast_enabled() and T == 4:
                 # LUT decode + upsample + conv1 + bias + ReLU in one kernel, straight from codes or floats
                 from . import conv1 as _c1
                 ok = state_matrix.stride(2) == 1 and state_matrix.stride(1) == 289
-                x = _c1.conv1_relu(state_matrix if ok else state_matrix.contiguous(), self.cnn_base[0])
+                xin = state_matrix if ok else state_matrix.contiguous()
+                stem = self.fused_stem and self.gemm_dgrad
+                # conv1 + conv2 as one autograd node: conv2's data gradient stays in parity planes (conv1._Stem)
+                x = _c1.stem_relu(xin, self.cnn_base[0], self.cnn_base[2]) if stem else _c1.conv1_relu(xin, self.cnn_base[0])
             else:
                 if state_matrix.dtype == torch.uint8:
                     state_matrix = decode_matrix(state_matrix)
@@ -136,7 +143,8 @@ class TINet(nn.Module):
                     x = self.cnn_base[:2](x)
             if self.gemm_dgrad and x.dtype == torch.bfloat16:
                 from . import conv1 as _c1
-                x = _c1.conv_s2_relu(x, self.cnn_base[2])
+                if not stem:
+                    x = _c1.conv_s2_relu(x, self.cnn_base[2])
                 x = _c1.conv_s2_relu(x, self.cnn_base[4])
             else:
                 x = self.cnn_base[2:6](x)

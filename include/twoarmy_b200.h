@@ -227,6 +227,13 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
                  void *y_bf16, void *stream);
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16,
                  int64_t batch, float *dw4, float *db4, void *stream);
+/* The same with dL/dy given as four parity planes: dy<py><px> = bfloat16 [batch][17-py][17-px][64] holds the
+ * gradient of the output pixels (2m+py, 2n+px).  That is the form in which the data gradient of TINet's second
+ * convolution (all_net.py:144, 3x3 stride 2) falls out of four stride-1 convolutions of its dz, one per pixel
+ * parity, and the phase structure of the folded first layer: no 33x33x64 gradient tensor is materialised. */
+int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy00,
+                        const void *dy01, const void *dy10, const void *dy11, int64_t batch, float *dw4, float *db4,
+                        void *stream);
 
 /* Data gradient helper for TINet's stride-2 unpadded convolutions (all_net.py:144-149) in channels-last
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].

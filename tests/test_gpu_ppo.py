@@ -125,6 +125,37 @@ def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
         assert float((a - b).norm()) <= 2e-2 * float(a.norm()), name
 
 
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_stem_parity_plane_dgrad_matches_unfused_layers(dtype):
+    """conv1._Stem (conv1 + conv2 in one autograd node; conv2's data gradient as four parity-class stride-1
+    convolutions read in place by ta_conv1_bwd_planes) == conv1_relu followed by conv_s2_relu (GEMM + col2im data
+    gradient, ta_conv1_bwd): same forward bit for bit, parameter gradients to bf16 rounding of the intermediate."""
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    C1 = importlib.import_module(pkg.__name__ + ".conv1")
+    torch.manual_seed(0)
+    net = P.TINet().cuda()
+    conv1, conv2 = net.cnn_base[0], net.cnn_base[2]
+    g = torch.Generator().manual_seed(2)
+    B = 301                                   # 301 * 289 positions: ragged last tile, several tiles per CTA
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)[torch.randint(0, 4, (B, 5, 289), generator=g)].cuda()
+    x_in = codes[:, 1:5] if dtype == "u8" else P.decode_matrix(codes[:, 1:5]).contiguous()
+    gy = None
+    outs = []
+    for mode in ("layers", "stem"):
+        for prm in (conv1.weight, conv1.bias, conv2.weight, conv2.bias):
+            prm.grad = None
+        y2 = C1.stem_relu(x_in, conv1, conv2) if mode == "stem" else C1.conv_s2_relu(C1.conv1_relu(x_in, conv1), conv2)
+        if gy is None:
+            gy = torch.randn(y2.shape, generator=torch.Generator().manual_seed(3)).cuda().to(torch.bfloat16)
+        (y2.float() * gy.float()).sum().backward()
+        outs.append((y2.detach().float().clone(), [prm.grad.detach().clone() for prm in (conv1.weight, conv1.bias, conv2.weight, conv2.bias)]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for name, a, b in zip(("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"), outs[0][1], outs[1][1]):
+        assert float((a - b).norm()) <= 1e-2 * float(a.norm()), name
+    assert pkg._capi.lib().ta_debug_conv1_tc_failed() == 0
+
+
 @pytest.mark.parametrize("shape", [(5, 7, 7, 128, 3), (3, 33, 33, 64, 3), (2, 16, 16, 64, 4), (1, 9, 8, 8, 3)])
 def test_im2col_s2_kernel_is_the_unfold_and_col2im_its_adjoint(shape):
     """ta_im2col_s2 == F.unfold(kernel k, stride 2) with columns ordered (ky, kx, c), bit for bit (it only moves
