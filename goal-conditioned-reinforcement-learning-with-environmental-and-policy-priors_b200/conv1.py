@@ -10,6 +10,7 @@ from float frames.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -114,10 +115,11 @@ def conv_s2_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
 
 
 def parity_class_weights(w: torch.Tensor):
-    """conv weight [cout, cin, 3, 3] (stride 2, no padding) -> the four conv2d weights [cin, cout, kh, kw] of its data
-    gradient split by the parity (pa, pb) of the input pixel: dx[2i+pa, 2j+pb] only receives taps ky = pa (mod 2),
-    kx = pb (mod 2), from dz[i - ky // 2, j - kx // 2] -- a STRIDE-1 convolution of dz with a 2x2 / 2x1 / 1x2 / 1x1
-    kernel and padding (1 - pa, 1 - pb).  Order: (0,0), (0,1), (1,0), (1,1)."""
+    """conv weight [cout, cin, k, k] (stride 2, no padding, k = 3 or 4) -> the four conv2d weights [cin, cout, kh, kw]
+    of its data gradient split by the parity (pa, pb) of the input pixel: dx[2i+pa, 2j+pb] only receives taps
+    ky = pa (mod 2), kx = pb (mod 2), from dz[i - ky // 2, j - kx // 2] -- a STRIDE-1 convolution of dz with the
+    (taps(pa) x taps(pb)) sub-kernel, flipped, and padding (taps - 1): 2x2 / 2x1 / 1x2 / 1x1 for k = 3, four 2x2
+    kernels for k = 4.  Order: (0,0), (0,1), (1,0), (1,1)."""
     out = []
     for pa in (0, 1):
         for pb in (0, 1):
@@ -126,16 +128,38 @@ def parity_class_weights(w: torch.Tensor):
     return out
 
 
+def _class_planes(dz: torch.Tensor, w: torch.Tensor):
+    """The data gradient of a 3x3 stride-2 unpadded conv with weight w, given dz (channels-last bf16), as four
+    contiguous channels-last parity planes [B, H', W', cin] (see parity_class_weights)."""
+    planes = []
+    for wk in parity_class_weights(w):
+        pl = torch.nn.functional.conv2d(dz, wk, padding=(wk.shape[2] - 1, wk.shape[3] - 1))
+        planes.append(pl.permute(0, 2, 3, 1).contiguous())
+    return planes
+
+
+def _wgrad_bgrad(dz: torch.Tensor, x_nchw: torch.Tensor, w: torch.Tensor, st):
+    """cuDNN weight gradient + channel-sum bias gradient of a stride-2 unpadded conv (dz, x channels-last bf16)."""
+    cout = w.shape[0]
+    _, gw, _ = torch.ops.aten.convolution_backward(dz, x_nchw, w, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1, [False, True, False])
+    dz_rows = dz.permute(0, 2, 3, 1).reshape(-1, cout)
+    gb = torch.empty((cout,), dtype=torch.float32, device=dz.device)
+    _capi.check(_capi.lib().ta_channel_sum_bf16(_ptr(dz_rows), dz_rows.shape[0], cout, _ptr(gb), st), "ta_channel_sum_bf16")
+    return gw, gb.to(w.dtype)
+
+
 class _Stem(torch.autograd.Function):
-    """conv1 (fused kernel) + conv2 (cuDNN fused conv + bias + ReLU) as ONE autograd node, so that conv2's data
-    gradient can stay in the form it is cheapest to produce: four stride-1 cuDNN convolutions of dz, one per parity
-    class of the 33x33 pixel (308 us at B = 4096; the plain GEMM + col2im path 780 us, cuDNN's strided dgrad 790 us;
-    scripts/probe_dgrad_classes.py).  The four planes are exactly the four output phases of the folded conv1, whose
-    tcgen05 weight-gradient kernel reads them in place (ta_conv1_bwd_planes) -- no interleaving pass, and the
-    33x33x64 gradient tensor is never materialised."""
+    """conv1 (fused kernel) + conv2 + conv3 (cuDNN fused conv + bias + ReLU) as ONE autograd node, so that the data
+    gradients of the two stride-2 3x3 convolutions can stay in the form that is cheapest to produce: four stride-1
+    cuDNN convolutions of dz, one per parity class of the input pixel (2.5x faster than the plain GEMM + col2im path
+    or cuDNN's strided dgrad on the probe shapes, scripts/probe_dgrad_classes*.py).
+      * conv3's planes are interleaved into the dense dz2 by the kernel that applies conv2's ReLU mask
+        (ta_planes_to_dense_relu: the traffic of the threshold_backward pass it replaces);
+      * conv2's planes are exactly the four output phases of the folded conv1, whose tcgen05 weight-gradient
+        kernel reads them in place (ta_conv1_bwd_planes): the 33x33x64 gradient tensor is never materialised."""
 
     @staticmethod
-    def forward(ctx, x, w4, b4, w2, b2):
+    def forward(ctx, x, w4, b4, w2, b2, w3, b3):
         assert x.is_cuda and x.dim() == 3 and x.shape[2] == 289 and x.shape[1] >= 4
         if x.dtype not in (torch.uint8, torch.float32):
             x = x.float()
@@ -148,38 +172,54 @@ class _Stem(torch.autograd.Function):
         _capi.check(_capi.lib().ta_conv1_fwd(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(w4d), _ptr(b4d), B,
                                              _ptr(y1), st), "ta_conv1_fwd")
         y2 = torch.cudnn_convolution_relu(y1.permute(0, 3, 1, 2), w2, b2, [2, 2], [0, 0], [1, 1], 1)
-        ctx.save_for_backward(x, y1, w2, y2)
-        return y2
+        if w3 is None:
+            ctx.save_for_backward(x, y1, w2, y2)
+            return y2
+        y3 = torch.cudnn_convolution_relu(y2, w3, b3, [2, 2], [0, 0], [1, 1], 1)
+        ctx.save_for_backward(x, y1, w2, y2, w3, y3)
+        return y3
 
     @staticmethod
-    def backward(ctx, dy2):
-        x, y1, w2, y2 = ctx.saved_tensors
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x, y1, w2, y2 = saved[:4]
         lib, st = _capi.lib(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        dz = torch.ops.aten.threshold_backward(dy2, y2, 0).contiguous(memory_format=torch.channels_last)
-        cout = w2.shape[0]
-        _, gw2, _ = torch.ops.aten.convolution_backward(dz, y1.permute(0, 3, 1, 2), w2, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
-                                                        [False, True, False])
-        dz_rows = dz.permute(0, 2, 3, 1).reshape(-1, cout)
-        gb2 = torch.empty((cout,), dtype=torch.float32, device=x.device)
-        _capi.check(lib.ta_channel_sum_bf16(_ptr(dz_rows), dz_rows.shape[0], cout, _ptr(gb2), st), "ta_channel_sum_bf16")
-        planes = []
-        for idx, wk in enumerate(parity_class_weights(w2)):
-            pa, pb = idx >> 1, idx & 1
-            pl = torch.nn.functional.conv2d(dz, wk, padding=(1 - pa, 1 - pb))        # [B, 64, 17 - pa, 17 - pb], channels-last
-            planes.append(pl.permute(0, 2, 3, 1).contiguous())
+        gw3 = gb3 = None
+        if len(saved) == 6:
+            w3, y3 = saved[4:]
+            dz3 = torch.ops.aten.threshold_backward(dy, y3, 0).contiguous(memory_format=torch.channels_last)
+            gw3, gb3 = _wgrad_bgrad(dz3, y2, w3, st)
+            p3 = _class_planes(dz3, w3)
+            Bn, Cc, H, W = y2.shape
+            dz2_nhwc = torch.empty((Bn, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+            y2_nhwc = y2.permute(0, 2, 3, 1)
+            assert y2_nhwc.is_contiguous()
+            _capi.check(lib.ta_planes_to_dense_relu(_ptr(p3[0]), _ptr(p3[1]), _ptr(p3[2]), _ptr(p3[3]), _ptr(y2_nhwc), _ptr(dz2_nhwc),
+                                                    Bn, H, W, Cc, w3.shape[2], st), "ta_planes_to_dense_relu")
+            dz2 = dz2_nhwc.permute(0, 3, 1, 2)
+        else:
+            dz2 = torch.ops.aten.threshold_backward(dy, y2, 0).contiguous(memory_format=torch.channels_last)
+        gw2, gb2 = _wgrad_bgrad(dz2, y1.permute(0, 3, 1, 2), w2, st)
+        p2 = _class_planes(dz2, w2)
         dw4 = torch.empty((256, 16), dtype=torch.float32, device=x.device)
         db4 = torch.empty((256,), dtype=torch.float32, device=x.device)
-        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(y1), _ptr(planes[0]),
-                                            _ptr(planes[1]), _ptr(planes[2]), _ptr(planes[3]), x.shape[0], _ptr(dw4), _ptr(db4), st),
+        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(y1), _ptr(p2[0]),
+                                            _ptr(p2[1]), _ptr(p2[2]), _ptr(p2[3]), x.shape[0], _ptr(dw4), _ptr(db4), st),
                     "ta_conv1_bwd_planes")
-        return None, dw4, db4, gw2, gb2.to(w2.dtype)
+        return None, dw4, db4, gw2, gb2, gw3, gb3
 
 
-def stem_relu(x: torch.Tensor, conv1: torch.nn.Conv2d, conv2: torch.nn.Conv2d) -> torch.Tensor:
-    """relu(conv2(relu(conv1(upsample4(decode(x)))))) as bf16 [B,128,16,16] (channels-last); see _Stem."""
+def _bf16_cl(conv: torch.nn.Conv2d):
+    return conv.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), conv.bias.to(torch.bfloat16)
+
+
+def stem_relu(x: torch.Tensor, conv1: torch.nn.Conv2d, conv2: torch.nn.Conv2d, conv3: torch.nn.Conv2d = None) -> torch.Tensor:
+    """relu(conv3(relu(conv2(relu(conv1(upsample4(decode(x)))))))) as bf16 channels-last ([B,128,7,7]; without conv3
+    [B,128,16,16]); see _Stem."""
     w4, b4 = fold(conv1.weight, conv1.bias)
-    return _Stem.apply(x, w4, b4, conv2.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
-                       conv2.bias.to(torch.bfloat16))
+    w2, b2 = _bf16_cl(conv2)
+    w3, b3 = _bf16_cl(conv3) if conv3 is not None else (None, None)
+    return _Stem.apply(x, w4, b4, w2, b2, w3, b3)
 
 
 class _Im2colS2(torch.autograd.Function):

@@ -248,6 +248,34 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4 *__restrict_
     }
 }
 
+// ---- parity planes -> dense, fused with the ReLU backward of the layer below ---------------------------------
+// The data gradient of a k x k stride-2 convolution (k = 3, 4), produced as four stride-1 convolutions of dz (one per
+// parity (pa, pb) of the input pixel; plane pa*2+pb = bf16 [B][OH+taps(pa)-1][OW+taps(pb)-1][C], taps(p) = (k-p+1)/2
+// kernel taps of that parity), interleaved back into the dense
+// channels-last tensor and masked with the ReLU of the layer that produced the input (y [B][H][W][C]):
+//   dz_out[b][h][w][c] = y > 0 ? plane[(h&1)*2 + (w&1)][b][h>>1][w>>1][c] : 0     (0 where the plane has no such pixel)
+// = aten::threshold_backward's traffic, so the interleave comes for free.
+struct C1PlanesU4 {
+    const uint4 *p[4];
+};
+__global__ void __launch_bounds__(256) planes_to_dense_relu_kernel(C1PlanesU4 planes, const uint4 *__restrict__ y, uint4 *__restrict__ out,
+                                                                  unsigned total, int H, int W, int c8n, int OH, int OW, int KS) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pix = i / (unsigned)c8n, c8 = i - pix * (unsigned)c8n;
+        const unsigned bh = pix / (unsigned)W, w = pix - bh * (unsigned)W;
+        const unsigned b = bh / (unsigned)H, h = bh - b * (unsigned)H;
+        const unsigned pa = h & 1u, pb = w & 1u, hp = h >> 1, wp = w >> 1;
+        const unsigned Hp = (unsigned)OH + ((unsigned)KS - pa + 1u) / 2u - 1u, Wp = (unsigned)OW + ((unsigned)KS - pb + 1u) / 2u - 1u;
+        uint4 g = make_uint4(0u, 0u, 0u, 0u);
+        if (hp < Hp && wp < Wp) g = __ldg(planes.p[pa * 2u + pb] + ((size_t)(b * Hp + hp) * Wp + wp) * c8n + c8);
+        const uint4 yv = __ldg(y + i);
+        auto m = [](uint32_t gw, uint32_t yw) {  // bf16 pairs; y is a ReLU output (>= +0)
+            return gw & (((yw & 0xFFFFu) ? 0xFFFFu : 0u) | ((yw >> 16) ? 0xFFFF0000u : 0u));
+        };
+        out[i] = make_uint4(m(g.x, yv.x), m(g.y, yv.y), m(g.z, yv.z), m(g.w, yv.w));
+    }
+}
+
 // ---- per-channel sum of a channels-last bf16 tensor (the bias gradient of a convolution) -------------
 // x bf16 [rows][C], C in {64, 128, 256}: a thread owns 8 channels (16-byte loads) and strides over the
 // rows of its CTA's slab; row lanes are combined through shared memory, one atomicAdd per channel and CTA.

@@ -636,6 +636,22 @@ int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int 
     return launch_ok("im2col_s2_kernel");
 }
 
+int ta_planes_to_dense_relu(const void *p00, const void *p01, const void *p10, const void *p11, const void *y_bf16, void *dz_bf16,
+                            int64_t batch, int H, int W, int C, int ksize, void *stream) {
+    if (!p00 || !p01 || !p10 || !p11 || !y_bf16 || !dz_bf16 || batch <= 0 || (ksize != 3 && ksize != 4) || H < ksize || W < ksize ||
+        C <= 0 || (C & 7))
+        return TA_E_INVALID;
+    if (((uintptr_t)p00 | (uintptr_t)p01 | (uintptr_t)p10 | (uintptr_t)p11 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16) & 15u) return TA_E_INVALID;
+    const long long total = (long long)batch * H * W * (C >> 3);
+    if (total >= (1ll << 31)) return TA_E_INVALID;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    C1PlanesU4 pl = {{(const uint4 *)p00, (const uint4 *)p01, (const uint4 *)p10, (const uint4 *)p11}};
+    planes_to_dense_relu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pl, (const uint4 *)y_bf16, (uint4 *)dz_bf16, (unsigned)total,
+                                                                                 H, W, C >> 3, (H - ksize) / 2 + 1, (W - ksize) / 2 + 1, ksize);
+    return launch_ok("planes_to_dense_relu_kernel");
+}
+
 int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream) {
     if (!dcols_bf16 || !dx_bf16 || batch <= 0 || H < ksize || W < ksize || C <= 0 || (C & 7) || (ksize != 3 && ksize != 4))
         return TA_E_INVALID;

@@ -77,8 +77,8 @@ class TINet(nn.Module):
     fold_conv1 = False
     # the hand-written kernel pair for this layer (csrc/ta_conv1.cuh), used on the GPU under bf16 autocast
     fused_conv1 = True
-    # conv1 + conv2 in one autograd node (conv2's data gradient as four parity-class convolutions feeding the conv1
-    # weight-gradient kernel directly)
+    # conv1 + conv2 + conv3 in one autograd node (the data gradients of conv2 / conv3 as four parity-class
+    # convolutions each; conv2's feed the conv1 weight-gradient kernel directly)
     fused_stem = True
     # data gradients of conv2 / conv3 as GEMM + col2im (csrc/ta_conv1.cuh) instead of cuDNN's strided dgrad
     gemm_dgrad = True
@@ -130,8 +130,8 @@ class TINet(nn.Module):
                 ok = state_matrix.stride(2) == 1 and state_matrix.stride(1) == 289
                 xin = state_matrix if ok else state_matrix.contiguous()
                 stem = self.fused_stem and self.gemm_dgrad
-                # conv1 + conv2 as one autograd node: conv2's data gradient stays in parity planes (conv1._Stem)
-                x = _c1.stem_relu(xin, self.cnn_base[0], self.cnn_base[2]) if stem else _c1.conv1_relu(xin, self.cnn_base[0])
+                # conv1 + conv2 + conv3 as one autograd node: the data gradients stay in parity planes (conv1._Stem)
+                x = _c1.stem_relu(xin, self.cnn_base[0], self.cnn_base[2], self.cnn_base[4]) if stem else _c1.conv1_relu(xin, self.cnn_base[0])
             else:
                 if state_matrix.dtype == torch.uint8:
                     state_matrix = decode_matrix(state_matrix)
@@ -145,7 +145,7 @@ class TINet(nn.Module):
                 from . import conv1 as _c1
                 if not stem:
                     x = _c1.conv_s2_relu(x, self.cnn_base[2])
-                x = _c1.conv_s2_relu(x, self.cnn_base[4])
+                    x = _c1.conv_s2_relu(x, self.cnn_base[4])
             else:
                 x = self.cnn_base[2:6](x)
             # The last conv (128 -> 256, 3x3 stride 2 on 7x7) as an explicit im2col + cuBLAS GEMM: for

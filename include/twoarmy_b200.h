@@ -239,6 +239,13 @@ int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].
  * k in {3, 4}, C a multiple of 8, OH = (H-k)/2+1. */
 int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
+/* The data gradient of a k x k (k = 3, 4) stride-2 unpadded convolution given as four parity planes (plane pa*2+pb =
+ * bfloat16 [batch][OH+t(pa)-1][OW+t(pb)-1][C], t(p) = (k-p+1)/2 taps of that parity: the stride-1 convolution of dz
+ * for input pixels (2i+pa, 2j+pb)) -> the dense
+ * channels-last gradient, masked with the ReLU of the layer below: dz_out = y > 0 ? plane value : 0
+ * (TINet's third convolution feeding its second, all_net.py:144-147). */
+int ta_planes_to_dense_relu(const void *p00, const void *p01, const void *p10, const void *p11, const void *y_bf16,
+                            void *dz_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
 /* Its forward: x [batch][H][W][C] -> cols [batch*OH*OW][k*k*C] (columns (ky,kx,c)), the operand of the plain GEMM
  * TINet's last convolution (all_net.py:150, 128 -> 256, 3x3 stride 2 on 7x7) runs as. */
 int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);

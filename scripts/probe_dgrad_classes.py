@@ -1,5 +1,6 @@
-"""Probe: conv2's data gradient (3x3, stride 2, 128 -> 64 channels, 16x16 -> 33x33) as four stride-1 convolutions of
-dz, one per output-pixel parity class, vs the GEMM + col2im path and cuDNN's own strided dgrad."""
+"""Probe: the data gradient of TINet's conv2 (3x3, stride 2, 64 -> 64 channels, dz 16x16 -> dx 33x33) and conv3 (4x4,
+stride 2, 64 -> 128 channels, dz 7x7 -> dx 16x16) as four stride-1 convolutions of dz, one per parity class of the
+input pixel, vs the GEMM + col2im path and cuDNN's own strided dgrad.   env: LAYER=2|3, B"""
 import importlib, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F, twoarmy_b200 as pkg
@@ -8,45 +9,33 @@ import ctypes as C
 dev = "cuda:0"
 B = int(os.environ.get("B", "4096"))
 torch.manual_seed(0)
-w = (torch.randn(128, 64, 3, 3, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)   # conv2.weight [co, ci, ky, kx]
-dz = torch.randn(B, 128, 16, 16, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-
-
-def class_weights(w):
-    """class (pa, pb) -> conv2d weight [ci, co, kh, kw] for out[i, j] = sum_{u, v} dz[i - u, j - v] . W[:, :, ky(u), kx(v)]"""
-    out = {}
-    for pa in (0, 1):
-        kys = [0, 2] if pa == 0 else [1]
-        for pb in (0, 1):
-            kxs = [0, 2] if pb == 0 else [1]
-            k = w[:, :, kys][:, :, :, kxs]                      # [co, ci, u, v]
-            k = k.flip(2, 3).permute(1, 0, 2, 3)                # conv2d correlates: flip; -> [ci, co, kh, kw]
-            out[(pa, pb)] = k.contiguous(memory_format=torch.channels_last)
-    return out
-
-
-cw = class_weights(w)
+LAYER = int(os.environ.get("LAYER", "2"))
+cout, cin, k, oh, hin = (64, 64, 3, 16, 33) if LAYER == 2 else (128, 64, 4, 7, 16)
+w = (torch.randn(cout, cin, k, k, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)   # [co, ci, ky, kx]
+dz = torch.randn(B, cout, oh, oh, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+cw = C1.parity_class_weights(w)
 
 
 def planes(dz):
-    return {(pa, pb): F.conv2d(dz, cw[(pa, pb)], padding=(1 - pa, 1 - pb)) for pa in (0, 1) for pb in (0, 1)}
+    return [F.conv2d(dz, wk, padding=(wk.shape[2] - 1, wk.shape[3] - 1)) for wk in cw]
 
 
 def gemm_col2im(dz):
-    dz_rows = dz.permute(0, 2, 3, 1).reshape(-1, 128)
-    dcols = dz_rows @ w.permute(0, 2, 3, 1).reshape(128, 9 * 64)
-    gx = torch.empty((B, 33, 33, 64), dtype=torch.bfloat16, device=dev)
+    dz_rows = dz.permute(0, 2, 3, 1).reshape(-1, cout)
+    dcols = dz_rows @ w.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+    gx = torch.empty((B, hin, hin, cin), dtype=torch.bfloat16, device=dev)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    pkg._capi.check(pkg._capi.lib().ta_col2im_s2(C.c_void_p(dcols.data_ptr()), C.c_void_p(gx.data_ptr()), B, 33, 33, 64, 3, st))
+    pkg._capi.check(pkg._capi.lib().ta_col2im_s2(C.c_void_p(dcols.data_ptr()), C.c_void_p(gx.data_ptr()), B, hin, hin, cin, k, st))
     return gx
 
 
 pl = planes(dz)
 ref = gemm_col2im(dz).float()
-for (pa, pb), t in pl.items():
-    got = t.permute(0, 2, 3, 1).float()                     # [B, Hc, Wc, 64]
-    want = ref[:, pa::2, pb::2]
-    print((pa, pb), tuple(t.shape), "max abs diff", float((got - want).abs().max()), "of", float(want.abs().max()))
+for idx, t in enumerate(pl):
+    pa, pb = idx >> 1, idx & 1
+    got = t.permute(0, 2, 3, 1).float()                     # [B, Hc, Wc, cin]
+    want = ref[:, pa::2, pb::2][:, :got.shape[1], :got.shape[2]]
+    print((pa, pb), tuple(t.shape), "max abs diff", float((got[:, :want.shape[1], :want.shape[2]] - want).abs().max()), "of", float(want.abs().max()))
 
 
 def timeit(fn, reps=10):
@@ -59,8 +48,6 @@ def timeit(fn, reps=10):
 
 
 torch.backends.cudnn.benchmark = True
-print(f"4 class convs: {timeit(lambda: planes(dz)):.1f} us;  GEMM + col2im: {timeit(lambda: gemm_col2im(dz)):.1f} us")
-for c in pl:
-    print(c, f"{timeit(lambda: F.conv2d(dz, cw[c], padding=(1 - c[0], 1 - c[1]))):.1f} us")
-x = torch.randn(B, 64, 33, 33, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+print(f"layer {LAYER}, B = {B}: 4 class convs {timeit(lambda: planes(dz)):.1f} us;  GEMM + col2im {timeit(lambda: gemm_col2im(dz)):.1f} us")
+x = torch.randn(B, cin, hin, hin, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 print(f"cuDNN strided dgrad: {timeit(lambda: torch.ops.aten.convolution_backward(dz, x, w, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1, [True, False, False])):.1f} us")

@@ -125,17 +125,18 @@ def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
         assert float((a - b).norm()) <= 2e-2 * float(a.norm()), name
 
 
-@pytest.mark.parametrize("dtype", ["u8", "f32"])
-def test_stem_parity_plane_dgrad_matches_unfused_layers(dtype):
-    """conv1._Stem (conv1 + conv2 in one autograd node; conv2's data gradient as four parity-class stride-1
-    convolutions read in place by ta_conv1_bwd_planes) == conv1_relu followed by conv_s2_relu (GEMM + col2im data
-    gradient, ta_conv1_bwd): same forward bit for bit, parameter gradients to bf16 rounding of the intermediate."""
+@pytest.mark.parametrize("dtype,depth", [("u8", 2), ("f32", 2), ("u8", 3)])
+def test_stem_parity_plane_dgrad_matches_unfused_layers(dtype, depth):
+    """conv1._Stem (conv1 + conv2 [+ conv3] in one autograd node; data gradients as four parity-class stride-1
+    convolutions, conv3's interleaved by ta_planes_to_dense_relu, conv2's read in place by ta_conv1_bwd_planes) ==
+    conv1_relu followed by conv_s2_relu (GEMM + col2im data gradient, ta_conv1_bwd): same forward bit for bit,
+    parameter gradients to bf16 rounding of the intermediates."""
     import twoarmy_b200 as pkg
     P = _ppo()
     C1 = importlib.import_module(pkg.__name__ + ".conv1")
     torch.manual_seed(0)
     net = P.TINet().cuda()
-    conv1, conv2 = net.cnn_base[0], net.cnn_base[2]
+    conv1, conv2, conv3 = net.cnn_base[0], net.cnn_base[2], net.cnn_base[4]
     g = torch.Generator().manual_seed(2)
     B = 301                                   # 301 * 289 positions: ragged last tile, several tiles per CTA
     codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)[torch.randint(0, 4, (B, 5, 289), generator=g)].cuda()
@@ -143,15 +144,20 @@ def test_stem_parity_plane_dgrad_matches_unfused_layers(dtype):
     gy = None
     outs = []
     for mode in ("layers", "stem"):
-        for prm in (conv1.weight, conv1.bias, conv2.weight, conv2.bias):
+        prms = (conv1.weight, conv1.bias, conv2.weight, conv2.bias) + ((conv3.weight, conv3.bias) if depth == 3 else ())
+        for prm in prms:
             prm.grad = None
-        y2 = C1.stem_relu(x_in, conv1, conv2) if mode == "stem" else C1.conv_s2_relu(C1.conv1_relu(x_in, conv1), conv2)
+        if mode == "stem":
+            y2 = C1.stem_relu(x_in, conv1, conv2, conv3 if depth == 3 else None)
+        else:
+            y2 = C1.conv_s2_relu(C1.conv1_relu(x_in, conv1), conv2)
+            y2 = C1.conv_s2_relu(y2, conv3) if depth == 3 else y2
         if gy is None:
             gy = torch.randn(y2.shape, generator=torch.Generator().manual_seed(3)).cuda().to(torch.bfloat16)
         (y2.float() * gy.float()).sum().backward()
-        outs.append((y2.detach().float().clone(), [prm.grad.detach().clone() for prm in (conv1.weight, conv1.bias, conv2.weight, conv2.bias)]))
+        outs.append((y2.detach().float().clone(), [prm.grad.detach().clone() for prm in prms]))
     assert torch.equal(outs[0][0], outs[1][0])
-    for name, a, b in zip(("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"), outs[0][1], outs[1][1]):
+    for name, a, b in zip(("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias"), outs[0][1], outs[1][1]):
         assert float((a - b).norm()) <= 1e-2 * float(a.norm()), name
     assert pkg._capi.lib().ta_debug_conv1_tc_failed() == 0
 
