@@ -120,11 +120,24 @@ def parity_class_weights(w: torch.Tensor):
     ky = pa (mod 2), kx = pb (mod 2), from dz[i - ky // 2, j - kx // 2] -- a STRIDE-1 convolution of dz with the
     (taps(pa) x taps(pb)) sub-kernel, flipped, and padding (taps - 1): 2x2 / 2x1 / 1x2 / 1x1 for k = 3, four 2x2
     kernels for k = 4.  Order: (0,0), (0,1), (1,0), (1,1)."""
+    cout, cin, k, _ = w.shape
+    if w.is_cuda and w.dtype == torch.bfloat16:  # one kernel instead of a dozen slice / flip / permute / copy launches
+        buf = torch.empty((cout * cin * k * k,), dtype=torch.bfloat16, device=w.device)
+        st = C.c_void_p(torch.cuda.current_stream(w.device).cuda_stream)
+        _capi.check(_capi.lib().ta_parity_class_weights(_ptr(w), w.stride(0), w.stride(1), w.stride(2), w.stride(3), cout, cin, k,
+                                                        _ptr(buf), st), "ta_parity_class_weights")
+        out, off = [], 0
+        for idx in range(4):
+            kh, kw = (k - (idx >> 1) + 1) // 2, (k - (idx & 1) + 1) // 2
+            n = cin * kh * kw * cout
+            out.append(buf[off:off + n].view(cin, kh, kw, cout).permute(0, 3, 1, 2))   # [cin, cout, kh, kw], channels-last
+            off += n
+        return out
     out = []
     for pa in (0, 1):
         for pb in (0, 1):
-            k = w[:, :, pa::2][:, :, :, pb::2]                            # taps {0, 2} for parity 0, {1} for parity 1
-            out.append(k.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last))
+            k_ = w[:, :, pa::2][:, :, :, pb::2]                           # taps {0, 2} / {1, 3} for parity 0 / 1
+            out.append(k_.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last))
     return out
 
 

@@ -248,6 +248,35 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4 *__restrict_
     }
 }
 
+// ---- the four parity-class kernels of a stride-2 convolution's data gradient, in one launch -------------------
+// w bf16 [cout][cin][k][k] (any strides) -> out: for class c = pa*2+pb, at element offset off[c], the conv2d weight
+// of the stride-1 convolution that produces plane c: logical [cin][cout][kh][kw] in channels-last memory
+// ([cin][kh][kw][cout]), kh = taps(pa), kw = taps(pb), taps(p) = (k-p+1)/2, flipped:
+//   out_c[ci][u][v][co] = w[co][ci][2*(kh-1-u)+pa][2*(kw-1-v)+pb]
+// (every tap of w lands in exactly one class: k*k*cin*cout elements in total).
+__global__ void __launch_bounds__(256) parity_class_weights_kernel(const __nv_bfloat16 *__restrict__ w, long long so, long long si,
+                                                                  long long sy, long long sx, int cout, int cin, int k,
+                                                                  __nv_bfloat16 *__restrict__ out) {
+    const int total = cout * cin * k * k;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int r = i, off = 0, c = 0, kh = 0, kw = 0;
+        for (; c < 4; c++) {  // which class block does element i fall into
+            kh = (k - (c >> 1) + 1) / 2;
+            kw = (k - (c & 1) + 1) / 2;
+            const int n = cin * kh * kw * cout;
+            if (r < n) break;
+            r -= n;
+            off += n;
+        }
+        const int co = r % cout; r /= cout;
+        const int v = r % kw; r /= kw;
+        const int u = r % kh;
+        const int ci = r / kh;
+        const int ky = 2 * (kh - 1 - u) + (c >> 1), kx = 2 * (kw - 1 - v) + (c & 1);
+        out[i] = w[co * so + ci * si + ky * sy + kx * sx];
+    }
+}
+
 // ---- parity planes -> dense, fused with the ReLU backward of the layer below ---------------------------------
 // The data gradient of a k x k stride-2 convolution (k = 3, 4), produced as four stride-1 convolutions of dz (one per
 // parity (pa, pb) of the input pixel; plane pa*2+pb = bf16 [B][OH+taps(pa)-1][OW+taps(pb)-1][C], taps(p) = (k-p+1)/2

@@ -636,6 +636,17 @@ int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int 
     return launch_ok("im2col_s2_kernel");
 }
 
+int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride_i, int64_t stride_y, int64_t stride_x, int cout, int cin,
+                            int ksize, void *out_bf16, void *stream) {
+    if (!w_bf16 || !out_bf16 || cout <= 0 || cin <= 0 || (ksize != 3 && ksize != 4)) return TA_E_INVALID;
+    const long long total = (long long)cout * cin * ksize * ksize;
+    if (total >= (1ll << 31)) return TA_E_INVALID;
+    parity_class_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)w_bf16, stride_o, stride_i,
+                                                                                      stride_y, stride_x, cout, cin, ksize,
+                                                                                      (__nv_bfloat16 *)out_bf16);
+    return launch_ok("parity_class_weights_kernel");
+}
+
 int ta_planes_to_dense_relu(const void *p00, const void *p01, const void *p10, const void *p11, const void *y_bf16, void *dz_bf16,
                             int64_t batch, int H, int W, int C, int ksize, void *stream) {
     if (!p00 || !p01 || !p10 || !p11 || !y_bf16 || !dz_bf16 || batch <= 0 || (ksize != 3 && ksize != 4) || H < ksize || W < ksize ||

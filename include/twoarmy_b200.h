@@ -239,6 +239,12 @@ int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].
  * k in {3, 4}, C a multiple of 8, OH = (H-k)/2+1. */
 int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
+/* The four parity-class kernels of that data gradient in one launch: w bfloat16 [cout][cin][k][k] with the given element
+ * strides -> out (cout*cin*k*k elements): class pa*2+pb after the previous ones, as the conv2d weight
+ * [cin][cout][kh][kw] in channels-last memory, kh = (k-pa+1)/2, kw = (k-pb+1)/2, taps flipped
+ * (out_c[ci][u][v][co] = w[co][ci][2(kh-1-u)+pa][2(kw-1-v)+pb]). */
+int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride_i, int64_t stride_y, int64_t stride_x,
+                            int cout, int cin, int ksize, void *out_bf16, void *stream);
 /* The data gradient of a k x k (k = 3, 4) stride-2 unpadded convolution given as four parity planes (plane pa*2+pb =
  * bfloat16 [batch][OH+t(pa)-1][OW+t(pb)-1][C], t(p) = (k-p+1)/2 taps of that parity: the stride-1 convolution of dz
  * for input pixels (2i+pa, 2j+pb)) -> the dense

@@ -125,6 +125,22 @@ def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
         assert float((a - b).norm()) <= 2e-2 * float(a.norm()), name
 
 
+@pytest.mark.parametrize("shape", [(64, 64, 3), (128, 64, 4), (8, 16, 3)])
+def test_parity_class_weights_kernel_matches_slicing(shape):
+    """ta_parity_class_weights (one launch) == slicing / flipping / permuting the conv weight in torch, for a
+    contiguous and a channels-last weight."""
+    import twoarmy_b200 as pkg
+    C1 = importlib.import_module(pkg.__name__ + ".conv1")
+    cout, cin, k = shape
+    w = torch.randn((cout, cin, k, k), generator=torch.Generator().manual_seed(4)).cuda().to(torch.bfloat16)
+    want = C1.parity_class_weights(w.float())                       # the torch path (not bf16 -> no kernel)
+    for wv in (w, w.contiguous(memory_format=torch.channels_last)):
+        got = C1.parity_class_weights(wv)
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and a.is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(a.float(), b)
+
+
 @pytest.mark.parametrize("dtype,depth", [("u8", 2), ("f32", 2), ("u8", 3)])
 def test_stem_parity_plane_dgrad_matches_unfused_layers(dtype, depth):
     """conv1._Stem (conv1 + conv2 [+ conv3] in one autograd node; data gradients as four parity-class stride-1
