@@ -114,41 +114,33 @@ def conv_s2_relu(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
                          conv.bias.to(torch.bfloat16))
 
 
-def parity_class_weights(w: torch.Tensor):
-    """conv weight [cout, cin, k, k] (stride 2, no padding, k = 3 or 4) -> the four conv2d weights [cin, cout, kh, kw]
-    of its data gradient split by the parity (pa, pb) of the input pixel: dx[2i+pa, 2j+pb] only receives taps
-    ky = pa (mod 2), kx = pb (mod 2), from dz[i - ky // 2, j - kx // 2] -- a STRIDE-1 convolution of dz with the
-    (taps(pa) x taps(pb)) sub-kernel, flipped, and padding (taps - 1): 2x2 / 2x1 / 1x2 / 1x1 for k = 3, four 2x2
-    kernels for k = 4.  Order: (0,0), (0,1), (1,0), (1,1)."""
+def parity_class_weights(w: torch.Tensor) -> torch.Tensor:
+    """conv weight [cout, cin, k, k] (stride 2, no padding, k = 3 or 4) -> the weight [4*cin, cout, 2, 2] (channels-last)
+    of the ONE stride-1 convolution (padding 1) that produces its data gradient as merged parity planes: output
+    channel block c = pa*2+pb at position (i, j) is dx[2i+pa, 2j+pb], which only receives the taps ky = pa, kx = pb
+    (mod 2) from dz[i - ky // 2, j - kx // 2].  A parity with a single tap along an axis (k = 3, odd parity) has a
+    zero in its other kernel slot, and its extra last row / column comes out as zero."""
     cout, cin, k, _ = w.shape
-    if w.is_cuda and w.dtype == torch.bfloat16:  # one kernel instead of a dozen slice / flip / permute / copy launches
-        buf = torch.empty((cout * cin * k * k,), dtype=torch.bfloat16, device=w.device)
+    if w.is_cuda and w.dtype == torch.bfloat16:  # one kernel instead of two dozen slice / flip / pad / copy launches
+        buf = torch.empty((4 * cin, 2, 2, cout), dtype=torch.bfloat16, device=w.device)
         st = C.c_void_p(torch.cuda.current_stream(w.device).cuda_stream)
         _capi.check(_capi.lib().ta_parity_class_weights(_ptr(w), w.stride(0), w.stride(1), w.stride(2), w.stride(3), cout, cin, k,
                                                         _ptr(buf), st), "ta_parity_class_weights")
-        out, off = [], 0
-        for idx in range(4):
-            kh, kw = (k - (idx >> 1) + 1) // 2, (k - (idx & 1) + 1) // 2
-            n = cin * kh * kw * cout
-            out.append(buf[off:off + n].view(cin, kh, kw, cout).permute(0, 3, 1, 2))   # [cin, cout, kh, kw], channels-last
-            off += n
-        return out
-    out = []
+        return buf.permute(0, 3, 1, 2)
+    blocks = []
     for pa in (0, 1):
         for pb in (0, 1):
-            k_ = w[:, :, pa::2][:, :, :, pb::2]                           # taps {0, 2} / {1, 3} for parity 0 / 1
-            out.append(k_.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last))
-    return out
+            sub = w[:, :, pa::2][:, :, :, pb::2].flip(2, 3)               # taps {0, 2} / {1, 3} (k = 4) or {1} for parity 0 / 1
+            sub = torch.nn.functional.pad(sub, (2 - sub.shape[3], 0, 2 - sub.shape[2], 0))   # single tap -> slot 1
+            blocks.append(sub.permute(1, 0, 2, 3))
+    return torch.cat(blocks, 0).contiguous(memory_format=torch.channels_last)
 
 
-def _class_planes(dz: torch.Tensor, w: torch.Tensor):
-    """The data gradient of a 3x3 stride-2 unpadded conv with weight w, given dz (channels-last bf16), as four
-    contiguous channels-last parity planes [B, H', W', cin] (see parity_class_weights)."""
-    planes = []
-    for wk in parity_class_weights(w):
-        pl = torch.nn.functional.conv2d(dz, wk, padding=(wk.shape[2] - 1, wk.shape[3] - 1))
-        planes.append(pl.permute(0, 2, 3, 1).contiguous())
-    return planes
+def _class_planes(dz: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """The data gradient of a k x k stride-2 unpadded conv with weight w, given dz (channels-last bf16), as merged
+    parity planes: contiguous [B, OH+1, OW+1, 4*cin] (see parity_class_weights)."""
+    pl = torch.nn.functional.conv2d(dz, parity_class_weights(w), padding=1)
+    return pl.permute(0, 2, 3, 1).contiguous()
 
 
 def _wgrad_bgrad(dz: torch.Tensor, x_nchw: torch.Tensor, w: torch.Tensor, st):
@@ -163,9 +155,9 @@ def _wgrad_bgrad(dz: torch.Tensor, x_nchw: torch.Tensor, w: torch.Tensor, st):
 
 class _Stem(torch.autograd.Function):
     """conv1 (fused kernel) + conv2 + conv3 (cuDNN fused conv + bias + ReLU) as ONE autograd node, so that the data
-    gradients of the two stride-2 3x3 convolutions can stay in the form that is cheapest to produce: four stride-1
-    cuDNN convolutions of dz, one per parity class of the input pixel (2.5x faster than the plain GEMM + col2im path
-    or cuDNN's strided dgrad on the probe shapes, scripts/probe_dgrad_classes*.py).
+    gradients of the two stride-2 convolutions can stay in the form that is cheapest to produce: ONE stride-1 cuDNN
+    convolution of dz whose output channels hold the four parity classes of the input pixel ("merged planes"; several
+    times faster than the plain GEMM + col2im path or cuDNN's strided dgrad, scripts/probe_dgrad_classes.py).
       * conv3's planes are interleaved into the dense dz2 by the kernel that applies conv2's ReLU mask
         (ta_planes_to_dense_relu: the traffic of the threshold_backward pass it replaces);
       * conv2's planes are exactly the four output phases of the folded conv1, whose tcgen05 weight-gradient
@@ -207,8 +199,8 @@ class _Stem(torch.autograd.Function):
             dz2_nhwc = torch.empty((Bn, H, W, Cc), dtype=torch.bfloat16, device=x.device)
             y2_nhwc = y2.permute(0, 2, 3, 1)
             assert y2_nhwc.is_contiguous()
-            _capi.check(lib.ta_planes_to_dense_relu(_ptr(p3[0]), _ptr(p3[1]), _ptr(p3[2]), _ptr(p3[3]), _ptr(y2_nhwc), _ptr(dz2_nhwc),
-                                                    Bn, H, W, Cc, w3.shape[2], st), "ta_planes_to_dense_relu")
+            _capi.check(lib.ta_planes_to_dense_relu(_ptr(p3), _ptr(y2_nhwc), _ptr(dz2_nhwc), Bn, H, W, Cc, w3.shape[2], st),
+                        "ta_planes_to_dense_relu")
             dz2 = dz2_nhwc.permute(0, 3, 1, 2)
         else:
             dz2 = torch.ops.aten.threshold_backward(dy, y2, 0).contiguous(memory_format=torch.channels_last)
@@ -216,9 +208,8 @@ class _Stem(torch.autograd.Function):
         p2 = _class_planes(dz2, w2)
         dw4 = torch.empty((256, 16), dtype=torch.float32, device=x.device)
         db4 = torch.empty((256,), dtype=torch.float32, device=x.device)
-        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(y1), _ptr(p2[0]),
-                                            _ptr(p2[1]), _ptr(p2[2]), _ptr(p2[3]), x.shape[0], _ptr(dw4), _ptr(db4), st),
-                    "ta_conv1_bwd_planes")
+        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(y1), _ptr(p2),
+                                            x.shape[0], _ptr(dw4), _ptr(db4), st), "ta_conv1_bwd_planes")
         return None, dw4, db4, gw2, gb2, gw3, gb3
 
 

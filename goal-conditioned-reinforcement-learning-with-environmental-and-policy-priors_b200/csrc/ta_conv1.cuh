@@ -248,55 +248,45 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4 *__restrict_
     }
 }
 
-// ---- the four parity-class kernels of a stride-2 convolution's data gradient, in one launch -------------------
-// w bf16 [cout][cin][k][k] (any strides) -> out: for class c = pa*2+pb, at element offset off[c], the conv2d weight
-// of the stride-1 convolution that produces plane c: logical [cin][cout][kh][kw] in channels-last memory
-// ([cin][kh][kw][cout]), kh = taps(pa), kw = taps(pb), taps(p) = (k-p+1)/2, flipped:
-//   out_c[ci][u][v][co] = w[co][ci][2*(kh-1-u)+pa][2*(kw-1-v)+pb]
-// (every tap of w lands in exactly one class: k*k*cin*cout elements in total).
+// ---- the four parity-class kernels of a stride-2 convolution's data gradient as ONE conv2d weight ------------
+// The data gradient of a k x k stride-2 unpadded convolution (k = 3, 4) splits by the parity (pa, pb) of the input
+// pixel: dx[2i+pa, 2j+pb] = sum over the taps ky = pa, kx = pb (mod 2) of dz[i - ky/2, j - kx/2] . w[:, :, ky, kx],
+// a stride-1 convolution of dz with a <= 2x2 sub-kernel.  All four are computed by one stride-1 convolution with
+// 4*cin output channels, a 2x2 kernel and padding 1 ("merged planes": output [B][OH+1][OW+1][4][cin], class
+// c = pa*2+pb in channel block c; a class with a single tap along an axis gets a zero in the other slot, and its
+// extra last row / column comes out as zero).  This kernel builds that weight:
+// w bf16 [cout][cin][k][k] (any strides) -> out = conv2d weight [4*cin][cout][2][2] in channels-last memory
+//   out[c*cin + ci][u][v][co] = w[co][ci][ky][kx],  ky = taps(pa) == 2 ? 2*(1-u)+pa : (u == 1 ? pa : none), kx alike
 __global__ void __launch_bounds__(256) parity_class_weights_kernel(const __nv_bfloat16 *__restrict__ w, long long so, long long si,
                                                                   long long sy, long long sx, int cout, int cin, int k,
                                                                   __nv_bfloat16 *__restrict__ out) {
-    const int total = cout * cin * k * k;
+    const int total = 4 * cin * 4 * cout;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int r = i, off = 0, c = 0, kh = 0, kw = 0;
-        for (; c < 4; c++) {  // which class block does element i fall into
-            kh = (k - (c >> 1) + 1) / 2;
-            kw = (k - (c & 1) + 1) / 2;
-            const int n = cin * kh * kw * cout;
-            if (r < n) break;
-            r -= n;
-            off += n;
-        }
+        int r = i;
         const int co = r % cout; r /= cout;
-        const int v = r % kw; r /= kw;
-        const int u = r % kh;
-        const int ci = r / kh;
-        const int ky = 2 * (kh - 1 - u) + (c >> 1), kx = 2 * (kw - 1 - v) + (c & 1);
-        out[i] = w[co * so + ci * si + ky * sy + kx * sx];
+        const int v = r & 1, u = (r >> 1) & 1; r >>= 2;
+        const int ci = r % cin, c = r / cin, pa = c >> 1, pb = c & 1;
+        const int kh = (k - pa + 1) / 2, kw = (k - pb + 1) / 2;
+        const int ky = kh == 2 ? 2 * (1 - u) + pa : (u == 1 ? pa : -1);
+        const int kx = kw == 2 ? 2 * (1 - v) + pb : (v == 1 ? pb : -1);
+        out[i] = (ky >= 0 && kx >= 0) ? w[co * so + ci * si + ky * sy + kx * sx] : __float2bfloat16(0.f);
     }
 }
 
-// ---- parity planes -> dense, fused with the ReLU backward of the layer below ---------------------------------
-// The data gradient of a k x k stride-2 convolution (k = 3, 4), produced as four stride-1 convolutions of dz (one per
-// parity (pa, pb) of the input pixel; plane pa*2+pb = bf16 [B][OH+taps(pa)-1][OW+taps(pb)-1][C], taps(p) = (k-p+1)/2
-// kernel taps of that parity), interleaved back into the dense
-// channels-last tensor and masked with the ReLU of the layer that produced the input (y [B][H][W][C]):
-//   dz_out[b][h][w][c] = y > 0 ? plane[(h&1)*2 + (w&1)][b][h>>1][w>>1][c] : 0     (0 where the plane has no such pixel)
+// ---- merged parity planes -> dense, fused with the ReLU backward of the layer below ------------------------------
+// planes bf16 [B][OH+1][OW+1][4][C] (see above) -> the dense channels-last gradient, masked with the ReLU of the
+// layer that produced the convolution's input (y [B][H][W][C]):
+//   dz_out[b][h][w][c] = y > 0 ? planes[b][h>>1][w>>1][(h&1)*2 + (w&1)][c] : 0
 // = aten::threshold_backward's traffic, so the interleave comes for free.
-struct C1PlanesU4 {
-    const uint4 *p[4];
-};
-__global__ void __launch_bounds__(256) planes_to_dense_relu_kernel(C1PlanesU4 planes, const uint4 *__restrict__ y, uint4 *__restrict__ out,
-                                                                  unsigned total, int H, int W, int c8n, int OH, int OW, int KS) {
+__global__ void __launch_bounds__(256) planes_to_dense_relu_kernel(const uint4 *__restrict__ planes, const uint4 *__restrict__ y,
+                                                                  uint4 *__restrict__ out, unsigned total, int H, int W, int c8n,
+                                                                  int OH, int OW) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const unsigned pix = i / (unsigned)c8n, c8 = i - pix * (unsigned)c8n;
         const unsigned bh = pix / (unsigned)W, w = pix - bh * (unsigned)W;
         const unsigned b = bh / (unsigned)H, h = bh - b * (unsigned)H;
-        const unsigned pa = h & 1u, pb = w & 1u, hp = h >> 1, wp = w >> 1;
-        const unsigned Hp = (unsigned)OH + ((unsigned)KS - pa + 1u) / 2u - 1u, Wp = (unsigned)OW + ((unsigned)KS - pb + 1u) / 2u - 1u;
-        uint4 g = make_uint4(0u, 0u, 0u, 0u);
-        if (hp < Hp && wp < Wp) g = __ldg(planes.p[pa * 2u + pb] + ((size_t)(b * Hp + hp) * Wp + wp) * c8n + c8);
+        const unsigned cls = (h & 1u) * 2u + (w & 1u), hp = h >> 1, wp = w >> 1;
+        const uint4 g = __ldg(planes + (((size_t)(b * (OH + 1) + hp) * (OW + 1) + wp) * 4u + cls) * c8n + c8);
         const uint4 yv = __ldg(y + i);
         auto m = [](uint32_t gw, uint32_t yw) {  // bf16 pairs; y is a ReLU output (>= +0)
             return gw & (((yw & 0xFFFFu) ? 0xFFFFu : 0u) | ((yw >> 16) ? 0xFFFF0000u : 0u));

@@ -269,18 +269,16 @@ __device__ __forceinline__ uint4 tcb_mask(uint4 g, uint4 yv) {
     return make_uint4(m(g.x, yv.x), m(g.y, yv.y), m(g.z, yv.z), m(g.w, yv.w));
 }
 
-// dL/dy either as one channels-last tensor [B][33][33][64] (PL = false, `dy`) or as four parity planes (PL = true):
-// plane py*2+px = bf16 [B][17-py][17-px][64] holds the gradient of the output pixels (2m+py, 2n+px) -- the form in
-// which conv2's data gradient is produced by four stride-1 convolutions of dz, one per parity class of the pixel
-// (conv1.py: _Stem); it is also exactly this kernel's phase structure, so no interleaving pass is needed.
-struct C1Planes {
-    const __nv_bfloat16 *p[4];
-};
+// dL/dy either as one channels-last tensor [B][33][33][64] (PL = false, `dy`) or as merged parity planes (PL = true):
+// planes bf16 [B][17][17][4][64], block py*2+px of position (m, n) = the gradient of output pixel (2m+py, 2n+px) -- the
+// form in which conv2's data gradient falls out of ONE stride-1 convolution of its dz (ta_conv1.cuh,
+// parity_class_weights_kernel; conv1.py: _Stem).  It is exactly this kernel's phase structure, so no interleaving
+// pass is needed and a position's four phases are 512 contiguous bytes.
 
 template <typename XT, bool PL>
 __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__restrict__ x, long long xstride,
                                                                  const __nv_bfloat16 *__restrict__ y,
-                                                                 const __nv_bfloat16 *__restrict__ dy, C1Planes planes, long long B,
+                                                                 const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ planes, long long B,
                                                                  float *__restrict__ dw4, float *__restrict__ db4, int swap_lbo_sbo,
                                                                  uint32_t zero, int *fail) {
     extern __shared__ __align__(128) uint8_t tcb_smem[];
@@ -355,9 +353,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
 #pragma unroll
                 for (int u = 0; u < TCB_BATCH; u++) {
                     const long long inf = rowinfo[(it0 + u) * 16 + psub];
-                    // (b, m, n) of the row for the plane addressing (npos < 2^31 is checked by the host)
-                    const uint32_t Pq = (uint32_t)(tile * TC_M) + (uint32_t)((it0 + u) * 16 + psub);
-                    const uint32_t bq = Pq / (uint32_t)NCELL, posq = Pq - bq * (uint32_t)NCELL, mq = posq / (uint32_t)GS, nq = posq - mq * (uint32_t)GS;
+                    // position index = (b * 17 + m) * 17 + n: the merged planes are indexed by it directly
+                    const long long Pq = tile * TC_M + (it0 + u) * 16 + psub;
 #pragma unroll
                     for (int px = 0; px < 2; px++) {
                         // a pixel that does not exist reads pixel 0 and is zeroed through its y (unconditional loads
@@ -365,8 +362,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
                         const bool ok = inf >= 0 && !(h && (inf & 2)) && !(px && (inf & 1));
                         const long long e = ok ? ((inf >> 2) + h * C1_OUT + px) * C1_CH + g8 * 8 : 0ll;
                         if constexpr (PL) {
-                            const long long eg = ok ? (((long long)bq * (GS - h) + mq) * (GS - px) + nq) * C1_CH + g8 * 8 : 0ll;
-                            gv[u][px] = tcb_ldg(planes.p[h * 2 + px] + eg);
+                            const long long eg = ok ? ((long long)Pq * 4 + (h * 2 + px)) * C1_CH + g8 * 8 : 0ll;
+                            gv[u][px] = tcb_ldg(planes + eg);
                         } else {
                             gv[u][px] = tcb_ldg(dy + e);
                         }

@@ -547,7 +547,7 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
 
 namespace {
 // the tcgen05 weight-gradient kernel; planes == nullptr: dy is one channels-last tensor
-int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, const void *const *planes,
+int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, const void *planes,
                         int64_t batch, float *dw4, float *db4, void *stream) {
     static int per_sm[4] = {0, 0, 0, 0}, sms = 0;
     const int dyn = TCB_A_BYTES + 2 * TCB_B_BYTES;
@@ -570,9 +570,7 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
     const int variant = (planes ? 2 : 0) + (x_dtype == TA_X_U8 ? 0 : 1);
     const long long cap = (long long)sms * per_sm[variant];
     const int g = (int)(ntiles < cap ? ntiles : cap);
-    C1Planes pl = {{nullptr, nullptr, nullptr, nullptr}};
-    if (planes)
-        for (int i = 0; i < 4; i++) pl.p[i] = (const __nv_bfloat16 *)planes[i];
+    const __nv_bfloat16 *pl = (const __nv_bfloat16 *)planes;
     const __nv_bfloat16 *yb = (const __nv_bfloat16 *)y_bf16, *dyb = (const __nv_bfloat16 *)dy_bf16;
     cudaStream_t st = (cudaStream_t)stream;
     switch (variant) {
@@ -587,16 +585,14 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
 
 extern "C" {
 
-int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy00, const void *dy01,
-                        const void *dy10, const void *dy11, int64_t batch, float *dw4, float *db4, void *stream) {
-    if (!x || !y_bf16 || !dy00 || !dy01 || !dy10 || !dy11 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL ||
-        (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
+int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *planes_bf16, int64_t batch,
+                        float *dw4, float *db4, void *stream) {
+    if (!x || !y_bf16 || !planes_bf16 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
-    if (((uintptr_t)y_bf16 | (uintptr_t)dy00 | (uintptr_t)dy01 | (uintptr_t)dy10 | (uintptr_t)dy11) & 15u) return TA_E_INVALID;
+    if (((uintptr_t)y_bf16 | (uintptr_t)planes_bf16) & 15u) return TA_E_INVALID;
     CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), (cudaStream_t)stream));
     CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
-    const void *planes[4] = {dy00, dy01, dy10, dy11};
-    return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, nullptr, planes, batch, dw4, db4, stream);
+    return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, nullptr, planes_bf16, batch, dw4, db4, stream);
 }
 
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, int64_t batch,
@@ -639,7 +635,7 @@ int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int 
 int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride_i, int64_t stride_y, int64_t stride_x, int cout, int cin,
                             int ksize, void *out_bf16, void *stream) {
     if (!w_bf16 || !out_bf16 || cout <= 0 || cin <= 0 || (ksize != 3 && ksize != 4)) return TA_E_INVALID;
-    const long long total = (long long)cout * cin * ksize * ksize;
+    const long long total = 16ll * cout * cin;
     if (total >= (1ll << 31)) return TA_E_INVALID;
     parity_class_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)w_bf16, stride_o, stride_i,
                                                                                       stride_y, stride_x, cout, cin, ksize,
@@ -647,19 +643,19 @@ int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride
     return launch_ok("parity_class_weights_kernel");
 }
 
-int ta_planes_to_dense_relu(const void *p00, const void *p01, const void *p10, const void *p11, const void *y_bf16, void *dz_bf16,
-                            int64_t batch, int H, int W, int C, int ksize, void *stream) {
-    if (!p00 || !p01 || !p10 || !p11 || !y_bf16 || !dz_bf16 || batch <= 0 || (ksize != 3 && ksize != 4) || H < ksize || W < ksize ||
-        C <= 0 || (C & 7))
+int ta_planes_to_dense_relu(const void *planes_bf16, const void *y_bf16, void *dz_bf16, int64_t batch, int H, int W, int C, int ksize,
+                            void *stream) {
+    if (!planes_bf16 || !y_bf16 || !dz_bf16 || batch <= 0 || (ksize != 3 && ksize != 4) || H < ksize || W < ksize || C <= 0 || (C & 7))
         return TA_E_INVALID;
-    if (((uintptr_t)p00 | (uintptr_t)p01 | (uintptr_t)p10 | (uintptr_t)p11 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16) & 15u) return TA_E_INVALID;
+    if (((uintptr_t)planes_bf16 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16) & 15u) return TA_E_INVALID;
+    if ((H - ksize) / 2 + 1 < (H - 1) / 2 || (W - ksize) / 2 + 1 < (W - 1) / 2) return TA_E_INVALID;  // every pixel has a plane entry
     const long long total = (long long)batch * H * W * (C >> 3);
     if (total >= (1ll << 31)) return TA_E_INVALID;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    C1PlanesU4 pl = {{(const uint4 *)p00, (const uint4 *)p01, (const uint4 *)p10, (const uint4 *)p11}};
-    planes_to_dense_relu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pl, (const uint4 *)y_bf16, (uint4 *)dz_bf16, (unsigned)total,
-                                                                                 H, W, C >> 3, (H - ksize) / 2 + 1, (W - ksize) / 2 + 1, ksize);
+    planes_to_dense_relu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4 *)planes_bf16, (const uint4 *)y_bf16,
+                                                                                 (uint4 *)dz_bf16, (unsigned)total, H, W, C >> 3,
+                                                                                 (H - ksize) / 2 + 1, (W - ksize) / 2 + 1);
     return launch_ok("planes_to_dense_relu_kernel");
 }
 

@@ -227,31 +227,30 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
                  void *y_bf16, void *stream);
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16,
                  int64_t batch, float *dw4, float *db4, void *stream);
-/* The same with dL/dy given as four parity planes: dy<py><px> = bfloat16 [batch][17-py][17-px][64] holds the
- * gradient of the output pixels (2m+py, 2n+px).  That is the form in which the data gradient of TINet's second
- * convolution (all_net.py:144, 3x3 stride 2) falls out of four stride-1 convolutions of its dz, one per pixel
- * parity, and the phase structure of the folded first layer: no 33x33x64 gradient tensor is materialised. */
-int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy00,
-                        const void *dy01, const void *dy10, const void *dy11, int64_t batch, float *dw4, float *db4,
-                        void *stream);
+/* Parity planes.  The data gradient of a k x k (k = 3, 4) stride-2 unpadded convolution splits by the parity (pa, pb)
+ * of the input pixel: dx[2i+pa][2j+pb] only receives the taps ky = pa, kx = pb (mod 2), from dz[i - ky/2][j - kx/2] --
+ * a stride-1 convolution of dz with a <= 2x2 sub-kernel.  All four classes come out of ONE stride-1 convolution
+ * (2x2 kernel, padding 1, 4*cin output channels): "merged planes" bfloat16 [batch][OH+1][OW+1][4][cin], class
+ * pa*2+pb in channel block c.  (TINet's second and third convolutions, all_net.py:144-147.)
+ *
+ * ta_parity_class_weights: w bfloat16 [cout][cin][k][k] with the given element strides -> out = that convolution's
+ *   weight [4*cin][cout][2][2] in channels-last memory (16*cin*cout elements).
+ * ta_planes_to_dense_relu: merged planes -> the dense channels-last gradient [batch][H][W][C], masked with the ReLU
+ *   of the layer below: dz_out = y > 0 ? planes[b][h>>1][w>>1][(h&1)*2+(w&1)] : 0.
+ * ta_conv1_bwd_planes: ta_conv1_bwd with dL/dy given as merged planes [batch][17][17][4][64] (block py*2+px of
+ *   position (m, n) = gradient of output pixel (2m+py, 2n+px)): the planes are the phase structure of the folded
+ *   first layer, so the 33x33x64 gradient tensor is never materialised. */
+int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride_i, int64_t stride_y, int64_t stride_x,
+                            int cout, int cin, int ksize, void *out_bf16, void *stream);
+int ta_planes_to_dense_relu(const void *planes_bf16, const void *y_bf16, void *dz_bf16, int64_t batch, int H, int W,
+                            int C, int ksize, void *stream);
+int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *planes_bf16,
+                        int64_t batch, float *dw4, float *db4, void *stream);
 
 /* Data gradient helper for TINet's stride-2 unpadded convolutions (all_net.py:144-149) in channels-last
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].
  * k in {3, 4}, C a multiple of 8, OH = (H-k)/2+1. */
 int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
-/* The four parity-class kernels of that data gradient in one launch: w bfloat16 [cout][cin][k][k] with the given element
- * strides -> out (cout*cin*k*k elements): class pa*2+pb after the previous ones, as the conv2d weight
- * [cin][cout][kh][kw] in channels-last memory, kh = (k-pa+1)/2, kw = (k-pb+1)/2, taps flipped
- * (out_c[ci][u][v][co] = w[co][ci][2(kh-1-u)+pa][2(kw-1-v)+pb]). */
-int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride_i, int64_t stride_y, int64_t stride_x,
-                            int cout, int cin, int ksize, void *out_bf16, void *stream);
-/* The data gradient of a k x k (k = 3, 4) stride-2 unpadded convolution given as four parity planes (plane pa*2+pb =
- * bfloat16 [batch][OH+t(pa)-1][OW+t(pb)-1][C], t(p) = (k-p+1)/2 taps of that parity: the stride-1 convolution of dz
- * for input pixels (2i+pa, 2j+pb)) -> the dense
- * channels-last gradient, masked with the ReLU of the layer below: dz_out = y > 0 ? plane value : 0
- * (TINet's third convolution feeding its second, all_net.py:144-147). */
-int ta_planes_to_dense_relu(const void *p00, const void *p01, const void *p10, const void *p11, const void *y_bf16,
-                            void *dz_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
 /* Its forward: x [batch][H][W][C] -> cols [batch*OH*OW][k*k*C] (columns (ky,kx,c)), the operand of the plain GEMM
  * TINet's last convolution (all_net.py:150, 128 -> 256, 3x3 stride 2 on 7x7) runs as. */
 int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);

@@ -13,11 +13,20 @@ LAYER = int(os.environ.get("LAYER", "2"))
 cout, cin, k, oh, hin = (64, 64, 3, 16, 33) if LAYER == 2 else (128, 64, 4, 7, 16)
 w = (torch.randn(cout, cin, k, k, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)   # [co, ci, ky, kx]
 dz = torch.randn(B, cout, oh, oh, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-cw = C1.parity_class_weights(w)
+cwm = C1.parity_class_weights(w)                                   # merged: [4*cin, cout, 2, 2]
+cw = []
+for c in range(4):                                                  # the four separate class kernels (for comparison)
+    blk = cwm[c * cin:(c + 1) * cin]
+    kh, kw = (k - (c >> 1) + 1) // 2, (k - (c & 1) + 1) // 2
+    cw.append(blk[:, :, 2 - kh:, 2 - kw:].contiguous(memory_format=torch.channels_last))
 
 
 def planes(dz):
     return [F.conv2d(dz, wk, padding=(wk.shape[2] - 1, wk.shape[3] - 1)) for wk in cw]
+
+
+def merged(dz):
+    return F.conv2d(dz, cwm, padding=1)
 
 
 def gemm_col2im(dz):
@@ -48,6 +57,10 @@ def timeit(fn, reps=10):
 
 
 torch.backends.cudnn.benchmark = True
-print(f"layer {LAYER}, B = {B}: 4 class convs {timeit(lambda: planes(dz)):.1f} us;  GEMM + col2im {timeit(lambda: gemm_col2im(dz)):.1f} us")
+mg = merged(dz)
+for idx, t in enumerate(pl):
+    sub = mg[:, idx * cin:(idx + 1) * cin, :t.shape[2], :t.shape[3]]
+    assert float((sub.float() - t.float()).abs().max()) <= 0.07, idx
+print(f"layer {LAYER}, B = {B}: merged conv {timeit(lambda: merged(dz)):.1f} us; 4 class convs {timeit(lambda: planes(dz)):.1f} us;  GEMM + col2im {timeit(lambda: gemm_col2im(dz)):.1f} us")
 x = torch.randn(B, cin, hin, hin, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 print(f"cuDNN strided dgrad: {timeit(lambda: torch.ops.aten.convolution_backward(dz, x, w, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1, [True, False, False])):.1f} us")

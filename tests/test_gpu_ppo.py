@@ -126,19 +126,29 @@ def test_conv_s2_gemm_dgrad_matches_cudnn(layer):
 
 
 @pytest.mark.parametrize("shape", [(64, 64, 3), (128, 64, 4), (8, 16, 3)])
-def test_parity_class_weights_kernel_matches_slicing(shape):
-    """ta_parity_class_weights (one launch) == slicing / flipping / permuting the conv weight in torch, for a
-    contiguous and a channels-last weight."""
+def test_parity_class_weights_and_merged_planes(shape):
+    """ta_parity_class_weights (one launch) == slicing / flipping / padding the conv weight in torch (contiguous and
+    channels-last input), and the merged-plane convolution built from it == conv_transpose2d (the data gradient)."""
     import twoarmy_b200 as pkg
+    import torch.nn.functional as F
     C1 = importlib.import_module(pkg.__name__ + ".conv1")
     cout, cin, k = shape
-    w = torch.randn((cout, cin, k, k), generator=torch.Generator().manual_seed(4)).cuda().to(torch.bfloat16)
+    w = (torch.randn((cout, cin, k, k), generator=torch.Generator().manual_seed(4)) * 0.1).cuda().to(torch.bfloat16)
     want = C1.parity_class_weights(w.float())                       # the torch path (not bf16 -> no kernel)
     for wv in (w, w.contiguous(memory_format=torch.channels_last)):
         got = C1.parity_class_weights(wv)
-        for a, b in zip(got, want):
-            assert a.shape == b.shape and a.is_contiguous(memory_format=torch.channels_last)
-            assert torch.equal(a.float(), b)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(got.float(), want)
+    oh = 6
+    dz = torch.randn((3, cout, oh, oh), generator=torch.Generator().manual_seed(5)).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    planes = C1._class_planes(dz, w).float()                        # [B, oh+1, oh+1, 4*cin]
+    dx = F.conv_transpose2d(dz.float(), w.float(), stride=2)        # [B, cin, 2*oh+k-2, ...]
+    H = dx.shape[2]
+    for c in range(4):
+        pa, pb = c >> 1, c & 1
+        want_c = dx[:, :, pa::2, pb::2].permute(0, 2, 3, 1)
+        got_c = planes[:, :want_c.shape[1], :want_c.shape[2], c * cin:(c + 1) * cin]
+        assert float((got_c - want_c).abs().max()) <= 2e-2 * float(want_c.abs().max()) + 1e-3, (c, H)
 
 
 @pytest.mark.parametrize("dtype,depth", [("u8", 2), ("f32", 2), ("u8", 3)])

@@ -181,3 +181,25 @@ def test_two_rank_gloo_gradient_allreduce_equals_single_rank_full_batch():
     agent.update(full, minibatch=n)
     want = _sums(agent.actor).tolist() + _sums(agent.critic).tolist()
     np.testing.assert_allclose(np.array(ret[0]), np.array(want), rtol=1e-5, atol=1e-5)
+
+
+def test_merged_parity_planes_are_the_strided_data_gradient():
+    """conv1.parity_class_weights (torch path): ONE stride-1 convolution of dz with the merged [4*cin, cout, 2, 2] weight
+    yields, per output-channel block pa*2+pb, the data gradient of the k x k stride-2 convolution at input pixels
+    (2i+pa, 2j+pb) -- i.e. conv_transpose2d, exactly (k = 3 and k = 4: TINet's second / third convolution)."""
+    import importlib
+    import torch.nn.functional as F
+    import twoarmy_b200 as pkg
+    C1 = importlib.import_module(pkg.__name__ + ".conv1")
+    g = torch.Generator().manual_seed(0)
+    for cout, cin, k, oh in [(5, 3, 3, 6), (4, 6, 4, 7), (8, 8, 3, 16)]:
+        w = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64)
+        dz = torch.randn(2, cout, oh, oh, generator=g, dtype=torch.float64)
+        planes = F.conv2d(dz, C1.parity_class_weights(w), padding=1)
+        dx = F.conv_transpose2d(dz, w, stride=2)
+        assert planes.shape == (2, 4 * cin, oh + 1, oh + 1)
+        for c in range(4):
+            want = dx[:, :, (c >> 1)::2, (c & 1)::2]
+            got = planes[:, c * cin:(c + 1) * cin]
+            assert torch.allclose(got[:, :, :want.shape[2], :want.shape[3]], want, rtol=0, atol=1e-12)
+            assert float(got[:, :, want.shape[2]:].abs().max() if want.shape[2] < oh + 1 else 0.0) == 0.0   # the extra row is zero
