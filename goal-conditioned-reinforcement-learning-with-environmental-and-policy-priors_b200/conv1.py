@@ -174,24 +174,26 @@ class _Stem(torch.autograd.Function):
         y1 = torch.empty((B, 33, 33, 64), dtype=torch.bfloat16, device=x.device)
         st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         w4d, b4d = w4.detach().float().contiguous(), b4.detach().float().contiguous()
-        _capi.check(_capi.lib().ta_conv1_fwd(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(w4d), _ptr(b4d), B,
-                                             _ptr(y1), st), "ta_conv1_fwd")
+        # the layer's ReLU mask as bits (8 bytes per output pixel): what the weight-gradient kernel reads instead of y1
+        mask = torch.empty((B * 289 * 8,), dtype=torch.int32, device=x.device)
+        _capi.check(_capi.lib().ta_conv1_fwd_mask(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(w4d), _ptr(b4d), B,
+                                                  _ptr(y1), _ptr(mask), st), "ta_conv1_fwd_mask")
         y2 = torch.cudnn_convolution_relu(y1.permute(0, 3, 1, 2), w2, b2, [2, 2], [0, 0], [1, 1], 1)
         if w3 is None:
-            ctx.save_for_backward(x, y1, w2, y2)
+            ctx.save_for_backward(x, y1, w2, y2, mask)
             return y2
         y3 = torch.cudnn_convolution_relu(y2, w3, b3, [2, 2], [0, 0], [1, 1], 1)
-        ctx.save_for_backward(x, y1, w2, y2, w3, y3)
+        ctx.save_for_backward(x, y1, w2, y2, mask, w3, y3)
         return y3
 
     @staticmethod
     def backward(ctx, dy):
         saved = ctx.saved_tensors
-        x, y1, w2, y2 = saved[:4]
+        x, y1, w2, y2, mask = saved[:5]
         lib, st = _capi.lib(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         gw3 = gb3 = None
-        if len(saved) == 6:
-            w3, y3 = saved[4:]
+        if len(saved) == 7:
+            w3, y3 = saved[5:]
             dz3 = torch.ops.aten.threshold_backward(dy, y3, 0).contiguous(memory_format=torch.channels_last)
             gw3, gb3 = _wgrad_bgrad(dz3, y2, w3, st)
             p3 = _class_planes(dz3, w3)
@@ -208,7 +210,7 @@ class _Stem(torch.autograd.Function):
         p2 = _class_planes(dz2, w2)
         dw4 = torch.empty((256, 16), dtype=torch.float32, device=x.device)
         db4 = torch.empty((256,), dtype=torch.float32, device=x.device)
-        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), _ptr(y1), _ptr(p2),
+        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), None, _ptr(mask), _ptr(p2),
                                             x.shape[0], _ptr(dw4), _ptr(db4), st), "ta_conv1_bwd_planes")
         return None, dw4, db4, gw2, gb2, gw3, gb3
 

@@ -82,10 +82,14 @@ __device__ __forceinline__ float tc_value(XT v) {
     else return (float)v;
 }
 
-template <typename XT>
+// MK: also write the layer's ReLU mask as bits (relu_mask uint32 [position][4 phases][2 halves of 32 channels]; in a
+// word, bit q = channel 2q of the half is non-zero, bit 16 + q = channel 2q + 1), 8 bytes per output pixel: what the
+// weight-gradient kernel reads instead of the 128 bytes of y.
+template <typename XT, bool MK>
 __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__restrict__ x, long long xstride,
                                                                  const float *__restrict__ w4, const float *__restrict__ b4,
-                                                                 long long B, __nv_bfloat16 *__restrict__ y, int *fail) {
+                                                                 long long B, __nv_bfloat16 *__restrict__ y, uint32_t *__restrict__ relu_mask,
+                                                                 int *fail) {
     // every operand is kept as a bf16 (hi, lo) pair, v = hi + lo to 2^-17: three MMAs (hi*hi + lo*hi + hi*lo) give
     // fp32-grade products, so the layer matches the FP32 kernel / cuDNN fp32 to rounding of the bf16 output
     __shared__ __align__(1024) uint8_t sA[2][TC_M * 32];   // 2 x 4 KB
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int c0 = half * 32;
                 // row `lane` of the warp's 32 x 64-byte staging block, 16-byte chunks XOR-swizzled by (row / 2) % 4
+                uint32_t mbits = 0;  // bit c: channel c0 + c of this row's output pixel is non-zero (the ReLU mask the backward needs)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const float4 b0 = *reinterpret_cast<const float4 *>(sbias + phase * 64 + c0 + 8 * j);
@@ -210,6 +215,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
                     const uint32_t o2 = tc_relu_pack(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
                     const uint32_t o3 = tc_relu_pack(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
                     *reinterpret_cast<uint4 *>(wout + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(o0, o1, o2, o3);
+                    if constexpr (MK) {
+                        // a ReLU output half is >= +0, so half + 0x7FFF has bit 15 set exactly when it is non-zero (no carry
+                        // into the other half); word 4j+i contributes bits 4j+i and 16+4j+i
+                        mbits |= (((o0 + 0x7FFF7FFFu) & 0x80008000u) >> (15 - 4 * j)) | (((o1 + 0x7FFF7FFFu) & 0x80008000u) >> (14 - 4 * j)) |
+                                 (((o2 + 0x7FFF7FFFu) & 0x80008000u) >> (13 - 4 * j)) | (((o3 + 0x7FFF7FFFu) & 0x80008000u) >> (12 - 4 * j));
+                    }
+                }
+                if constexpr (MK) {
+                    if (valid) relu_mask[(P * 4 + phase) * 2 + half] = mbits;
                 }
                 __syncwarp();
                 // transposed read-out: 4 lanes per row -> a store instruction covers 8 rows x 64 contiguous bytes
@@ -275,10 +289,13 @@ __device__ __forceinline__ uint4 tcb_mask(uint4 g, uint4 yv) {
 // parity_class_weights_kernel; conv1.py: _Stem).  It is exactly this kernel's phase structure, so no interleaving
 // pass is needed and a position's four phases are 512 contiguous bytes.
 
-template <typename XT, bool PL>
+// MK (with PL): the ReLU mask comes from the forward kernel's bit mask (uint32 [position][4 phases][2], see
+// conv1_fwd_tc_kernel; 8 bytes per pixel instead of the 128 bytes of y) and y is not read at all.
+template <typename XT, bool PL, bool MK>
 __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__restrict__ x, long long xstride,
                                                                  const __nv_bfloat16 *__restrict__ y,
-                                                                 const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ planes, long long B,
+                                                                 const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ planes,
+                                                                 const uint32_t *__restrict__ relu_mask, long long B,
                                                                  float *__restrict__ dw4, float *__restrict__ db4, int swap_lbo_sbo,
                                                                  uint32_t zero, int *fail) {
     extern __shared__ __align__(128) uint8_t tcb_smem[];
@@ -347,18 +364,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             // dz chunks: lane group of 8 = the 128 bytes of one pixel; 16 positions per pass
+            constexpr int NB = MK ? 8 : TCB_BATCH;  // with the bit mask a whole half tile (16 x 16-byte + 16 x 1-byte loads) is one batch
 #pragma unroll 1
-            for (int it0 = 0; it0 < 8; it0 += TCB_BATCH) {  // TCB_BATCH x 4 16-byte loads in flight per thread
-                uint4 gv[TCB_BATCH][2], yv[TCB_BATCH][2];
+            for (int it0 = 0; it0 < 8; it0 += NB) {  // NB x 2 (x 2 without the bit mask) 16-byte loads in flight per thread
+                uint4 gv[NB][2], yv[NB][2];
+                uint32_t mbv[NB][2];
 #pragma unroll
-                for (int u = 0; u < TCB_BATCH; u++) {
+                for (int u = 0; u < NB; u++) {
                     const long long inf = rowinfo[(it0 + u) * 16 + psub];
-                    // position index = (b * 17 + m) * 17 + n: the merged planes are indexed by it directly
+                    // position index = (b * 17 + m) * 17 + n: the merged planes / the bit mask are indexed by it directly
                     const long long Pq = tile * TC_M + (it0 + u) * 16 + psub;
 #pragma unroll
                     for (int px = 0; px < 2; px++) {
-                        // a pixel that does not exist reads pixel 0 and is zeroed through its y (unconditional loads
-                        // keep all of the batch in flight)
+                        // a pixel that does not exist reads pixel 0 and is zeroed through its y / mask (unconditional
+                        // loads keep all of the batch in flight)
                         const bool ok = inf >= 0 && !(h && (inf & 2)) && !(px && (inf & 1));
                         const long long e = ok ? ((inf >> 2) + h * C1_OUT + px) * C1_CH + g8 * 8 : 0ll;
                         if constexpr (PL) {
@@ -367,22 +386,40 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
                         } else {
                             gv[u][px] = tcb_ldg(dy + e);
                         }
-                        yv[u][px] = tcb_ldg(y + e);
-                        if (!ok) yv[u][px] = make_uint4(0u, 0u, 0u, 0u);
+                        if constexpr (MK) {
+                            // the mask word of the 32-channel half that holds channels 8*g8 .. 8*g8+7
+                            mbv[u][px] = ok ? __ldg(relu_mask + (Pq * 4 + (h * 2 + px)) * 2 + (g8 >> 2)) : 0u;
+                        } else {
+                            yv[u][px] = tcb_ldg(y + e);
+                            if (!ok) yv[u][px] = make_uint4(0u, 0u, 0u, 0u);
+                        }
                     }
                 }
                 // every store's address depends on every load of the batch, so all of them are in flight together
                 // (ptxas otherwise interleaves loads and stores to save registers: 3 dependent round trips per batch)
                 uint32_t live = 0;
 #pragma unroll
-                for (int u = 0; u < TCB_BATCH; u++) live |= gv[u][0].x | yv[u][0].x | gv[u][1].x | yv[u][1].x;
+                for (int u = 0; u < NB; u++) {
+                    live |= gv[u][0].x | gv[u][1].x;
+                    if constexpr (MK) live |= mbv[u][0] | mbv[u][1];
+                    else live |= yv[u][0].x | yv[u][1].x;
+                }
                 const uint32_t nudge = live & zero;  // zero == 0 at run time
 #pragma unroll
-                for (int u = 0; u < TCB_BATCH; u++) {
+                for (int u = 0; u < NB; u++) {
                     const int p = (it0 + u) * 16 + psub;
 #pragma unroll
-                    for (int px = 0; px < 2; px++)
-                        *reinterpret_cast<uint4 *>(sG + (px * 8 + g8) * TCB_SBO + (p >> 3) * 128 + (p & 7) * 16 + nudge) = tcb_mask(gv[u][px], yv[u][px]);
+                    for (int px = 0; px < 2; px++) {
+                        uint4 yy;
+                        if constexpr (MK) {  // mask bits -> a "non-zero" pattern per bf16 half
+                            // words 4*(g8&3) .. +3 of the half: bit q = even channel, bit 16+q = odd channel of word q
+                            const uint32_t mb = mbv[u][px] >> (4 * (g8 & 3));
+                            yy = make_uint4(mb & 0x00010001u, (mb >> 1) & 0x00010001u, (mb >> 2) & 0x00010001u, (mb >> 3) & 0x00010001u);
+                        } else {
+                            yy = yv[u][px];
+                        }
+                        *reinterpret_cast<uint4 *>(sG + (px * 8 + g8) * TCB_SBO + (p >> 3) * 128 + (p & 7) * 16 + nudge) = tcb_mask(gv[u][px], yy);
+                    }
                 }
             }
             fence_proxy_async();

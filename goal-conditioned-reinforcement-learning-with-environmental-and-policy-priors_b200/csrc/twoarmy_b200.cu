@@ -498,19 +498,47 @@ int conv1_grid(K kern, long long batch, int *grid) {
 
 extern "C" {
 
+}  // extern "C"
+
+namespace {
+int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch, void *y_bf16,
+                   uint32_t *relu_mask, void *stream);
+}
+
+extern "C" {
+
 int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch, void *y_bf16,
                  void *stream) {
+    return conv1_fwd_impl(x, x_dtype, x_stride, w4, b4, batch, y_bf16, nullptr, stream);
+}
+
+int ta_conv1_fwd_mask(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch, void *y_bf16,
+                      uint32_t *relu_mask, void *stream) {
+    if (!relu_mask || ((uintptr_t)relu_mask & 3u) || batch * NCELL >= (1ll << 31)) return TA_E_INVALID;
+    return conv1_fwd_impl(x, x_dtype, x_stride, w4, b4, batch, y_bf16, relu_mask, stream);
+}
+
+}  // extern "C"
+
+namespace {
+int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch, void *y_bf16,
+                   uint32_t *relu_mask, void *stream) {
     if (!x || !w4 || !b4 || !y_bf16 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
     if ((uintptr_t)y_bf16 & 7u) return TA_E_INVALID;
     if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) != 0 : 1; }
-    if (g_use_tc) {  // tcgen05 version of the layer (TA_CONV1_TC=0 / ta_debug_conv1_tc(0) select the FP32-FMA kernel)
+    if (g_use_tc || relu_mask) {  // tcgen05 version of the layer (the only one that writes the ReLU bit mask) (TA_CONV1_TC=0 / ta_debug_conv1_tc(0) select the FP32-FMA kernel)
         static int per_sm_u8 = 0, per_sm_f32 = 0, sms = 0;
         if (!sms) {
             int dev = 0;
             CK(cudaGetDevice(&dev));
-            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<uint8_t>, TC_THREADS, 0, TC_NT, &per_sm_u8)) return rc;
-            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<float>, TC_THREADS, 0, TC_NT, &per_sm_f32)) return rc;
+            int a = 0, b = 0;
+            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<uint8_t, false>, TC_THREADS, 0, TC_NT, &a)) return rc;
+            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<uint8_t, true>, TC_THREADS, 0, TC_NT, &b)) return rc;
+            per_sm_u8 = a < b ? a : b;
+            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<float, false>, TC_THREADS, 0, TC_NT, &a)) return rc;
+            if (int rc = tc_ctas_per_sm((const void *)conv1_fwd_tc_kernel<float, true>, TC_THREADS, 0, TC_NT, &b)) return rc;
+            per_sm_f32 = a < b ? a : b;
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm_u8, per_sm_f32, sms);
         }
@@ -522,12 +550,16 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
         const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
         const long long cap = (long long)sms * per_sm;
         const int g = (int)(ntiles < cap ? ntiles : cap);
-        if (x_dtype == TA_X_U8)
-            conv1_fwd_tc_kernel<uint8_t><<<g, TC_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)x, x_stride, w4, b4, batch,
-                                                                                (__nv_bfloat16 *)y_bf16, g_tc_fail);
+        cudaStream_t st = (cudaStream_t)stream;
+        __nv_bfloat16 *yb = (__nv_bfloat16 *)y_bf16;
+        if (x_dtype == TA_X_U8 && relu_mask)
+            conv1_fwd_tc_kernel<uint8_t, true><<<g, TC_THREADS, 0, st>>>((const uint8_t *)x, x_stride, w4, b4, batch, yb, relu_mask, g_tc_fail);
+        else if (x_dtype == TA_X_U8)
+            conv1_fwd_tc_kernel<uint8_t, false><<<g, TC_THREADS, 0, st>>>((const uint8_t *)x, x_stride, w4, b4, batch, yb, nullptr, g_tc_fail);
+        else if (relu_mask)
+            conv1_fwd_tc_kernel<float, true><<<g, TC_THREADS, 0, st>>>((const float *)x, x_stride, w4, b4, batch, yb, relu_mask, g_tc_fail);
         else
-            conv1_fwd_tc_kernel<float><<<g, TC_THREADS, 0, (cudaStream_t)stream>>>((const float *)x, x_stride, w4, b4, batch,
-                                                                              (__nv_bfloat16 *)y_bf16, g_tc_fail);
+            conv1_fwd_tc_kernel<float, false><<<g, TC_THREADS, 0, st>>>((const float *)x, x_stride, w4, b4, batch, yb, nullptr, g_tc_fail);
         return launch_ok("conv1_fwd_tc_kernel");
     }
     int grid = 1;
@@ -543,23 +575,23 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
     return launch_ok("conv1_fwd_kernel");
 }
 
-}  // extern "C"
-
-namespace {
-// the tcgen05 weight-gradient kernel; planes == nullptr: dy is one channels-last tensor
+// the tcgen05 weight-gradient kernel; planes == nullptr: dy is one channels-last tensor; relu_mask (with planes): y is not read
 int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, const void *planes,
-                        int64_t batch, float *dw4, float *db4, void *stream) {
-    static int per_sm[4] = {0, 0, 0, 0}, sms = 0;
+                        const void *relu_mask, int64_t batch, float *dw4, float *db4, void *stream) {
+    static int per_sm[6] = {0, 0, 0, 0, 0, 0}, sms = 0;
     const int dyn = TCB_A_BYTES + 2 * TCB_B_BYTES;
     if (!sms) {
         int dev = 0;
         CK(cudaGetDevice(&dev));
-        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[0])) return rc;
-        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[1])) return rc;
-        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t, true>, TC_THREADS, dyn, TCB_COLS, &per_sm[2])) return rc;
-        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float, true>, TC_THREADS, dyn, TCB_COLS, &per_sm[3])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t, false, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[0])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float, false, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[1])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t, true, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[2])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float, true, false>, TC_THREADS, dyn, TCB_COLS, &per_sm[3])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<uint8_t, true, true>, TC_THREADS, dyn, TCB_COLS, &per_sm[4])) return rc;
+        if (int rc = tc_ctas_per_sm((const void *)conv1_bwd_tc_kernel<float, true, true>, TC_THREADS, dyn, TCB_COLS, &per_sm[5])) return rc;
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_bwd_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm[0], per_sm[1], sms);
+        if (getenv("TA_VERBOSE"))
+            fprintf(stderr, "conv1_bwd_tc: %d / %d / %d CTAs per SM (dense / planes / planes + bit mask), %d SMs\n", per_sm[0], per_sm[2], per_sm[4], sms);
     }
     if (!g_tc_fail) {
         CK(cudaMalloc(&g_tc_fail, sizeof(int)));
@@ -567,32 +599,38 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
     }
     if (batch * NCELL >= (1ll << 31)) return TA_E_INVALID;
     const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
-    const int variant = (planes ? 2 : 0) + (x_dtype == TA_X_U8 ? 0 : 1);
+    const int variant = (planes ? (relu_mask ? 4 : 2) : 0) + (x_dtype == TA_X_U8 ? 0 : 1);
     const long long cap = (long long)sms * per_sm[variant];
     const int g = (int)(ntiles < cap ? ntiles : cap);
     const __nv_bfloat16 *pl = (const __nv_bfloat16 *)planes;
     const __nv_bfloat16 *yb = (const __nv_bfloat16 *)y_bf16, *dyb = (const __nv_bfloat16 *)dy_bf16;
     cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t *mk = (const uint32_t *)relu_mask;
+#define TA_BWD_ARGS(XT) (const XT *)x, x_stride, yb, dyb, pl, mk, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail
     switch (variant) {
-        case 0: conv1_bwd_tc_kernel<uint8_t, false><<<g, TC_THREADS, dyn, st>>>((const uint8_t *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
-        case 1: conv1_bwd_tc_kernel<float, false><<<g, TC_THREADS, dyn, st>>>((const float *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
-        case 2: conv1_bwd_tc_kernel<uint8_t, true><<<g, TC_THREADS, dyn, st>>>((const uint8_t *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
-        default: conv1_bwd_tc_kernel<float, true><<<g, TC_THREADS, dyn, st>>>((const float *)x, x_stride, yb, dyb, pl, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail); break;
+        case 0: conv1_bwd_tc_kernel<uint8_t, false, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(uint8_t)); break;
+        case 1: conv1_bwd_tc_kernel<float, false, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(float)); break;
+        case 2: conv1_bwd_tc_kernel<uint8_t, true, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(uint8_t)); break;
+        case 3: conv1_bwd_tc_kernel<float, true, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(float)); break;
+        case 4: conv1_bwd_tc_kernel<uint8_t, true, true><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(uint8_t)); break;
+        default: conv1_bwd_tc_kernel<float, true, true><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(float)); break;
     }
+#undef TA_BWD_ARGS
     return launch_ok("conv1_bwd_tc_kernel");
 }
 }  // namespace
 
 extern "C" {
 
-int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *planes_bf16, int64_t batch,
-                        float *dw4, float *db4, void *stream) {
-    if (!x || !y_bf16 || !planes_bf16 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
+int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const uint32_t *relu_mask,
+                        const void *planes_bf16, int64_t batch, float *dw4, float *db4, void *stream) {
+    if (!x || (!y_bf16 && !relu_mask) || !planes_bf16 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL ||
+        (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
     if (((uintptr_t)y_bf16 | (uintptr_t)planes_bf16) & 15u) return TA_E_INVALID;
     CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), (cudaStream_t)stream));
     CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
-    return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, nullptr, planes_bf16, batch, dw4, db4, stream);
+    return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, nullptr, planes_bf16, relu_mask, batch, dw4, db4, stream);
 }
 
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, int64_t batch,
@@ -605,7 +643,7 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
     CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
     if (g_bwd_tc < 0) { const char *e = getenv("TA_CONV1_BWD_TC"); g_bwd_tc = e ? atoi(e) != 0 : 1; }
     if (g_bwd_tc && !(((uintptr_t)y_bf16 | (uintptr_t)dy_bf16) & 15u) && batch * NCELL < (1ll << 31))
-        return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, dy_bf16, nullptr, batch, dw4, db4, stream);
+        return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, dy_bf16, nullptr, nullptr, batch, dw4, db4, stream);
     int grid = 1;
     if (x_dtype == TA_X_U8) {
         if (int rc = conv1_grid(conv1_bwd_kernel<uint8_t>, batch, &grid)) return rc;

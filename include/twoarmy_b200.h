@@ -244,8 +244,14 @@ int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride
                             int cout, int cin, int ksize, void *out_bf16, void *stream);
 int ta_planes_to_dense_relu(const void *planes_bf16, const void *y_bf16, void *dz_bf16, int64_t batch, int H, int W,
                             int C, int ksize, void *stream);
-int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *planes_bf16,
-                        int64_t batch, float *dw4, float *db4, void *stream);
+int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const uint32_t *relu_mask,
+                        const void *planes_bf16, int64_t batch, float *dw4, float *db4, void *stream);
+/* ta_conv1_fwd that also writes the layer's ReLU mask as bits: relu_mask uint32 [batch*289 positions][4 phases][2
+ * halves of 32 channels]; in a word, bit q / bit 16+q = channel 2q / 2q+1 of the half of output pixel (2m+py, 2n+px)
+ * is non-zero.  Given to ta_conv1_bwd_planes (y_bf16 may then be NULL) the weight gradient reads 8 bytes per pixel
+ * instead of the 128 bytes of y. */
+int ta_conv1_fwd_mask(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch,
+                      void *y_bf16, uint32_t *relu_mask, void *stream);
 
 /* Data gradient helper for TINet's stride-2 unpadded convolutions (all_net.py:144-149) in channels-last
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].

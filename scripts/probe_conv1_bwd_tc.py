@@ -64,3 +64,19 @@ for tc in (0, 1):
     for _ in range(20): L.ta_conv1_fwd(vp(x), 1, x.stride(0), vp(w4), vp(b4), B, vp(yo), st)
     e1.record(); torch.cuda.synchronize()
     print(f"tc={tc}: ta_conv1_fwd B={B}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call  (y = {yo.numel() * 2 / 1e6:.0f} MB)")
+planes = torch.randn((B, 17, 17, 4, 64), device="cuda").to(torch.bfloat16)
+mask = torch.empty((B * 289 * 8,), dtype=torch.int32, device="cuda")
+for _ in range(3): L.ta_conv1_fwd_mask(vp(x), 1, x.stride(0), vp(w4), vp(b4), B, vp(yo), vp(mask), st)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20): L.ta_conv1_fwd_mask(vp(x), 1, x.stride(0), vp(w4), vp(b4), B, vp(yo), vp(mask), st)
+e1.record(); torch.cuda.synchronize()
+print(f"ta_conv1_fwd_mask B={B}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call")
+for name, yarg, marg in (("y", vp(y), None), ("bit mask", None, vp(mask))):
+    for _ in range(3): L.ta_conv1_bwd_planes(vp(x), 1, x.stride(0), yarg, marg, vp(planes), B, vp(dw4), vp(db4), st)
+    res = dw4.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): L.ta_conv1_bwd_planes(vp(x), 1, x.stride(0), yarg, marg, vp(planes), B, vp(dw4), vp(db4), st)
+    e1.record(); torch.cuda.synchronize()
+    print(f"ta_conv1_bwd_planes ({name}) B={B}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call; |dw4| = {float(res.abs().sum()):.1f}")
