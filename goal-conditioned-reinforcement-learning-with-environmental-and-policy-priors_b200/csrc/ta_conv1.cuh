@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) planes_to_dense_relu_kernel(const uint4 *
 }
 
 // ---- per-channel sum of a channels-last bf16 tensor (the bias gradient of a convolution) -------------
-// x bf16 [rows][C], C in {64, 128, 256}: a thread owns 8 channels (16-byte loads) and strides over the
+// x bf16 [rows][C], C in {64, 128, ..., 2048}: a thread owns 8 channels (16-byte loads) and strides over the
 // rows of its CTA's slab; row lanes are combined through shared memory, one atomicAdd per channel and CTA.
 // (aten::sum over (N,H,W) of a channels-last tensor runs far below the HBM rate; this is one streaming pass.)
 __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(const __nv_bfloat16 *__restrict__ x, long long rows, int C,
@@ -317,11 +317,11 @@ __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(const __nv_bfloat
 #pragma unroll
     for (int q = 0; q < 8; q++) sacc[threadIdx.x][q] = acc[q];
     __syncthreads();
-    if (threadIdx.x < C) {  // channel threadIdx.x: sum over the row lanes
-        const int g = threadIdx.x >> 3, q = threadIdx.x & 7;
+    for (int ch = threadIdx.x; ch < C; ch += 256) {  // channel ch: sum over the row lanes
+        const int g = ch >> 3, q = ch & 7;
         float s = 0.f;
         for (int l = 0; l < nrl; l++) s += sacc[l * c8n + g][q];
-        atomicAdd(out + threadIdx.x, s);
+        atomicAdd(out + ch, s);
     }
 }
 

@@ -714,7 +714,7 @@ int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, in
 }
 
 int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, void *stream) {
-    if (!x_bf16 || !out || rows <= 0 || (C != 64 && C != 128 && C != 256) || ((uintptr_t)x_bf16 & 15u)) return TA_E_INVALID;
+    if (!x_bf16 || !out || rows <= 0 || C < 64 || C > 2048 || (C & (C - 1)) || ((uintptr_t)x_bf16 & 15u)) return TA_E_INVALID;
     CK(cudaMemsetAsync(out, 0, C * sizeof(float), (cudaStream_t)stream));
     const int nrl = 256 / (C / 8);
     unsigned nb = blocks_for(rows, (long long)nrl * 16);

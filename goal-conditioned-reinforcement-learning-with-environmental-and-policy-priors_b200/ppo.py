@@ -80,6 +80,8 @@ class TINet(nn.Module):
     # conv1 + conv2 + conv3 in one autograd node (the data gradients of conv2 / conv3 as four parity-class
     # convolutions each; conv2's feed the conv1 weight-gradient kernel directly)
     fused_stem = True
+    # Linear + ReLU layers through conv1._LinearReLU on the GPU under bf16 autocast
+    fused_linear = True
     # data gradients of conv2 / conv3 as GEMM + col2im (csrc/ta_conv1.cuh) instead of cuDNN's strided dgrad
     gemm_dgrad = True
 
@@ -116,7 +118,12 @@ class TINet(nn.Module):
         """state_matrix [B,4,289]: float matrix_env values, or (GPU) the uint8 featuriser codes."""
         B, T, _ = state_matrix.shape
         position = position.contiguous().view(-1, 8)
-        position_goal = torch.relu(self.positionnet(torch.cat([position, goal], 1)))
+        fast = state_matrix.is_cuda and torch.is_autocast_enabled() and self.fused_linear
+        if fast:  # bias + ReLU in the GEMM epilogue, bias gradient from the channel-sum kernel (conv1._LinearReLU)
+            from . import conv1 as _c1
+            position_goal = _c1.linear_relu(torch.cat([position, goal], 1).to(torch.bfloat16), self.positionnet)
+        else:
+            position_goal = torch.relu(self.positionnet(torch.cat([position, goal], 1)))
         if not state_matrix.is_cuda:  # the reference's layer sequence, verbatim
             if state_matrix.dtype == torch.uint8:
                 state_matrix = decode_matrix(state_matrix)
@@ -161,10 +168,15 @@ class TINet(nn.Module):
             else:
                 cols = xn.reshape(B, 49, 128).index_select(1, self._conv4_index(x.device))
             w = conv4.weight.permute(0, 2, 3, 1).reshape(256, -1).to(cols.dtype)
-            y = F.linear(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype))   # [B*9, 256]
-            x = torch.relu(y).view(B, 9, 256).transpose(1, 2).reshape(B, 2304)     # Flatten of [B, 256, 3, 3]
-            x = torch.relu(self.fc0(x))
+            if fast and cols.dtype == torch.bfloat16:
+                y = _c1._LinearReLU.apply(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype))   # [B*9, 256], ReLU applied
+            else:
+                y = torch.relu(F.linear(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype)))
+            x = y.view(B, 9, 256).transpose(1, 2).reshape(B, 2304)                 # Flatten of [B, 256, 3, 3]
+            x = _c1.linear_relu(x, self.fc0) if fast and x.dtype == torch.bfloat16 else torch.relu(self.fc0(x))
         x = torch.cat([x, position_goal.to(x.dtype)], 1)
+        if fast and x.dtype == torch.bfloat16:
+            return _c1.linear_relu(x, self.fc1)
         return torch.relu(self.fc1(x))
 
 

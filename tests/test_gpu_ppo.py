@@ -210,6 +210,32 @@ def test_im2col_s2_kernel_is_the_unfold_and_col2im_its_adjoint(shape):
     assert float((got_dx - want_dx).abs().max()) <= 2e-2 * float(want_dx.abs().max())
 
 
+@pytest.mark.parametrize("dims", [(10, 128), (2304, 256), (384, 512)])
+def test_linear_relu_matches_autograd(dims):
+    """conv1.linear_relu (bias + ReLU in the GEMM epilogue, channel-sum bias gradient) == relu(F.linear) autograd in bf16."""
+    import twoarmy_b200 as pkg
+    C1 = importlib.import_module(pkg.__name__ + ".conv1")
+    fin, fout = dims
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(fin, fout).cuda()
+    x0 = torch.randn(517, fin, device="cuda").to(torch.bfloat16)
+    gy = torch.randn(517, fout, device="cuda").to(torch.bfloat16)
+    outs = []
+    for mode in ("ref", "fused"):
+        lin.weight.grad = None; lin.bias.grad = None
+        x = x0.clone().requires_grad_(True)
+        if mode == "ref":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = torch.relu(lin(x))
+        else:
+            y = C1.linear_relu(x, lin)
+        (y.float() * gy.float()).sum().backward()
+        outs.append((y.detach().float(), x.grad.float(), lin.weight.grad.clone(), lin.bias.grad.clone()))
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2e-2 * float(outs[0][0].abs().max())
+    for name, a, b in zip(("dx", "dw", "db"), outs[0][1:], outs[1][1:]):
+        assert float((a - b).norm()) <= 2e-2 * float(a.norm()), name
+
+
 def test_predictor_agent_rollout_and_update_on_gpu():
     """BASELINE configs[4] plumbing: ppo_predictor drives VecRollout and updates on the device."""
     import twoarmy_b200 as pkg
