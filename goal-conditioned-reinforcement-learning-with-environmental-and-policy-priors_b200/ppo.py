@@ -172,8 +172,14 @@ class TINet(nn.Module):
                 y = _c1._LinearReLU.apply(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype))   # [B*9, 256], ReLU applied
             else:
                 y = torch.relu(F.linear(cols.reshape(B * 9, -1), w, conv4.bias.to(cols.dtype)))
-            x = y.view(B, 9, 256).transpose(1, 2).reshape(B, 2304)                 # Flatten of [B, 256, 3, 3]
-            x = _c1.linear_relu(x, self.fc0) if fast and x.dtype == torch.bfloat16 else torch.relu(self.fc0(x))
+            if fast and y.dtype == torch.bfloat16:
+                # Flatten of [B, 256, 3, 3] orders the features (c, o); y is (o, c): permute fc0's 0.6 M weights instead
+                # of transposing the activations (and their gradient) of every sample
+                w0 = self.fc0.weight.view(256, 256, 9).permute(0, 2, 1).reshape(256, 2304)
+                x = _c1._LinearReLU.apply(y.view(B, 2304), w0.to(torch.bfloat16), self.fc0.bias.to(torch.bfloat16))
+            else:
+                x = y.view(B, 9, 256).transpose(1, 2).reshape(B, 2304)             # Flatten of [B, 256, 3, 3]
+                x = torch.relu(self.fc0(x))
         x = torch.cat([x, position_goal.to(x.dtype)], 1)
         if fast and x.dtype == torch.bfloat16:
             return _c1.linear_relu(x, self.fc1)
