@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
                                                                  const __nv_bfloat16 *__restrict__ y,
                                                                  const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ planes,
                                                                  const uint32_t *__restrict__ relu_mask, long long B,
-                                                                 float *__restrict__ dw4, float *__restrict__ db4, int swap_lbo_sbo,
+                                                                 float *__restrict__ dw4, float *__restrict__ db4,
                                                                  uint32_t zero, int *fail) {
     extern __shared__ __align__(128) uint8_t tcb_smem[];
     uint8_t *sG = tcb_smem;                               // A: TCB_A_BYTES
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     // K-direction (positions) core-matrix stride 128 B, MN-direction group stride TCB_SBO
-    const uint32_t lbo = swap_lbo_sbo ? TCB_SBO : 128u, sbo = swap_lbo_sbo ? 128u : TCB_SBO;
+    const uint32_t lbo = 128u, sbo = TCB_SBO;  // (measured: the fields are not interchangeable -- swapped, the result is garbage)
     const uint64_t descA = tcb_smem_desc(sG, lbo, sbo), descBh = tcb_smem_desc(sP, lbo, sbo),
                    descBl = tcb_smem_desc(sP + TCB_B_BYTES, lbo, sbo);
     const long long npos = B * NCELL, ntiles = (npos + TC_M - 1) / TC_M;

@@ -462,7 +462,6 @@ int *g_tc_fail = nullptr;  // set by conv1_fwd_tc_kernel if its MMA-completion b
 int g_use_tc = -1;         // -1: read TA_CONV1_TC on first use (default 1)
 
 int g_bwd_tc = -1;         // conv1 weight gradient on tcgen05: -1 = read TA_CONV1_BWD_TC on first use
-int g_bwd_swap = 0;        // probe: exchange the LBO / SBO fields of the MN-major descriptors
 
 // Resident CTAs per SM of a TMEM-allocating kernel from its own footprint (the occupancy API answers 1 for such
 // kernels): registers, shared memory with the large carve-out, and 512 TMEM columns per SM.
@@ -606,7 +605,7 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
     const __nv_bfloat16 *yb = (const __nv_bfloat16 *)y_bf16, *dyb = (const __nv_bfloat16 *)dy_bf16;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t *mk = (const uint32_t *)relu_mask;
-#define TA_BWD_ARGS(XT) (const XT *)x, x_stride, yb, dyb, pl, mk, batch, dw4, db4, g_bwd_swap, 0u, g_tc_fail
+#define TA_BWD_ARGS(XT) (const XT *)x, x_stride, yb, dyb, pl, mk, batch, dw4, db4, 0u, g_tc_fail
     switch (variant) {
         case 0: conv1_bwd_tc_kernel<uint8_t, false, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(uint8_t)); break;
         case 1: conv1_bwd_tc_kernel<float, false, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(float)); break;
@@ -772,15 +771,11 @@ int ta_debug_conv1_tc(int on) {
     return prev;
 }
 
-/* test hooks for the tcgen05 weight-gradient kernel: on/off (returns the previous setting), descriptor probe */
+/* test hook for the tcgen05 weight-gradient kernel: on/off (returns the previous setting) */
 int ta_debug_conv1_bwd_tc(int on) {
     const int prev = g_bwd_tc;
     g_bwd_tc = on != 0;
     return prev;
-}
-int ta_debug_conv1_bwd_swap(int on) {
-    g_bwd_swap = on != 0;
-    return 0;
 }
 
 /* check for the tcgen05 conv1 kernel: 1 if any launch gave up waiting for its MMA (synchronises) */

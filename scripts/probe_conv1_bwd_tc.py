@@ -22,14 +22,13 @@ for B in (37, 700, 4096):
     gy = torch.randn((B, 64, 33, 33), generator=torch.Generator().manual_seed(3)).cuda().to(torch.bfloat16).float()
     L.ta_debug_conv1_bwd_tc(0)
     gw0, gb0 = grads(codes, gy)
-    for swap in (0, 1):
-        L.ta_debug_conv1_bwd_tc(1); L.ta_debug_conv1_bwd_swap(swap)
+    if True:
+        L.ta_debug_conv1_bwd_tc(1)
         gw, gb = grads(codes, gy)
-        print(f"B {B} swap {swap}: fail flag {L.ta_debug_conv1_tc_failed()}  dW max abs diff {float((gw - gw0).abs().max()):.5f} of {float(gw0.abs().max()):.3f}"
+        print(f"B {B}: fail flag {L.ta_debug_conv1_tc_failed()}  dW max abs diff {float((gw - gw0).abs().max()):.5f} of {float(gw0.abs().max()):.3f}"
               f"   db max abs diff {float((gb - gb0).abs().max()):.5f} of {float(gb0.abs().max()):.3f}", flush=True)
-swap = int(os.environ.get("SWAP", "0"))
 for tc in (0, 1):
-    L.ta_debug_conv1_bwd_tc(tc); L.ta_debug_conv1_bwd_swap(swap)
+    L.ta_debug_conv1_bwd_tc(tc)
     y = C1.conv1_relu(codes[:, 1:5], conv)
     gyb = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     for _ in range(3): grads(codes, gy)
