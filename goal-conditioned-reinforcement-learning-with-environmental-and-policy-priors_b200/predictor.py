@@ -132,6 +132,9 @@ class ppo_predictor(PPO):
         self.predictor = LSTM().to(self.device)
         super().__init__(device=device, autocast=autocast, flat_grads=flat_grads, _nets=(actor, critic))
         self.encoder.device = self.predictor.device = self.device
+        # h_0 / c_0 are plain attributes in the reference (moved on every forward); keep them on the device so the
+        # forward has no host-to-device copy (not capturable in the CUDA graph of the optimiser step)
+        self.predictor.h_0, self.predictor.c_0 = self.predictor.h_0.to(self.device), self.predictor.c_0.to(self.device)
         self.encoder_lr = self.decoder_lr = self.predictor_lr = 0.00001
 
     def load_predictor(self, state):

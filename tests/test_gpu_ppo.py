@@ -250,6 +250,9 @@ def test_predictor_agent_rollout_and_update_on_gpu():
     al, vl = agent.update(buf.flat(), minibatch=1024, epochs=1)
     assert np.isfinite(al) and np.isfinite(vl)
     assert any(not torch.equal(a, b) for a, b in zip(before, agent.critic.parameters()))
+    # 8 full minibatches: the third one on is replayed from the CUDA graph of the step (predictor forward included)
+    al, vl = agent.update(buf.flat(), minibatch=256, epochs=1)
+    assert np.isfinite(al) and np.isfinite(vl)
     # GPU (bf16) prediction stays close to the fp32 CPU one for the same weights
     x = P.decode_matrix(buf.s[3, :8, 0:4]).float()
     got = agent.pred_states(x)[0].cpu()
