@@ -3,7 +3,9 @@
 // The folded layer is a GEMM with a tiny reduction: D[position, (phase, channel)] = P[position, 16] x W4^T[16, 256].
 // tcgen05.mma (M = 128 positions, N = 64 = one output phase, K = 16, bf16 inputs, fp32 accumulators in TMEM)
 // covers 128 input positions x 64 channels; the FP32-FMA version of the same work is bound by
-// the FMA pipe (4.6 GFMA per 4096 samples), this one by its 570 MB of output.
+// the FMA pipe (4.6 GFMA per 4096 samples: 326 us), this one by its 570 MB of output and the serial stage -> MMA ->
+// epilogue chain of a CTA (151 us, 3.8 TB/s).  Every operand is a bf16 (hi, lo) pair and a product is three MMAs
+// (hi*hi + lo*hi + hi*lo), so the result matches the FP32 kernel to the rounding of the bf16 output.
 //
 //   CTA = 128 threads = 4 warps; thread r owns row r of the tile = one input position (sample b, m, n):
 //     build   the tile's 128 + 18 input positions are loaded / LUT-decoded once (4 frames each) into shared
@@ -15,7 +17,7 @@
 //             private, __syncwarp only) -> read back transposed so that one store instruction covers 8 output
 //             pixels x 64 contiguous bytes (per-thread rows would touch 32 cache lines per instruction)
 //   W4 (bf16 hi/lo, canonical layout, 2 x 8 KB) and the bias stay in shared memory for the CTA's lifetime.
-//   TMEM: 64 columns per CTA (one output phase at a time), so 8 CTAs share an SM's 512 columns.
+//   TMEM: 64 columns per CTA (one output phase at a time); registers (80) and 38 KB of shared memory allow 6 CTAs per SM.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -26,7 +28,7 @@ namespace ta {
 constexpr int TC_THREADS = 128;
 constexpr int TC_M = 128, TC_N = 256;
 constexpr int TC_HALO = GS + 1;  // a row's patch reaches 18 positions ahead
-constexpr int TC_NT = 64;  // columns per MMA = TMEM columns per CTA: one output phase; 8 CTAs fit an SM's 512 columns
+constexpr int TC_NT = 64;  // columns per MMA = TMEM columns per CTA: one output phase
 // shared-memory descriptor of a K-major, no-swizzle operand with K = 16 bf16 (two 16-byte chunks per row):
 // element (row r, chunk c) at byte (r / 8) * 256 + c * 128 + (r % 8) * 16, i.e. LBO = 128 B, SBO = 256 B
 __device__ __forceinline__ uint64_t tc_smem_desc(const void *smem) {
