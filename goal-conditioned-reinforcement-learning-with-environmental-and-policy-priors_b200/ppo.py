@@ -565,6 +565,11 @@ class PPO:
             self._last = tuple(x.clone() for x in self._last)
             del graph
         self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)
+        if dev.type == "cuda":
+            # the tcgen05 kernels bound their MMA-barrier waits and raise a flag instead of hanging: fail loudly here
+            from . import _capi
+            if _capi.lib().ta_debug_conv1_tc_failed() != 0:
+                raise RuntimeError("a tcgen05 conv1 kernel gave up waiting for its MMA barrier: the results of this update are invalid")
         if self.use_lr_decay:
             self.scheduler_actor.step()
             self.scheduler_critic.step()
