@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.ta_view.argtypes = [vp]
     L.ta_version.argtypes = [vp]
     L.ta_reset.argtypes = [vp, vp, i32, vp, vp]
+    L.ta_observe_general.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.ta_step.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     L.ta_step_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     L.ta_rollout.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]

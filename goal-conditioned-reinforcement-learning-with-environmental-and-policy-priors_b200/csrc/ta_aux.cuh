@@ -62,6 +62,78 @@ __global__ void observe_kernel(const uint32_t *grid, const uint4 *sc0, uint8_t *
     o[2] = 0;
 }
 
+// gen_obs for ANY agent_dir and either visibility mode (minigrid.py:1443-1496): get_view_exts (:1262-1293) ->
+// Grid.slice (:641-660, off-grid = wall) -> rotate_left x (dir + 1) (:627-639) -> Grid.process_vis (:795-832) when
+// see_through_walls is False -> agent cell := carrying (None) -> Grid.encode(vis_mask) (:749-772).
+// Dead code for the registered Twoarmy envs (agent_dir == 3 and see_through_walls=True are hard-coded,
+// twoarmy_v4.py:34,68), so this is the plain form: ONE THREAD PER ENV keeps the rotated V x V view as one 2-bit code
+// word pair per row and the visibility flood as one bit mask per row, exactly the reference's sweep order
+// (rows bottom-up; in a row left-to-right, then right-to-left; only walls block: Wall.see_behind, :422).
+__global__ void observe_general_kernel(const uint32_t *grid, const uint4 *sc0, const uint8_t *dirs, int dir_all,
+                                       const uint8_t *stws, int stw_all, uint8_t *obs, int V, long long n) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint32_t m = sc0[e].x;
+    const int ax = (int)(m & 0xFFu), ay = (int)((m >> 8) & 0xFFu);
+    const int dir = (dirs ? dirs[e] : dir_all) & 3;
+    const bool see_through = (stws ? stws[e] : stw_all) != 0;
+    const int hs = V / 2;
+    int topX, topY;  // get_view_exts
+    if (dir == 0) { topX = ax; topY = ay - hs; }
+    else if (dir == 1) { topX = ax - hs; topY = ay; }
+    else if (dir == 2) { topX = ax - V + 1; topY = ay - hs; }
+    else { topX = ax - hs; topY = ay - V + 1; }
+    const uint32_t *rec = grid + e * REC_WORDS;
+    unsigned long long code[GS];   // row r of the rotated view: 2 bits per column
+    uint32_t wall[GS], vis[GS];
+    for (int r = 0; r < V; r++) {
+        unsigned long long cw = 0;
+        uint32_t ww = 0;
+        for (int c = 0; c < V; c++) {
+            // one rotate_left maps old (col i, row j) to new (col j, row V-1-i); undo it dir+1 times
+            int ci = c, rj = r;
+            for (int k = 0; k <= dir; k++) {
+                const int oi = V - 1 - rj, oj = ci;
+                ci = oi;
+                rj = oj;
+            }
+            const int x = topX + ci, y = topY + rj;
+            const uint32_t cd = inb(x, y) ? cell_get(rec, x, y) : C_WALL;
+            cw |= (unsigned long long)cd << (2 * c);
+            ww |= (cd == C_WALL ? 1u : 0u) << c;
+        }
+        code[r] = cw;
+        wall[r] = ww;
+        vis[r] = see_through ? 0xFFFFFFFFu : 0u;
+    }
+    if (!see_through) {  // Grid.process_vis
+        vis[V - 1] = 1u << hs;
+        for (int j = V - 1; j >= 0; j--) {
+            for (int i = 0; i < V - 1; i++) {
+                if (!((vis[j] >> i) & 1u) || ((wall[j] >> i) & 1u)) continue;
+                vis[j] |= 1u << (i + 1);
+                if (j > 0) vis[j - 1] |= (1u << (i + 1)) | (1u << i);
+            }
+            for (int i = V - 1; i >= 1; i--) {
+                if (!((vis[j] >> i) & 1u) || ((wall[j] >> i) & 1u)) continue;
+                vis[j] |= 1u << (i - 1);
+                if (j > 0) vis[j - 1] |= (1u << (i - 1)) | (1u << i);
+            }
+        }
+    }
+    code[V - 1] &= ~(3ull << (2 * hs));  // the agent's own cell holds `carrying` = None
+    uint8_t *o = obs + e * (3ll * V * V);
+    for (int i = 0; i < V; i++)       // image[i][j][c]: column first
+        for (int j = 0; j < V; j++) {
+            const uint32_t cd = (uint32_t)(code[j] >> (2 * i)) & 3u;
+            const bool seen = (vis[j] >> i) & 1u;
+            o[0] = seen ? (uint8_t)(0x08060201u >> (8 * cd)) : 0;
+            o[1] = seen ? (uint8_t)(0x01040500u >> (8 * cd)) : 0;
+            o[2] = 0;
+            o += 3;
+        }
+}
+
 // Export / import: ta_env_state records (328 B, see include/twoarmy_b200.h).
 struct EnvStateRec {
     uint8_t grid[289];

@@ -258,6 +258,15 @@ int ta_reset(ta_handle h, const uint8_t *mask, int hard, uint8_t *obs_out, void 
     return do_reset(h, mask, hard, obs_out, (cudaStream_t)stream, false);
 }
 
+int ta_observe_general(ta_handle h, const uint8_t *agent_dirs, int agent_dir, const uint8_t *see_through, int see_through_all,
+                       uint8_t *obs_out, void *stream) {
+    if (!h || !obs_out || (!agent_dirs && (agent_dir < 0 || agent_dir > 3))) return TA_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    observe_general_kernel<<<blocks_for(h->n, 128), 128, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, agent_dirs, agent_dir, see_through,
+                                                                                   see_through_all, obs_out, h->view, h->n);
+    return launch_ok("observe_general_kernel");
+}
+
 static int step_launch(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags, int T,
                        uint8_t *obs_out, float *reward_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *consumed_out,
                        void *stream) {
@@ -783,6 +792,7 @@ int ta_debug_conv1_tc_failed(void) {
     if (!g_tc_fail) return 0;
     int v = 0;
     if (cudaMemcpy(&v, g_tc_fail, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (v != 0) cudaMemset(g_tc_fail, 0, sizeof(int));  // reported once: later updates start clean
     return v;
 }
 

@@ -406,18 +406,24 @@ class PPO:
             return
         ws = dist.get_world_size(group)
         if name in self._flat:
+            probe = getattr(self, "_probe_events", None)
+            if probe is not None:   # probe_step(): device time of the collective alone
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             dist.all_reduce(self._flat[name], group=group)
+            if probe is not None:
+                e1.record()
+                probe.append((name, e0, e1))
             self._flat[name].div_(ws)
         else:
             for p in net.parameters():
                 dist.all_reduce(p.grad, group=group)
                 p.grad.div_(ws)
 
-    def update(self, buffer, device=None, i_ep: int = 0, minibatch: Optional[int] = None, epochs: Optional[int] = None,
-               group=None, sampler_generator=None):
-        """PPO.py:103-158.  `buffer` is a dict of tensors with the reference's field names
-        (s [B,5,289] float or uint8 codes, p [B,5,2], a [B,1], g [B,2], r [B,1], a_logp [B,1]) or
-        a numpy structured array like Buffer_gridworld.buffer."""
+    def _make_step(self, buffer, minibatch: Optional[int] = None, group=None):
+        """Moves the buffer to the device, runs the two critic passes and the advantage kernel
+        (PPO.py:105-115) and returns (step, B, bs, src): step(idx) is one optimiser step on the
+        minibatch idx (PPO.py:124-144) and returns the two detached losses."""
         if not isinstance(buffer, dict):
             buffer = {k: torch.as_tensor(buffer[k]) for k in ("s", "p", "a", "g", "r", "a_logp")}
         dev = self.device
@@ -442,20 +448,6 @@ class PPO:
         bs = minibatch or self.batch_size
         self.actor.train()
         self.critic.train()
-
-        def minibatches():
-            # PPO.py:122: BatchSampler(SubsetRandomSampler(range(len(buffer))), batch_size, drop_last=False).
-            # On the CPU that exact sampler (same torch RNG stream as the reference); on the GPU the
-            # same thing -- a fresh random permutation per epoch cut into batches -- drawn on the device
-            # (a Python-level sampler over millions of indices would cost more than the update itself).
-            if dev.type != "cuda" or sampler_generator is not None:
-                for sample_index in BatchSampler(SubsetRandomSampler(range(B), generator=sampler_generator), batch_size=bs,
-                                                 drop_last=False):
-                    yield torch.as_tensor(sample_index, device=dev)
-            else:
-                perm = torch.randperm(B, device=dev)
-                for i in range(0, B, bs):
-                    yield perm[i:i + bs]
 
         streams = None
         if dev.type == "cuda" and self.two_streams:
@@ -489,6 +481,12 @@ class PPO:
                 surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv[idx]
                 loss = (-torch.min(surr1, surr2) - self.entropy_coef * dist_entropy).mean()
                 loss.backward()
+                # this network's gradient all-reduce and optimiser step follow its backward on ITS stream: with two
+                # streams the collective overlaps the other network's backward
+                self._allreduce("actor", self.actor, group)
+                if self.use_grad_clip:
+                    torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
+                self.optimizer_actor.step()
                 return loss.detach()
 
             def critic_part():
@@ -496,14 +494,18 @@ class PPO:
                     vpred = self.critic(sb, pb, gb)
                 loss = F.smooth_l1_loss(vpred, target_v[idx])
                 loss.backward()
+                self._allreduce("critic", self.critic, group)
+                if self.use_grad_clip:
+                    torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
+                self.optimizer_critic.step()
                 return loss.detach()
 
             if streams is None:
                 action_loss, value_loss = actor_part(), critic_part()
             else:
-                # the two networks are independent: their forward / backward run on two streams so
-                # that one net's small kernels fill the gaps of the other's (the reference's order
-                # of operations inside each network is unchanged)
+                # the two networks are independent: their forward / backward / all-reduce / Adam run on two
+                # streams so that one net's small kernels and its collective fill the gaps of the other's (the
+                # reference's order of operations inside each network is unchanged)
                 cur = torch.cuda.current_stream(dev)
                 for st in streams:
                     st.wait_stream(cur)
@@ -513,14 +515,84 @@ class PPO:
                     value_loss = critic_part()
                 for st in streams:
                     cur.wait_stream(st)
-            self._allreduce("actor", self.actor, group)
-            self._allreduce("critic", self.critic, group)
-            if self.use_grad_clip:
-                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
-                torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
-            self.optimizer_actor.step()
-            self.optimizer_critic.step()
             return action_loss, value_loss
+
+        return step, B, bs, src
+
+    def probe_step(self, buffer, minibatch: Optional[int] = None, group=None):
+        """Measurement aid (bench.py, outside every timed region): ONE eager optimiser step on the first minibatch of
+        `buffer`, instrumented -- kernels launched by the step (torch profiler) and device time of each network's
+        gradient all-reduce (CUDA events around the collective)."""
+        if self.device.type != "cuda":
+            return {}
+        bs = minibatch or self.batch_size
+        sub = {k: (v[:bs] if torch.is_tensor(v) else v) for k, v in buffer.items()}
+        step, B, bs, _ = self._make_step(sub, bs, group)
+        idx = torch.arange(min(B, bs), device=self.device)
+        step(idx)
+        torch.cuda.synchronize(self.device)
+        out = {}
+        self._probe_events = []
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step(idx)
+                torch.cuda.synchronize(self.device)
+            kernels = [e for e in prof.events() if str(e.device_type).endswith("CUDA") and not e.name.lower().startswith("memcpy")
+                       and not e.name.lower().startswith("memset")]
+            out["launches_per_optimizer_step"] = len(kernels)
+            own = [e for e in kernels if "ta::" in e.name]
+            out["own_launches_per_optimizer_step"] = len(own)
+            out["kernel_time_per_optimizer_step_us"] = float(sum(e.device_time for e in kernels))
+        except Exception as exc:  # noqa: BLE001 -- CUPTI not available: the count is skipped, not guessed
+            out["launches_per_optimizer_step"] = None
+            out["profiler_error"] = f"{type(exc).__name__}: {exc}"[:200]
+            step(idx)
+            torch.cuda.synchronize(self.device)
+        if self._probe_events:
+            out["allreduce_us_per_optimizer_step"] = {n: e0.elapsed_time(e1) * 1e3 for n, e0, e1 in self._probe_events}
+        self._probe_events = None
+        return out
+
+    def _common_steps(self, B: int, bs: int, group) -> int:
+        """Optimiser steps per epoch, agreed between ranks: every rank issues one all-reduce per step, so all of
+        them must run the same number of steps.  With equal B (the plain rollout) this is ceil(B / bs) as in the
+        reference; when B differs between ranks (hindsight relabels append a data-dependent number of samples per
+        rank) every rank runs min over ranks of B // bs full minibatches of its own permutation and drops the rest."""
+        import torch.distributed as dist
+        n_steps = (B + bs - 1) // bs
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return n_steps
+        t = torch.tensor([B, -B], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        b_min, b_max = int(t[0].item()), -int(t[1].item())
+        if b_min == b_max:
+            return n_steps
+        return max(1, b_min // bs)
+
+    def update(self, buffer, device=None, i_ep: int = 0, minibatch: Optional[int] = None, epochs: Optional[int] = None,
+               group=None, sampler_generator=None):
+        """PPO.py:103-158.  `buffer` is a dict of tensors with the reference's field names
+        (s [B,5,289] float or uint8 codes, p [B,5,2], a [B,1], g [B,2], r [B,1], a_logp [B,1]) or
+        a numpy structured array like Buffer_gridworld.buffer."""
+        dev = self.device
+        step, B, bs, src = self._make_step(buffer, minibatch, group)
+        n_steps = self._common_steps(B, bs, group)
+
+        def minibatches():
+            # PPO.py:122: BatchSampler(SubsetRandomSampler(range(len(buffer))), batch_size, drop_last=False).
+            # On the CPU that exact sampler (same torch RNG stream as the reference); on the GPU the
+            # same thing -- a fresh random permutation per epoch cut into batches -- drawn on the device
+            # (a Python-level sampler over millions of indices would cost more than the update itself).
+            if dev.type != "cuda" or sampler_generator is not None:
+                for k, sample_index in enumerate(BatchSampler(SubsetRandomSampler(range(B), generator=sampler_generator),
+                                                              batch_size=bs, drop_last=False)):
+                    if k < n_steps:
+                        yield torch.as_tensor(sample_index, device=dev)
+            else:
+                perm = torch.randperm(B, device=dev)
+                for k in range(n_steps):
+                    yield perm[k * bs:(k + 1) * bs]
 
         # The step is ~300 small launches; driven from Python the update is CPU-bound.  On one GPU the
         # whole step (gather, both nets forward / backward, Adam) is captured ONCE per update() into a
@@ -614,6 +686,11 @@ class VecRollout:
         self.env, self.agent, self.T = env, agent, int(horizon)
         N, dev = env.num_envs, env.device
         assert not env.autoreset, "VecRollout drives the resets itself (the terminal frame is part of the record)"
+        # record t is written in place at byte offset t * N * 1445 of the buffer; ta_stack_push wants 16-byte aligned
+        # records, so the per-step stride must be a multiple of 16 bytes (1445 is odd)
+        if env.num_envs % 16:
+            raise ValueError(f"VecRollout needs num_envs % 16 == 0 (got {env.num_envs}): the device rollout buffer is written "
+                             f"in place by 16-byte vector stores; pad the env count per rank")
         self.buffer = RolloutBuffer(self.T, N, dev)
         self.buffer.g[:] = torch.tensor([float(env.goal_pos[1]), float(env.goal_pos[0])], device=dev)  # data_env: (y, x)
         self.amap = torch.tensor(POLICY_TO_ENV_ACTION, dtype=torch.uint8, device=dev)
@@ -658,6 +735,4 @@ class VecRollout:
             self.ep_return.masked_fill_(done.bool(), 0.0)
             self.prev_s, self.prev_p, self.prev_done = buf.s[t], buf.p[t], done.clone()
             env.reset_masked(done)
-        if self.T >= 2:  # record T-1 is read while record 0 of the next collect() is written
-            pass
         return buf

@@ -110,6 +110,22 @@ class TwoarmyVecEnv:
         _capi.check(self._L.ta_reset(self._h, _ptr(none), 0, _ptr(obs), self._stream()), "ta_reset(observe)")
         return obs
 
+    def observe_general(self, agent_dir=3, see_through_walls=True) -> torch.Tensor:
+        """gen_obs() of the current state for any agent_dir (int, or a uint8 tensor [N]) and either visibility
+        mode (bool, or a uint8 tensor [N]; False runs Grid.process_vis) -- minigrid.py:1443-1496, 795-832."""
+        dirs = stw = None
+        if torch.is_tensor(agent_dir):
+            dirs = agent_dir.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert dirs.numel() == self.num_envs
+        if torch.is_tensor(see_through_walls):
+            stw = see_through_walls.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert stw.numel() == self.num_envs
+        obs = self._new_obs()
+        _capi.check(self._L.ta_observe_general(self._h, _ptr(dirs), 0 if dirs is not None else int(agent_dir), _ptr(stw),
+                                               1 if stw is not None else int(bool(see_through_walls)), _ptr(obs), self._stream()),
+                    "ta_observe_general")
+        return obs
+
     def step(self, actions: torch.Tensor, draws: Optional[torch.Tensor] = None, out: Optional[dict] = None,
              want_consumed: bool = False):
         """One env.step for every env.  Returns (obs, reward, terminated, truncated, info).

@@ -100,6 +100,16 @@ int ta_version(ta_handle h);
  * bits.  obs_out (nullable): uint8 [n][V][V][3], the gen_obs() of EVERY env after the call. */
 int ta_reset(ta_handle h, const uint8_t *mask, int hard, uint8_t *obs_out, void *stream);
 
+/* Replaces MiniGridEnv.gen_obs in its GENERAL form (minigrid.py:1443-1496): any agent_dir, and
+ * see_through_walls=False -> Grid.process_vis (minigrid.py:795-832).  The registered Twoarmy envs hard-code
+ * agent_dir 3 / see_through_walls=True (twoarmy_v4.py:34,68), for which ta_reset / ta_step produce the
+ * observation; this entry point exists so that the whole of gen_obs has a device form.
+ *   agent_dirs   nullable uint8 [n] (0 right, 1 down, 2 left, 3 up); NULL: agent_dir for every env
+ *   see_through  nullable uint8 [n]; NULL: see_through_all for every env
+ *   obs_out      uint8 [n][V][V][3]; unseen cells are (0,0,0) as Grid.encode leaves them */
+int ta_observe_general(ta_handle h, const uint8_t *agent_dirs, int agent_dir, const uint8_t *see_through, int see_through_all,
+                       uint8_t *obs_out, void *stream);
+
 /* Replaces Twoarmy_v4.step / Twoarmy_v6.step (twoarmy_v4.py:82-322, twoarmy_v6.py:83-325)
  * including MiniGridEnv.step (minigrid.py:1333-1441) and gen_obs (minigrid.py:1443-1496),
  * for all n envs in one fused kernel.

@@ -12,9 +12,24 @@ import numpy as np
 REFERENCE_ROOT = "/root/reference"
 
 
-def install():
+def find_root():
+    """Where the Python reference lives: /root/reference in the build container; on the GPU box the
+    git-ignored copy __graft_entry__.build() ships under baseline/_ref (used by bench.py's CPU arm only)."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    shipped = os.path.join(os.path.dirname(os.path.dirname(here)), "baseline", "_ref")
+    for root in (os.environ.get("TA_REFERENCE_ROOT"), REFERENCE_ROOT, shipped):
+        if root and os.path.isfile(os.path.join(root, "gym_minigrid", "minigrid.py")):
+            return root
+    return None
+
+
+def install(root=None):
     if "gym_minigrid" in sys.modules:
         return
+    root = root or find_root()
+    if root is None:
+        raise FileNotFoundError("the Python reference is neither at /root/reference nor shipped under baseline/_ref")
     gym = types.ModuleType("gym")
 
     class Env:
@@ -81,8 +96,8 @@ def install():
                       ("gym.envs.registration", reg), ("gym.core", core),
                       ("matplotlib", mpl), ("matplotlib.pyplot", plt), ("turtle", turtle)]:
         sys.modules[name] = mod
-    sys.path.insert(0, REFERENCE_ROOT)
-    sys.path.insert(0, REFERENCE_ROOT + "/soa")
+    sys.path.insert(0, root)
+    sys.path.insert(0, root + "/soa")
     import gym_minigrid
 
     gym_minigrid.register_minigrid_envs()

@@ -43,6 +43,19 @@ def test_oracle_matches_reference_trajectories(golden, version, view):
     check_traj(OracleImpl(version, fx["actions"].shape[1], view), fx, view)
 
 
+@pytest.mark.parametrize("view", [17, 7])
+def test_oracle_matches_scripted_rare_branch_trajectories(golden, view):
+    """tests/golden/traj_scripted_v4.npz (make_golden_scripted.py): reference trajectories steered into every
+    patrol-collision direction, every adjacency penalty, risk_count > 5, the room-2 bonus, step-50 truncation
+    and clamped actions -- and the fixture really contains each of them."""
+    fx = golden("traj_scripted_v4.npz")
+    cov = dict(zip(fx["coverage_names"].tolist(), fx["coverage_counts"].tolist()))
+    for k in ("o1_up", "o1_down", "o2_left", "o2_right", "mid", "risk_trunc", "room2", "t50", "adj"):
+        assert cov[k] >= 1, k
+    assert int((fx["actions"] >= 7).sum()) >= 5
+    check_traj(OracleImpl(4, fx["actions"].shape[1], view), fx, view)
+
+
 SURVEY_DIGESTS = {(4, 17): "6dfb44abb94dd12a", (4, 7): "37f72f56ae52bacc",
                   (6, 17): "3015ddbb3f89096f", (6, 7): "3c292dc5e32c818c"}
 SURVEY_DRAWS = {4: (2212, "67768b5ade107503"), 6: (200, "850e170d38b84205")}

@@ -183,6 +183,40 @@ def test_two_rank_gloo_gradient_allreduce_equals_single_rank_full_batch():
     np.testing.assert_allclose(np.array(ret[0]), np.array(want), rtol=1e-5, atol=1e-5)
 
 
+def _ddp_unequal_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    P = _ppo()
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    agent = P.PPO(device="cpu", autocast=False)
+    agent.broadcast_parameters()
+    agent.K_epochs = 2
+    g = torch.Generator().manual_seed(11 + rank)
+    n = 40 if rank == 0 else 23           # hindsight relabels make B data-dependent per rank
+    buf = {"s": torch.randint(0, 3, (n, 5, 289), generator=g, dtype=torch.uint8), "p": torch.randint(1, 16, (n, 5, 2), generator=g).float(),
+           "a": torch.randint(0, 5, (n, 1), generator=g), "g": torch.tensor([[2.0, 14.0]]).repeat(n, 1),
+           "r": torch.rand(n, 1, generator=g) - 0.5, "a_logp": torch.log(torch.rand(n, 1, generator=g) * 0.3 + 0.1)}
+    agent.update(buf, minibatch=8)        # rank 0 alone would run 5 steps per epoch, rank 1 three: both must run 2 (23 // 8)
+    ret[rank] = (agent.update_count, _sums(agent.actor).tolist() + _sums(agent.critic).tolist())
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_unequal_batch_sizes_agree_on_the_step_count():
+    """with --her the number of samples differs per rank; every rank must issue the same number of gradient
+    all-reduces (a mismatch deadlocks NCCL).  Both ranks run min(B) // bs full minibatches per epoch and end with
+    identical parameters."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ddp_unequal_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0][0] == ret[1][0] == 2 * (23 // 8)
+    assert ret[0][1] == pytest.approx(ret[1][1], rel=0, abs=0)
+
+
 def test_merged_parity_planes_are_the_strided_data_gradient():
     """conv1.parity_class_weights (torch path): ONE stride-1 convolution of dz with the merged [4*cin, cout, 2, 2] weight
     yields, per output-channel block pa*2+pb, the data gradient of the k x k stride-2 convolution at input pixels
