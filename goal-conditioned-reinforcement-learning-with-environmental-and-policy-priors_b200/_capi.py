@@ -19,11 +19,12 @@ LIB_PATH = CSRC / "libtwoarmy_b200.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-lpthread",
 ]
 
 TA_OK = 0
 TA_STEP_AUTORESET = 1
+TA_STEP_HOST_DMA = 2
 ACT_I32, ACT_U8, ACT_I64 = 0, 1, 2
 ENV_ERR_BAD_ACTION, ENV_ERR_NONE_POS, ENV_ERR_OOB_MOVE = 1, 2, 4
 F_PONE, F_PATROL, F_UP1, F_RIGHT2, F_UPD_H, F_UPD_L, F_FIRST_ROOM2 = 1, 2, 4, 8, 16, 32, 64
@@ -91,6 +92,9 @@ def lib() -> C.CDLL:
     L.ta_observe_general.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.ta_step.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     L.ta_step_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    L.ta_step_packed.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    L.ta_decode_packed_host.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp]
+    L.ta_step_host_d2h_bytes.argtypes = [vp]; L.ta_step_host_d2h_bytes.restype = i64
     L.ta_rollout.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.ta_state_matrix.argtypes = [vp, vp, vp, vp, vp]
     L.ta_stack_roll.argtypes = [vp, vp, vp, vp, i32, vp]

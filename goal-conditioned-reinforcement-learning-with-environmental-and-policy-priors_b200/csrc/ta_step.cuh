@@ -83,6 +83,7 @@ struct StepArgs {
     uint8_t *term;
     uint8_t *trunc;
     uint8_t *consumed;
+    uint8_t *status;  // nullable [T][npad]: reward index | terminated << 3 | truncated << 4 (the host call's one-byte result)
     long long n;
     int ntiles;
     int T;  // env steps per launch; outputs / actions / draws are [T][n]
@@ -90,6 +91,9 @@ struct StepArgs {
     int flags;  // bit 0 autoreset, bit 1 never use bulk stores for the obs (test hook),
                 // bits 2,3 timing experiments only: skip the obs pass / the scalar phases,
                 // bit 4 observe only: gen_obs() of the current state, nothing else read or written
+                // bit 5 packed observations: `obs` receives the tile's cell stream as 2-bit codes (uint32 [ntiles][2*V*V],
+                //       word r = the 16 cells of run r) instead of the 3 bytes per cell of Grid.encode -- the transfer
+                //       form of ta_step_host, expanded to the same bytes by the host side of that call
     int action_dtype;
     uint32_t seed_lo, seed_hi;
     unsigned long long env_id0;
@@ -292,16 +296,35 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
     const int lane = threadIdx.x & 31;
     uint32_t *G = gs + GUARD0_WORDS + lane * SLOT_WORDS;  // this lane's env record
 
-    // Programmatic dependent launch: the next kernel in the stream may be scheduled as soon as
-    // every CTA of this grid has got here, and this grid may have been scheduled before its
-    // predecessor finished -- nothing the predecessor may write (actions, draws, this handle's
-    // state) is read, and nothing is written to global memory, before griddep_wait() below.
-    griddep_launch_dependents();
+    // Programmatic dependent launch (flags bits 6..8, set by the host when the launch carries the attribute).  The
+    // kernel that follows in the stream may be scheduled once every CTA of this grid has executed launch_dependents
+    // (or exited); it may then run its preamble while this grid drains, and blocks in griddep_wait() until this grid
+    // has completed and flushed.  Nothing is WRITTEN to global memory before griddep_wait(), and the only global
+    // reads before it are the constant template and -- flags bit 6, which the host sets only when the kernel launched
+    // before this one did not write this handle's state -- the first tile's env state, so that its DRAM latency
+    // overlaps the previous grid's tail instead of heading this one.
+    //   trigger (flags bits 7,8): 0 at the top (the next grid's CTAs queue for SM resources at once), 1 right after this
+    //   grid's own wait (so at most one grid runs ahead: the grid before this one has completed), 2 after the last tile's
+    //   observation pass
+    const int pdl_trigger = (a.flags >> 7) & 3;
+    if (pdl_trigger == 0) griddep_launch_dependents();
     // one-time setup: the reset template word of this lane (guards: see below)
     const uint32_t tmpl_word = lane < REC_WORDS ? __ldg(a.tmpl + lane) : 0u;
+    const long long tile_first = (long long)blockIdx.x * warps_per_cta + warp, tile_stride = (long long)gridDim.x * warps_per_cta;
+    uint4 piece[5], s0, s1;
+    bool preloaded = false;
+    if ((a.flags & 64) && tile_first < a.ntiles) {
+        const uint4 *gsrc = reinterpret_cast<const uint4 *>(a.grid + tile_first * (TILE * REC_WORDS));
+#pragma unroll
+        for (int k = 0; k < 5; k++) piece[k] = gsrc[lane + 32 * k];
+        s0 = a.sc0[tile_first * TILE + lane];
+        s1 = a.sc1[tile_first * TILE + lane];
+        preloaded = true;
+    }
     __syncwarp();
     bool first_tile = true;
     griddep_wait();
+    if (pdl_trigger == 1) griddep_launch_dependents();
     // the two look-up words live in ordinary registers: loaded through a lane-dependent address
     // (tmpl[20..23] = TYPE, COLOR, TYPE, COLOR) so that ptxas cannot turn them back into immediates
     // / uniform registers, which it re-materialises in front of every permute
@@ -310,19 +333,21 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
     uint32_t gi = 0;  // obs chunks emitted so far (ring slot = gi % RING)
     const bool v4 = a.version == 4;
 
-    for (long long tile = (long long)blockIdx.x * warps_per_cta + warp; tile < a.ntiles;
-         tile += (long long)gridDim.x * warps_per_cta) {
+    for (long long tile = tile_first; tile < a.ntiles; tile += tile_stride) {
         // ---- tile prologue: packed grids -> smem, state of 32 envs -> registers ------------------
         const long long env = tile * TILE + lane;
         const bool live = env < a.n;
         long long nvalid = a.n - tile * TILE;
         nvalid = nvalid > TILE ? TILE : nvalid;
         // the tile's 32 records are 160 contiguous 16-byte pieces: piece q = lane + 32k belongs to env q / 5
-        const uint4 *gsrc = reinterpret_cast<const uint4 *>(a.grid + tile * (TILE * REC_WORDS));
-        uint4 piece[5];
+        if (!preloaded) {
+            const uint4 *gsrc = reinterpret_cast<const uint4 *>(a.grid + tile * (TILE * REC_WORDS));
 #pragma unroll
-        for (int k = 0; k < 5; k++) piece[k] = gsrc[lane + 32 * k];
-        const uint4 s0 = a.sc0[env], s1 = a.sc1[env];
+            for (int k = 0; k < 5; k++) piece[k] = gsrc[lane + 32 * k];
+            s0 = a.sc0[env];
+            s1 = a.sc1[env];
+        }
+        preloaded = false;
         if (first_tile) {  // guard words (never written again), while the loads are in flight
             first_tile = false;
             const uint4 w4 = make_uint4(WALLS16, WALLS16, WALLS16, WALLS16);
@@ -457,7 +482,14 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
                 build_envview<V>(gs, ev, lane, ax, ay);
             }
             __syncwarp();
-            if (!(a.flags & 4)) {
+            if (a.flags & 32) {
+                uint32_t *cdst = reinterpret_cast<uint32_t *>(a.obs) + ((long long)t * a.ntiles + tile) * C::RUNS;
+#pragma unroll 1
+                for (int it = 0; it < C::ITERS; it++) {
+                    const int r = it * 32 + lane;
+                    if (r < C::RUNS) cdst[r] = run_codes<V>(r, gs, meta, head, ev);
+                }
+            } else if (!(a.flags & 4)) {
                 uint8_t *dst = a.obs + ((long long)t * a.n + tile * TILE) * C::OBS;
                 const bool fast = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && !(a.flags & 2) && nvalid == TILE;
                 if (fast) {
@@ -507,6 +539,7 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
                     }
                 }
             }
+            if (pdl_trigger == 2 && t == a.T - 1 && tile + tile_stride >= a.ntiles) griddep_launch_dependents();
             if constexpr (V == 17) {
                 __syncwarp();
                 if (agent_cell != C_EMPTY) cell_set(G, ax, ay, agent_cell);
@@ -585,9 +618,13 @@ __global__ void __launch_bounds__(32 * STEP_MAX_WARPS) step_obs_kernel(const Ste
                 }
             }
             if (live && !observe_only) {
-                a.reward[out_idx] = reward_value(reward);
-                a.term[out_idx] = term ? 1 : 0;
-                a.trunc[out_idx] = trunc ? 1 : 0;
+                if (a.status) {
+                    a.status[(long long)t * a.ntiles * TILE + env] = (uint8_t)(reward | (term ? 8 : 0) | (trunc ? 16 : 0));
+                } else {
+                    a.reward[out_idx] = reward_value(reward);
+                    a.term[out_idx] = term ? 1 : 0;
+                    a.trunc[out_idx] = trunc ? 1 : 0;
+                }
                 if (a.consumed) a.consumed[out_idx] = (uint8_t)d.consumed;
             }
             // autoreset: MiniGridEnv.reset (minigrid.py:947-980) -- grid, balls, agent, step_count

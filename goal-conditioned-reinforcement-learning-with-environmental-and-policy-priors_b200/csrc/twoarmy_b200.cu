@@ -14,6 +14,7 @@
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
 #include "ta_her.cuh"
+#include "ta_host.cuh"
 #include "ta_step.cuh"
 
 using namespace ta;
@@ -47,6 +48,8 @@ inline unsigned blocks_for(long long work, int threads) { return (unsigned)((wor
 
 }  // namespace
 
+constexpr int HOST_CHUNKS = 8;  // D2H pieces of the packed observations: piece k+1 is on the wire while k is decoded
+
 struct ta_batch {
     int version, view, device, sm_count;
     long long n, npad;
@@ -62,15 +65,38 @@ struct ta_batch {
     // host-call path (ta_step_host)
     cudaStream_t own_stream = nullptr;
     void *d_act = nullptr;
-    uint8_t *d_obs = nullptr;
-    float *d_rew = nullptr;
-    uint8_t *d_term = nullptr, *d_trunc = nullptr;
+    uint8_t *d_obs = nullptr;        // expanded observations (TA_STEP_HOST_DMA)
+    uint32_t *d_codes = nullptr;     // packed observations [ntiles][2*V*V] followed by the status bytes [npad]
+    uint8_t *h_codes = nullptr;      // pinned staging of the same
+    cudaEvent_t chunk_ev[HOST_CHUNKS] = {};
+    ta_host::Pool *pool = nullptr;
+    ta_host::Job job;
+    long long last_d2h_bytes = 0;
     // timing
     int timing = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace {
+
+// Which handle's state did the kernel this library launched last on a stream write?  The step kernel may load its
+// first tile's state ahead of the programmatic-dependency wait only if that was a different handle (ta_step.cuh).
+struct StreamWriter { cudaStream_t stream; const ta_batch *handle; };
+StreamWriter g_writers[32];
+int g_nwriters = 0;
+bool g_writers_overflow = false;
+const ta_batch *last_writer(cudaStream_t st) {
+    for (int i = 0; i < g_nwriters; i++)
+        if (g_writers[i].stream == st) return g_writers[i].handle;
+    return nullptr;
+}
+void note_writer(cudaStream_t st, const ta_batch *h) {
+    for (int i = 0; i < g_nwriters; i++)
+        if (g_writers[i].stream == st) { g_writers[i].handle = h; return; }
+    if (g_nwriters < 32) g_writers[g_nwriters++] = {st, h};
+    // table full: a stream we forget could still have this handle's writer in flight, so stop loading early for good
+    else g_writers_overflow = true;
+}
 
 // the _gen_grid record (twoarmy_v4.py:38-80); padding cells 289..319 hold the wall code
 void build_template(uint32_t *tm) {
@@ -80,7 +106,14 @@ void build_template(uint32_t *tm) {
 }
 
 template <int V>
-int launch_step_t(ta_batch *h, const StepArgs &a, cudaStream_t st) {
+int launch_step_t(ta_batch *h, const StepArgs &a_in, cudaStream_t st) {
+    StepArgs a = a_in;
+    if (h->pdl >= 2) {  // trigger after the wait (2) / after the last observation pass (3); early state load when safe
+        a.flags |= (h->pdl == 2 ? 1 : 2) << 7;
+        const ta_batch *prev = last_writer(st);
+        if (!g_writers_overflow && prev != nullptr && prev != h) a.flags |= 64;
+    }
+    if (!(a.flags & 16)) note_writer(st, h);
     static int ctas_per_sm[64][STEP_MAX_WARPS + 1] = {};
     auto kern = step_obs_kernel<V>;
     // warps (= independent 32-env tiles) per CTA: whatever spreads the tiles most evenly over the
@@ -156,6 +189,7 @@ int launch_observe(ta_batch *h, uint8_t *obs_out, cudaStream_t st) {
 int do_reset(ta_batch *h, const uint8_t *mask, int hard, uint8_t *obs_out, cudaStream_t st, bool pad_too) {
     // padded tail envs (>= n) are reset only at creation
     const long long cnt = pad_too ? h->npad : h->n;
+    note_writer(st, h);
     reset_grid_kernel<<<blocks_for(cnt * REC_WORDS, 256), 256, 0, st>>>(
         h->grid, h->tmpl, mask, cnt);
     if (int rc = launch_ok("reset_grid_kernel")) return rc;
@@ -204,7 +238,7 @@ int ta_create(ta_handle *out, int version, int64_t n_envs, int view, int device,
         int v = atoi(e);
         if (v >= 1 && v <= STEP_MAX_WARPS) h->warps_per_cta = v;
     }
-    if (const char *e = getenv("TA_PDL")) h->pdl = atoi(e) != 0;
+    if (const char *e = getenv("TA_PDL")) h->pdl = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : 0;
     if (const char *e = getenv("TA_DEBUG_FLAGS")) h->debug_flags = atoi(e) & 3;
     if (const char *e = getenv("TA_CTAS_PER_SM")) {  // tuning knob for experiments
         int v = atoi(e);
@@ -240,7 +274,11 @@ int ta_destroy(ta_handle h) {
     if (!h) return TA_E_INVALID;
     cudaSetDevice(h->device);
     cudaFree(h->grid); cudaFree(h->sc0); cudaFree(h->sc1); cudaFree(h->tmpl);
-    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_codes);
+    if (h->h_codes) cudaFreeHost(h->h_codes);
+    for (int c = 0; c < HOST_CHUNKS; c++)
+        if (h->chunk_ev[c]) cudaEventDestroy(h->chunk_ev[c]);
+    delete h->pool;
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -269,17 +307,21 @@ int ta_observe_general(ta_handle h, const uint8_t *agent_dirs, int agent_dir, co
 
 static int step_launch(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags, int T,
                        uint8_t *obs_out, float *reward_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *consumed_out,
-                       void *stream) {
-    if (!h || !actions || !obs_out || !reward_out || !term_out || !trunc_out || T <= 0) return TA_E_INVALID;
+                       void *stream, uint8_t *status_out = nullptr, bool packed_obs = false) {
+    if (!h || !actions || !obs_out || T <= 0) return TA_E_INVALID;
+    if (!status_out && (!reward_out || !term_out || !trunc_out)) return TA_E_INVALID;
     if (action_dtype < 0 || action_dtype > 2) return TA_E_INVALID;
     if (((uintptr_t)obs_out & 15u) || (draws && ((uintptr_t)draws & 7u))) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
-    StepArgs a;
+    StepArgs a = {};
     a.grid = h->grid; a.sc0 = h->sc0; a.sc1 = h->sc1; a.tmpl = h->tmpl;
     a.actions = actions; a.draws = draws;
     a.obs = obs_out; a.reward = reward_out; a.term = term_out; a.trunc = trunc_out; a.consumed = consumed_out;
+    a.status = status_out;
     a.n = h->n; a.ntiles = (int)(h->npad / TILE); a.T = T;
-    a.version = h->version; a.flags = (flags & 1) | (g_force_generic ? 2 : 0) | (h->debug_flags << 2); a.action_dtype = action_dtype;
+    a.version = h->version;
+    a.flags = (flags & 1) | (g_force_generic ? 2 : 0) | (h->debug_flags << 2) | (packed_obs ? 32 : 0);
+    a.action_dtype = action_dtype;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32);
     a.env_id0 = h->env_id0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -295,29 +337,106 @@ int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *d
                        stream);
 }
 
+int ta_step_packed(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags, uint32_t *codes_out,
+                   uint8_t *status_out, uint8_t *consumed_out, void *stream) {
+    if (!status_out || ((uintptr_t)codes_out & 3u)) return TA_E_INVALID;
+    return step_launch(h, actions, action_dtype, draws, flags, 1, (uint8_t *)codes_out, nullptr, nullptr, nullptr, consumed_out, stream,
+                       status_out, true);
+}
+
+// ta_step_host: H2D actions -> fused kernel -> D2H results -> (packed form) decode on the host threads
 int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, uint8_t *obs_out, float *reward_out,
                  uint8_t *term_out, uint8_t *trunc_out) {
     if (!h || !actions || !obs_out || !reward_out || !term_out || !trunc_out) return TA_E_INVALID;
     if (action_dtype < 0 || action_dtype > 2) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
     const size_t asz = action_dtype == TA_ACT_I32 ? 4 : (action_dtype == TA_ACT_U8 ? 1 : 8);
-    const size_t obs_bytes = (size_t)h->n * 3 * h->view * h->view;
-    if (!h->d_obs) {
+    const int V = h->view, runs = 2 * V * V, obs_bytes = 3 * V * V;
+    const long long ntiles = h->npad / TILE;
+    const size_t codes_bytes = (size_t)ntiles * runs * 4, status_bytes = (size_t)h->npad;
+    if (!h->d_codes) {
         CK(cudaMalloc(&h->d_act, (size_t)h->n * 8));
-        CK(cudaMalloc(&h->d_obs, obs_bytes));
-        CK(cudaMalloc(&h->d_rew, (size_t)h->n * 4));
-        CK(cudaMalloc(&h->d_term, (size_t)h->n));
-        CK(cudaMalloc(&h->d_trunc, (size_t)h->n));
+        CK(cudaMalloc(&h->d_codes, codes_bytes + status_bytes));
+        CK(cudaHostAlloc(&h->h_codes, codes_bytes + status_bytes, cudaHostAllocDefault));
+        for (int c = 0; c < HOST_CHUNKS; c++) CK(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
     }
     cudaStream_t st = h->own_stream;
+    uint8_t *d_status = (uint8_t *)h->d_codes + codes_bytes, *h_status = h->h_codes + codes_bytes;
     CK(cudaMemcpyAsync(h->d_act, actions, (size_t)h->n * asz, cudaMemcpyHostToDevice, st));
-    int rc = ta_step(h, h->d_act, action_dtype, nullptr, flags, h->d_obs, h->d_rew, h->d_term, h->d_trunc, nullptr, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(obs_out, h->d_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(reward_out, h->d_rew, (size_t)h->n * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(term_out, h->d_term, (size_t)h->n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(trunc_out, h->d_trunc, (size_t)h->n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    ta_host::Job &job = h->job;
+    job.status = h_status; job.reward = reward_out; job.term = term_out; job.trunc = trunc_out;
+    job.n = h->n; job.ntiles = ntiles; job.runs = runs; job.obs_bytes = obs_bytes; job.obs = obs_out;
+    if (flags & TA_STEP_HOST_DMA) {
+        // the expanded observations straight over PCIe into the caller's array (pinned: one DMA); the status bytes
+        // (reward index, terminated, truncated) through the staging buffer, decoded here
+        if (!h->d_obs) CK(cudaMalloc(&h->d_obs, (size_t)h->n * obs_bytes));
+        if (int rc = step_launch(h, h->d_act, action_dtype, nullptr, flags & 1, 1, h->d_obs, nullptr, nullptr, nullptr, nullptr, st,
+                                 d_status, false))
+            return rc;
+        CK(cudaMemcpyAsync(obs_out, h->d_obs, (size_t)h->n * obs_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_status, d_status, status_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (long long e = 0; e < h->n; e++) {
+            const uint8_t s = h_status[e];
+            memcpy(reward_out + e, &ta_host::REWARD_BITS[s & 7u], 4);
+            term_out[e] = (s >> 3) & 1u;
+            trunc_out[e] = (s >> 4) & 1u;
+        }
+        h->last_d2h_bytes = (long long)h->n * obs_bytes + (long long)status_bytes;
+        return TA_OK;
+    }
+    if (!h->pool) {
+        const int nt = ta_host::default_threads();
+        h->pool = new (std::nothrow) ta_host::Pool(nt > 1 ? nt - 1 : 0);  // the calling thread decodes too
+        if (!h->pool) return TA_E_NOMEM;
+    }
+    if (int rc = step_launch(h, h->d_act, action_dtype, nullptr, flags & 1, 1, (uint8_t *)h->d_codes, nullptr, nullptr, nullptr, nullptr, st,
+                             d_status, true))
+        return rc;
+    // status first (small), then the packed observations in HOST_CHUNKS pieces, an event behind each
+    CK(cudaMemcpyAsync(h_status, d_status, status_bytes, cudaMemcpyDeviceToHost, st));
+    long long unit_tiles = 32768 / (TILE * obs_bytes);
+    if (unit_tiles < 1) unit_tiles = 1;
+    job.unit_tiles = (int)unit_tiles;
+    job.nunits = (ntiles + unit_tiles - 1) / unit_tiles;
+    job.codes = reinterpret_cast<const uint32_t *>(h->h_codes);
+    job.next.store(0); job.ready.store(0); job.finished.store(0);
+    long long chunk_end[HOST_CHUNKS];
+    int nchunks = 0;
+    for (int c = 0; c < HOST_CHUNKS; c++) {
+        long long u0 = job.nunits * c / HOST_CHUNKS, u1 = job.nunits * (c + 1) / HOST_CHUNKS;
+        if (u1 == u0) continue;
+        long long t0 = u0 * unit_tiles, t1 = u1 * unit_tiles < ntiles ? u1 * unit_tiles : ntiles;
+        CK(cudaMemcpyAsync(h->h_codes + (size_t)t0 * runs * 4, (const uint8_t *)h->d_codes + (size_t)t0 * runs * 4, (size_t)(t1 - t0) * runs * 4,
+                           cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(h->chunk_ev[nchunks], st));
+        chunk_end[nchunks++] = u1;
+    }
+    h->pool->start(&job);
+    cudaError_t err = cudaSuccess;
+    for (int c = 0; c < nchunks; c++) {
+        const cudaError_t e = cudaEventSynchronize(h->chunk_ev[c]);
+        if (e != cudaSuccess) err = e;
+        job.ready.store(chunk_end[c], std::memory_order_release);  // (on an error too: the workers must not spin forever)
+    }
+    h->pool->finish(&job);
+    if (err != cudaSuccess) return cuda_fail(err, "ta_step_host: D2H");
+    h->last_d2h_bytes = (long long)(codes_bytes + status_bytes);
+    return TA_OK;
+}
+
+int64_t ta_step_host_d2h_bytes(ta_handle h) { return h ? h->last_d2h_bytes : 0; }
+
+int ta_decode_packed_host(const uint32_t *codes, const uint8_t *status, int64_t n, int view, uint8_t *obs_out, float *reward_out,
+                          uint8_t *term_out, uint8_t *trunc_out) {
+    if (!codes || !status || !obs_out || !reward_out || !term_out || !trunc_out || n <= 0 || view < 3 || view > 17 || !(view & 1))
+        return TA_E_INVALID;
+    ta_host::Job job;
+    job.codes = codes; job.status = status; job.obs = obs_out; job.reward = reward_out; job.term = term_out; job.trunc = trunc_out;
+    job.n = n; job.ntiles = (n + TILE - 1) / TILE; job.runs = 2 * view * view; job.obs_bytes = 3 * view * view;
+    job.unit_tiles = 1; job.nunits = job.ntiles;
+    job.ready.store(job.nunits);
+    ta_host::work(job);
     return TA_OK;
 }
 
@@ -403,6 +522,7 @@ int ta_export_state(ta_handle h, ta_env_state *out, void *stream) {
 int ta_import_state(ta_handle h, const ta_env_state *in, void *stream) {
     if (!h || !in) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
+    note_writer((cudaStream_t)stream, h);
     import_kernel<<<blocks_for(h->n * REC_WORDS, 256), 256, 0, (cudaStream_t)stream>>>(
         h->grid, h->sc0, h->sc1, reinterpret_cast<const EnvStateRec *>(in), h->n);
     return launch_ok("import_kernel");

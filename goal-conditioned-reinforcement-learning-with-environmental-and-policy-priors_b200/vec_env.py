@@ -157,16 +157,37 @@ class TwoarmyVecEnv:
         return obs, rew, term.view(torch.bool), trunc.view(torch.bool), info
 
     def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, terminated: np.ndarray,
-                  truncated: np.ndarray):
-        """End-to-end call with HOST arrays (numpy; pinned torch memory viewed as numpy is
-        fastest): H2D actions, fused kernel, D2H results, synchronised on return."""
+                  truncated: np.ndarray, dma: bool = False):
+        """End-to-end call with HOST arrays (numpy): H2D actions, fused kernel, D2H results, synchronised on
+        return.  Default: the observations cross PCIe as 2-bit codes and host threads expand them into `obs`
+        (ta_step_host); dma=True: the expanded bytes are copied straight into `obs` (pin it for speed)."""
         assert actions.dtype in (np.int32, np.uint8, np.int64) and actions.size == self.num_envs
+        assert obs.dtype == np.uint8 and obs.size == self.num_envs * 3 * self.view * self.view and obs.flags.c_contiguous
+        assert reward.dtype == np.float32 and terminated.dtype == np.uint8 and truncated.dtype == np.uint8
         dt = {np.dtype(np.int32): 0, np.dtype(np.uint8): 1, np.dtype(np.int64): 2}[actions.dtype]
-        flags = _capi.TA_STEP_AUTORESET if self.autoreset else 0
+        flags = (_capi.TA_STEP_AUTORESET if self.autoreset else 0) | (_capi.TA_STEP_HOST_DMA if dma else 0)
         _capi.check(self._L.ta_step_host(self._h, C.c_void_p(actions.ctypes.data), dt, flags,
                                          C.c_void_p(obs.ctypes.data), C.c_void_p(reward.ctypes.data),
                                          C.c_void_p(terminated.ctypes.data), C.c_void_p(truncated.ctypes.data)),
                     "ta_step_host")
+
+    def host_d2h_bytes(self) -> int:
+        """Device-to-host bytes the last step_host() moved."""
+        return int(self._L.ta_step_host_d2h_bytes(self._h))
+
+    def step_packed(self, actions: torch.Tensor):
+        """One env.step with the results in transfer form (ta_step_packed): (codes uint32 [npad/32, 2*V*V],
+        status uint8 [npad])."""
+        if actions.dtype not in _ACT_DTYPES:
+            actions = actions.to(torch.int32)
+        actions = actions.to(self.device).contiguous()
+        ntiles = (self.num_envs + 31) // 32
+        codes = torch.empty((ntiles, 2 * self.view * self.view), dtype=torch.int32, device=self.device)
+        status = torch.zeros(ntiles * 32, dtype=torch.uint8, device=self.device)
+        flags = _capi.TA_STEP_AUTORESET if self.autoreset else 0
+        _capi.check(self._L.ta_step_packed(self._h, _ptr(actions), _ACT_DTYPES[actions.dtype], None, flags, _ptr(codes),
+                                           _ptr(status), None, self._stream()), "ta_step_packed")
+        return codes, status
 
     def rollout(self, actions: torch.Tensor):
         """T steps with a pre-sampled [T, N] action tensor (autoreset, Philox draws)."""

@@ -127,11 +127,35 @@ int ta_step(ta_handle h, const void *actions, int action_dtype, const uint8_t *d
             uint8_t *obs_out, float *reward_out, uint8_t *term_out, uint8_t *trunc_out,
             uint8_t *consumed_out, void *stream);
 
-/* Same call with HOST buffers (pinned or pageable): copies actions in, launches, copies the
- * four outputs back on the handle's own stream and synchronises before returning. This is
- * the end-to-end path bench.py times. */
+/* ta_step with the results in TRANSFER form (what ta_step_host ships over PCIe):
+ *   codes_out   uint32 [npad/32][2*V*V]: the observations of a 32-env tile as one cell stream (env-major, then
+ *               image[x][y]) of 2-bit cell codes, 16 cells per word (cell q of a word = bits 2q, 2q+1); expanding
+ *               code c to (type, color, 0) = ((1,0),(2,5),(6,4),(8,1))[c] yields exactly obs_out of ta_step
+ *   status_out  uint8 [npad]: reward index (0..4 = -0.01, -0.1, -0.9, 0.2, 0.9) | terminated << 3 | truncated << 4
+ * npad = n rounded up to 32. */
+int ta_step_packed(ta_handle h, const void *actions, int action_dtype, const uint8_t *draws, int flags,
+                   uint32_t *codes_out, uint8_t *status_out, uint8_t *consumed_out, void *stream);
+
+/* The reference-facing call: env.step for every env with HOST arrays in and out (what a gym caller holds,
+ * gym_minigrid/minigrid.py:1439-1441: obs["image"] is a numpy array).  H2D actions, the fused kernel, D2H results,
+ * synchronised before returning; this is the end-to-end path bench.py times.
+ *   default            the observations cross PCIe in the packed transfer form above (72.25 B instead of 867 B per
+ *                      env at V = 17), in pieces, and a pool of host threads (TA_HOST_THREADS, default: the cores of
+ *                      this process / LOCAL_WORLD_SIZE) expands each piece into obs_out while the next one is on the
+ *                      wire.  obs_out may be pageable; 16-byte alignment enables streaming stores.
+ *   TA_STEP_HOST_DMA   the expanded observations are copied straight into obs_out by the DMA engine (fastest when
+ *                      obs_out is pinned and host cores are scarce); reward / flags still travel as one status byte.
+ * Same bytes either way (tests/test_gpu_parity.py::test_step_host_equals_device_step). */
+#define TA_STEP_HOST_DMA 2
 int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, uint8_t *obs_out,
                  float *reward_out, uint8_t *term_out, uint8_t *trunc_out);
+/* The decode stage of ta_step_host on its own (pure host code, calling thread only): HOST copies of
+ * ta_step_packed's codes / status -> the arrays ta_step would have produced.  For consumers that keep the transfer
+ * form (replay storage, sockets) and expand it where the observations are needed. */
+int ta_decode_packed_host(const uint32_t *codes, const uint8_t *status, int64_t n, int view, uint8_t *obs_out,
+                          float *reward_out, uint8_t *term_out, uint8_t *trunc_out);
+/* device->host bytes the last ta_step_host call moved */
+int64_t ta_step_host_d2h_bytes(ta_handle h);
 
 /* T consecutive steps with a pre-sampled action tensor [T][n] (random-policy rollouts,
  * soa/datacol_predictor.py:106 style).  Outputs are [T][n]... ; always autoreset, Philox draws. */

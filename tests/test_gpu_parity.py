@@ -230,22 +230,63 @@ def test_invalid_actions_set_error_and_freeze_env():
     assert (after["error"][ok] == 0).all() and (after["step_count"][ok] == 1).all()
 
 
-def test_step_host_equals_device_step():
+@pytest.mark.parametrize("version,view,n", [(4, 17, 4096), (4, 17, 1000), (6, 7, 4099), (4, 5, 77), (6, 3, 33), (4, 9, 31)])
+def test_step_host_equals_device_step(version, view, n):
+    """The reference-facing host call (H2D actions, kernel, D2H + host-thread decode of the packed transfer form, or
+    plain DMA of the expanded bytes) returns exactly the bytes of the device call, for whole and ragged tiles, aligned
+    and unaligned host arrays."""
     P = _pkg()
-    n = 4096
-    a_env = P.TwoarmyVecEnv(4, n, 17, seed=1)
-    b_env = P.TwoarmyVecEnv(4, n, 17, seed=1)
-    a_env.reset(); b_env.reset()
+    a_env = P.TwoarmyVecEnv(version, n, view, seed=1)
+    envs = {mode: P.TwoarmyVecEnv(version, n, view, seed=1) for mode in ("packed", "dma", "packed_unaligned")}
+    a_env.reset()
+    for e in envs.values():
+        e.reset()
     rng = np.random.default_rng(2)
-    obs = np.empty((n, 17, 17, 3), np.uint8); rew = np.empty(n, np.float32)
-    te = np.empty(n, np.uint8); tr = np.empty(n, np.uint8)
+    raw = np.zeros(n * view * view * 3 + 64, np.uint8)
+    base = (-raw.ctypes.data) % 16
+    bufs = {"packed": raw[base:base + n * view * view * 3], "dma": np.empty(n * view * view * 3, np.uint8),
+            "packed_unaligned": raw[base + 1:base + 1 + n * view * view * 3]}
+    rew = np.empty(n, np.float32); te = np.empty(n, np.uint8); tr = np.empty(n, np.uint8)
     for t in range(60):
         a = _random_actions(rng, n)
         o, r, t1, t2, _ = a_env.step(torch.as_tensor(a))
-        b_env.step_host(a, obs, rew, te, tr)
-        assert np.array_equal(o.cpu().numpy(), obs) and np.array_equal(r.cpu().numpy(), rew)
-        assert np.array_equal(t1.cpu().numpy().astype(np.uint8), te)
-        assert np.array_equal(t2.cpu().numpy().astype(np.uint8), tr)
+        want = o.cpu().numpy().reshape(-1)
+        for mode, env in envs.items():
+            if mode == "packed_unaligned" and t >= 8:
+                continue
+            obs = bufs[mode]
+            obs[:] = 0xEE; rew[:] = np.nan; te[:] = 9; tr[:] = 9
+            env.step_host(a, obs, rew, te, tr, dma=(mode == "dma"))
+            assert np.array_equal(want, obs), (mode, t)
+            assert np.array_equal(r.cpu().numpy(), rew) and np.array_equal(t1.cpu().numpy().astype(np.uint8), te)
+            assert np.array_equal(t2.cpu().numpy().astype(np.uint8), tr)
+            if mode != "dma":
+                ntiles = (n + 31) // 32
+                assert env.host_d2h_bytes() == ntiles * (2 * view * view * 4 + 32)
+    if base + 1 + n * view * view * 3 < raw.size:
+        assert raw[base + 1 + n * view * view * 3] == 0     # nothing written past the caller's array
+
+
+def test_step_packed_is_the_cell_stream_of_the_obs():
+    """ta_step_packed's transfer form decodes (numpy restatement of the layout the header documents) to ta_step's obs."""
+    P = _pkg()
+    n, V = 200, 17
+    a_env, b_env = P.TwoarmyVecEnv(4, n, V, seed=3), P.TwoarmyVecEnv(4, n, V, seed=3)
+    a_env.reset(); b_env.reset()
+    rng = np.random.default_rng(5)
+    enc = np.array([[1, 0, 0], [2, 5, 0], [6, 4, 0], [8, 1, 0]], np.uint8)
+    rlut = np.array([-0.01, -0.1, -0.9, 0.2, 0.9], np.float64).astype(np.float32)
+    for t in range(55):
+        a = torch.as_tensor(_random_actions(rng, n))
+        o, r, te, tr, _ = a_env.step(a)
+        codes, status = b_env.step_packed(a)
+        w = codes.cpu().numpy().view(np.uint32).reshape(-1)
+        cells = ((w[:, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3).reshape(-1, 32 * V * V)   # per tile: 32 envs x V*V cells
+        img = enc[cells.reshape(-1, V * V)][:n].reshape(n, V, V, 3)
+        assert np.array_equal(img, o.cpu().numpy()), t
+        st = status.cpu().numpy()[:n]
+        assert np.array_equal(rlut[st & 7], r.cpu().numpy())
+        assert np.array_equal((st >> 3) & 1, te.cpu().numpy().astype(np.uint8)) and np.array_equal((st >> 4) & 1, tr.cpu().numpy().astype(np.uint8))
 
 
 def test_rollout_equals_stepwise():
