@@ -43,11 +43,14 @@ def gae(reward: torch.Tensor, value: torch.Tensor, done: Optional[torch.Tensor] 
     ret = torch.empty_like(reward)
     L = _capi.lib()
     st = _stream(reward.device)
-    _capi.check(L.ta_gae(_ptr(reward), _ptr(value), _ptr(v_next), _ptr(last_value), _ptr(done), float(gamma), float(lam),
-                         int(bool(use_mask)), T, N, _ptr(adv), _ptr(ret), st), "ta_gae")
-    if normalize:
+    if not normalize:
+        _capi.check(L.ta_gae(_ptr(reward), _ptr(value), _ptr(v_next), _ptr(last_value), _ptr(done), float(gamma), float(lam),
+                             int(bool(use_mask)), T, N, _ptr(adv), _ptr(ret), st), "ta_gae")
+    else:
+        # the moments of adv come out of the same launch; normalising is one more pass over adv
         stats = torch.empty(3, dtype=torch.float64, device=reward.device)
-        _capi.check(L.ta_adv_stats(_ptr(adv), T * N, _ptr(stats), st), "ta_adv_stats")
+        _capi.check(L.ta_gae_stats(_ptr(reward), _ptr(value), _ptr(v_next), _ptr(last_value), _ptr(done), float(gamma), float(lam),
+                                   int(bool(use_mask)), T, N, _ptr(adv), _ptr(ret), _ptr(stats), st), "ta_gae_stats")
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                  and torch.distributed.get_world_size() > 1):
             torch.distributed.all_reduce(stats, group=group)

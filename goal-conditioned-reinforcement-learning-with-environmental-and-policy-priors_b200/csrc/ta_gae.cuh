@@ -97,14 +97,20 @@ constexpr int GV_MAX_THREADS = 1024;
 
 __device__ __forceinline__ float f4get(const float4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-template <int GV_L, int GV_CH>
-__global__ void __launch_bounds__(32 * GV_CH)
+// GV_X = float4 columns per CTA (threadIdx.x): 32 for large batches; 8 (one 128-byte line per row) when the rollout is
+// small -- BASELINE configs[3] is 128 x 16384 = 36 MB -- so that there are several CTAs per SM and one pass covers all of
+// T (16 chunks x 8 steps): the launch is then bound by one DRAM round trip instead of two dependent ones.
+// stats (nullable): the launch also accumulates (sum, sum of squares, count) of adv in float64 -- the moments of
+// PPO.py:115's normalisation -- so that normalising costs one more pass over adv instead of two.
+template <int GV_L, int GV_CH, int GV_X>
+__global__ void __launch_bounds__(GV_X * GV_CH)
 gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const float *__restrict__ v_next,
                 const float *__restrict__ last_v, const uint8_t *__restrict__ done, float gamma, float lam, int use_mask,
-                int T, long long n, float *__restrict__ adv, float *__restrict__ ret) {
-    __shared__ float sP[GV_CH][32][4], sA[GV_CH][32][4];
+                int T, long long n, float *__restrict__ adv, float *__restrict__ ret, double *__restrict__ stats) {
+    __shared__ float sP[GV_CH][GV_X][4], sA[GV_CH][GV_X][4];
     const int lx = threadIdx.x, cy = threadIdx.y, CH = blockDim.y;
-    const long long col = ((long long)blockIdx.x * 32 + lx) * 4;  // first of this thread's 4 envs
+    const long long col = ((long long)blockIdx.x * GV_X + lx) * 4;  // first of this thread's 4 envs
+    double st_s = 0.0, st_ss = 0.0;
     const bool valid = col < n;
     const int span = GV_L * CH;
     const float gl = __fmul_rn(gamma, lam);
@@ -199,11 +205,29 @@ gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const 
                 const long long idx = (long long)t * n + col;
                 *reinterpret_cast<float4 *>(adv + idx) = make_float4(ao[0], ao[1], ao[2], ao[3]);
                 *reinterpret_cast<float4 *>(ret + idx) = make_float4(ro[0], ro[1], ro[2], ro[3]);
+                if (stats) {
+                    st_s += (double)ao[0] + (double)ao[1] + (double)ao[2] + (double)ao[3];
+                    st_ss += (double)ao[0] * ao[0] + (double)ao[1] * ao[1] + (double)ao[2] * ao[2] + (double)ao[3] * ao[3];
+                }
             }
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; i++) carry[i] = cnext[i];
+    }
+    if (stats) {  // CTA-wide sum through the (now free) scan buffers, then one atomic pair per CTA
+        double *red = reinterpret_cast<double *>(&sP[0][0][0]);  // GV_CH * GV_X * 4 floats = room for 2 doubles per thread
+        const int tid = cy * GV_X + lx, nth = GV_X * CH;
+        red[2 * tid] = st_s;
+        red[2 * tid + 1] = st_ss;
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, b = 0.0;
+            for (int k = 0; k < nth; k++) { a += red[2 * k]; b += red[2 * k + 1]; }
+            atomicAdd(&stats[0], a);
+            atomicAdd(&stats[1], b);
+            if (blockIdx.x == 0) atomicAdd(&stats[2], (double)T * (double)n);
+        }
     }
 }
 

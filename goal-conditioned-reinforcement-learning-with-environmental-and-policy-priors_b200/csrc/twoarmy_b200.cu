@@ -57,8 +57,11 @@ struct ta_batch {
     uint32_t *grid = nullptr;
     uint4 *sc0 = nullptr, *sc1 = nullptr;
     int ctas_per_sm = 0;   // 0 = whatever fits (tuning knob: TA_CTAS_PER_SM)
-    int pdl = 0;           // programmatic dependent launch of the step kernel (TA_PDL=1 turns it on;
-                           // measured slower on B200: 19.2 vs 16.8 us per 65536-env launch, so off)
+    int pdl = 3;           // programmatic dependent launch of the step kernel (TA_PDL): 0 off; 1 trigger at the top of the
+                           // kernel; 2 trigger after the kernel's own dependency wait + early state load when the previous
+                           // writer on the stream was another handle; 3 (default) the same with the trigger after the last
+                           // observation pass.  Measured on B200, 65536 envs, graph-replayed single-step launches over 8
+                           // rotating batches: 16.0 / 15.2 / 14.4 / 14.3 us (V = 17), 8.85 / 8.02 / 7.27 / 7.26 us (V = 7)
     int warps_per_cta = 0; // independent tiles per CTA; 0 = chosen per launch (TA_WARPS_PER_CTA, 1..8)
     int debug_flags = 0;   // TA_DEBUG_FLAGS: timing experiments (StepArgs::flags bits 2,3)
     uint32_t *tmpl = nullptr;  // [20] the _gen_grid record
@@ -150,7 +153,7 @@ int launch_step_t(ta_batch *h, const StepArgs &a_in, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = h->pdl ? 1 : 0;
+    cfg.numAttrs = h->pdl ? 1 : 0;  // (without the attribute the kernel's griddepcontrol instructions are no-ops)
     CK(cudaLaunchKernelEx(&cfg, kern, a));
     return launch_ok("step_obs_kernel");
 }
@@ -528,32 +531,59 @@ int ta_import_state(ta_handle h, const ta_env_state *in, void *stream) {
     return launch_ok("import_kernel");
 }
 
-int ta_gae(const float *reward, const float *v, const float *v_next, const float *last_v, const uint8_t *done, float gamma,
-           float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, void *stream) {
+static int gae_launch(const float *reward, const float *v, const float *v_next, const float *last_v, const uint8_t *done, float gamma,
+                      float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, double *stats3, void *stream) {
     if (!reward || !v || !adv_out || !ret_out || T <= 0 || n <= 0) return TA_E_INVALID;
     if (!v_next && !last_v) return TA_E_INVALID;
     if (use_mask && !done) return TA_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stats3) CK(cudaMemsetAsync(stats3, 0, 3 * sizeof(double), st));
     const uintptr_t al = (uintptr_t)reward | (uintptr_t)v | (uintptr_t)v_next | (uintptr_t)last_v | (uintptr_t)adv_out |
                          (uintptr_t)ret_out;
     if ((n & 3) == 0 && (al & 15u) == 0 && ((uintptr_t)done & 3u) == 0) {  // four envs per thread, 16-byte accesses
-        // 8 steps per thread; time chunks per CTA: TA_GAE_CH (tuning knob, default 16 = 128 steps a pass)
+        // 8 steps per thread; time chunks per CTA: TA_GAE_CH (tuning knob)
         // measured on B200 (T = 128): 4 chunks (32 steps a pass, 128-thread CTAs) reach 0.89 of the HBM
         // peak once there are enough CTAs; small problems want the extra time-parallelism of 8
         static int gch = -1;
         if (gch < 0) { const char *e = getenv("TA_GAE_CH"); gch = e ? atoi(e) : 0; if (gch < 0 || gch > 16) gch = 0; }
+        const int steps_chunks = (T + 7) / 8;
+        if (!gch && n / 128 < 2 * 148) {
+            // small rollout (fewer than two 128-env CTAs per SM): 32-env CTAs, up to 16 chunks = 128 steps in one pass
+            int chv = steps_chunks < 16 ? steps_chunks : 16;
+            gae_vec4_kernel<8, 16, 8><<<blocks_for(n / 4, 8), dim3(8, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T,
+                                                                                      n, adv_out, ret_out, stats3);
+            return launch_ok("gae_vec4_kernel<8,16,8>");
+        }
         int want = gch ? gch : (n / 128 >= 4 * 148 ? 4 : 8);
-        int chv = (T + 7) / 8;
+        int chv = steps_chunks;
         if (chv > want) chv = want;
-        gae_vec4_kernel<8, 16><<<blocks_for(n / 4, 32), dim3(32, chv), 0, (cudaStream_t)stream>>>(
-            reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out, ret_out);
+        gae_vec4_kernel<8, 16, 32><<<blocks_for(n / 4, 32), dim3(32, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n,
+                                                                                    adv_out, ret_out, stats3);
         return launch_ok("gae_vec4_kernel");
     }
     int ch = (T + GAE_L - 1) / GAE_L;
     if (ch > GAE_CH) ch = GAE_CH;
     dim3 block(32, ch);
-    gae_kernel<<<blocks_for(n, 32), block, 0, (cudaStream_t)stream>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T,
-                                                                     n, adv_out, ret_out);
-    return launch_ok("gae_kernel");
+    gae_kernel<<<blocks_for(n, 32), block, 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out, ret_out);
+    if (int rc = launch_ok("gae_kernel")) return rc;
+    if (stats3) {  // the scalar kernel has no fused moments: the separate pass
+        unsigned nb = blocks_for((long long)T * n, 256 * 16);
+        if (nb > 148 * 8) nb = 148 * 8;
+        adv_stats_kernel<<<nb, 256, 0, st>>>(adv_out, (long long)T * n, stats3);
+        return launch_ok("adv_stats_kernel");
+    }
+    return TA_OK;
+}
+
+int ta_gae(const float *reward, const float *v, const float *v_next, const float *last_v, const uint8_t *done, float gamma,
+           float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, void *stream) {
+    return gae_launch(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out, ret_out, nullptr, stream);
+}
+
+int ta_gae_stats(const float *reward, const float *v, const float *v_next, const float *last_v, const uint8_t *done, float gamma,
+                 float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, double *stats3, void *stream) {
+    if (!stats3) return TA_E_INVALID;
+    return gae_launch(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out, ret_out, stats3, stream);
 }
 
 int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream) {

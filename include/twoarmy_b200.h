@@ -222,6 +222,11 @@ int ta_import_state(ta_handle h, const ta_env_state *in, void *stream);
 int ta_gae(const float *reward, const float *v, const float *v_next, const float *last_v,
            const uint8_t *done, float gamma, float lam, int use_mask, int T, int64_t n,
            float *adv_out, float *ret_out, void *stream);
+/* ta_gae that also leaves (sum, sum of squares, count) of adv_out in stats3 (overwritten) from the same launch:
+ * normalising then costs ta_adv_normalize only. */
+int ta_gae_stats(const float *reward, const float *v, const float *v_next, const float *last_v,
+                 const uint8_t *done, float gamma, float lam, int use_mask, int T, int64_t n,
+                 float *adv_out, float *ret_out, double *stats3, void *stream);
 int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream);
 int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stream);
 
