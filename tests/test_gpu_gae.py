@@ -46,11 +46,13 @@ def test_gae_matches_float64_oracle(T, N, lam, use_mask):
     assert np.max(np.abs(ret.cpu().numpy() - want_ret) / scale) < RTOL
 
 
-def test_gae_with_per_sample_v_next_and_normalisation():
+@pytest.mark.parametrize("T,N", [(128, 4096), (24, 65536), (40, 1003)])
+def test_gae_with_per_sample_v_next_and_normalisation(T, N):
+    """normalize=True: the moments come out of the GAE launch itself (ta_gae_stats; the 32-env-CTA kernel for small
+    rollouts, the 128-env-CTA kernel for large ones, the scalar kernel + separate pass when N % 4 != 0)."""
     from oracle import oracle as O
     A = _adv()
     rng = np.random.default_rng(3)
-    T, N = 128, 4096
     r = rng.standard_normal((T, N)).astype(np.float32) * 0.1
     v = rng.standard_normal((T, N)).astype(np.float32)
     vn = rng.standard_normal((T, N)).astype(np.float32)
