@@ -75,6 +75,13 @@ def lib() -> C.CDLL:
         except Exception as exc:  # no nvcc on this machine
             raise TwoarmyLibraryError(
                 f"{LIB_PATH} is missing and could not be built ({exc}); the product has no CPU path") from exc
+    elif LIB_PATH.stat().st_mtime < max(p.stat().st_mtime for p in sources()):
+        # a source is newer than the library: never run a stale build (rebuild where nvcc exists, else say so)
+        try:
+            build()
+        except Exception as exc:
+            import warnings
+            warnings.warn(f"{LIB_PATH} is older than its sources and could not be rebuilt ({exc})")
     try:
         L = C.CDLL(str(LIB_PATH))
     except OSError as exc:

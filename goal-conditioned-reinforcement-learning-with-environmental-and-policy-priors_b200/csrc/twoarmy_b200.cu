@@ -547,12 +547,22 @@ static int gae_launch(const float *reward, const float *v, const float *v_next, 
         static int gch = -1;
         if (gch < 0) { const char *e = getenv("TA_GAE_CH"); gch = e ? atoi(e) : 0; if (gch < 0 || gch > 16) gch = 0; }
         const int steps_chunks = (T + 7) / 8;
-        if (!gch && n / 128 < 2 * 148) {
-            // small rollout (fewer than two 128-env CTAs per SM): 32-env CTAs, up to 16 chunks = 128 steps in one pass
-            int chv = steps_chunks < 16 ? steps_chunks : 16;
-            gae_vec4_kernel<8, 16, 8><<<blocks_for(n / 4, 8), dim3(8, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T,
-                                                                                      n, adv_out, ret_out, stats3);
-            return launch_ok("gae_vec4_kernel<8,16,8>");
+        static int gvar = -1;  // TA_GAE_SMALL (tuning knob for small rollouts): 0 off, 1 = 128-env CTAs x 16 chunks, 2 = 64-env CTAs, 3 = 32-env CTAs
+        if (gvar < 0) { const char *e = getenv("TA_GAE_SMALL"); gvar = e ? atoi(e) : 1; if (gvar < 0 || gvar > 3) gvar = 1; }
+        if (!gch && gvar && n / 128 < 2 * 148) {
+            // small rollout (fewer than two 128-env CTAs per SM; BASELINE configs[3] is 128 x 16384): up to 16 chunks, so
+            // that one pass covers 128 steps -- one DRAM round trip instead of two dependent ones
+            const int chv = steps_chunks < 16 ? steps_chunks : 16;
+            if (gvar == 1)
+                gae_vec4_kernel<8, 16, 32><<<blocks_for(n / 4, 32), dim3(32, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask,
+                                                                                            T, n, adv_out, ret_out, stats3);
+            else if (gvar == 2)
+                gae_vec4_kernel<8, 16, 16><<<blocks_for(n / 4, 16), dim3(16, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask,
+                                                                                            T, n, adv_out, ret_out, stats3);
+            else
+                gae_vec4_kernel<8, 16, 8><<<blocks_for(n / 4, 8), dim3(8, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T,
+                                                                                          n, adv_out, ret_out, stats3);
+            return launch_ok("gae_vec4_kernel (small rollout)");
         }
         int want = gch ? gch : (n / 128 >= 4 * 148 ? 4 : 8);
         int chv = steps_chunks;

@@ -602,8 +602,7 @@ class PPO:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(group)
         # (with several ranks the gradient all-reduce is captured too: every rank replays the same graph)
-        want_graph = (dev.type == "cuda" and self.use_graph and (world == 1 or self.graph_with_nccl) and bool(self._flat)
-                      and sampler_generator is None)
+        want_graph = dev.type == "cuda" and self.use_graph and (world == 1 or self.graph_with_nccl) and bool(self._flat)
         graph, idx_static, loss_static, eager_full = None, None, None, 0
         side = torch.cuda.Stream(device=dev) if want_graph else None
 
