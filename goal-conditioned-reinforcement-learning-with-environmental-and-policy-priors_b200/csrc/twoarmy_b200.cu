@@ -16,6 +16,7 @@
 #include "ta_her.cuh"
 #include "ta_host.cuh"
 #include "ta_step.cuh"
+#include "ta_train.cuh"
 
 using namespace ta;
 
@@ -889,6 +890,91 @@ int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, voi
     if (nb > 148u * 8u) nb = 148u * 8u;
     channel_sum_bf16_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x_bf16, rows, C, out);
     return launch_ok("channel_sum_bf16_kernel");
+}
+
+/* ---- the small kernels of the hand-scheduled optimiser step (ta_train.cuh) ---- */
+static_assert(sizeof(ta_tinet_prep_args) == sizeof(PrepArgs), "public and device struct must match");
+static_assert(sizeof(ta_tinet_grad_args) == sizeof(GradArgs), "public and device struct must match");
+
+int64_t ta_relu_bwd_bias_scratch_floats(int64_t rows, int C) {
+    long long g = (rows + 63) / 64;
+    if (g > 2 * 148) g = 2 * 148;
+    if (g < 1) g = 1;
+    return g * C + 1;
+}
+
+int ta_relu_bwd_bias(const void *dy_bf16, int64_t ld_dy, const void *y_bf16, void *dz_bf16, int64_t rows, int C, float *db_out,
+                     float *scratch, void *stream) {
+    if (!dy_bf16 || !db_out || !scratch || rows <= 0 || C < 64 || C > 2048 || (C & 7) || (256 % (C >> 3)) || ld_dy < C || (ld_dy & 7))
+        return TA_E_INVALID;
+    if ((y_bf16 == nullptr) != (dz_bf16 == nullptr)) return TA_E_INVALID;
+    if (((uintptr_t)dy_bf16 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16) & 15u) return TA_E_INVALID;
+    long long g = (rows + 63) / 64;
+    if (g > 2 * 148) g = 2 * 148;
+    relu_bwd_bias_kernel<<<(unsigned)g, RB_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dy_bf16, ld_dy, (const __nv_bfloat16 *)y_bf16,
+                                                                             (__nv_bfloat16 *)dz_bf16, rows, C, db_out, scratch);
+    return launch_ok("relu_bwd_bias_kernel");
+}
+
+int ta_ppo_actor_loss(const void *logits_bf16, const int32_t *act, const float *old_logp, const float *adv, int B, float clip,
+                      float ent_coef, void *dlogits_bf16, float *loss_out, float *db_head, float *step_counter, void *stream) {
+    if (!logits_bf16 || !act || !old_logp || !adv || !dlogits_bf16 || !loss_out || !db_head || B <= 0) return TA_E_INVALID;
+    if (((uintptr_t)logits_bf16 | (uintptr_t)dlogits_bf16) & 15u) return TA_E_INVALID;
+    ppo_actor_loss_kernel<<<1, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)logits_bf16, act, old_logp, adv, B, clip, ent_coef,
+                                                                      (__nv_bfloat16 *)dlogits_bf16, loss_out, db_head, step_counter);
+    return launch_ok("ppo_actor_loss_kernel");
+}
+
+int ta_ppo_critic_loss(const void *v_bf16, const float *target, int B, void *dv_bf16, float *loss_out, float *db_head,
+                       float *step_counter, void *stream) {
+    if (!v_bf16 || !target || !dv_bf16 || !loss_out || !db_head || B <= 0) return TA_E_INVALID;
+    if (((uintptr_t)v_bf16 | (uintptr_t)dv_bf16) & 15u) return TA_E_INVALID;
+    ppo_critic_loss_kernel<<<1, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)v_bf16, target, B, (__nv_bfloat16 *)dv_bf16, loss_out,
+                                                                       db_head, step_counter);
+    return launch_ok("ppo_critic_loss_kernel");
+}
+
+int ta_adam_shadow(float *p, const float *g, float *m, float *v, void *p_bf16, int64_t n, const float *step_counter, float lr,
+                   float beta1, float beta2, float eps, float grad_scale, void *stream) {
+    if (!p || !g || !m || !v || !p_bf16 || !step_counter || n <= 0) return TA_E_INVALID;
+    unsigned nb = blocks_for(n, 256 * 4);
+    if (nb > 148u * 8u) nb = 148u * 8u;
+    adam_shadow_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16 *)p_bf16, n, step_counter, lr, beta1, beta2, eps, grad_scale);
+    return launch_ok("adam_shadow_kernel");
+}
+
+int ta_tinet_prep(const ta_tinet_prep_args *args, void *stream) {
+    if (!args || !args->w1 || !args->b1 || !args->w4 || !args->b4 || !args->fc0 || !args->fc0p || !args->pos || !args->pos16 || !args->head ||
+        !args->head_b || !args->head8 || !args->head_b8 || args->nh < 1 || args->nh > 8)
+        return TA_E_INVALID;
+    PrepArgs a;
+    memcpy(&a, args, sizeof(a));
+    tinet_prep_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_ok("tinet_prep_kernel");
+}
+
+int ta_tinet_grad(const ta_tinet_grad_args *args, void *stream) {
+    if (!args || !args->dw4 || !args->db4 || !args->g_w1 || !args->g_b1 || !args->fc0p || !args->g_fc0 || !args->pos16 || !args->g_pos ||
+        !args->head8 || !args->g_head || args->nh < 1 || args->nh > 8)
+        return TA_E_INVALID;
+    for (int k = 0; k < 4; k++)
+        if (args->n[k] < 0 || (args->n[k] > 0 && (!args->src[k] || !args->dst[k]))) return TA_E_INVALID;
+    GradArgs a;
+    memcpy(&a, args, sizeof(a));
+    tinet_grad_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_ok("tinet_grad_kernel");
+}
+
+int ta_gather_minibatch(const uint8_t *s, const float *p, const float *g, const int64_t *a, const float *old_logp, const float *adv,
+                        const float *target_v, const int64_t *idx, const int64_t *src, int bs, uint8_t *sb, void *pg16_bf16, int32_t *a_mb,
+                        float *old_mb, float *adv_mb, float *tv_mb, void *stream) {
+    if (!s || !p || !g || !a || !old_logp || !adv || !target_v || !idx || bs <= 0 || !sb || !pg16_bf16 || !a_mb || !old_mb || !adv_mb || !tv_mb)
+        return TA_E_INVALID;
+    if ((uintptr_t)sb & 3u) return TA_E_INVALID;
+    gather_minibatch_kernel<<<(unsigned)bs, 128, 0, (cudaStream_t)stream>>>(s, p, g, (const long long *)a, old_logp, adv, target_v,
+                                                                          (const long long *)idx, (const long long *)src, bs, sb,
+                                                                          (__nv_bfloat16 *)pg16_bf16, a_mb, old_mb, adv_mb, tv_mb);
+    return launch_ok("gather_minibatch_kernel");
 }
 
 int ta_set_timing(ta_handle h, int on) {

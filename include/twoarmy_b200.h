@@ -303,6 +303,77 @@ int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int 
  * {64, 128, 256}); out float32 [C] is overwritten. */
 int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, void *stream);
 
+/* ---- the hand-scheduled PPO optimiser step (soa/agent/PPO.py:124-144 without autograd; fused_step.py) ----------------
+ * Everything around the convolutions / GEMMs of one optimiser step, as single kernels with deterministic reductions.
+ *
+ * ta_relu_bwd_bias: dz = dy * [y > 0] (bf16 [rows][C]; dy rows ld_dy elements apart) and db_out[c] = sum over rows of
+ *   dz[.][c] (float32) in one pass: a Linear / conv layer's ReLU backward and bias gradient.  y_bf16 == dz_bf16 == NULL:
+ *   plain column sum of dy.  C a multiple of 8 with 256 % (C/8) == 0.  scratch: ta_relu_bwd_bias_scratch_floats(rows, C)
+ *   floats, zero before the first use (the kernel leaves its counter zero); one scratch per concurrent stream.
+ * ta_ppo_actor_loss: logits bf16 [B][8] (5 used) -> loss_out[0] = mean_i( -min(r_i A_i, clamp(r_i, 1-clip, 1+clip) A_i)
+ *   - ent_coef H_i ), r_i = exp(log softmax(logits_i)[a_i] - old_logp_i) (PPO.py:124-132); dlogits bf16 [B][8] its
+ *   gradient, db_head[5] the column sums of dlogits; step_counter[0] += 1 (the optimiser step count ta_adam_shadow reads).
+ * ta_ppo_critic_loss: v bf16 [B][8] (column 0) -> mean smooth_l1(v, target) (PPO.py:133), dv, db_head[1].
+ * ta_adam_shadow: torch.optim.Adam's update (PPO.py:57-58: lr, eps = 1e-5, betas (0.9, 0.999), no weight decay) on flat
+ *   float32 p / m / v of n elements from gradient g * grad_scale, at step t = step_counter[0]; also writes the bf16
+ *   copy p_bf16 the forward / backward kernels read. */
+int64_t ta_relu_bwd_bias_scratch_floats(int64_t rows, int C);
+int ta_relu_bwd_bias(const void *dy_bf16, int64_t ld_dy, const void *y_bf16, void *dz_bf16, int64_t rows, int C,
+                     float *db_out, float *scratch, void *stream);
+int ta_ppo_actor_loss(const void *logits_bf16, const int32_t *act, const float *old_logp, const float *adv, int B,
+                      float clip, float ent_coef, void *dlogits_bf16, float *loss_out, float *db_head,
+                      float *step_counter, void *stream);
+int ta_ppo_critic_loss(const void *v_bf16, const float *target, int B, void *dv_bf16, float *loss_out, float *db_head,
+                       float *step_counter, void *stream);
+int ta_adam_shadow(float *p, const float *g, float *m, float *v, void *p_bf16, int64_t n, const float *step_counter,
+                   float lr, float beta1, float beta2, float eps, float grad_scale, void *stream);
+
+/* Per-step weight forms of one network derived from its master copy (device pointers; w1 strides in elements):
+ * the folded first layer (all_net.py:142-143,157 -> [256][16] / [256], see ta_conv1_fwd), fc0 with its input features
+ * permuted to the (pixel, channel) order conv4's GEMM produces, positionnet / head padded to 16 columns / 8 rows. */
+typedef struct {
+    const float *w1;
+    int64_t s_o, s_c, s_y, s_x;
+    const float *b1;
+    float *w4, *b4;
+    const void *fc0;      /* bf16 [256][2304] */
+    void *fc0p;           /* bf16 [256][9][256] */
+    const void *pos;      /* bf16 [128][10] */
+    void *pos16;          /* bf16 [128][16] */
+    const void *head, *head_b;   /* bf16 [nh][512], [nh] */
+    void *head8, *head_b8;       /* bf16 [8][512], [8] */
+    int nh;
+} ta_tinet_prep_args;
+int ta_tinet_prep(const ta_tinet_prep_args *args, void *stream);
+
+/* The inverse for the gradients: folded conv1 gradients, the bf16 weight gradients the GEMMs / cuDNN leave (4 dense
+ * segments), the permuted fc0 and padded positionnet / head gradients -> the flat float32 gradient buffer. */
+typedef struct {
+    const float *dw4, *db4;
+    float *g_w1;
+    int64_t s_o, s_c, s_y, s_x;
+    float *g_b1;
+    const void *src[4];   /* bf16 */
+    float *dst[4];
+    int64_t n[4];
+    const void *fc0p;
+    float *g_fc0;
+    const void *pos16;
+    float *g_pos;
+    const void *head8;
+    float *g_head;
+    int nh;
+} ta_tinet_grad_args;
+int ta_tinet_grad(const ta_tinet_grad_args *args, void *stream);
+
+/* Minibatch gather for the update (PPO.py:122-127): sample idx[i] (through src for hindsight-relabelled samples) ->
+ * sb uint8 [bs][4][289] (frames 0..3), pg16 bf16 [bs][16] (4 positions + goal, zero padded), a_mb int32, old_logp /
+ * adv / target_v float32 [bs]. */
+int ta_gather_minibatch(const uint8_t *s, const float *p, const float *g, const int64_t *a, const float *old_logp,
+                        const float *adv, const float *target_v, const int64_t *idx, const int64_t *src, int bs,
+                        uint8_t *sb, void *pg16_bf16, int32_t *a_mb, float *old_mb, float *adv_mb, float *tv_mb,
+                        void *stream);
+
 /* introspection */
 int ta_abi_version(void);
 const char *ta_strerror(int code);

@@ -115,9 +115,12 @@ def test_gpu_update_bf16_fused_path_tracks_reference_fixture(golden):
         assert float(dg.abs().max()) <= 6 * 1.05e-4           # 6 Adam steps of lr 1e-4
 
 
-@pytest.mark.parametrize("autocast", [False, True])
+@pytest.mark.parametrize("autocast", [True])
 def test_graph_replay_equals_eager_steps(golden, autocast):
-    """The CUDA-graph replay of the optimiser step vs the same steps launched eagerly (same weights, same minibatches).
+    """The CUDA-graph replay of the PRODUCTION optimiser step (bf16 autocast, fused kernels) vs the same steps launched
+    eagerly (same weights, same minibatches).  (The fp32 debugging path goes through cuDNN's fp32 convolutions, whose
+    algorithm choice differs between capture and eager launches; it is pinned to the reference fixture instead,
+    test_gpu_update_matches_reference_fixture_fp32.)
     Every kernel of the step is deterministic except the float atomics that finish the conv1 weight gradient and the
     channel sums (cross-CTA accumulation order), so gradients agree to ~1e-6 relative and the first Adam steps, which
     normalise each gradient element by its own magnitude, can amplify that only where |g| is at round-off level:
@@ -198,15 +201,19 @@ def test_fused_conv1_matches_cudnn_layer(dtype, conv1_kernel):
     # forward: one bf16 rounding of the fp32-grade result -> within 1 bf16 ulp (2^-8 relative) of the float64 value
     err = (got.double().cpu() - want).abs()
     assert bool((err <= want.abs() * (1.02 * 2.0 ** -8) + 1e-4).all()), float((err - want.abs() * 2.0 ** -8).max())
-    # gradients for the same upstream gradient, the ReLU mask taken from the kernel's own output in both
+    # gradients for the same upstream gradient AND the same ReLU mask (the kernel's own output > 0) on both sides: the
+    # reference differentiates the linear layer only, so that pre-activations within round-off of zero -- where a float64
+    # and an fp32-grade evaluation may disagree about the sign -- do not enter the comparison
     mask = (got.detach().cpu() > 0).double()
     conv.weight.grad = None; conv.bias.grad = None
     got.backward(gy.cuda().to(torch.bfloat16))
     gy16 = gy.to(torch.bfloat16).double()           # the kernel consumes the bf16-rounded upstream gradient
-    (torch.relu(conv64(torch.nn.functional.interpolate(xf, scale_factor=4, mode="nearest"))) * (gy16 * mask)).sum().backward()
+    (conv64(torch.nn.functional.interpolate(xf, scale_factor=4, mode="nearest")) * (gy16 * mask)).sum().backward()
     gw, gb = conv64.weight.grad, conv64.bias.grad
-    assert float((conv.weight.grad.double().cpu() - gw).abs().max()) <= 1e-3 * float(gw.abs().max())
-    assert float((conv.bias.grad.double().cpu() - gb).abs().max()) <= 1e-3 * float(gb.abs().max())
+    ew = float((conv.weight.grad.double().cpu() - gw).abs().max()) / float(gw.abs().max())
+    eb = float((conv.bias.grad.double().cpu() - gb).abs().max()) / float(gb.abs().max())
+    print(f"conv1 {conv1_kernel} {dtype}: weight-gradient error {ew:.2e}, bias-gradient error {eb:.2e} (relative to the largest entry)")
+    assert ew <= 1e-3 and eb <= 1e-3, (ew, eb)
 
 
 @pytest.mark.parametrize("layer", [2, 4])
