@@ -124,6 +124,14 @@ def lib() -> C.CDLL:
     L.ta_gae_stats.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp, vp]
     L.ta_adv_stats.argtypes = [vp, i64, vp, vp]
     L.ta_adv_normalize.argtypes = [vp, i64, vp, vp]
+    L.ta_relu_bwd_bias_scratch_floats.argtypes = [i64, i32]; L.ta_relu_bwd_bias_scratch_floats.restype = i64
+    L.ta_relu_bwd_bias.argtypes = [vp, i64, vp, vp, i64, i32, vp, vp, vp]
+    L.ta_ppo_actor_loss.argtypes = [vp, vp, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp]
+    L.ta_ppo_critic_loss.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.ta_adam_shadow.argtypes = [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp]
+    L.ta_tinet_prep.argtypes = [vp, vp]
+    L.ta_tinet_grad.argtypes = [vp, vp]
+    L.ta_gather_minibatch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.ta_strerror.argtypes = [i32]; L.ta_strerror.restype = C.c_char_p
     L.ta_last_cuda_error.restype = C.c_char_p
     L.ta_launch_count.restype = i64

@@ -323,6 +323,10 @@ class PPO:
         # 2 GPUs, 4096-sample minibatches: 3.8 ms per step from the graph, 6.1 ms eager (the step is ~450 launches)
         self.graph_with_nccl = os.environ.get("TA_PPO_GRAPH_NCCL", "1") == "1"
         self._streams = None
+        # the hand-scheduled optimiser step (fused_step.py: explicit kernel list, no autograd, flat fp32 master + bf16
+        # shadow + own Adam): built on the first update() of a plain PPO agent on a GPU under bf16 autocast
+        self.fused_step = os.environ.get("TA_PPO_FUSED_STEP", "1") == "1"
+        self._fused = None
         self.last_action_loss = float("nan")
         self.last_value_loss = float("nan")
 
@@ -455,6 +459,11 @@ class PPO:
                 self._streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
             streams = self._streams
 
+        fused = self._fused_nets() if (s.dtype == torch.uint8 and s.is_contiguous() and p.is_contiguous()) else None
+        if fused is not None:
+            step = self._fused_step_fn(fused, s, p, g, a, old_a_logp, adv, target_v, src, streams, group)
+            return step, B, bs, src
+
         def step(idx):
             """One optimiser step on the minibatch `idx` (PPO.py:124-144); returns the two losses."""
             rows = idx if src is None else src[idx]
@@ -554,6 +563,77 @@ class PPO:
         self._probe_events = None
         return out
 
+    def _fused_nets(self):
+        """The two networks under the hand-scheduled step (fused_step.FusedNet), or None where it does not apply."""
+        from . import fused_step
+        if not (self.fused_step and fused_step.supported(self)):
+            return None
+        if self._fused is None:
+            self._fused = {"actor": fused_step.FusedNet(self.actor, "actor", self.lr, 1e-5),
+                           "critic": fused_step.FusedNet(self.critic, "critic", self.lr, 1e-5)}
+            for name, fn in self._fused.items():      # the all-reduce operand is the fused net's flat gradient buffer
+                self._flat[name] = fn.G32
+                opt = self.optimizer_actor if name == "actor" else self.optimizer_critic
+                fn.import_adam_state(opt.state_dict())
+        return self._fused
+
+    def _fused_step_fn(self, fused, s, p, g, a, old_a_logp, adv, target_v, src, streams, group):
+        """step(idx) through fused_step.FusedNet: gather kernel, then per network (on its own stream) forward, loss,
+        backward, gradient all-reduce, Adam + bf16 shadow refresh."""
+        import ctypes as C
+        from . import _capi
+        L, dev = _capi.lib(), self.device
+        fa, fc = fused["actor"], fused["critic"]
+        fa.lr = float(self.optimizer_actor.param_groups[0]["lr"])
+        fc.lr = float(self.optimizer_critic.param_groups[0]["lr"])
+        a = a.contiguous(); old_a_logp = old_a_logp.contiguous(); adv = adv.contiguous(); target_v = target_v.contiguous(); g = g.contiguous()
+        clip, ent = float(self.clip_param), float(self.entropy_coef)
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+
+        def step(idx):
+            bs = idx.numel()
+            st = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            sb = torch.empty((bs, 4, 289), dtype=torch.uint8, device=dev)
+            pg16 = torch.empty((bs, 16), dtype=torch.bfloat16, device=dev)
+            a_mb = torch.empty(bs, dtype=torch.int32, device=dev)
+            old_mb = torch.empty(bs, dtype=torch.float32, device=dev)
+            adv_mb = torch.empty(bs, dtype=torch.float32, device=dev)
+            tv_mb = torch.empty(bs, dtype=torch.float32, device=dev)
+            _capi.check(L.ta_gather_minibatch(ptr(s), ptr(p), ptr(g), ptr(a), ptr(old_a_logp), ptr(adv), ptr(target_v), ptr(idx), ptr(src), bs,
+                                              ptr(sb), ptr(pg16), ptr(a_mb), ptr(old_mb), ptr(adv_mb), ptr(tv_mb), st()), "ta_gather_minibatch")
+
+            def actor_loss(out, d_out, db_head):
+                _capi.check(L.ta_ppo_actor_loss(ptr(out), ptr(a_mb), ptr(old_mb), ptr(adv_mb), bs, clip, ent, ptr(d_out), ptr(fa.loss),
+                                                ptr(db_head), ptr(fa.step_t), st()), "ta_ppo_actor_loss")
+
+            def critic_loss(out, d_out, db_head):
+                _capi.check(L.ta_ppo_critic_loss(ptr(out), ptr(tv_mb), bs, ptr(d_out), ptr(fc.loss), ptr(db_head), ptr(fc.step_t), st()),
+                            "ta_ppo_critic_loss")
+
+            def part(fn, name, net, loss_fn):
+                fn.forward_backward(sb, pg16, loss_fn)
+                self._allreduce(name, net, group)
+                fn.adam()
+                return fn.loss
+
+            if streams is None:
+                la, lc = part(fa, "actor", self.actor, actor_loss), part(fc, "critic", self.critic, critic_loss)
+            else:
+                cur = torch.cuda.current_stream(dev)
+                for sx in streams:
+                    sx.wait_stream(cur)
+                with torch.cuda.stream(streams[0]):
+                    la = part(fa, "actor", self.actor, actor_loss)
+                with torch.cuda.stream(streams[1]):
+                    lc = part(fc, "critic", self.critic, critic_loss)
+                for sx in streams:
+                    cur.wait_stream(sx)
+                for t in (sb, pg16, a_mb, old_mb, adv_mb, tv_mb, idx):   # read on the side streams
+                    t.record_stream(streams[0]); t.record_stream(streams[1])
+            return la, lc
+
+        return step
+
     def _common_steps(self, B: int, bs: int, group) -> int:
         """Optimiser steps per epoch, agreed between ranks: every rank issues one all-reduce per step, so all of
         them must run the same number of steps.  With equal B (the plain rollout) this is ceil(B / bs) as in the
@@ -648,9 +728,12 @@ class PPO:
 
     # ------------------------------------------------------------------ checkpoints (PPO.py:94-101)
     def state_dict(self, i_ep: int = 0):
+        oa, oc = self.optimizer_actor.state_dict(), self.optimizer_critic.state_dict()
+        if self._fused is not None:   # the Adam moments live in the fused nets' flat buffers: same torch.optim.Adam format
+            oa = self._fused["actor"].export_adam_state(self.optimizer_actor)
+            oc = self._fused["critic"].export_adam_state(self.optimizer_critic)
         return {"model_actor": self.actor.state_dict(), "model_critic": self.critic.state_dict(),
-                "optimizer_actor": self.optimizer_actor.state_dict(), "optimizer_critic": self.optimizer_critic.state_dict(),
-                "epoch": i_ep}
+                "optimizer_actor": oa, "optimizer_critic": oc, "epoch": i_ep}
 
     def load_state_dict(self, state):
         self.actor.load_state_dict(state["model_actor"])
@@ -658,6 +741,11 @@ class PPO:
         if "optimizer_actor" in state:
             self.optimizer_actor.load_state_dict(state["optimizer_actor"])
             self.optimizer_critic.load_state_dict(state["optimizer_critic"])
+        if self._fused is not None:
+            for name, fn in self._fused.items():
+                fn.refresh()
+                if "optimizer_" + name in state:
+                    fn.import_adam_state(state["optimizer_" + name])
 
     def save_param(self, path, i_ep: int = 0):
         torch.save(self.state_dict(i_ep), path)
@@ -668,6 +756,9 @@ class PPO:
             for net in (self.actor, self.critic):
                 for t in list(net.parameters()) + list(net.buffers()):
                     dist.broadcast(t.data, src, group=group)
+            if self._fused is not None:
+                for fn in self._fused.values():
+                    fn.refresh()
 
 
 class VecRollout:

@@ -138,6 +138,63 @@ def test_graph_replay_equals_eager_steps(golden, autocast):
     assert outs[0][1] == pytest.approx(outs[1][1], rel=1e-3, abs=1e-5) and outs[0][2] == pytest.approx(outs[1][2], rel=1e-3, abs=1e-5)
 
 
+def _random_buffer(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)[torch.randint(0, 4, (n, 5, 289), generator=g)]
+    return {"s": codes, "p": torch.randint(1, 16, (n, 5, 2), generator=g).float(), "a": torch.randint(0, 5, (n, 1), generator=g),
+            "g": torch.tensor([[2.0, 14.0]]).repeat(n, 1), "r": (torch.rand(n, 1, generator=g) - 0.5) * 0.2,
+            "a_logp": torch.log(torch.rand(n, 1, generator=g) * 0.3 + 0.1)}
+
+
+@pytest.mark.parametrize("n", [512, 300])
+def test_fused_step_gradients_match_autograd_step(n):
+    """fused_step.FusedNet (explicit forward / backward, analytic loss gradients, deterministic bias sums) against the
+    autograd step of ppo.py on the same minibatch and weights, both in bf16: every parameter's gradient within 3 % in
+    the Frobenius norm (the two paths round intermediates at different points), the losses within 1e-3.  lr = 0, so the
+    gradients are still in the flat buffers afterwards."""
+    P = _ppo()
+    buf = {k: v.cuda() for k, v in _random_buffer(n, 7).items()}
+    grads, losses = {}, {}
+    for mode in ("autograd", "fused"):
+        torch.manual_seed(0)
+        agent = P.PPO(device="cuda:0")
+        agent.fused_step = mode == "fused"
+        for opt in (agent.optimizer_actor, agent.optimizer_critic):
+            opt.param_groups[0]["lr"] = 0.0
+        step, B, bs, _ = agent._make_step(buf, minibatch=n)
+        la, lc = step(torch.arange(n, device="cuda"))
+        torch.cuda.synchronize()
+        assert (agent._fused is not None) == (mode == "fused")
+        losses[mode] = (float(la), float(lc))
+        grads[mode] = [p.grad.detach().float().clone() for net in (agent.actor, agent.critic) for p in net.parameters()]
+        names = [f"{nn}.{k}" for nn, net in (("actor", agent.actor), ("critic", agent.critic)) for k, _ in net.named_parameters()]
+    assert losses["fused"][0] == pytest.approx(losses["autograd"][0], rel=1e-3, abs=1e-4)
+    assert losses["fused"][1] == pytest.approx(losses["autograd"][1], rel=1e-3, abs=1e-4)
+    for name, a, b in zip(names, grads["fused"], grads["autograd"]):
+        assert a.shape == b.shape
+        err = float((a - b).norm()) / max(float(b.norm()), 1e-12)
+        assert err <= 3e-2, (name, err, float(b.norm()))
+
+
+def test_fused_step_is_bitwise_reproducible(golden):
+    """Every reduction of the hand-scheduled step except the conv1 weight gradient's final float atomics has a fixed order:
+    two updates from the same state give the same parameters except where |gradient| is at round-off level
+    (>= 99.99 % of the elements bit-identical), and checkpoints carry the Adam moments in torch.optim.Adam's format."""
+    P = _ppo()
+    fx = golden("ppo_ref.npz")
+    outs = []
+    for _ in range(2):
+        agent, _ = _fixture_update(P, fx, "cuda:0", autocast=True, use_graph=True)
+        outs.append(torch.cat([_flat_params(agent.actor), _flat_params(agent.critic)]))
+    assert float((outs[0] == outs[1]).float().mean()) >= 0.9999
+    sd = agent.state_dict()
+    st = sd["optimizer_actor"]["state"]
+    assert len(st) == 16 and float(st[0]["step"]) == 6.0 and st[2]["exp_avg"].shape == (64, 64, 3, 3)
+    other = P.PPO(device="cuda:0")
+    other.load_state_dict(sd)
+    assert torch.equal(_flat_params(other.actor), _flat_params(agent.actor))
+
+
 def test_conv1_weight_gradient_run_to_run_bound():
     """conv1_bwd_tc_kernel finishes with one float atomicAdd per value and CTA: the accumulation order over CTAs is not
     fixed, so the gradient is reproducible only to fp32 round-off.  Documented bound: 1e-5 of the largest entry."""
