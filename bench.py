@@ -277,6 +277,9 @@ def ppo_measure(args, rank, world, dev, dist, clock_index=None):
                         "note": "nominal FLOPs of the reference network (47.53 MFLOP forward per sample per net)", "peak_source": tf_src},
            "losses": {"action": losses[0], "value": losses[1]}, "own_kernel_launches": int(own_launches), "clocks": clocks}
     out.update(probe)
+    if getattr(agent, "last_replay_stats", None):
+        out["graph_replayed_optimizer_steps"] = agent.last_replay_stats   # CUDA events around the replays of the last update()
+    out["fused_step"] = bool(getattr(agent, "_fused", None))
     return out
 
 

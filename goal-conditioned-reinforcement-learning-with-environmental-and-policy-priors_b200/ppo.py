@@ -684,6 +684,8 @@ class PPO:
         # (with several ranks the gradient all-reduce is captured too: every rank replays the same graph)
         want_graph = dev.type == "cuda" and self.use_graph and (world == 1 or self.graph_with_nccl) and bool(self._flat)
         graph, idx_static, loss_static, eager_full = None, None, None, 0
+        ev_first = ev_last = None
+        n_replayed = 0
         side = torch.cuda.Stream(device=dev) if want_graph else None
 
         self._last = None
@@ -699,8 +701,12 @@ class PPO:
                     with torch.cuda.graph(graph):
                         loss_static = step(idx_static)
                 if graph is not None and full:
+                    if ev_first is None:
+                        ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ev_first.record()
                     idx_static.copy_(idx)
                     graph.replay()
+                    n_replayed += 1
                     self._last = loss_static
                 elif want_graph and full:
                     side.wait_stream(torch.cuda.current_stream(dev))
@@ -712,7 +718,11 @@ class PPO:
                     self._last = step(idx)
                 self.update_count += 1
         if graph is not None:
+            if ev_first is not None:
+                ev_last.record()
             torch.cuda.synchronize(dev)
+            if ev_first is not None:   # device time of the graph-replayed optimiser steps alone (bench.py reports it)
+                self.last_replay_stats = {"steps": n_replayed, "ms_per_step": ev_first.elapsed_time(ev_last) / max(1, n_replayed)}
             self._last = tuple(x.clone() for x in self._last)
             del graph
         self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)

@@ -148,32 +148,48 @@ def _random_buffer(n, seed):
 
 @pytest.mark.parametrize("n", [512, 300])
 def test_fused_step_gradients_match_autograd_step(n):
-    """fused_step.FusedNet (explicit forward / backward, analytic loss gradients, deterministic bias sums) against the
-    autograd step of ppo.py on the same minibatch and weights, both in bf16: every parameter's gradient within 3 % in
-    the Frobenius norm (the two paths round intermediates at different points), the losses within 1e-3.  lr = 0, so the
-    gradients are still in the flat buffers afterwards."""
+    """fused_step.FusedNet (explicit forward / backward, analytic loss gradients, deterministic bias sums) on one minibatch
+    against (a) the fp32 autograd step (TF32 off) and (b) the bf16 autograd step it replaces, same weights.  bf16
+    activations put several per cent of noise on the early layers' gradients of a 512-sample minibatch (measured: 9-11 %
+    on conv1, 1-3 % on the head for BOTH bf16 paths), so the bar is relative: for every parameter the fused step's
+    distance to the fp32 gradient is at most 1.5 x the bf16 autograd step's (+ 1 % of the gradient norm), and the losses
+    agree to 1e-3.  lr = 0 keeps the gradients in the flat buffers."""
     P = _ppo()
     buf = {k: v.cuda() for k, v in _random_buffer(n, 7).items()}
     grads, losses = {}, {}
-    for mode in ("autograd", "fused"):
-        torch.manual_seed(0)
-        agent = P.PPO(device="cuda:0")
-        agent.fused_step = mode == "fused"
-        for opt in (agent.optimizer_actor, agent.optimizer_critic):
-            opt.param_groups[0]["lr"] = 0.0
-        step, B, bs, _ = agent._make_step(buf, minibatch=n)
-        la, lc = step(torch.arange(n, device="cuda"))
-        torch.cuda.synchronize()
-        assert (agent._fused is not None) == (mode == "fused")
-        losses[mode] = (float(la), float(lc))
-        grads[mode] = [p.grad.detach().float().clone() for net in (agent.actor, agent.critic) for p in net.parameters()]
-        names = [f"{nn}.{k}" for nn, net in (("actor", agent.actor), ("critic", agent.critic)) for k, _ in net.named_parameters()]
-    assert losses["fused"][0] == pytest.approx(losses["autograd"][0], rel=1e-3, abs=1e-4)
-    assert losses["fused"][1] == pytest.approx(losses["autograd"][1], rel=1e-3, abs=1e-4)
-    for name, a, b in zip(names, grads["fused"], grads["autograd"]):
-        assert a.shape == b.shape
-        err = float((a - b).norm()) / max(float(b.norm()), 1e-12)
-        assert err <= 3e-2, (name, err, float(b.norm()))
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for mode in ("fp32", "autograd", "fused"):
+            torch.manual_seed(0)
+            agent = P.PPO(device="cuda:0", autocast=mode != "fp32")
+            agent.fused_step = mode == "fused"
+            # (no clipping here: a sample whose ratio sits at the clip boundary contributes all or nothing, so a bf16-sized
+            # change of one logit moves the whole gradient by 1/B -- the clipped branch is covered by the update tests)
+            agent.clip_param = 1e9
+            for opt in (agent.optimizer_actor, agent.optimizer_critic):
+                opt.param_groups[0]["lr"] = 0.0
+            step, B, bs, _ = agent._make_step(buf, minibatch=n)
+            la, lc = step(torch.arange(n, device="cuda"))
+            torch.cuda.synchronize()
+            assert (agent._fused is not None) == (mode == "fused")
+            losses[mode] = (float(la), float(lc))
+            grads[mode] = [p.grad.detach().float().clone() for net in (agent.actor, agent.critic) for p in net.parameters()]
+            names = [f"{nn}.{k}" for nn, net in (("actor", agent.actor), ("critic", agent.critic)) for k, _ in net.named_parameters()]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    for k in (0, 1):
+        assert losses["fused"][k] == pytest.approx(losses["autograd"][k], rel=1e-3, abs=1e-4)
+        assert losses["fused"][k] == pytest.approx(losses["fp32"][k], rel=2e-2, abs=1e-3)
+    bad = {}
+    for name, ref, a, f in zip(names, grads["fp32"], grads["autograd"], grads["fused"]):
+        nr = max(float(ref.norm()), 1e-12)
+        ea, ef = float((a - ref).norm()) / nr, float((f - ref).norm()) / nr
+        print(f"{name:40s} |g| {nr:.3e}   bf16 autograd vs fp32 {ea:.4f}   fused vs fp32 {ef:.4f}")
+        if ef > 1.5 * ea + 1e-2:
+            bad[name] = (round(ea, 4), round(ef, 4))
+    assert not bad, bad
 
 
 def test_fused_step_is_bitwise_reproducible(golden):
