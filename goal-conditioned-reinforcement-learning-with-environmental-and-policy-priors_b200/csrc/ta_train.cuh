@@ -21,6 +21,7 @@ namespace ta {
 // y == nullptr: no mask and no dz (plain column sum of dy).  scratch: float [grid][C] followed by one uint32 counter (zero
 // before the first launch; the kernel leaves it zero).
 constexpr int RB_THREADS = 256;
+constexpr int RB_UNROLL = 4;   // rows in flight per thread
 __global__ void __launch_bounds__(RB_THREADS) relu_bwd_bias_kernel(const __nv_bfloat16 *__restrict__ dy, long long ld_dy,
                                                                    const __nv_bfloat16 *__restrict__ y, __nv_bfloat16 *__restrict__ dz,
                                                                    long long rows, int C, float *__restrict__ db, float *scratch) {
@@ -31,21 +32,34 @@ __global__ void __launch_bounds__(RB_THREADS) relu_bwd_bias_kernel(const __nv_bf
     const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * per_cta, r1 = r0 + per_cta < rows ? r0 + per_cta : rows;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long long r = r0 + rsub; r < r1; r += rpp) {
-        uint4 g = *reinterpret_cast<const uint4 *>(dy + r * ld_dy + col * 8);
-        if (y) {
-            const uint4 yv = *reinterpret_cast<const uint4 *>(y + r * (long long)C + col * 8);
-            auto mk = [](uint32_t gw, uint32_t yw) {  // y is a ReLU output (>= +0): non-zero bits <=> y > 0
-                return gw & (((yw & 0x7FFFu) ? 0xFFFFu : 0u) | ((yw & 0x7FFF0000u) ? 0xFFFF0000u : 0u));
-            };
-            g = make_uint4(mk(g.x, yv.x), mk(g.y, yv.y), mk(g.z, yv.z), mk(g.w, yv.w));
-            *reinterpret_cast<uint4 *>(dz + r * (long long)C + col * 8) = g;
-        }
-        const uint32_t w[4] = {g.x, g.y, g.z, g.w};
+    auto mk = [](uint32_t gw, uint32_t yw) {  // y is a ReLU output (>= +0): non-zero bits <=> y > 0
+        return gw & (((yw & 0x7FFFu) ? 0xFFFFu : 0u) | ((yw & 0x7FFF0000u) ? 0xFFFF0000u : 0u));
+    };
+    for (long long rb = r0 + rsub; rb < r1; rb += (long long)rpp * RB_UNROLL) {
+        uint4 g[RB_UNROLL], yv[RB_UNROLL];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            acc[2 * q] += __uint_as_float(w[q] << 16);
-            acc[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+        for (int u = 0; u < RB_UNROLL; u++) {  // all loads of the batch first: RB_UNROLL (x 2) 16-byte loads in flight per thread
+            const long long r = rb + (long long)u * rpp;
+            g[u] = make_uint4(0u, 0u, 0u, 0u);
+            yv[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (r < r1) {
+                g[u] = __ldg(reinterpret_cast<const uint4 *>(dy + r * ld_dy + col * 8));
+                if (y) yv[u] = __ldg(reinterpret_cast<const uint4 *>(y + r * (long long)C + col * 8));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB_UNROLL; u++) {
+            const long long r = rb + (long long)u * rpp;
+            if (y) {
+                g[u] = make_uint4(mk(g[u].x, yv[u].x), mk(g[u].y, yv[u].y), mk(g[u].z, yv[u].z), mk(g[u].w, yv[u].w));
+                if (r < r1) *reinterpret_cast<uint4 *>(dz + r * (long long)C + col * 8) = g[u];
+            }
+            const uint32_t w[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // fixed order: rows ascending within a thread
+                acc[2 * q] += __uint_as_float(w[q] << 16);
+                acc[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+            }
         }
     }
 #pragma unroll
@@ -67,10 +81,33 @@ __global__ void __launch_bounds__(RB_THREADS) relu_bwd_bias_kernel(const __nv_bf
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int c = tid; c < C; c += RB_THREADS) {  // partials in CTA index order, whoever arrives last
-        float s = 0.f;
-        for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(scratch + (long long)b * C + c);
-        db[c] = s;
+    // the last CTA to arrive sums the per-CTA partials in CTA index order (the result does not depend on which CTA that
+    // is): C / 4 threads cover a partial row as float4, the remaining thread dimension splits the CTA range into
+    // contiguous slices whose sums are then added slice 0 first
+    const int c4n = C >> 2, nsl = RB_THREADS / c4n > 0 ? RB_THREADS / c4n : 1;
+    float4 *red4 = reinterpret_cast<float4 *>(&red[0][0]);   // RB_THREADS float4 fit in red
+    for (int cbase = 0; cbase < c4n; cbase += RB_THREADS) {   // (C / 4 > 256 never happens for the supported C <= 1024; kept general)
+        const int c4 = cbase + (tid % (c4n < RB_THREADS ? c4n : RB_THREADS)), sl = c4n < RB_THREADS ? tid / c4n : 0;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < c4n && sl < nsl) {
+            const unsigned int per = (gridDim.x + nsl - 1) / nsl, b0 = sl * per, b1 = b0 + per < gridDim.x ? b0 + per : gridDim.x;
+#pragma unroll 8
+            for (unsigned int b = b0; b < b1; b++) {
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(scratch + (long long)b * C) + c4);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        }
+        red4[tid] = s;
+        __syncthreads();
+        if (c4 < c4n && sl == 0) {
+            float4 t = red4[tid];
+            for (int j = 1; j < nsl; j++) {
+                const float4 v = red4[j * c4n + (tid % c4n)];
+                t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+            }
+            reinterpret_cast<float4 *>(db)[c4] = t;
+        }
+        __syncthreads();
     }
     if (tid == 0) *counter = 0u;
 }

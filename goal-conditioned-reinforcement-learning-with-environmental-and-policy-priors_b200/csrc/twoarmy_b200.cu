@@ -896,21 +896,20 @@ int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, voi
 static_assert(sizeof(ta_tinet_prep_args) == sizeof(PrepArgs), "public and device struct must match");
 static_assert(sizeof(ta_tinet_grad_args) == sizeof(GradArgs), "public and device struct must match");
 
-int64_t ta_relu_bwd_bias_scratch_floats(int64_t rows, int C) {
-    long long g = (rows + 63) / 64;
-    if (g > 2 * 148) g = 2 * 148;
-    if (g < 1) g = 1;
-    return g * C + 1;
+static long long relu_bwd_grid(long long rows) {   // CTAs: 32 rows each at least, at most 4 per SM
+    long long g = (rows + 31) / 32;
+    if (g > 4 * 148) g = 4 * 148;
+    return g < 1 ? 1 : g;
 }
+int64_t ta_relu_bwd_bias_scratch_floats(int64_t rows, int C) { return relu_bwd_grid(rows) * C + 4; }
 
 int ta_relu_bwd_bias(const void *dy_bf16, int64_t ld_dy, const void *y_bf16, void *dz_bf16, int64_t rows, int C, float *db_out,
                      float *scratch, void *stream) {
     if (!dy_bf16 || !db_out || !scratch || rows <= 0 || C < 64 || C > 2048 || (C & 7) || (256 % (C >> 3)) || ld_dy < C || (ld_dy & 7))
         return TA_E_INVALID;
     if ((y_bf16 == nullptr) != (dz_bf16 == nullptr)) return TA_E_INVALID;
-    if (((uintptr_t)dy_bf16 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16) & 15u) return TA_E_INVALID;
-    long long g = (rows + 63) / 64;
-    if (g > 2 * 148) g = 2 * 148;
+    if (((uintptr_t)dy_bf16 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16 | (uintptr_t)db_out | (uintptr_t)scratch) & 15u) return TA_E_INVALID;
+    const long long g = relu_bwd_grid(rows);
     relu_bwd_bias_kernel<<<(unsigned)g, RB_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dy_bf16, ld_dy, (const __nv_bfloat16 *)y_bf16,
                                                                              (__nv_bfloat16 *)dz_bf16, rows, C, db_out, scratch);
     return launch_ok("relu_bwd_bias_kernel");
