@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
     L.ta_adv_stats.argtypes = [vp, i64, vp, vp]
     L.ta_adv_normalize.argtypes = [vp, i64, vp, vp]
     L.ta_relu_bwd_bias_scratch_floats.argtypes = [i64, i32]; L.ta_relu_bwd_bias_scratch_floats.restype = i64
+    L.ta_planes_relu_bwd_bias.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]
     L.ta_relu_bwd_bias.argtypes = [vp, i64, vp, vp, i64, i32, vp, vp, vp]
     L.ta_ppo_actor_loss.argtypes = [vp, vp, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp]
     L.ta_ppo_critic_loss.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]

@@ -22,9 +22,13 @@ namespace ta {
 // before the first launch; the kernel leaves it zero).
 constexpr int RB_THREADS = 256;
 constexpr int RB_UNROLL = 4;   // rows in flight per thread
+// PH > 0: dy is not a dense matrix but the merged parity planes of a stride-2 convolution's data gradient
+// (bf16 [B][(PH+1)/2][(PW+1)/2][4][C], ta_conv1.cuh): row r = pixel (b, h, w) of the [B][PH][PW][C] map reads plane block
+// (h & 1) * 2 + (w & 1) of position (h >> 1, w >> 1) -- planes_to_dense_relu_kernel's interleave, fused with the bias sum.
 __global__ void __launch_bounds__(RB_THREADS) relu_bwd_bias_kernel(const __nv_bfloat16 *__restrict__ dy, long long ld_dy,
                                                                    const __nv_bfloat16 *__restrict__ y, __nv_bfloat16 *__restrict__ dz,
-                                                                   long long rows, int C, float *__restrict__ db, float *scratch) {
+                                                                   long long rows, int C, float *__restrict__ db, float *scratch,
+                                                                   int PH, int PW) {
     __shared__ float red[RB_THREADS][8];
     __shared__ bool is_last;
     const int cg = C >> 3, tid = threadIdx.x;
@@ -43,7 +47,13 @@ __global__ void __launch_bounds__(RB_THREADS) relu_bwd_bias_kernel(const __nv_bf
             g[u] = make_uint4(0u, 0u, 0u, 0u);
             yv[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             if (r < r1) {
-                g[u] = __ldg(reinterpret_cast<const uint4 *>(dy + r * ld_dy + col * 8));
+                long long src = r * ld_dy;
+                if (PH > 0) {
+                    const long long bh = r / PW, b = bh / PH;
+                    const int w = (int)(r - bh * PW), h = (int)(bh - b * PH);
+                    src = (((b * ((PH + 1) / 2) + (h >> 1)) * ((PW + 1) / 2) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) * (long long)C;
+                }
+                g[u] = __ldg(reinterpret_cast<const uint4 *>(dy + src + col * 8));
                 if (y) yv[u] = __ldg(reinterpret_cast<const uint4 *>(y + r * (long long)C + col * 8));
             }
         }

@@ -911,8 +911,20 @@ int ta_relu_bwd_bias(const void *dy_bf16, int64_t ld_dy, const void *y_bf16, voi
     if (((uintptr_t)dy_bf16 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16 | (uintptr_t)db_out | (uintptr_t)scratch) & 15u) return TA_E_INVALID;
     const long long g = relu_bwd_grid(rows);
     relu_bwd_bias_kernel<<<(unsigned)g, RB_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dy_bf16, ld_dy, (const __nv_bfloat16 *)y_bf16,
-                                                                             (__nv_bfloat16 *)dz_bf16, rows, C, db_out, scratch);
+                                                                             (__nv_bfloat16 *)dz_bf16, rows, C, db_out, scratch, 0, 0);
     return launch_ok("relu_bwd_bias_kernel");
+}
+
+int ta_planes_relu_bwd_bias(const void *planes_bf16, const void *y_bf16, void *dz_bf16, int64_t batch, int H, int W, int C, float *db_out,
+                            float *scratch, void *stream) {
+    if (!planes_bf16 || !y_bf16 || !dz_bf16 || !db_out || !scratch || batch <= 0 || H < 2 || W < 2 || C < 64 || C > 2048 ||
+        (C & 7) || (256 % (C >> 3)))
+        return TA_E_INVALID;
+    if (((uintptr_t)planes_bf16 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16 | (uintptr_t)db_out | (uintptr_t)scratch) & 15u) return TA_E_INVALID;
+    const long long rows = batch * H * W, g = relu_bwd_grid(rows);
+    relu_bwd_bias_kernel<<<(unsigned)g, RB_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)planes_bf16, 0, (const __nv_bfloat16 *)y_bf16,
+                                                                             (__nv_bfloat16 *)dz_bf16, rows, C, db_out, scratch, H, W);
+    return launch_ok("relu_bwd_bias_kernel (planes)");
 }
 
 int ta_ppo_actor_loss(const void *logits_bf16, const int32_t *act, const float *old_logp, const float *adv, int B, float clip,

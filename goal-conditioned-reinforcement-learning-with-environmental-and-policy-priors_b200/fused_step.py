@@ -202,8 +202,9 @@ class FusedNet:
         dz2 = torch.empty((B, 16, 16, 64), dtype=bf, device=dev)
         y2n = y2.permute(0, 2, 3, 1)
         assert y2n.is_contiguous()
-        _capi.check(L.ta_planes_to_dense_relu(_ptr(p3), _ptr(y2n), _ptr(dz2), B, 16, 16, 64, 4, st), "ta_planes_to_dense_relu")
-        self._relu_bwd("c2", dz2, 64, None, B * 256, 64, "b2")
+        # planes -> dense interleave + conv2's ReLU mask + conv2's bias gradient in one pass
+        _capi.check(L.ta_planes_relu_bwd_bias(_ptr(p3), _ptr(y2n), _ptr(dz2), B, 16, 16, 64, _ptr(g32["b2"]),
+                                              _ptr(self._scr("c2", B * 256, 64)), st), "ta_planes_relu_bwd_bias")
         dz2v = dz2.permute(0, 3, 1, 2)
         gw2 = torch.ops.aten.convolution_backward(dz2v, y1v, p16["w2"], None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
                                                   [False, True, False])[1].contiguous(memory_format=torch.channels_last)

@@ -316,8 +316,12 @@ int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, voi
  * ta_ppo_critic_loss: v bf16 [B][8] (column 0) -> mean smooth_l1(v, target) (PPO.py:133), dv, db_head[1].
  * ta_adam_shadow: torch.optim.Adam's update (PPO.py:57-58: lr, eps = 1e-5, betas (0.9, 0.999), no weight decay) on flat
  *   float32 p / m / v of n elements from gradient g * grad_scale, at step t = step_counter[0]; also writes the bf16
- *   copy p_bf16 the forward / backward kernels read. */
+ *   copy p_bf16 the forward / backward kernels read.
+ * ta_planes_relu_bwd_bias: ta_relu_bwd_bias with dy given as merged parity planes bf16 [batch][(H+1)/2][(W+1)/2][4][C]
+ *   of the map [batch][H][W][C]: ta_planes_to_dense_relu and the bias gradient in one pass (rows = batch*H*W). */
 int64_t ta_relu_bwd_bias_scratch_floats(int64_t rows, int C);
+int ta_planes_relu_bwd_bias(const void *planes_bf16, const void *y_bf16, void *dz_bf16, int64_t batch, int H, int W, int C,
+                            float *db_out, float *scratch, void *stream);
 int ta_relu_bwd_bias(const void *dy_bf16, int64_t ld_dy, const void *y_bf16, void *dz_bf16, int64_t rows, int C,
                      float *db_out, float *scratch, void *stream);
 int ta_ppo_actor_loss(const void *logits_bf16, const int32_t *act, const float *old_logp, const float *adv, int B,

@@ -54,6 +54,27 @@ def test_relu_bwd_bias(rows, Cc, ld):
     assert float((db.double() - want).abs().max()) <= 1e-5 * max(1.0, float(dy.double().abs().sum(0).max()))
 
 
+@pytest.mark.parametrize("B,H,Cc", [(37, 16, 64), (5, 33, 64), (3, 7, 128)])
+def test_planes_relu_bwd_bias(B, H, Cc):
+    """ta_planes_relu_bwd_bias == ta_planes_to_dense_relu followed by the column sum: merged parity planes -> dense
+    gradient masked with the ReLU of the layer below (bit for bit) + its bias gradient."""
+    L, check = _lib()
+    g = torch.Generator(device="cuda").manual_seed(B * H)
+    PHn = (H + 1) // 2
+    planes = torch.randn((B, PHn, PHn, 4, Cc), generator=g, device="cuda").to(torch.bfloat16)
+    y = torch.relu(torch.randn((B, H, H, Cc), generator=g, device="cuda")).to(torch.bfloat16)
+    dz = torch.empty((B, H, H, Cc), dtype=torch.bfloat16, device="cuda")
+    db = torch.empty((Cc,), device="cuda")
+    scratch = torch.zeros(int(L.ta_relu_bwd_bias_scratch_floats(B * H * H, Cc)), device="cuda")
+    check(L.ta_planes_relu_bwd_bias(_p(planes), _p(y), _p(dz), B, H, H, Cc, _p(db), _p(scratch), _st()), "ta_planes_relu_bwd_bias")
+    hh = torch.arange(H, device="cuda")
+    dense = planes[:, hh[:, None] // 2, hh[None, :] // 2, (hh[:, None] % 2) * 2 + (hh[None, :] % 2)]      # [B,H,H,C]
+    want = torch.where(y > 0, dense, torch.zeros_like(dense))
+    assert torch.equal(dz, want)
+    ws = want.double().sum((0, 1, 2))
+    assert float((db.double() - ws).abs().max()) <= 1e-5 * max(1.0, float(want.double().abs().sum((0, 1, 2)).max()))
+
+
 @pytest.mark.parametrize("B", [4096, 300, 1])
 def test_ppo_actor_loss_and_gradient(B):
     """ta_ppo_actor_loss == the reference's lines (PPO.py:124-132: Categorical(probs=softmax(logits)).entropy / log_prob,
