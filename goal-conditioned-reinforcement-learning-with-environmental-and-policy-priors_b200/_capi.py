@@ -129,7 +129,7 @@ def lib() -> C.CDLL:
     L.ta_relu_bwd_bias.argtypes = [vp, i64, vp, vp, i64, i32, vp, vp, vp]
     L.ta_ppo_actor_loss.argtypes = [vp, vp, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp]
     L.ta_ppo_critic_loss.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
-    L.ta_adam_shadow.argtypes = [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp]
+    L.ta_adam_shadow.argtypes = [vp, vp, vp, vp, vp, i64, vp, f32, C.c_double, C.c_double, f32, f32, vp]
     L.ta_tinet_prep.argtypes = [vp, vp]
     L.ta_tinet_grad.argtypes = [vp, vp]
     L.ta_gather_minibatch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]

@@ -227,15 +227,17 @@ __global__ void __launch_bounds__(LOSS_THREADS) ppo_critic_loss_kernel(const __n
 // g is first scaled by grad_scale (1 / world size after the all-reduce SUM).
 __global__ void __launch_bounds__(256) adam_shadow_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                                           float *__restrict__ v, __nv_bfloat16 *__restrict__ p16, long long n,
-                                                          const float *__restrict__ step_counter, float lr, float b1, float b2, float eps,
+                                                          const float *__restrict__ step_counter, float lr, double beta1, double beta2, float eps,
                                                           float grad_scale) {
-    const float t = step_counter[0];
-    const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
-    const float step_size = lr / bc1, bc2s = sqrtf(bc2);
+    // the scalar factors in double, as torch.optim.Adam forms them on the host (1 - beta2 and 1 - beta2^t cancel badly in fp32)
+    const double t = (double)step_counter[0];
+    const double bc1 = 1.0 - pow(beta1, t), bc2 = 1.0 - pow(beta2, t);
+    const float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
+    const float b1 = (float)beta1, b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
-        const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
-        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        const float mi = m[i] + (gi - m[i]) * omb1;
+        const float vi = b2 * v[i] + omb2 * gi * gi;
         const float pi = p[i] - step_size * (mi / (sqrtf(vi) / bc2s + eps));
         m[i] = mi;
         v[i] = vi;

@@ -946,7 +946,7 @@ int ta_ppo_critic_loss(const void *v_bf16, const float *target, int B, void *dv_
 }
 
 int ta_adam_shadow(float *p, const float *g, float *m, float *v, void *p_bf16, int64_t n, const float *step_counter, float lr,
-                   float beta1, float beta2, float eps, float grad_scale, void *stream) {
+                   double beta1, double beta2, float eps, float grad_scale, void *stream) {
     if (!p || !g || !m || !v || !p_bf16 || !step_counter || n <= 0) return TA_E_INVALID;
     unsigned nb = blocks_for(n, 256 * 4);
     if (nb > 148u * 8u) nb = 148u * 8u;

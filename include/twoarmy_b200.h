@@ -330,7 +330,7 @@ int ta_ppo_actor_loss(const void *logits_bf16, const int32_t *act, const float *
 int ta_ppo_critic_loss(const void *v_bf16, const float *target, int B, void *dv_bf16, float *loss_out, float *db_head,
                        float *step_counter, void *stream);
 int ta_adam_shadow(float *p, const float *g, float *m, float *v, void *p_bf16, int64_t n, const float *step_counter,
-                   float lr, float beta1, float beta2, float eps, float grad_scale, void *stream);
+                   float lr, double beta1, double beta2, float eps, float grad_scale, void *stream);
 
 /* Per-step weight forms of one network derived from its master copy (device pointers; w1 strides in elements):
  * the folded first layer (all_net.py:142-143,157 -> [256][16] / [256], see ta_conv1_fwd), fc0 with its input features

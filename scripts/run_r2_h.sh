@@ -1,5 +1,2 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_fused_kernels.py -q -x 2>&1 | grep -vE "^\s*$" | tail -40
-timeout 900 python -m pytest tests/test_gpu_ppo.py -q 2>&1 | tail -5
-TWO=0 timeout 600 python scripts/prof_fused_timeline.py > gpurun_out/r2_fused_timeline_1stream.txt 2>&1; grep -E "replay:|activities" gpurun_out/r2_fused_timeline_1stream.txt
-timeout 600 python scripts/prof_fused_timeline.py 2>&1 | grep -E "replay:|activities"
+timeout 900 python -m pytest tests/test_gpu_fused_kernels.py -q -k adam 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_ppo.py -q -s -k "fused_step_gradients" 2>&1 | grep -E "^(actor|critic)\.|passed|failed|Error" | head -80
