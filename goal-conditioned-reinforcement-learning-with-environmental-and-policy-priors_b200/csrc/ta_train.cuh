@@ -317,9 +317,11 @@ struct GradArgs {
     float *g_head;
     int nh;
 };
+// (every group is optional -- dw4 / fc0p / pos16 / head8 == nullptr, n[k] == 0 -- so that the late layers' gradients can be
+// finalised, and their all-reduce started, before the convolution stem's backward has run)
 __global__ void __launch_bounds__(256) tinet_grad_kernel(const GradArgs a) {
-    const long long n_w1 = 64 * 4 * 4 * 4, n_b1 = 64, n_fc0 = 256ll * 2304, n_pos = 128 * 10;
-    const long long n_head = (long long)a.nh * 512;
+    const long long n_w1 = a.dw4 ? 64 * 4 * 4 * 4 : 0, n_b1 = a.dw4 ? 64 : 0, n_fc0 = a.fc0p ? 256ll * 2304 : 0, n_pos = a.pos16 ? 128 * 10 : 0;
+    const long long n_head = a.head8 ? (long long)a.nh * 512 : 0;
     const long long total = n_w1 + n_b1 + a.n[0] + a.n[1] + a.n[2] + a.n[3] + n_fc0 + n_pos + n_head;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long j = i;

@@ -965,9 +965,9 @@ int ta_tinet_prep(const ta_tinet_prep_args *args, void *stream) {
 }
 
 int ta_tinet_grad(const ta_tinet_grad_args *args, void *stream) {
-    if (!args || !args->dw4 || !args->db4 || !args->g_w1 || !args->g_b1 || !args->fc0p || !args->g_fc0 || !args->pos16 || !args->g_pos ||
-        !args->head8 || !args->g_head || args->nh < 1 || args->nh > 8)
-        return TA_E_INVALID;
+    if (!args || args->nh < 1 || args->nh > 8) return TA_E_INVALID;
+    if (args->dw4 && (!args->db4 || !args->g_w1 || !args->g_b1)) return TA_E_INVALID;
+    if ((args->fc0p && !args->g_fc0) || (args->pos16 && !args->g_pos) || (args->head8 && !args->g_head)) return TA_E_INVALID;
     for (int k = 0; k < 4; k++)
         if (args->n[k] < 0 || (args->n[k] > 0 && (!args->src[k] || !args->dst[k]))) return TA_E_INVALID;
     GradArgs a;

@@ -151,9 +151,31 @@ class FusedNet:
                                              _ptr(self._scr(key, rows, Cc)), self._st()), "ta_relu_bwd_bias")
         return dz
 
-    def forward_backward(self, sb, pg16, loss_fn):
+    def _finalise(self, conv1=False, dense=(), fc0=False, pos=False, head=False):
+        """ta_tinet_grad on a subset of the gradient groups."""
+        g32 = self.g32
+        a = _GradArgs()
+        if conv1:
+            a.dw4, a.db4 = self.dw4.data_ptr(), self.db4.data_ptr()
+            a.g_w1, a.g_b1 = g32["w1"].data_ptr(), g32["b1"].data_ptr()
+            a.s_o, a.s_c, a.s_y, a.s_x = g32["w1"].stride()
+        for k, (src, name) in enumerate(dense):
+            a.src[k], a.dst[k], a.n[k] = src.data_ptr(), g32[name].data_ptr(), g32[name].numel()
+        if fc0:
+            a.fc0p, a.g_fc0 = self.g_fc0p.data_ptr(), g32["wfc0"].data_ptr()
+        if pos:
+            a.pos16, a.g_pos = self.g_pos16.data_ptr(), g32["wpos"].data_ptr()
+        if head:
+            a.head8, a.g_head = self.g_head8.data_ptr(), g32["wh"].data_ptr()
+        a.nh = self.nh
+        _capi.check(self._L.ta_tinet_grad(C.byref(a), self._st()), "ta_tinet_grad")
+
+    def forward_backward(self, sb, pg16, loss_fn, reduce_fn=None):
         """sb uint8 [B,4,289] codes, pg16 bf16 [B,16]; loss_fn(head_out bf16 [B,8], d_out bf16 [B,8], db_head fp32 view)
-        launches the loss kernel.  Leaves every gradient in self.G32 and the mean loss in self.loss."""
+        launches the loss kernel.  Leaves every gradient in self.G32 and the mean loss in self.loss.
+        reduce_fn(flat_slice, last) is the gradient all-reduce hook: it is called with the late layers' slice of G32
+        (conv4 ... head: 91 % of the parameters) as soon as those gradients are final -- before the convolution stem's
+        backward, which it then overlaps -- and with the stem's slice (last=True) at the end."""
         L, st, dev = self._L, self._st(), self.device
         B = sb.shape[0]
         p16, g32 = self.p16, self.g32
@@ -191,6 +213,10 @@ class FusedNet:
         dy4 = dz5 @ self.fc0p                                                                         # [B,2304] = [B*9,256]
         dz4 = self._relu_bwd("c4", dy4, 256, y4, B * 9, 256, "b4c")
         torch.mm(dz4.t(), cols4, out=self.g_w4c)
+        # conv4 ... head: every gradient of the late layers is final -> flat buffer, all-reduce may start
+        self._finalise(dense=((self.g_w4c, "w4c"), (self.g_wfc1, "wfc1")), fc0=True, pos=True, head=True)
+        if reduce_fn is not None:
+            reduce_fn(self.G32[self.off[6]:], False)
         dcols = dz4 @ w4c                                                                             # [B*9,1152]
         dy3 = torch.empty((B, 7, 7, 128), dtype=bf, device=dev)
         _capi.check(L.ta_col2im_s2(_ptr(dcols), _ptr(dy3), B, 7, 7, 128, 3, st), "ta_col2im_s2")
@@ -211,21 +237,10 @@ class FusedNet:
         p2 = F.conv2d(dz2v, self.pcw2, padding=1).permute(0, 2, 3, 1).contiguous()
         _capi.check(L.ta_conv1_bwd_planes(_ptr(sb), 1, sb.stride(0), None, _ptr(mask), _ptr(p2), B, _ptr(self.dw4), _ptr(self.db4), st),
                     "ta_conv1_bwd_planes")
-        # ---------------- every weight gradient into the flat fp32 buffer
-        a = _GradArgs()
-        a.dw4, a.db4 = self.dw4.data_ptr(), self.db4.data_ptr()
-        a.g_w1, a.g_b1 = g32["w1"].data_ptr(), g32["b1"].data_ptr()
-        a.s_o, a.s_c, a.s_y, a.s_x = g32["w1"].stride()
-        srcs = (gw2, gw3, self.g_w4c, self.g_wfc1)
-        dsts = (g32["w2"], g32["w3"], g32["w4c"], g32["wfc1"])
-        for k in range(4):
-            a.src[k], a.dst[k], a.n[k] = srcs[k].data_ptr(), dsts[k].data_ptr(), dsts[k].numel()
-        a.fc0p, a.g_fc0 = self.g_fc0p.data_ptr(), g32["wfc0"].data_ptr()
-        a.pos16, a.g_pos = self.g_pos16.data_ptr(), g32["wpos"].data_ptr()
-        a.head8, a.g_head = self.g_head8.data_ptr(), g32["wh"].data_ptr()
-        a.nh = self.nh
-        _capi.check(L.ta_tinet_grad(C.byref(a), st), "ta_tinet_grad")
-        self._keep = (gw2, gw3)      # (their memory is read by the kernel just enqueued; the allocator is stream-ordered)
+        # ---------------- the stem's weight gradients into the flat fp32 buffer
+        self._finalise(conv1=True, dense=((gw2, "w2"), (gw3, "w3")))
+        if reduce_fn is not None:
+            reduce_fn(self.G32[:self.off[6]], True)
         return self.loss
 
     def adam(self, grad_scale: float = 1.0):

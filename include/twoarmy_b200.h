@@ -351,7 +351,9 @@ typedef struct {
 int ta_tinet_prep(const ta_tinet_prep_args *args, void *stream);
 
 /* The inverse for the gradients: folded conv1 gradients, the bf16 weight gradients the GEMMs / cuDNN leave (4 dense
- * segments), the permuted fc0 and padded positionnet / head gradients -> the flat float32 gradient buffer. */
+ * segments), the permuted fc0 and padded positionnet / head gradients -> the flat float32 gradient buffer.  Every group is
+ * optional (dw4 / fc0p / pos16 / head8 NULL, n[k] 0): the late layers are finalised first so that their all-reduce
+ * overlaps the convolution stem's backward. */
 typedef struct {
     const float *dw4, *db4;
     float *g_w1;
