@@ -370,7 +370,9 @@ class PPO:
         x = self._net_in(frames if frames.dtype == torch.uint8 else frames.float())
         with self._amp():
             a_prob = self.actor(x, positions.float(), goal.float())
-        dist = Categorical(probs=a_prob)
+        # (argument validation reads the probabilities back on the host every step: off on the GPU, where it would also
+        # make the rollout impossible to capture in a CUDA graph)
+        dist = Categorical(probs=a_prob, validate_args=None if a_prob.device.type != "cuda" else False)
         a = dist.sample()
         return a, dist.log_prob(a)
 
@@ -834,7 +836,10 @@ class VecRollout:
         self.reset_s, self.reset_p = s0[0, 1:5].clone(), p0[0, 1:5].clone()
         self.prev_s = self.prev_p = None
         self.prev_done = torch.ones(N, dtype=torch.uint8, device=dev)
+        self._done_buf = torch.zeros(N, dtype=torch.uint8, device=dev)   # persistent: the captured rollout graph reads / writes it
         self._out = {}
+        self.use_graph = os.environ.get("TA_ROLLOUT_GRAPH", "1") == "1"
+        self._graph = None
 
     def current_frames(self):
         """The policy's input: the four newest frames / positions of every env."""
@@ -849,7 +854,30 @@ class VecRollout:
         """T steps of the reference's inner loop (train_ppo.py:108-123) for every env: select
         action, env.step (no autoreset), featurise the post-step state into record t, then
         MiniGridEnv.reset for the envs whose episode ended (what the reference does at the top of
-        its next episode, train_ppo.py:104-105)."""
+        its next episode, train_ppo.py:104-105).
+
+        On a GPU the whole T-step loop is launch-bound from Python (~110 launches per step), so from the second call on
+        it is captured ONCE into a CUDA graph (every buffer it touches is persistent: the rollout buffer, the env
+        state, the previous record) and replayed: same kernels, same order, fresh random actions per replay (the
+        sampler's Philox offset advances with every replay)."""
+        buf = self.buffer
+        if self._graph is not None:
+            self._graph.replay()
+            buf.counter = self.T
+            return buf
+        if self.use_graph and self.prev_s is not None and type(self.agent) is PPO and self.env.device.type == "cuda":
+            dev = self.env.device
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._collect_eager()
+            self._graph = g
+            g.replay()
+            buf.counter = self.T
+            return buf
+        return self._collect_eager()
+
+    def _collect_eager(self):
         env, buf = self.env, self.buffer
         buf.counter = 0
         for t in range(self.T):
@@ -864,6 +892,7 @@ class VecRollout:
             buf.counter += 1
             self.ep_return += rew
             self.ep_return.masked_fill_(done.bool(), 0.0)
-            self.prev_s, self.prev_p, self.prev_done = buf.s[t], buf.p[t], done.clone()
+            self._done_buf.copy_(done)
+            self.prev_s, self.prev_p, self.prev_done = buf.s[t], buf.p[t], self._done_buf
             env.reset_masked(done)
         return buf

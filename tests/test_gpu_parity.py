@@ -380,7 +380,9 @@ def test_stack_roll_codes_equals_float_stack_roll(golden):
 def test_vec_rollout_records_follow_reference_loop():
     """VecRollout.collect == the reference loop (train_ppo.py:108-123) replayed on the oracle with
     the actions the policy sampled: rewards, done, and the 5-frame records (terminal frame kept,
-    new episode tiled)."""
+    new episode tiled) -- over FOUR consecutive collects: the first runs eagerly, the second captures the T-step loop
+    into a CUDA graph, the third and fourth replay it (the env state and the frame stack carry over between them,
+    and every replay must draw fresh actions)."""
     import importlib
     pkg, O = _pkg(), _oracle()
     P = importlib.import_module(pkg.__name__ + ".ppo")
@@ -389,27 +391,35 @@ def test_vec_rollout_records_follow_reference_loop():
     agent = P.PPO(device="cuda:0")
     env = pkg.TwoarmyVecEnv(6, n, 17, seed=5, autoreset=False)
     roll = P.VecRollout(env, agent, T)
-    buf = roll.collect()
     ora = O.OracleBatch(6, n, 17, seed=5)
     ora.reset()
     lut = np.array([0.9, -0.9, -0.5, 0.0, 0.3], np.float32)
     def feat():
-        m = ora.matrix().astype(np.float32)           # [n,289] float matrix_env
-        return m
+        return ora.matrix().astype(np.float32)           # [n,289] float matrix_env
     stack = np.repeat(feat()[:, None, :], 5, 1)
     amap = np.array([0, 1, 2, 3, 6], np.int32)
-    a = buf.a.cpu().numpy()
-    for t in range(T):
-        out = ora.step(amap[a[t]], None, autoreset=False)
-        stack = np.concatenate([stack[:, 1:], feat()[:, None, :]], 1)
-        np.testing.assert_array_equal(buf.r[t].cpu().numpy(), out["reward"])
-        np.testing.assert_array_equal(buf.d[t].cpu().numpy(), out["terminated"].astype(np.float32))
-        np.testing.assert_array_equal(lut[buf.s[t].cpu().numpy()], stack)
-        done = (out["terminated"] | out["truncated"]).astype(bool)
-        if done.any():
-            ora.reset(done.astype(np.uint8))
-            f = feat()
-            stack[done] = np.repeat(f[done][:, None, :], 5, 1)
+    actions = []
+    for it in range(4):
+        buf = roll.collect()
+        assert buf.counter == T and (roll._graph is not None) == (it >= 1)
+        a = buf.a.cpu().numpy()
+        actions.append(a.copy())
+        for t in range(T):
+            out = ora.step(amap[a[t]], None, autoreset=False)
+            stack = np.concatenate([stack[:, 1:], feat()[:, None, :]], 1)
+            np.testing.assert_array_equal(buf.r[t].cpu().numpy(), out["reward"], err_msg=f"collect {it} step {t}")
+            np.testing.assert_array_equal(buf.d[t].cpu().numpy(), out["terminated"].astype(np.float32))
+            np.testing.assert_array_equal(lut[buf.s[t].cpu().numpy()], stack, err_msg=f"collect {it} step {t}")
+            done = (out["terminated"] | out["truncated"]).astype(bool)
+            np.testing.assert_array_equal(buf.ended[t].cpu().numpy().astype(bool), done)
+            if done.any():
+                ora.reset(done.astype(np.uint8))
+                f = feat()
+                stack[done] = np.repeat(f[done][:, None, :], 5, 1)
+        lp = buf.a_logp.cpu().numpy()
+        assert np.isfinite(lp).all() and (lp <= 0).all()
+    assert not np.array_equal(actions[2], actions[3])        # replays sample anew
+    assert len({x.tobytes() for x in actions}) == 4
 
 
 @pytest.mark.parametrize("n", [300, 16, 65])
