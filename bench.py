@@ -18,7 +18,7 @@ of exactly K kernel nodes (no eager launch inside the timed region).
 
 extra.ppo (BASELINE.json configs[3]): 16384 envs GLOBAL x 128-step horizon, the reference's
 K_epochs = 10, 4096-sample minibatches per rank, GAE/advantages on the GPU, NCCL gradient all-reduce
-when N > 1; one cheap warm-up iteration, one timed iteration.
+when N > 1; two cheap warm-up iterations (K_epochs = 1), one timed iteration.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every key.
 """
@@ -199,7 +199,7 @@ def reference_arm_ppo(args):
 # PPO rollout+update loop (BASELINE configs[3]; configs[4] with --ppo-predictor)
 # ---------------------------------------------------------------------------------------------
 def ppo_measure(args, rank, world, dev, dist, clock_index=None):
-    """One cheap warm-up iteration (K_epochs = 1) and `--ppo-steps` timed iterations of
+    """Two cheap warm-up iterations (K_epochs = 1) and `--ppo-steps` timed iterations of
     VecRollout.collect + PPO.update.  Returns the extra.ppo object on rank 0 (None elsewhere)."""
     import importlib
     import torch
@@ -227,6 +227,7 @@ def ppo_measure(args, rank, world, dev, dist, clock_index=None):
         return agent.update(buf.flat(), minibatch=args.ppo_minibatch, epochs=epochs)
 
     one_step(1)   # warm-up: allocator, cuDNN / cuBLAS plans, NCCL channels
+    one_step(1)   # second warm-up: VecRollout captures its T-step loop into a CUDA graph on its second collect
     barrier()
     sampler = ClockSampler(clock_index) if (rank == 0 and clock_index is not None) else None
     if sampler:

@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "ta_conv1.cuh"
 
 namespace ta {
@@ -84,6 +86,55 @@ __device__ __forceinline__ float tc_value(XT v) {
     else return (float)v;
 }
 
+// The tile's 128 + 18 input positions (4 frames each) as raw values: slot tid and, for tid < TC_HALO, slot 128 + tid.
+// Loaded one tile AHEAD into registers (the loads of tile k+1 are issued as soon as tile k's values have been decoded and
+// complete under tile k's MMA / epilogue): ncu showed 40 % of the forward kernel's stall samples on these four small loads.
+template <typename XT>
+struct TcRaw {   // uint8 codes: the 4 frames of a position packed in one register; float frames: 4 registers (scalars, not an
+    typename std::conditional<sizeof(XT) == 1, uint32_t, float4>::type a, b;   // array: ptxas must keep them in registers)
+};
+template <typename XT>
+__device__ __forceinline__ auto tc_load_slot(const XT *__restrict__ x, long long xstride, long long npos, long long tile, int slot) {
+    const long long Q = tile * TC_M + slot;
+    const bool in = slot < TC_M + TC_HALO && Q < npos;
+    const long long qb = in ? Q / NCELL : 0;
+    const XT *xq = x + qb * xstride + (in ? (int)(Q - qb * NCELL) : 0);
+    if constexpr (sizeof(XT) == 1) {
+        uint32_t w = 0;
+        if (in) w = (uint32_t)xq[0] | ((uint32_t)xq[NCELL] << 8) | ((uint32_t)xq[2 * NCELL] << 16) | ((uint32_t)xq[3 * NCELL] << 24);
+        return w;
+    } else {
+        return in ? make_float4(xq[0], xq[NCELL], xq[2 * NCELL], xq[3 * NCELL]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <typename XT>
+__device__ __forceinline__ void tc_load_raw(const XT *__restrict__ x, long long xstride, long long npos, long long tile, int tid, TcRaw<XT> &raw) {
+    raw.a = tc_load_slot<XT>(x, xstride, npos, tile, tid);
+    raw.b = tc_load_slot<XT>(x, xstride, npos, tile, tid + TC_M);
+}
+template <typename XT, typename RT>
+__device__ __forceinline__ void tc_decode_slot(const RT &r, long long npos, long long tile, int slot, uint4 *sDec) {
+    if (slot < TC_M + TC_HALO) {
+        uint32_t hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
+        if (tile * TC_M + slot < npos) {
+            float f0, f1, f2, f3;
+            if constexpr (sizeof(XT) == 1) {
+                f0 = c1_decode(r & 0xFFu); f1 = c1_decode((r >> 8) & 0xFFu); f2 = c1_decode((r >> 16) & 0xFFu); f3 = c1_decode(r >> 24);
+            } else {
+                f0 = r.x; f1 = r.y; f2 = r.z; f3 = r.w;
+            }
+            tc_split(f0, f1, hi0, lo0);
+            tc_split(f2, f3, hi1, lo1);
+        }
+        sDec[slot] = make_uint4(hi0, hi1, lo0, lo1);
+    }
+}
+template <typename XT>
+__device__ __forceinline__ void tc_decode_raw(const TcRaw<XT> &raw, long long npos, long long tile, int tid, uint4 *sDec) {
+    tc_decode_slot<XT>(raw.a, npos, tile, tid, sDec);
+    tc_decode_slot<XT>(raw.b, npos, tile, tid + TC_M, sDec);
+}
+
 // MK: also write the layer's ReLU mask as bits (relu_mask uint32 [position][4 phases][2 halves of 32 channels]; in a
 // word, bit q = channel 2q of the half is non-zero, bit 16 + q = channel 2q + 1), 8 bytes per output pixel: what the
 // weight-gradient kernel reads instead of the 128 bytes of y.
@@ -129,6 +180,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
     const long long npos = B * NCELL, ntiles = (npos + TC_M - 1) / TC_M;
     uint32_t parity = 0;
     bool dead = false;
+    TcRaw<XT> raw;
+    if ((long long)blockIdx.x < ntiles) tc_load_raw<XT>(x, xstride, npos, blockIdx.x, tid, raw);
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long P = tile * TC_M + tid;
@@ -137,22 +190,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
         const int pos = valid ? (int)(P - b * NCELL) : 0, m = pos / GS, n = pos - GS * m;
         // ---- A tile, k = (dy*2+dx)*4 + c -------------------------------------------------------------------
         // stage 1: positions tile*128 .. +127+18 -> decoded (hi, lo) bf16 of the 4 frames, 16 bytes per position
-        // (each input cell feeds up to four rows of the tile, so it is loaded and decoded once)
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-            const int slot = tid + rep * TC_M;
-            if (slot < TC_M + TC_HALO) {
-                const long long Q = tile * TC_M + slot;
-                uint32_t hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
-                if (Q < npos) {
-                    const long long qb = Q / NCELL;
-                    const XT *xq = x + qb * xstride + (int)(Q - qb * NCELL);
-                    tc_split(tc_value<XT>(xq[0]), tc_value<XT>(xq[NCELL]), hi0, lo0);
-                    tc_split(tc_value<XT>(xq[2 * NCELL]), tc_value<XT>(xq[3 * NCELL]), hi1, lo1);
-                }
-                sDec[slot] = make_uint4(hi0, hi1, lo0, lo1);
-            }
-        }
+        // (each input cell feeds up to four rows of the tile, so it is loaded and decoded once); the raw values were
+        // loaded during the previous tile, the next tile's loads are issued now
+        tc_decode_raw<XT>(raw, npos, tile, tid, sDec);
+        if (tile + gridDim.x < ntiles) tc_load_raw<XT>(x, xstride, npos, tile + gridDim.x, tid, raw);
         __syncthreads();
         // stage 2: row r = the 2x2 patch at positions r, r+1, r+17, r+18 (zero past the right / bottom edge)
         {
@@ -326,24 +367,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
     uint32_t parity = 0;
     bool dead = false, any = false;
     const int g8 = tid & 7, psub = tid >> 3;
+    TcRaw<XT> raw;
+    if ((long long)blockIdx.x < ntiles) tc_load_raw<XT>(x, xstride, npos, blockIdx.x, tid, raw);
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- B tile: decoded inputs (as in the forward kernel), then the 2x2 patch of every position ----------
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-            const int slot = tid + rep * TC_M;
-            if (slot < TC_M + TC_HALO) {
-                const long long Q = tile * TC_M + slot;
-                uint32_t hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
-                if (Q < npos) {
-                    const long long qb = Q / NCELL;
-                    const XT *xq = x + qb * xstride + (int)(Q - qb * NCELL);
-                    tc_split(tc_value<XT>(xq[0]), tc_value<XT>(xq[NCELL]), hi0, lo0);
-                    tc_split(tc_value<XT>(xq[2 * NCELL]), tc_value<XT>(xq[3 * NCELL]), hi1, lo1);
-                }
-                sDec[slot] = make_uint4(hi0, hi1, lo0, lo1);
-            }
-        }
+        // ---- B tile: decoded inputs (as in the forward kernel, raw values loaded one tile ahead), then the 2x2 patch
+        tc_decode_raw<XT>(raw, npos, tile, tid, sDec);
+        if (tile + gridDim.x < ntiles) tc_load_raw<XT>(x, xstride, npos, tile + gridDim.x, tid, raw);
         const long long P = tile * TC_M + tid;
         const bool valid = P < npos;
         const long long b = valid ? P / NCELL : 0;
@@ -412,15 +442,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
                     const int p = (it0 + u) * 16 + psub;
 #pragma unroll
                     for (int px = 0; px < 2; px++) {
-                        uint4 yy;
-                        if constexpr (MK) {  // mask bits -> a "non-zero" pattern per bf16 half
+                        uint4 dzv;
+                        if constexpr (MK) {  // mask bits -> all-ones per selected bf16 half: (bit | bit << 16) * 0xFFFF
                             // words 4*(g8&3) .. +3 of the half: bit q = even channel, bit 16+q = odd channel of word q
                             const uint32_t mb = mbv[u][px] >> (4 * (g8 & 3));
-                            yy = make_uint4(mb & 0x00010001u, (mb >> 1) & 0x00010001u, (mb >> 2) & 0x00010001u, (mb >> 3) & 0x00010001u);
+                            const uint4 g = gv[u][px];
+                            dzv = make_uint4(g.x & ((mb & 0x00010001u) * 0xFFFFu), g.y & (((mb >> 1) & 0x00010001u) * 0xFFFFu),
+                                             g.z & (((mb >> 2) & 0x00010001u) * 0xFFFFu), g.w & (((mb >> 3) & 0x00010001u) * 0xFFFFu));
                         } else {
-                            yy = yv[u][px];
+                            dzv = tcb_mask(gv[u][px], yv[u][px]);
                         }
-                        *reinterpret_cast<uint4 *>(sG + (px * 8 + g8) * TCB_SBO + (p >> 3) * 128 + (p & 7) * 16 + nudge) = tcb_mask(gv[u][px], yy);
+                        *reinterpret_cast<uint4 *>(sG + (px * 8 + g8) * TCB_SBO + (p >> 3) * 128 + (p & 7) * 16 + nudge) = dzv;
                     }
                 }
             }

@@ -213,20 +213,44 @@ __global__ void __launch_bounds__(FEAT_THREADS) stack_push_codes_tile_kernel(con
     if (!init_all) {
         const uint8_t *in = s_prev + e0 * STACK_ELEMS;
         const long long in_bytes = (n - e0) * STACK_ELEMS;  // bytes of s_prev from `in` to its end
-        for (int q0 = threadIdx.x * 16; q0 < total; q0 += FEAT_THREADS * 16) {
+        // every load of the CTA's slice is issued before the first shared-memory store (the kernel is bound by the
+        // latency of these loads: ncu showed 38 % of all stall samples on the first use of `a`); the 17th byte of a
+        // chunk is the first byte of the next lane's chunk -- one shuffle instead of a second load per chunk
+        constexpr int NIT = (FEAT_ENVS * STACK_ELEMS + FEAT_THREADS * 16 - 1) / (FEAT_THREADS * 16);   // 6
+        uint4 av[NIT];
+        uint32_t lastv[NIT];
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int q0 = (it * FEAT_THREADS + threadIdx.x) * 16;
+            av[it] = make_uint4(0u, 0u, 0u, 0u);
+            lastv[it] = 0u;
+            const bool full = q0 < total && (long long)q0 + NCELL + 16 <= in_bytes;
+            if (full) av[it] = __ldg(reinterpret_cast<const uint4 *>(in + q0 + NCELL - 1));
+            if (full && lane == 31) lastv[it] = in[q0 + NCELL + 15];
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int q0 = (it * FEAT_THREADS + threadIdx.x) * 16;
+            const bool full = q0 < total && (long long)q0 + NCELL + 16 <= in_bytes;
+            // the next lane's first loaded byte (its chunk starts 16 bytes further on); a lane whose neighbour did not take
+            // the fast path re-reads the byte itself
+            const uint32_t nb = __shfl_down_sync(0xFFFFFFFFu, av[it].x, 1) & 0xFFu;
+            const bool nfull = __shfl_down_sync(0xFFFFFFFFu, (int)full, 1) != 0;
             uint4 o;
-            if ((long long)q0 + NCELL + 16 <= in_bytes) {
-                const uint4 a = *reinterpret_cast<const uint4 *>(in + q0 + NCELL - 1);
-                const uint32_t last = in[q0 + NCELL + 15];
+            if (full) {
+                uint32_t last = lane == 31 ? lastv[it] : nb;
+                if (lane != 31 && !nfull) last = in[q0 + NCELL + 15];
+                const uint4 a = av[it];
                 o = make_uint4(__funnelshift_r(a.x, a.y, 8), __funnelshift_r(a.y, a.z, 8), __funnelshift_r(a.z, a.w, 8),
                                (a.w >> 8) | (last << 24));
-            } else {  // the last chunks of the last env: stay inside the array
+            } else if (q0 < total) {  // the last chunks of the last env: stay inside the array
                 uint32_t w[4] = {0, 0, 0, 0};
                 for (int k = 0; k < 16; k++)
                     if ((long long)q0 + NCELL + k < in_bytes) w[k >> 2] |= (uint32_t)in[q0 + NCELL + k] << (8 * (k & 3));
                 o = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            if (q0 + 16 <= FEAT_ENVS * STACK_ELEMS) *reinterpret_cast<uint4 *>(tile + q0) = o;
+            if (q0 < total && q0 + 16 <= FEAT_ENVS * STACK_ELEMS) *reinterpret_cast<uint4 *>(tile + q0) = o;
         }
     }
     __syncthreads();
