@@ -210,7 +210,7 @@ class _Stem(torch.autograd.Function):
         p2 = _class_planes(dz2, w2)
         dw4 = torch.empty((256, 16), dtype=torch.float32, device=x.device)
         db4 = torch.empty((256,), dtype=torch.float32, device=x.device)
-        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), None, _ptr(mask), _ptr(p2),
+        _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), 1 if x.dtype == torch.uint8 else 0, x.stride(0), None, _ptr(mask), _ptr(p2), 0,
                                             x.shape[0], _ptr(dw4), _ptr(db4), st), "ta_conv1_bwd_planes")
         return None, dw4, db4, gw2, gb2, gw3, gb3
 

@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
                                                                  const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ planes,
                                                                  const uint32_t *__restrict__ relu_mask, long long B,
                                                                  float *__restrict__ dw4, float *__restrict__ db4,
-                                                                 uint32_t zero, int *fail) {
+                                                                 uint32_t zero, int *fail, long long pl_pos_stride, long long pl_cls_stride) {
+    // planes addressing (elements): block c of position P at P * pl_pos_stride + c * pl_cls_stride -- position-major
+    // [P][4][64] (256, 64: cuDNN's merged planes) or class-major [4][P][64] (64, npos * 64: conv2_dgrad_planes_ws_kernel)
     extern __shared__ __align__(128) uint8_t tcb_smem[];
     uint8_t *sG = tcb_smem;                               // A: TCB_A_BYTES
     uint8_t *sP = tcb_smem + TCB_A_BYTES;                 // B hi, B lo: 2 x TCB_B_BYTES
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
                         const bool ok = inf >= 0 && !(h && (inf & 2)) && !(px && (inf & 1));
                         const long long e = ok ? ((inf >> 2) + h * C1_OUT + px) * C1_CH + g8 * 8 : 0ll;
                         if constexpr (PL) {
-                            const long long eg = ok ? ((long long)Pq * 4 + (h * 2 + px)) * C1_CH + g8 * 8 : 0ll;
+                            const long long eg = ok ? (long long)Pq * pl_pos_stride + (h * 2 + px) * pl_cls_stride + g8 * 8 : 0ll;
                             gv[u][px] = tcb_ldg(planes + eg);
                         } else {
                             gv[u][px] = tcb_ldg(dy + e);

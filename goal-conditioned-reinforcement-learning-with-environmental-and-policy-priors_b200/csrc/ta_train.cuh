@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) adam_shadow_kernel(float *__restrict__ p,
     const double t = (double)step_counter[0];
     const double bc1 = 1.0 - pow(beta1, t), bc2 = 1.0 - pow(beta2, t);
     const float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
-    const float b1 = (float)beta1, b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
+    const float b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = m[i] + (gi - m[i]) * omb1;

@@ -11,6 +11,7 @@
 #include "ta_aux.cuh"
 #include "ta_conv1.cuh"
 #include "ta_conv1_tc.cuh"
+#include "ta_dgrad_tc.cuh"
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
 #include "ta_her.cuh"
@@ -746,7 +747,7 @@ int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4
 
 // the tcgen05 weight-gradient kernel; planes == nullptr: dy is one channels-last tensor; relu_mask (with planes): y is not read
 int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, const void *planes,
-                        const void *relu_mask, int64_t batch, float *dw4, float *db4, void *stream) {
+                        const void *relu_mask, int64_t batch, float *dw4, float *db4, void *stream, int class_major = 0) {
     static int per_sm[6] = {0, 0, 0, 0, 0, 0}, sms = 0;
     const int dyn = TCB_A_BYTES + 2 * TCB_B_BYTES;
     if (!sms) {
@@ -775,7 +776,8 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
     const __nv_bfloat16 *yb = (const __nv_bfloat16 *)y_bf16, *dyb = (const __nv_bfloat16 *)dy_bf16;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t *mk = (const uint32_t *)relu_mask;
-#define TA_BWD_ARGS(XT) (const XT *)x, x_stride, yb, dyb, pl, mk, batch, dw4, db4, 0u, g_tc_fail
+    const long long pl_pos = class_major ? 64 : 256, pl_cls = class_major ? batch * NCELL * 64 : 64;
+#define TA_BWD_ARGS(XT) (const XT *)x, x_stride, yb, dyb, pl, mk, batch, dw4, db4, 0u, g_tc_fail, pl_pos, pl_cls
     switch (variant) {
         case 0: conv1_bwd_tc_kernel<uint8_t, false, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(uint8_t)); break;
         case 1: conv1_bwd_tc_kernel<float, false, false><<<g, TC_THREADS, dyn, st>>>(TA_BWD_ARGS(float)); break;
@@ -792,14 +794,14 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
 extern "C" {
 
 int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const uint32_t *relu_mask,
-                        const void *planes_bf16, int64_t batch, float *dw4, float *db4, void *stream) {
+                        const void *planes_bf16, int class_major, int64_t batch, float *dw4, float *db4, void *stream) {
     if (!x || (!y_bf16 && !relu_mask) || !planes_bf16 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL ||
         (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
     if (((uintptr_t)y_bf16 | (uintptr_t)planes_bf16) & 15u) return TA_E_INVALID;
     CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), (cudaStream_t)stream));
     CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), (cudaStream_t)stream));
-    return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, nullptr, planes_bf16, relu_mask, batch, dw4, db4, stream);
+    return launch_conv1_bwd_tc(x, x_dtype, x_stride, y_bf16, nullptr, planes_bf16, relu_mask, batch, dw4, db4, stream, class_major != 0);
 }
 
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, int64_t batch,
@@ -824,6 +826,71 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
             (const float *)x, x_stride, (const __nv_bfloat16 *)y_bf16, (const __nv_bfloat16 *)dy_bf16, batch, dw4, db4);
     }
     return launch_ok("conv1_bwd_kernel");
+}
+
+/* development probe (not part of the ABI): device buffer of 8 int64 that CTA 0 of conv2_dgrad_planes_ws_kernel fills with the
+ * cycles its roles spend waiting (ta_dgrad_tc.cuh); NULL switches it off */
+static long long *g_dgrad_prof = nullptr;
+int ta_debug_dgrad_profile(long long *prof8) {
+    g_dgrad_prof = prof8;
+    return TA_OK;
+}
+
+int ta_conv2_dgrad_prep(const void *w_bf16, int64_t stride_o, int64_t stride_i, int64_t stride_y, int64_t stride_x, void *wimg_bf16,
+                        void *stream) {
+    if (!w_bf16 || !wimg_bf16 || ((uintptr_t)wimg_bf16 & 15u)) return TA_E_INVALID;
+    conv2_dgrad_prep_kernel<<<36, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)w_bf16, stride_o, stride_i, stride_y, stride_x,
+                                                                 (__nv_bfloat16 *)wimg_bf16);
+    return launch_ok("conv2_dgrad_prep_kernel");
+}
+
+int ta_conv2_dgrad_planes(const void *dz_bf16, const void *wimg_bf16, const uint32_t *relu_mask, int64_t batch, int class_major,
+                          void *planes_bf16, void *stream) {
+    if (!dz_bf16 || !wimg_bf16 || !planes_bf16 || batch <= 0 || batch * (DG_P * DG_P) >= (1ll << 31)) return TA_E_INVALID;
+    if (((uintptr_t)dz_bf16 | (uintptr_t)wimg_bf16 | (uintptr_t)planes_bf16) & 15u) return TA_E_INVALID;
+    static int sms = 0;
+    const int ws = class_major != 0;   // class-major output: the warp-specialised kernel; position-major: the single-role one
+    if (!sms) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaFuncSetAttribute(conv2_dgrad_planes_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+        CK(cudaFuncSetAttribute(conv2_dgrad_planes_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DGW_SMEM));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (!g_tc_fail) {
+        CK(cudaMalloc(&g_tc_fail, sizeof(int)));
+        CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
+    }
+    const long long ntiles = (batch * (DG_P * DG_P) + TC_M - 1) / TC_M;
+    const int g = (int)(ntiles < sms ? ntiles : sms);   // one persistent CTA per SM (208 / 216 KB of shared memory each)
+    if (ws) {
+        // the class-major planes [4][npos][64] as a rank-3 tensor; the kernel stores boxes of 32 positions x 64 channels of one
+        // class from 128-byte-swizzled shared memory
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static encode_fn encode = nullptr;
+        if (!encode) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+            if (!fn || qr != cudaDriverEntryPointSuccess) return cuda_fail(cudaErrorNotSupported, "cuTensorMapEncodeTiled is not available in this driver");
+            encode = (encode_fn)fn;
+        }
+        const cuuint64_t npos = (cuuint64_t)batch * (DG_P * DG_P);
+        const cuuint64_t dims[3] = {64, npos, 4}, strides[2] = {128, npos * 128};
+        const cuuint32_t box[3] = {64, 32, 1}, estr[3] = {1, 1, 1};
+        CUtensorMap map;
+        const CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, planes_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (class-major planes)");
+        conv2_dgrad_planes_ws_kernel<<<g, DGW_THREADS, DGW_SMEM, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dz_bf16, (const uint4 *)wimg_bf16,
+                                                                                       relu_mask, batch, map, g_tc_fail, g_dgrad_prof);
+        return launch_ok("conv2_dgrad_planes_ws_kernel");
+    }
+    conv2_dgrad_planes_tc_kernel<<<g, DG_THREADS, DG_SMEM, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dz_bf16, (const uint4 *)wimg_bf16, relu_mask,
+                                                                                  batch, (__nv_bfloat16 *)planes_bf16, g_tc_fail);
+    return launch_ok("conv2_dgrad_planes_tc_kernel");
 }
 
 int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream) {

@@ -99,6 +99,9 @@ class FusedNet:
         self.dw4 = torch.empty((256, 16), dtype=torch.float32, device=dev)
         self.db4 = torch.empty((256,), dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.wimg2 = torch.empty(9 * 64 * 64, dtype=torch.bfloat16, device=dev)    # conv2 taps as the dgrad kernel's B operands
+        import os
+        self.tc_dgrad = os.environ.get("TA_CONV2_DGRAD_TC", "1") == "1"            # 0: cuDNN's merged-plane convolution
         self._scratch = {}
         self._L = _capi.lib()
         self.refresh()
@@ -140,7 +143,12 @@ class FusedNet:
         a.head8, a.head_b8 = self.head8.data_ptr(), self.head_b8.data_ptr()
         a.nh = self.nh
         _capi.check(L.ta_tinet_prep(C.byref(a), st), "ta_tinet_prep")
-        self.pcw2 = _c1.parity_class_weights(self.p16["w2"])
+        # conv2's data gradient runs on the tcgen05 per-class kernel (its operand image); conv3's as cuDNN's merged-plane convolution
+        w2 = self.p16["w2"]
+        _capi.check(L.ta_conv2_dgrad_prep(_ptr(w2), w2.stride(0), w2.stride(1), w2.stride(2), w2.stride(3), _ptr(self.wimg2), st),
+                    "ta_conv2_dgrad_prep")
+        if not self.tc_dgrad:
+            self.pcw2 = _c1.parity_class_weights(self.p16["w2"])
         self.pcw3 = _c1.parity_class_weights(self.p16["w3"])
 
     # ------------------------------------------------------------------ one step
@@ -234,9 +242,15 @@ class FusedNet:
         dz2v = dz2.permute(0, 3, 1, 2)
         gw2 = torch.ops.aten.convolution_backward(dz2v, y1v, p16["w2"], None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
                                                   [False, True, False])[1].contiguous(memory_format=torch.channels_last)
-        p2 = F.conv2d(dz2v, self.pcw2, padding=1).permute(0, 2, 3, 1).contiguous()
-        _capi.check(L.ta_conv1_bwd_planes(_ptr(sb), 1, sb.stride(0), None, _ptr(mask), _ptr(p2), B, _ptr(self.dw4), _ptr(self.db4), st),
-                    "ta_conv1_bwd_planes")
+        if self.tc_dgrad:   # per-class tap lists on tcgen05 (warp-specialised), conv1's ReLU mask applied in the epilogue; class-major planes
+            p2 = torch.empty((4, B * 289, 64), dtype=bf, device=dev)
+            # (conv1's ReLU mask is applied by ta_conv1_bwd_planes, where it costs one multiply per word; in this kernel's
+            # epilogue it quintuples the instructions per converted pair, and the epilogue warps are its critical path)
+            _capi.check(L.ta_conv2_dgrad_planes(_ptr(dz2), _ptr(self.wimg2), None, B, 1, _ptr(p2), st), "ta_conv2_dgrad_planes")
+        else:
+            p2 = F.conv2d(dz2v, self.pcw2, padding=1).permute(0, 2, 3, 1).contiguous()
+        _capi.check(L.ta_conv1_bwd_planes(_ptr(sb), 1, sb.stride(0), None, _ptr(mask), _ptr(p2), 1 if self.tc_dgrad else 0, B,
+                                          _ptr(self.dw4), _ptr(self.db4), st), "ta_conv1_bwd_planes")
         # ---------------- the stem's weight gradients into the flat fp32 buffer
         self._finalise(conv1=True, dense=((gw2, "w2"), (gw3, "w3")))
         if reduce_fn is not None:

@@ -284,13 +284,29 @@ int ta_parity_class_weights(const void *w_bf16, int64_t stride_o, int64_t stride
 int ta_planes_to_dense_relu(const void *planes_bf16, const void *y_bf16, void *dz_bf16, int64_t batch, int H, int W,
                             int C, int ksize, void *stream);
 int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const uint32_t *relu_mask,
-                        const void *planes_bf16, int64_t batch, float *dw4, float *db4, void *stream);
+                        const void *planes_bf16, int class_major, int64_t batch, float *dw4, float *db4, void *stream);
 /* ta_conv1_fwd that also writes the layer's ReLU mask as bits: relu_mask uint32 [batch*289 positions][4 phases][2
  * halves of 32 channels]; in a word, bit q / bit 16+q = channel 2q / 2q+1 of the half of output pixel (2m+py, 2n+px)
  * is non-zero.  Given to ta_conv1_bwd_planes (y_bf16 may then be NULL) the weight gradient reads 8 bytes per pixel
  * instead of the 128 bytes of y. */
 int ta_conv1_fwd_mask(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch,
                       void *y_bf16, uint32_t *relu_mask, void *stream);
+
+/* Data gradient of TINet's second convolution (Conv2d(64, 64, 3, stride 2), all_net.py:144-145) as merged parity planes
+ * on the tensor cores (tcgen05), every parity class with its own tap list (9 tap products per position instead of the 16
+ * of the merged stride-1 convolution):
+ *   ta_conv2_dgrad_prep    w bf16 [64][64][3][3] with the given element strides -> wimg, the 73728-byte operand image
+ *                          (once per optimiser step)
+ *   ta_conv2_dgrad_planes  dz bf16 [batch][16][16][64] (channels-last) -> planes bf16; class_major = 1: [4][batch*289][64]
+ *                          (the warp-specialised kernel: cp.async producer warp, MMA warp, four epilogue warps writing 4 KB
+ *                          TMA bulk stores), class_major = 0: [batch][17][17][4][64] like the cuDNN merged-plane convolution
+ *                          (single-role kernel).  relu_mask (nullable): the first layer's ReLU bit mask (ta_conv1_fwd_mask)
+ *                          applied in the epilogue, so the planes are already d loss / d (conv1 pre-activation).
+ * ta_conv1_bwd_planes takes either layout (its class_major argument). */
+int ta_conv2_dgrad_prep(const void *w_bf16, int64_t stride_o, int64_t stride_i, int64_t stride_y, int64_t stride_x,
+                        void *wimg_bf16, void *stream);
+int ta_conv2_dgrad_planes(const void *dz_bf16, const void *wimg_bf16, const uint32_t *relu_mask, int64_t batch,
+                          int class_major, void *planes_bf16, void *stream);
 
 /* Data gradient helper for TINet's stride-2 unpadded convolutions (all_net.py:144-149) in channels-last
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].

@@ -72,10 +72,10 @@ for _ in range(20): L.ta_conv1_fwd_mask(vp(x), 1, x.stride(0), vp(w4), vp(b4), B
 e1.record(); torch.cuda.synchronize()
 print(f"ta_conv1_fwd_mask B={B}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call")
 for name, yarg, marg in (("y", vp(y), None), ("bit mask", None, vp(mask))):
-    for _ in range(3): L.ta_conv1_bwd_planes(vp(x), 1, x.stride(0), yarg, marg, vp(planes), B, vp(dw4), vp(db4), st)
+    for _ in range(3): L.ta_conv1_bwd_planes(vp(x), 1, x.stride(0), yarg, marg, vp(planes), 0, B, vp(dw4), vp(db4), st)
     res = dw4.clone()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(20): L.ta_conv1_bwd_planes(vp(x), 1, x.stride(0), yarg, marg, vp(planes), B, vp(dw4), vp(db4), st)
+    for _ in range(20): L.ta_conv1_bwd_planes(vp(x), 1, x.stride(0), yarg, marg, vp(planes), 0, B, vp(dw4), vp(db4), st)
     e1.record(); torch.cuda.synchronize()
     print(f"ta_conv1_bwd_planes ({name}) B={B}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call; |dw4| = {float(res.abs().sum()):.1f}")

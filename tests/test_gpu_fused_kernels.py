@@ -75,6 +75,56 @@ def test_planes_relu_bwd_bias(B, H, Cc):
     assert float((db.double() - ws).abs().max()) <= 1e-5 * max(1.0, float(want.double().abs().sum((0, 1, 2)).max()))
 
 
+@pytest.mark.parametrize("B", [1, 7, 300, 1500])
+@pytest.mark.parametrize("with_mask", [False, True])
+@pytest.mark.parametrize("class_major", [1, 0])
+def test_conv2_dgrad_planes_tcgen05(B, with_mask, class_major):
+    """ta_conv2_dgrad_planes (tcgen05, per-class tap lists; class_major = 1 the warp-specialised kernel with bulk stores,
+    0 the single-role kernel) == conv_transpose2d(dz, w, stride 2) regrouped into merged
+    parity planes [B][17][17][4][64], evaluated in float64 from the same bf16 inputs: every entry within bf16 rounding of
+    the exact value (2^-8 relative + 1e-3 of the tensor's scale for the fp32 accumulation of 256 products); entries whose
+    pixel does not exist (row / column 33) are zero; with the first layer's ReLU bit mask the masked entries are zero.
+    B = 1500 gives every persistent CTA several tiles (double-buffered cp.async staging, TMEM reuse)."""
+    import torch.nn.functional as F
+    L, check = _lib()
+    g = torch.Generator(device="cuda").manual_seed(B)
+    w = (torch.randn((64, 64, 3, 3), generator=g, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dz = torch.randn((B, 16, 16, 64), generator=g, device="cuda").to(torch.bfloat16)
+    wimg = torch.empty(9 * 64 * 64, dtype=torch.bfloat16, device="cuda")
+    check(L.ta_conv2_dgrad_prep(_p(w), w.stride(0), w.stride(1), w.stride(2), w.stride(3), _p(wimg), _st()), "ta_conv2_dgrad_prep")
+    mask = None
+    if with_mask:
+        mask = torch.randint(0, 2 ** 31 - 1, (B * 289 * 8,), generator=g, device="cuda", dtype=torch.int32)
+        mask = mask ^ (torch.randint(0, 2, (B * 289 * 8,), generator=g, device="cuda", dtype=torch.int32) << 31)
+    planes = torch.full((B, 17, 17, 4, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    guard = torch.zeros(4096, dtype=torch.bfloat16, device="cuda")      # allocated right behind: a write past the end would show
+    check(L.ta_conv2_dgrad_planes(_p(dz), _p(wimg), _p(mask), B, class_major, _p(planes), _st()), "ta_conv2_dgrad_planes")
+    torch.cuda.synchronize()
+    assert float(guard.float().abs().max()) == 0.0
+    if class_major:      # [4][B*289][64] (the warp-specialised kernel) -> the position-major view the checks below use
+        planes = planes.view(4, B, 17, 17, 64).permute(1, 2, 3, 0, 4).contiguous()
+    assert L.ta_debug_conv1_tc_failed() == 0
+    dx = F.conv_transpose2d(dz.permute(0, 3, 1, 2).double(), w.double(), stride=2)          # [B,64,33,33]
+    want = torch.zeros((B, 17, 17, 4, 64), dtype=torch.float64, device="cuda")
+    for c in range(4):
+        pa, pb = c >> 1, c & 1
+        sub = dx[:, :, pa::2, pb::2].permute(0, 2, 3, 1)
+        want[:, :sub.shape[1], :sub.shape[2], c] = sub
+    if with_mask:
+        mb = mask.view(B, 17, 17, 4, 2).to(torch.int64) & 0xFFFFFFFF
+        q = torch.arange(16, device="cuda")
+        even = ((mb[..., None] >> q) & 1).bool()                                             # [.., 2, 16]: channel half*32 + 2q
+        odd = ((mb[..., None] >> (16 + q)) & 1).bool()
+        keep = torch.stack([even, odd], -1).reshape(B, 17, 17, 4, 64)
+        want = want * keep
+    got = planes.double()
+    assert bool(torch.isfinite(got).all())
+    scale = float(want.abs().max())
+    err = (got - want).abs()
+    assert bool((err <= want.abs() * 2.0 ** -8 + 1e-3 * scale).all()), float((err - want.abs() * 2.0 ** -8).max() / scale)
+    assert float(got[:, 16, :, 2:].abs().max()) == 0.0 and float(got[:, :, 16, 1::2].abs().max()) == 0.0      # pixels of row / column 33
+
+
 @pytest.mark.parametrize("B", [4096, 300, 1])
 def test_ppo_actor_loss_and_gradient(B):
     """ta_ppo_actor_loss == the reference's lines (PPO.py:124-132: Categorical(probs=softmax(logits)).entropy / log_prob,
