@@ -280,6 +280,8 @@ def ppo_measure(args, rank, world, dev, dist, clock_index=None):
     out.update(probe)
     if getattr(agent, "last_replay_stats", None):
         out["graph_replayed_optimizer_steps"] = agent.last_replay_stats   # CUDA events around the replays of the last update()
+    if getattr(agent, "last_update_phases", None):
+        out["update_phases_ms"] = agent.last_update_phases   # TA_PPO_TIMING=1 only (synchronising marks: a diagnosis run, not a bench value)
     out["fused_step"] = bool(getattr(agent, "_fused", None))
     return out
 

@@ -689,8 +689,22 @@ class PPO:
         (s [B,5,289] float or uint8 codes, p [B,5,2], a [B,1], g [B,2], r [B,1], a_logp [B,1]) or
         a numpy structured array like Buffer_gridworld.buffer."""
         dev = self.device
+        timing = os.environ.get("TA_PPO_TIMING", "0") == "1" and dev.type == "cuda"   # measurement aid: synchronising wall-clock marks
+
+        def mark(name, _t=[None]):
+            if timing:
+                import time
+                torch.cuda.synchronize(dev)
+                now = time.perf_counter()
+                if _t[0] is not None:
+                    self.last_update_phases[name] = self.last_update_phases.get(name, 0.0) + (now - _t[0]) * 1e3
+                _t[0] = now
+
+        self.last_update_phases = {}
+        mark("start")
         step, B, bs, src = self._make_step(buffer, minibatch, group)
         n_steps = self._common_steps(B, bs, group)
+        mark("prepare_ms")
 
         def minibatches():
             # PPO.py:122: BatchSampler(SubsetRandomSampler(range(len(buffer))), batch_size, drop_last=False).
@@ -730,9 +744,11 @@ class PPO:
                     # step once (capture records, it does not execute) and replay it from here on
                     idx_static = idx.clone()
                     torch.cuda.synchronize(dev)
+                    mark("eager_steps_ms")
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         loss_static = step(idx_static)
+                    mark("capture_ms")
                 if graph is not None and full:
                     if ev_first is None:
                         ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -742,11 +758,13 @@ class PPO:
                     n_replayed += 1
                     self._last = loss_static
                 elif want_graph and full:
+                    mark("sampler_ms")
                     side.wait_stream(torch.cuda.current_stream(dev))
                     with torch.cuda.stream(side):   # warm-up steps run on a side stream, as capture will
                         self._last = step(idx)
                     torch.cuda.current_stream(dev).wait_stream(side)
                     eager_full += 1
+                    mark("eager_step%d_ms" % eager_full)
                 else:
                     self._last = step(idx)
                 self.update_count += 1
@@ -757,7 +775,9 @@ class PPO:
             if ev_first is not None:   # device time of the graph-replayed optimiser steps alone (bench.py reports it)
                 self.last_replay_stats = {"steps": n_replayed, "ms_per_step": ev_first.elapsed_time(ev_last) / max(1, n_replayed)}
             self._last = tuple(x.clone() for x in self._last)
+            mark("replay_ms")
             del graph
+            mark("graph_free_ms")
         self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)
         if dev.type == "cuda":
             # the tcgen05 kernels bound their MMA-barrier waits and raise a flag instead of hanging: fail loudly here
