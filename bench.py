@@ -340,6 +340,8 @@ def main():
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION and up) on stdout: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     if args.workload == "ppo":
