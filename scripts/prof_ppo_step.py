@@ -1,5 +1,5 @@
-"""One PPO optimiser step (minibatch 4096, both nets, eager launches) for an ncu launch list: after two
-warm-up steps the third runs between cudaProfilerStart/Stop (ncu --profile-from-start off)."""
+"""ONE PPO optimiser step (minibatch 4096, both nets, the fused hand-scheduled step, eager launches) for an ncu launch list:
+after three warm-up steps the fourth runs between cudaProfilerStart/Stop (ncu --profile-from-start off)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,11 +15,13 @@ buf = {"s": torch.randint(0, 3, (B, 5, 289), generator=g, device=dev, dtype=torc
        "p": torch.randint(1, 16, (B, 5, 2), generator=g, device=dev).float(),
        "a": torch.randint(0, 5, (B, 1), generator=g, device=dev), "g": torch.tensor([[2.0, 14.0]], device=dev).repeat(B, 1),
        "r": torch.rand(B, 1, generator=g, device=dev) - 0.5, "a_logp": torch.log(torch.rand(B, 1, generator=g, device=dev) * 0.3 + 0.1)}
-for _ in range(2):
-    agent.update(buf, minibatch=mb, epochs=1)
+step, Bn, bs, _ = agent._make_step(buf, minibatch=mb)   # (the critic passes / advantages of update() stay outside the capture)
+idx = torch.randperm(B, device=dev)[:mb].contiguous()
+for _ in range(3):
+    step(idx)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-agent.update(buf, minibatch=mb, epochs=1)
+step(idx)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("done")
