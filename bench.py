@@ -618,9 +618,12 @@ def main():
                      "timing": "CUDA events on the launching stream around ONE replay of a CUDA graph of exactly K step launches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": e2e_d2h,
                 "steps": args.e2e_steps, "host_threads": int(os.environ.get("TA_HOST_THREADS", 0)) or max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", "1"))),
-                "call": "TwoarmyVecEnv.step_host -> ta_step_host: H2D actions from pinned memory, fused kernel, D2H of the packed "
-                        "observations (2-bit cell codes) + status bytes in 8 pieces, expanded by host threads into the caller's "
-                        "uint8 [n,V,V,3] / float32 / uint8 arrays; synchronous per step"},
+                "call": ("TwoarmyVecEnv.step_host -> ta_step_host: H2D actions from pinned memory, fused kernel, D2H of the packed "
+                         "observations (2-bit cell codes) + status bytes in 8 pieces, expanded by host threads into the caller's "
+                         "uint8 [n,V,V,3] / float32 / uint8 arrays; synchronous per step") if e2e_d2h < n * 3 * V * V else
+                        ("TwoarmyVecEnv.step_host -> ta_step_host: H2D actions from pinned memory, fused kernel, expanded observations "
+                         "copied by the DMA engine into the pinned array (the library's own choice: at most 4 host threads for this "
+                         "rank) + status bytes; synchronous per step")},
         "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -48,10 +48,11 @@ __global__ void __launch_bounds__(RB_THREADS) relu_bwd_bias_kernel(const __nv_bf
             yv[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             if (r < r1) {
                 long long src = r * ld_dy;
-                if (PH > 0) {
-                    const long long bh = r / PW, b = bh / PH;
-                    const int w = (int)(r - bh * PW), h = (int)(bh - b * PH);
-                    src = (((b * ((PH + 1) / 2) + (h >> 1)) * ((PW + 1) / 2) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) * (long long)C;
+                if (PH > 0) {   // (rows < 2^32, checked by the host: 32-bit divisions -- the 64-bit ones cost more than the row's loads)
+                    const unsigned bh = (unsigned)r / (unsigned)PW, b = bh / (unsigned)PH;
+                    const unsigned w = (unsigned)r - bh * (unsigned)PW, h = bh - b * (unsigned)PH;
+                    src = (long long)(((b * (unsigned)((PH + 1) / 2) + (h >> 1)) * (unsigned)((PW + 1) / 2) + (w >> 1)) * 4u + ((h & 1u) * 2u + (w & 1u))) *
+                          (long long)C;
                 }
                 g[u] = __ldg(reinterpret_cast<const uint4 *>(dy + src + col * 8));
                 if (y) yv[u] = __ldg(reinterpret_cast<const uint4 *>(y + r * (long long)C + col * 8));

@@ -77,6 +77,7 @@ struct ta_batch {
     ta_host::Pool *pool = nullptr;
     ta_host::Job job;
     long long last_d2h_bytes = 0;
+    int auto_dma = -1;               // -1 undecided, 0 host threads expand the packed form, 1 DMA of the expanded form
     // timing
     int timing = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -371,6 +372,18 @@ int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, 
     ta_host::Job &job = h->job;
     job.status = h_status; job.reward = reward_out; job.term = term_out; job.trunc = trunc_out;
     job.n = h->n; job.ntiles = ntiles; job.runs = runs; job.obs_bytes = obs_bytes; job.obs = obs_out;
+    // Few host threads for this rank (many ranks sharing a small host) and a pinned destination: the DMA engine alone
+    // (~54 GB/s of expanded observations) beats the threads' expansion (~11 GB/s each); TA_STEP_HOST_AUTO=0 disables the choice
+    if (!(flags & TA_STEP_HOST_DMA) && h->auto_dma < 0) {
+        const char *e = getenv("TA_STEP_HOST_AUTO");
+        h->auto_dma = 0;
+        if (!(e && atoi(e) == 0) && ta_host::default_threads() <= 4) {
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, obs_out) == cudaSuccess && pa.type == cudaMemoryTypeHost) h->auto_dma = 1;
+            (void)cudaGetLastError();
+        }
+    }
+    if (h->auto_dma > 0) flags |= TA_STEP_HOST_DMA;
     if (flags & TA_STEP_HOST_DMA) {
         // the expanded observations straight over PCIe into the caller's array (pinned: one DMA); the status bytes
         // (reward index, terminated, truncated) through the staging buffer, decoded here
@@ -989,6 +1002,7 @@ int ta_planes_relu_bwd_bias(const void *planes_bf16, const void *y_bf16, void *d
         return TA_E_INVALID;
     if (((uintptr_t)planes_bf16 | (uintptr_t)y_bf16 | (uintptr_t)dz_bf16 | (uintptr_t)db_out | (uintptr_t)scratch) & 15u) return TA_E_INVALID;
     const long long rows = batch * H * W, g = relu_bwd_grid(rows);
+    if (rows * 4 >= (1ll << 32)) return TA_E_INVALID;   // the kernel's plane addressing divides in 32 bits
     relu_bwd_bias_kernel<<<(unsigned)g, RB_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)planes_bf16, 0, (const __nv_bfloat16 *)y_bf16,
                                                                              (__nv_bfloat16 *)dz_bf16, rows, C, db_out, scratch, H, W);
     return launch_ok("relu_bwd_bias_kernel (planes)");

@@ -327,6 +327,13 @@ class PPO:
         # shadow + own Adam): built on the first update() of a plain PPO agent on a GPU under bf16 autocast
         self.fused_step = os.environ.get("TA_PPO_FUSED_STEP", "1") == "1"
         self._fused = None
+        # the captured optimiser-step graph is kept across update() calls while it stays valid (same buffer storage, sizes
+        # and hyper-parameters): the small per-update tensors it reads are persistent copies (TA_PPO_KEEP_GRAPH=0: re-capture
+        # in every update, as before)
+        self.keep_graph = os.environ.get("TA_PPO_KEEP_GRAPH", "1") == "1"
+        self._static = None
+        self._graph_cache = None
+        self._step_key = None
         self.last_action_loss = float("nan")
         self.last_value_loss = float("nan")
 
@@ -613,6 +620,21 @@ class PPO:
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(group)
+        self._step_key = None
+        if self.keep_graph and self.use_graph and src is None:
+            # everything the step reads besides the (large, caller-owned) frame codes `s` moves into persistent tensors, so
+            # that a graph captured over them can be replayed by later update() calls on the same rollout buffer
+            small = {"p": p, "g": g, "a": a, "old_a_logp": old_a_logp, "adv": adv, "target_v": target_v}
+            sig = tuple((k, tuple(t.shape), t.dtype) for k, t in small.items())
+            if self._static is None or self._static["sig"] != sig:
+                self._static = {"sig": sig, "t": {k: torch.empty_like(t, memory_format=torch.contiguous_format) for k, t in small.items()}}
+                self._graph_cache = None
+            for k, t in small.items():
+                self._static["t"][k].copy_(t)
+            st_t = self._static["t"]
+            p, g, a, old_a_logp, adv, target_v = (st_t[k] for k in ("p", "g", "a", "old_a_logp", "adv", "target_v"))
+            self._step_key = (sig, s.data_ptr(), tuple(s.shape), tuple(s.stride()), world, id(group), fa.lr, fc.lr, clip, ent,
+                              id(fa), id(fc), fa.tc_dgrad, None if streams is None else tuple(id(x) for x in streams))
 
         def step(idx):
             bs = idx.numel()
@@ -731,6 +753,11 @@ class PPO:
         # (with several ranks the gradient all-reduce is captured too: every rank replays the same graph)
         want_graph = dev.type == "cuda" and self.use_graph and (world == 1 or self.graph_with_nccl) and bool(self._flat)
         graph, idx_static, loss_static, eager_full = None, None, None, 0
+        key = (self._step_key, bs) if (want_graph and self._step_key is not None) else None
+        if key is not None and self._graph_cache is not None and self._graph_cache["key"] == key:
+            graph, idx_static, loss_static = (self._graph_cache[k] for k in ("graph", "idx", "loss"))
+        elif self._graph_cache is not None:
+            self._graph_cache = None     # (frees the stale graph and its memory pool)
         ev_first = ev_last = None
         n_replayed = 0
         side = torch.cuda.Stream(device=dev) if want_graph else None
@@ -776,6 +803,8 @@ class PPO:
                 self.last_replay_stats = {"steps": n_replayed, "ms_per_step": ev_first.elapsed_time(ev_last) / max(1, n_replayed)}
             self._last = tuple(x.clone() for x in self._last)
             mark("replay_ms")
+            if key is not None:
+                self._graph_cache = {"key": key, "graph": graph, "idx": idx_static, "loss": loss_static}
             del graph
             mark("graph_free_ms")
         self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)

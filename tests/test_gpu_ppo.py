@@ -460,3 +460,41 @@ def test_predictor_agent_rollout_and_update_on_gpu():
     assert float((got - want).abs().max()) < 0.05 * max(1.0, float(want.abs().max()))
     idx, e = M.pre_transition_records(buf.ended[:16])
     assert idx.shape[1] == 9 and idx.shape[0] == e.shape[0]
+
+
+def test_step_graph_kept_across_updates_equals_recapture():
+    """The optimiser-step graph captured by the first update() is replayed by later ones on the same rollout buffer
+    (PPO.keep_graph); the small per-update tensors it reads (advantages, targets, positions ...) are persistent copies that
+    every update() refreshes.  Three updates, rewards and frames rewritten in place in between, against re-capturing in
+    every update.  At this size two runs of the SAME mode already differ in most parameter bits (conv1's float atomics and
+    cuDNN's split-K weight gradients accumulate in a run-dependent order, Adam amplifies round-off on near-zero gradients;
+    measured <= 1e-3 absolute after three updates, scripts/probe_keep_graph.py), so the comparison is by the losses of every
+    update (a stale advantage / target tensor would reproduce the previous update's losses instead) and a parameter bound."""
+    P = _ppo()
+    dev = torch.device("cuda:0")
+    B, mb = 2048, 512
+    outs, losses, reused = [], [], []
+    for keep in (True, False):
+        torch.manual_seed(0)
+        agent = P.PPO(device=dev)
+        agent.K_epochs, agent.keep_graph = 2, keep
+        g = torch.Generator(device=dev).manual_seed(1)
+        buf = {"s": torch.randint(0, 3, (B, 5, 289), generator=g, device=dev, dtype=torch.uint8),
+               "p": torch.randint(1, 16, (B, 5, 2), generator=g, device=dev).float(),
+               "a": torch.randint(0, 5, (B, 1), generator=g, device=dev), "g": torch.tensor([[2.0, 14.0]], device=dev).repeat(B, 1),
+               "r": torch.rand(B, 1, generator=g, device=dev) - 0.5, "a_logp": torch.log(torch.rand(B, 1, generator=g, device=dev) * 0.3 + 0.1)}
+        n, ls = 0, []
+        for it in range(3):
+            torch.manual_seed(10 + it)
+            ls.append(agent.update(buf, minibatch=mb))
+            n += int(agent._graph_cache is not None)
+            buf["r"].copy_((torch.rand(B, 1, generator=g, device=dev) - 0.5) * (it + 2))      # same storage, new values
+            buf["s"][:, :, ::7] = (buf["s"][:, :, ::7] + 1) % 3
+        reused.append(n)
+        losses.append(np.array(ls))
+        outs.append(torch.cat([_flat_params(agent.actor), _flat_params(agent.critic)]))
+    assert reused == [3, 0]
+    np.testing.assert_allclose(losses[0], losses[1], rtol=3e-2, atol=2e-3)
+    # the updates are not interchangeable: the value loss follows the rescaled rewards (what a stale target would miss)
+    assert losses[1][2, 1] > 1.5 * losses[1][0, 1]
+    assert float((outs[0] - outs[1]).abs().max()) < 5e-3
