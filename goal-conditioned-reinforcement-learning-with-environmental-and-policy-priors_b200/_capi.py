@@ -117,6 +117,7 @@ def lib() -> C.CDLL:
     L.ta_conv1_fwd_mask.argtypes = [vp, i32, i64, vp, vp, i64, vp, vp, vp]
     L.ta_conv2_dgrad_prep.argtypes = [vp, i64, i64, i64, i64, vp, vp]
     L.ta_conv2_dgrad_planes.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    L.ta_conv2_dgrad_conv1_bwd.argtypes = [vp, vp, vp, vp, i32, i64, i64, vp, vp, vp]
     L.ta_col2im_s2.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp]
     L.ta_im2col_s2.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp]
     L.ta_render.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]

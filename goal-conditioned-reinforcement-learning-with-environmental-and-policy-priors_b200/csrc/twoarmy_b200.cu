@@ -16,6 +16,7 @@
 #include "ta_gae.cuh"
 #include "ta_her.cuh"
 #include "ta_host.cuh"
+#include "ta_stem_bwd_tc.cuh"
 #include "ta_step.cuh"
 #include "ta_train.cuh"
 
@@ -841,8 +842,8 @@ int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf1
     return launch_ok("conv1_bwd_kernel");
 }
 
-/* development probe (not part of the ABI): device buffer of 8 int64 that CTA 0 of conv2_dgrad_planes_ws_kernel fills with the
- * cycles its roles spend waiting (ta_dgrad_tc.cuh); NULL switches it off */
+/* development probe (not part of the ABI): device buffer of 16 int64 that CTA 0 of conv2_dgrad_planes_ws_kernel (8 values) /
+ * conv2_dgrad_conv1_wgrad_kernel (10 values) fills with the cycles its roles spend waiting; NULL switches it off */
 static long long *g_dgrad_prof = nullptr;
 int ta_debug_dgrad_profile(long long *prof8) {
     g_dgrad_prof = prof8;
@@ -904,6 +905,38 @@ int ta_conv2_dgrad_planes(const void *dz_bf16, const void *wimg_bf16, const uint
     conv2_dgrad_planes_tc_kernel<<<g, DG_THREADS, DG_SMEM, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dz_bf16, (const uint4 *)wimg_bf16, relu_mask,
                                                                                   batch, (__nv_bfloat16 *)planes_bf16, g_tc_fail);
     return launch_ok("conv2_dgrad_planes_tc_kernel");
+}
+
+int ta_conv2_dgrad_conv1_bwd(const void *dz_bf16, const void *wimg_bf16, const uint32_t *relu_mask, const void *x, int x_dtype,
+                             int64_t x_stride, int64_t batch, float *dw4, float *db4, void *stream) {
+    if (!dz_bf16 || !wimg_bf16 || !relu_mask || !x || !dw4 || !db4 || batch <= 0 || batch * (DG_P * DG_P) >= (1ll << 31) ||
+        x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
+        return TA_E_INVALID;
+    if ((((uintptr_t)dz_bf16 | (uintptr_t)wimg_bf16 | (uintptr_t)relu_mask) & 15u)) return TA_E_INVALID;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaFuncSetAttribute(conv2_dgrad_conv1_wgrad_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+        CK(cudaFuncSetAttribute(conv2_dgrad_conv1_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (!g_tc_fail) {
+        CK(cudaMalloc(&g_tc_fail, sizeof(int)));
+        CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), st));
+    CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), st));
+    const long long ntiles = (batch * (DG_P * DG_P) + TC_M - 1) / TC_M;
+    const int g = (int)(ntiles < sms ? ntiles : sms);   // one persistent CTA per SM (221 KB of shared memory, all 512 TMEM columns)
+    if (x_dtype == TA_X_U8)
+        conv2_dgrad_conv1_wgrad_kernel<uint8_t><<<g, SB_THREADS, SB_SMEM, st>>>((const __nv_bfloat16 *)dz_bf16, (const uint4 *)wimg_bf16, relu_mask,
+                                                                               (const uint8_t *)x, x_stride, batch, dw4, db4, g_tc_fail, g_dgrad_prof);
+    else
+        conv2_dgrad_conv1_wgrad_kernel<float><<<g, SB_THREADS, SB_SMEM, st>>>((const __nv_bfloat16 *)dz_bf16, (const uint4 *)wimg_bf16, relu_mask,
+                                                                             (const float *)x, x_stride, batch, dw4, db4, g_tc_fail, g_dgrad_prof);
+    return launch_ok("conv2_dgrad_conv1_wgrad_kernel");
 }
 
 int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream) {

@@ -310,6 +310,14 @@ int ta_conv2_dgrad_prep(const void *w_bf16, int64_t stride_o, int64_t stride_i, 
 int ta_conv2_dgrad_planes(const void *dz_bf16, const void *wimg_bf16, const uint32_t *relu_mask, int64_t batch,
                           int class_major, void *planes_bf16, void *stream);
 
+/* ta_conv2_dgrad_planes followed by ta_conv1_bwd_planes in ONE kernel (csrc/ta_stem_bwd_tc.cuh): the gradient of the first
+ * layer's output goes from the tensor core's accumulators through shared memory into the weight-gradient GEMM and is never
+ * written to memory.  dz_bf16 [batch][16][16][64] = the (ReLU-masked) gradient of the second convolution's output, wimg_bf16
+ * from ta_conv2_dgrad_prep, relu_mask from ta_conv1_fwd_mask, x / x_dtype / x_stride as in ta_conv1_bwd;
+ * dw4 float [256][16], db4 float [256] are overwritten (all_net.py:142-145 backward). */
+int ta_conv2_dgrad_conv1_bwd(const void *dz_bf16, const void *wimg_bf16, const uint32_t *relu_mask, const void *x, int x_dtype,
+                             int64_t x_stride, int64_t batch, float *dw4, float *db4, void *stream);
+
 /* Data gradient helper for TINet's stride-2 unpadded convolutions (all_net.py:144-149) in channels-last
  * bf16: dcols [batch*OH*OW][k*k*C] (= dY x W from a plain GEMM, columns (ky,kx,c)) -> dx [batch][H][W][C].
  * k in {3, 4}, C a multiple of 8, OH = (H-k)/2+1. */

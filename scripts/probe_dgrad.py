@@ -14,7 +14,7 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 pkg._capi.check(L.ta_conv2_dgrad_prep(vp(w), w.stride(0), w.stride(1), w.stride(2), w.stride(3), vp(wimg), st))
 planes = torch.empty((4, B * 289, 64), dtype=torch.bfloat16, device="cuda")
 mask = torch.randint(0, 2 ** 31 - 1, (B * 289 * 8,), generator=g, device="cuda", dtype=torch.int32)
-prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+prof = torch.zeros(16, dtype=torch.int64, device="cuda")
 for use_mask in (False, True):
     for cm in (1, 0):
         L.ta_debug_dgrad_profile(vp(prof) if cm else None)
@@ -31,3 +31,27 @@ for use_mask in (False, True):
             tiles = (B * 289 + 127) // 128 / 148
             print(f"   CTA 0 ({tiles:.1f} tiles): producer wait a_empty {p[0]} of {p[1]} cycles | MMA wait a_full {p[2]}, acc_empty {p[3]} of {p[4]} | "
                   f"epilogue warp 0 wait acc_full {p[5]}, staging {p[6]} of {p[7]}")
+
+# the fused kernel (data gradient + conv1's weight gradient) against the two kernels it replaces
+xc = torch.randint(0, 3, (B, 5, 289), generator=g, device="cuda", dtype=torch.uint8)
+dw4 = torch.empty((256, 16), device="cuda"); db4 = torch.empty(256, device="cuda")
+pl = torch.empty((4, B * 289, 64), dtype=torch.bfloat16, device="cuda")
+def fused():
+    pkg._capi.check(L.ta_conv2_dgrad_conv1_bwd(vp(dz), vp(wimg), vp(mask), vp(xc), 1, xc.stride(0), B, vp(dw4), vp(db4), st))
+def two():
+    pkg._capi.check(L.ta_conv2_dgrad_planes(vp(dz), vp(wimg), None, B, 1, vp(pl), st))
+    pkg._capi.check(L.ta_conv1_bwd_planes(vp(xc), 1, xc.stride(0), None, vp(mask), vp(pl), 1, B, vp(dw4), vp(db4), st))
+L.ta_debug_dgrad_profile(None)
+for name, fn in (("fused dgrad + conv1 wgrad", fused), ("dgrad planes, then conv1 wgrad", two)):
+    if fn is fused:
+        L.ta_debug_dgrad_profile(vp(prof)); fused(); torch.cuda.synchronize(); q = prof.cpu().tolist(); L.ta_debug_dgrad_profile(None)
+        print(f"   fused, CTA 0: producer waits ring {q[0]}, p_empty {q[1]} of {q[2]} | MMA waits slot_full {q[3]}, acc_empty {q[4]}, a2_full/p_full {q[5]} of {q[6]} | "
+              f"epilogue warp 0 waits acc_full {q[7]}, a2_empty {q[8]} of {q[9]}")
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us; fail {L.ta_debug_conv1_tc_failed()}")

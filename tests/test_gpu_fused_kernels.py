@@ -125,6 +125,68 @@ def test_conv2_dgrad_planes_tcgen05(B, with_mask, class_major):
     assert float(got[:, 16, :, 2:].abs().max()) == 0.0 and float(got[:, :, 16, 1::2].abs().max()) == 0.0      # pixels of row / column 33
 
 
+@pytest.mark.parametrize("B", [1, 7, 300, 1500])
+@pytest.mark.parametrize("codes", [True, False])
+def test_conv2_dgrad_conv1_bwd_fused(B, codes):
+    """ta_conv2_dgrad_conv1_bwd (one kernel: conv2's data gradient on tcgen05 -> ReLU mask -> conv1's weight / bias gradient
+    GEMM, the planes never leaving the SM) against an independent float64 evaluation from the same bf16 inputs:
+        planes = bf16(conv_transpose2d(dz, w2, stride 2)) regrouped by output parity, masked with the bit mask,
+        dW4[(c, ch), k] = sum over positions planes[pos, c, ch] * patch[pos, k],  db4 = sum over positions planes
+    (patch = the decoded 2x2 input patch in the folded layer's tap order, conv1.fold).  Tolerance 2e-3 of the largest entry
+    (the kernel rounds the planes to bf16 exactly like the two-kernel path; fp32 accumulation over up to 433 k positions),
+    and agreement with the two-kernel path (ta_conv2_dgrad_planes + ta_conv1_bwd_planes) to 1e-3 of the largest entry."""
+    import torch.nn.functional as F
+    L, check = _lib()
+    g = torch.Generator(device="cuda").manual_seed(B + 5)
+    w = (torch.randn((64, 64, 3, 3), generator=g, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dz = torch.randn((B, 16, 16, 64), generator=g, device="cuda").to(torch.bfloat16)
+    wimg = torch.empty(9 * 64 * 64, dtype=torch.bfloat16, device="cuda")
+    check(L.ta_conv2_dgrad_prep(_p(w), w.stride(0), w.stride(1), w.stride(2), w.stride(3), _p(wimg), _st()), "ta_conv2_dgrad_prep")
+    mask = torch.randint(0, 2 ** 31 - 1, (B * 289 * 8,), generator=g, device="cuda", dtype=torch.int32)
+    mask = mask ^ (torch.randint(0, 2, (B * 289 * 8,), generator=g, device="cuda", dtype=torch.int32) << 31)
+    lut = torch.tensor([0.9, -0.9, -0.5, 0.0, 0.3], device="cuda")
+    xc = torch.tensor([0, 1, 2, 4], dtype=torch.uint8, device="cuda")[torch.randint(0, 4, (B, 5, 289), generator=g, device="cuda")]
+    if codes:
+        x, x_dtype = xc, 1
+    else:
+        x, x_dtype = torch.randn((B, 5, 289), generator=g, device="cuda"), 0
+    dw4 = torch.full((256, 16), float("nan"), device="cuda")
+    db4 = torch.full((256,), float("nan"), device="cuda")
+    check(L.ta_conv2_dgrad_conv1_bwd(_p(dz), _p(wimg), _p(mask), _p(x), x_dtype, x.stride(0), B, _p(dw4), _p(db4), _st()), "ta_conv2_dgrad_conv1_bwd")
+    torch.cuda.synchronize()
+    assert L.ta_debug_conv1_tc_failed() == 0
+    # ---- the two-kernel path
+    planes = torch.empty((4, B * 289, 64), dtype=torch.bfloat16, device="cuda")
+    dw4b, db4b = torch.empty_like(dw4), torch.empty_like(db4)
+    check(L.ta_conv2_dgrad_planes(_p(dz), _p(wimg), None, B, 1, _p(planes), _st()), "ta_conv2_dgrad_planes")
+    check(L.ta_conv1_bwd_planes(_p(x), x_dtype, x.stride(0), None, _p(mask), _p(planes), 1, B, _p(dw4b), _p(db4b), _st()), "ta_conv1_bwd_planes")
+    # ---- float64
+    dx = F.conv_transpose2d(dz.permute(0, 3, 1, 2).double(), w.double(), stride=2)          # [B,64,33,33]
+    pl = torch.zeros((B, 17, 17, 4, 64), dtype=torch.float64, device="cuda")
+    for c in range(4):
+        pa, pb = c >> 1, c & 1
+        sub = dx[:, :, pa::2, pb::2].permute(0, 2, 3, 1)
+        pl[:, :sub.shape[1], :sub.shape[2], c] = sub
+    pl = pl.to(torch.bfloat16).double()
+    mb = mask.view(B, 17, 17, 4, 2).to(torch.int64) & 0xFFFFFFFF
+    q = torch.arange(16, device="cuda")
+    even = ((mb[..., None] >> q) & 1).bool()
+    odd = ((mb[..., None] >> (16 + q)) & 1).bool()
+    pl = pl * torch.stack([even, odd], -1).reshape(B, 17, 17, 4, 64)
+    vals = (lut[x[:, :4].long()] if codes else x[:, :4]).double().view(B, 4, 17, 17)          # frames 0..3 as a [17][17] grid (cell = m*17+n)
+    vp = F.pad(vals, (0, 1, 0, 1))                                                          # neighbours past the edge are zero
+    # tap k = (dm*2 + dn) * 4 + frame: the patch order of conv1.fold / the kernels' (d00, d01, d10, d11) x 4 frames
+    patch = torch.stack([vp[:, f, dm:dm + 17, dn:dn + 17] for dm in (0, 1) for dn in (0, 1) for f in range(4)], -1)   # [B,17,17,16]
+    want_w = torch.einsum("bmncd,bmnk->cdk", pl, patch).reshape(256, 16)
+    want_b = pl.sum((0, 1, 2)).reshape(256)
+    sw, sb_ = float(want_w.abs().max()), float(want_b.abs().max())
+    assert bool(torch.isfinite(dw4).all()) and bool(torch.isfinite(db4).all())
+    assert float((dw4b.double() - want_w).abs().max()) <= 2e-3 * sw       # (the reference construction itself, via the two-kernel path)
+    assert float((dw4.double() - want_w).abs().max()) <= 2e-3 * sw
+    assert float((db4.double() - want_b).abs().max()) <= 2e-3 * sb_
+    assert float((dw4 - dw4b).abs().max()) <= 1e-3 * sw and float((db4 - db4b).abs().max()) <= 1e-3 * sb_
+
+
 @pytest.mark.parametrize("B", [4096, 300, 1])
 def test_ppo_actor_loss_and_gradient(B):
     """ta_ppo_actor_loss == the reference's lines (PPO.py:124-132: Categorical(probs=softmax(logits)).entropy / log_prob,
