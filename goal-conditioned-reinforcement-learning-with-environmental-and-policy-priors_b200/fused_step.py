@@ -102,6 +102,7 @@ class FusedNet:
         self.wimg2 = torch.empty(9 * 64 * 64, dtype=torch.bfloat16, device=dev)    # conv2 taps as the dgrad kernel's B operands
         import os
         self.tc_dgrad = os.environ.get("TA_CONV2_DGRAD_TC", "1") == "1"            # 0: cuDNN's merged-plane convolution
+        self.stem_bwd_fused = os.environ.get("TA_STEM_BWD_FUSED", "1") == "1"      # 0: data gradient and conv1's weight gradient as two kernels
         self._scratch = {}
         self._L = _capi.lib()
         self.refresh()
@@ -242,6 +243,14 @@ class FusedNet:
         dz2v = dz2.permute(0, 3, 1, 2)
         gw2 = torch.ops.aten.convolution_backward(dz2v, y1v, p16["w2"], None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
                                                   [False, True, False])[1].contiguous(memory_format=torch.channels_last)
+        if self.tc_dgrad and self.stem_bwd_fused:
+            # conv2's data gradient and conv1's weight / bias gradient in ONE tcgen05 kernel: the 605 MB of planes stay on the SM
+            _capi.check(L.ta_conv2_dgrad_conv1_bwd(_ptr(dz2), _ptr(self.wimg2), _ptr(mask), _ptr(sb), 1, sb.stride(0), B,
+                                                   _ptr(self.dw4), _ptr(self.db4), st), "ta_conv2_dgrad_conv1_bwd")
+            self._finalise(conv1=True, dense=((gw2, "w2"), (gw3, "w3")))
+            if reduce_fn is not None:
+                reduce_fn(self.G32[:self.off[6]], True)
+            return self.loss
         if self.tc_dgrad:   # per-class tap lists on tcgen05 (warp-specialised), conv1's ReLU mask applied in the epilogue; class-major planes
             p2 = torch.empty((4, B * 289, 64), dtype=bf, device=dev)
             # (conv1's ReLU mask is applied by ta_conv1_bwd_planes, where it costs one multiply per word; in this kernel's

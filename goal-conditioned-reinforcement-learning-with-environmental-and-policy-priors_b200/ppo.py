@@ -634,7 +634,7 @@ class PPO:
             st_t = self._static["t"]
             p, g, a, old_a_logp, adv, target_v = (st_t[k] for k in ("p", "g", "a", "old_a_logp", "adv", "target_v"))
             self._step_key = (sig, s.data_ptr(), tuple(s.shape), tuple(s.stride()), world, id(group), fa.lr, fc.lr, clip, ent,
-                              id(fa), id(fc), fa.tc_dgrad, None if streams is None else tuple(id(x) for x in streams))
+                              id(fa), id(fc), fa.tc_dgrad, fa.stem_bwd_fused, None if streams is None else tuple(id(x) for x in streams))
 
         def step(idx):
             bs = idx.numel()

@@ -14,7 +14,7 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 pkg._capi.check(L.ta_conv2_dgrad_prep(vp(w), w.stride(0), w.stride(1), w.stride(2), w.stride(3), vp(wimg), st))
 planes = torch.empty((4, B * 289, 64), dtype=torch.bfloat16, device="cuda")
 mask = torch.randint(0, 2 ** 31 - 1, (B * 289 * 8,), generator=g, device="cuda", dtype=torch.int32)
-prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+prof = torch.zeros(16 + 3 * 160, dtype=torch.int64, device="cuda")
 for use_mask in (False, True):
     for cm in (1, 0):
         L.ta_debug_dgrad_profile(vp(prof) if cm else None)
@@ -44,8 +44,15 @@ def two():
 L.ta_debug_dgrad_profile(None)
 for name, fn in (("fused dgrad + conv1 wgrad", fused), ("dgrad planes, then conv1 wgrad", two)):
     if fn is fused:
-        L.ta_debug_dgrad_profile(vp(prof)); fused(); torch.cuda.synchronize(); q = prof.cpu().tolist(); L.ta_debug_dgrad_profile(None)
-        print(f"   fused, CTA 0: producer waits ring {q[0]}, p_empty {q[1]} of {q[2]} | MMA waits slot_full {q[3]}, acc_empty {q[4]}, a2_full/p_full {q[5]} of {q[6]} | "
+        prof.zero_(); L.ta_debug_dgrad_profile(vp(prof)); fused(); torch.cuda.synchronize(); q = prof.cpu().tolist(); L.ta_debug_dgrad_profile(None)
+        print(f"   CTA 0 lifetime {q[11] / 1e3:.1f} us; longest CTA {q[12]} cycles, {q[13] / 1e3:.1f} us")
+        per = sorted((q[17 + 3 * i] / 1e3, q[16 + 3 * i], q[18 + 3 * i], i) for i in range(148))
+        print("   per-CTA lifetime us (cycles, smid, cta): fastest", per[:4], "median", per[74], "slowest", per[-6:])
+        import collections
+        by = collections.defaultdict(list)
+        for us, cyc, sm, i in per: by[sm // 2 % 4 if False else sm % 2].append(us)
+        print("   mean by smid parity", {k: sum(v) / len(v) for k, v in by.items()}, "MHz", [round(c / u) for u, c, _, _ in per[::37]])
+        print(f"   fused, CTA 0: producer waits ring {q[0]} of {q[2]} | decoder waits p_empty {q[1]} of {q[10]} | MMA waits slot_full {q[3]}, acc_empty {q[4]}, a2_full/p_full {q[5]} of {q[6]} | "
               f"epilogue warp 0 waits acc_full {q[7]}, a2_empty {q[8]} of {q[9]}")
     for _ in range(3):
         fn()
