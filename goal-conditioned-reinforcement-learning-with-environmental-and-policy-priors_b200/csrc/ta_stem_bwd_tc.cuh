@@ -8,7 +8,7 @@
 //   GEMM 2 (ta_conv1_tc.cuh)   dW4[(c, ci), k] += sum_positions dz1[position, (c, ci)] x P[position, k],  P = the decoded 2x2
 //                              input patch (bf16 hi / lo pair) and a ones column for the bias gradient
 //
-// One persistent CTA of 416 threads per SM, warp-specialised, no CTA-wide barrier in the tile loop:
+// One persistent CTA of 544 threads per SM, warp-specialised, no CTA-wide barrier in the tile loop:
 //   warps 4-7  producers   cp.async of the tile's four shifted dz tiles into a ring of SIX 16 KB slots (a tile's slots are
 //                          queued in the order sh3, sh2, sh1, sh0 and released in that order: the first class pair is the
 //                          last user of sh3 / sh2, the second of sh1 / sh0)
@@ -17,8 +17,9 @@
 //                          role it doubled the producers' time per tile and starved the MMA issuer
 //   warp 8     MMA issuer  per class PAIR (classes 2h, 2h+1 = 128 rows of dW4): GEMM 1 into one of THREE 128-column TMEM
 //                          slots, then GEMM 2 of the PREVIOUS pair (its operand is ready by then) into 2 x 32 resident columns
-//   warps 0-3  epilogue    tcgen05.ld of the pair's two classes (lane = position), mask, bf16, 16-byte chunks written in the
-//                          MN-major operand layout of GEMM 2 (32 lanes = 512 contiguous bytes: conflict-free)
+//   warps 0-3, 13-16  epilogue  tcgen05.ld of one class of the pair (lane = position; the two groups take the even / odd
+//                          class), mask, bf16, 16-byte chunks written in the MN-major operand layout of GEMM 2 (32 lanes =
+//                          512 contiguous bytes: conflict-free)
 // TMEM: 3 x 128 (GEMM 1) + 2 x 64 (dW4, db4: hi and lo operand halves) = all 512 columns.  Shared memory: W 72 KB + ring 96 KB + dz1 operand
 // 32 KB + P 16 KB + decode scratch 4.6 KB = 221 KB.  Every mbarrier wait is bounded and raises `fail`.
 #pragma once
@@ -26,7 +27,7 @@
 
 namespace ta {
 
-constexpr int SB_THREADS = 416;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9-12 decoders
+constexpr int SB_THREADS = 544;   // warps 0-3 and 13-16 epilogue, 4-7 producers, 8 MMA issuer, 9-12 decoders
 constexpr int SB_SLOTS = 6;
 constexpr int SB_OFF_RING = DG_W_BYTES;                          // 73728 (1024-aligned)
 constexpr int SB_OFF_A2 = SB_OFF_RING + SB_SLOTS * DG_A_BYTES;   // 172032
@@ -43,9 +44,17 @@ __device__ __forceinline__ bool sb_wait_warp(uint64_t *bar, uint32_t parity) { r
 // tcgen05.mma with an explicit instruction descriptor.  The tensor core spends ~75 cycles on an M = 128, K = 16 step almost
 // regardless of N <= 128 (measured through the issuer's busy time: 36 N = 64 steps = 2.7 k cycles per tile), so taps that
 // share an A tile and write neighbouring classes go out as ONE N = 128 step, and GEMM 2's hi / lo operands as one N = 64 step.
+// The MMA warp runs CONVERGED (all 32 lanes execute the issue loop, one elected lane issues): with the loop inside an
+// `if (lane == 0)` the descriptors live in vector registers and every tcgen05.mma costs ~15 instructions of R2UR moves and
+// an ELECT / BRA.U.ANY loop (SASS) -- ~115 cycles per MMA in the issuing thread, more than the tensor core needs.
 __device__ __forceinline__ void sb_mma(uint32_t tmem, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
-                 "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+    asm volatile(
+        "{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
+        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void sb_commit(uint64_t *bar) {
+    asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
                  : "memory");
 }
 // D f32, A / B bf16 K-major, M = 128
@@ -85,9 +94,9 @@ __global__ void __launch_bounds__(SB_THREADS, 1) conv2_dgrad_conv1_wgrad_kernel(
         }
         for (int s = 0; s < 3; s++) {
             dg_mbar_init(&acc_full[s], 1);      // one tcgen05.commit
-            dg_mbar_init(&acc_empty[s], 4);     // the four epilogue warps
+            dg_mbar_init(&acc_empty[s], 8);     // the eight epilogue warps
         }
-        dg_mbar_init(&a2_full, 4);              // the four epilogue warps
+        dg_mbar_init(&a2_full, 8);              // the eight epilogue warps
         dg_mbar_init(&a2_empty, 1);
         dg_mbar_init(&p_full, 128);             // the producer threads
         dg_mbar_init(&p_empty, 1);
@@ -111,41 +120,46 @@ __global__ void __launch_bounds__(SB_THREADS, 1) conv2_dgrad_conv1_wgrad_kernel(
         // ---------------- producers ----------------
         const int pw = warp - 4, ptid = tid - 128;
         int it = 0;
+        const int rsub = lane >> 3, ch = lane & 7;   // lane = (row within a quad, 16-byte chunk): 4 rows x 128 contiguous bytes per instruction
         for (long long tile = blockIdx.x; tile < ntiles && !dead; tile += gridDim.x, it++) {
-            // ---- the four shifted dz tiles: ring entries 4 it .. 4 it + 3 hold shifts 3, 2, 1, 0
-            uint32_t sbase[4];
+            // this thread's 8 rows: element offset of the pixel's chunk in dz and which of the four shifts exist
+            unsigned roff[8], rok = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int seq = it * 4 + j, slot = seq % SB_SLOTS, n = seq / SB_SLOTS;
-                const long long tw = clock64();
-                if (!dead && !tc_mbar_wait(&slot_empty[slot], (uint32_t)((n & 1) ^ 1))) dead = true;   // (passes at once on a slot's first use)
-                t_a += clock64() - tw;
-                sbase[3 - j] = smem_u32(sRing + slot * DG_A_BYTES);
-            }
-            const int rsub = lane >> 3, ch = lane & 7;   // lane = (row within a quad, 16-byte chunk): 4 rows x 128 contiguous bytes per instruction
-#pragma unroll 4
             for (int i = 0; i < 8; i++) {
                 const int row = pw * 32 + 4 * i + rsub;
                 const unsigned P = (unsigned)(tile * TC_M) + (unsigned)row;     // (batch * 289 < 2^31, checked by the host)
                 const bool valid = (long long)P < npos;
                 const unsigned b = P / (unsigned)(DG_P * DG_P), pos = P - b * (unsigned)(DG_P * DG_P), m = pos / (unsigned)DG_P, nn = pos - m * (unsigned)DG_P;
-                const __nv_bfloat16 *base = dz + ((long long)((b * DG_OH + m) * DG_OH + nn)) * 64 + ch * 8;
-                const uint32_t doff = dg_row_chunk(row, ch);
+                roff[i] = ((b * DG_OH + m) * DG_OH + nn) * 64u + ch * 8u;    // (< 2^31 elements: batch * 256 * 64)
 #pragma unroll
                 for (int sh = 0; sh < 4; sh++) {
-                    const int dy = sh >> 1, dx = sh & 1;
-                    const bool ok = valid && m >= (unsigned)dy && m - dy < (unsigned)DG_OH && nn >= (unsigned)dx && nn - dx < (unsigned)DG_OH;
-                    dg_cp_async16(sbase[sh] + doff, ok ? base - (dy * DG_OH + dx) * 64 : dz, ok ? 16u : 0u);
+                    const unsigned dy = sh >> 1, dx = sh & 1;
+                    const bool ok = valid && m >= dy && m - dy < (unsigned)DG_OH && nn >= dx && nn - dx < (unsigned)DG_OH;
+                    rok |= (ok ? 1u : 0u) << (4 * i + sh);
                 }
             }
+            // ring entries 4 it .. 4 it + 3 hold shifts 3, 2, 1, 0: each is filled as soon as ITS slot is free (the first two
+            // are released half a tile earlier than the others)
 #pragma unroll
-            for (int j = 0; j < 4; j++)   // this lane's copies arrive on each of the tile's slots when they have landed
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&slot_full[(it * 4 + j) % SB_SLOTS])) : "memory");
-
+            for (int j = 0; j < 4; j++) {
+                const int seq = it * 4 + j, slot = seq % SB_SLOTS, n = seq / SB_SLOTS, sh = 3 - j;
+                const long long tw = clock64();
+                if (!dead && !tc_mbar_wait(&slot_empty[slot], (uint32_t)((n & 1) ^ 1))) dead = true;   // (passes at once on a slot's first use)
+                t_a += clock64() - tw;
+                const uint32_t sbase = smem_u32(sRing + slot * DG_A_BYTES);
+                const int back = ((sh >> 1) * DG_OH + (sh & 1)) * 64;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const bool ok = (rok >> (4 * i + sh)) & 1u;
+                    dg_cp_async16(sbase + dg_row_chunk(pw * 32 + 4 * i + rsub, ch), ok ? dz + roff[i] - back : dz, ok ? 16u : 0u);
+                }
+                // this lane's copies of the slot arrive on its barrier when they have landed
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&slot_full[slot])) : "memory");
+            }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         if (pr && ptid == 0) { prof[0] = t_a; prof[2] = clock64() - t_start; }
-    } else if (warp >= 9) {
+    } else if (warp >= 9 && warp < 13) {
         // ---------------- decoders: the tile's P operand (thread = position) ----------------
         // (a thread whose wait gave up keeps going without waiting -- it must reach the named barrier of the next tile,
         // where all 128 leave together)
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) conv2_dgrad_conv1_wgrad_kernel(
         if (pr && ptid == 0) { prof[1] = t_b; prof[10] = clock64() - t_start; }
     } else if (warp == 8) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0 && my_tiles > 0) {
+        if (my_tiles > 0) {   // (all 32 lanes, converged: see sb_mma)
             uint64_t dW[DG_TAPS];
 #pragma unroll
             for (int t = 0; t < DG_TAPS; t++) dW[t] = dg_smem_desc(sW + t * DG_WTAP_BYTES);
@@ -193,8 +207,8 @@ __global__ void __launch_bounds__(SB_THREADS, 1) conv2_dgrad_conv1_wgrad_kernel(
             auto wgrad = [&](long long k) -> bool {
                 const int pair = (int)(k & 1);
                 const long long tw = clock64();
-                if (pair == 0 && !tc_mbar_wait(&p_full, (uint32_t)((k >> 1) & 1))) return false;
-                if (!tc_mbar_wait(&a2_full, (uint32_t)(k & 1))) return false;
+                if (pair == 0 && !sb_wait_warp(&p_full, (uint32_t)((k >> 1) & 1))) return false;
+                if (!sb_wait_warp(&a2_full, (uint32_t)(k & 1))) return false;
                 t_c += clock64() - tw;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 fence_proxy_async();
@@ -202,73 +216,94 @@ __global__ void __launch_bounds__(SB_THREADS, 1) conv2_dgrad_conv1_wgrad_kernel(
 #pragma unroll
                 for (int ks = 0; ks < TC_M / 16; ks++) {   // columns 0..31: hi operand, 32..63: lo operand (adjacent row groups of sP)
                     const uint64_t koff = (uint64_t)((ks * 256) >> 4);
+#ifndef SB_EXPERIMENT_SKIP_W
                     sb_mma(d, descA2 + koff, descPh + koff, SB_IDESC_W, (k >= 2 || ks) ? 1u : 0u);
+#endif
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&a2_empty)) : "memory");
-                if (pair == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&p_empty)) : "memory");
+                sb_commit(&a2_empty);
+                if (pair == 1) sb_commit(&p_empty);
                 return true;
             };
             long long k = 0;
             for (long long itl = 0; itl < my_tiles && !dead; itl++) {
                 const int it = (int)itl;
                 uint64_t dA[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
+                auto ring_wait = [&](int j) -> bool {   // ring entry j of the tile = shift 3 - j
                     const int seq = it * 4 + j, slot = seq % SB_SLOTS, n = seq / SB_SLOTS;
                     const long long tw = clock64();
-                    if (!dead && !tc_mbar_wait(&slot_full[slot], (uint32_t)(n & 1))) dead = true;
+                    const bool ok = sb_wait_warp(&slot_full[slot], (uint32_t)(n & 1));
                     t_a += clock64() - tw;
                     dA[3 - j] = dg_smem_desc(sRing + slot * DG_A_BYTES);
-                }
-                if (dead) break;
+                    return ok;
+                };
+                auto ring_release = [&](int j) {
+                    sb_commit(&slot_empty[(it * 4 + j) % SB_SLOTS]);
+                };
 #pragma unroll
                 for (int pair = 0; pair < 2; pair++, k++) {
                     const int aslot = (int)(k % 3);
                     const long long tw = clock64();
-                    if (!tc_mbar_wait(&acc_empty[aslot], (uint32_t)(((k / 3) & 1) ^ 1))) { dead = true; break; }
+                    if (!sb_wait_warp(&acc_empty[aslot], (uint32_t)(((k / 3) & 1) ^ 1))) { dead = true; break; }
                     t_b += clock64() - tw;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    fence_proxy_async();   // the producers' generic-proxy writes, acquired through the barriers -> the tensor core's async-proxy reads
-                    // pair 0 = classes (0,0), (0,1): taps 0|1 from shift 0 and 6|7 from shift 2 feed both classes (N = 128: the
-                    // second tap's rows follow the first's in the weight image), taps 2 (shift 1) and 8 (shift 3) class (0,0) only;
-                    // pair 1 = classes (1,0), (1,1): taps 3|4 from shift 0, tap 5 (shift 1) class (1,0) only
+                    // pair 0 = classes (0,0), (0,1): taps 6|7 from shift 2 and 0|1 from shift 0 feed both classes (N = 128: the
+                    // second tap's rows follow the first's in the weight image), taps 8 (shift 3) and 2 (shift 1) class (0,0) only;
+                    // pair 1 = classes (1,0), (1,1): taps 3|4 from shift 0, tap 5 (shift 1) class (1,0) only.
+                    // Shifts 3 and 2 go first and their ring slots are released before the rest of the pair is issued.
                     const uint32_t dcol = tmem_base + (uint32_t)(aslot * 128);
+                    if (pair == 0) {
+                        if (!ring_wait(1) || !ring_wait(0)) { dead = true; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        fence_proxy_async();   // the producers' writes, acquired through the barriers -> the tensor core's async-proxy reads
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const uint64_t koff = (uint64_t)(ks * DG_KSTEP);
-                        if (pair == 0) {
-                            sb_mma(dcol, dA[0] + koff, dW[0] + koff, SB_IDESC_N128, ks ? 1u : 0u);
-                            sb_mma(dcol, dA[2] + koff, dW[6] + koff, SB_IDESC_N128, 1u);
-                            sb_mma(dcol, dA[1] + koff, dW[2] + koff, SB_IDESC_N64, 1u);
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t koff = (uint64_t)(ks * DG_KSTEP);
+                            sb_mma(dcol, dA[2] + koff, dW[6] + koff, SB_IDESC_N128, ks ? 1u : 0u);
                             sb_mma(dcol, dA[3] + koff, dW[8] + koff, SB_IDESC_N64, 1u);
-                        } else {
+                        }
+                        ring_release(0);
+                        ring_release(1);
+                        if (!ring_wait(2) || !ring_wait(3)) { dead = true; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        fence_proxy_async();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t koff = (uint64_t)(ks * DG_KSTEP);
+                            sb_mma(dcol, dA[0] + koff, dW[0] + koff, SB_IDESC_N128, 1u);
+                            sb_mma(dcol, dA[1] + koff, dW[2] + koff, SB_IDESC_N64, 1u);
+                        }
+                    } else {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t koff = (uint64_t)(ks * DG_KSTEP);
                             sb_mma(dcol, dA[0] + koff, dW[3] + koff, SB_IDESC_N128, ks ? 1u : 0u);
                             sb_mma(dcol, dA[1] + koff, dW[5] + koff, SB_IDESC_N64, 1u);
                         }
+                        ring_release(2);
+                        ring_release(3);
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&acc_full[aslot])) : "memory");
-                    // the pair was the last reader of two of the tile's ring entries (pair 0: shifts 3, 2; pair 1: shifts 1, 0)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&slot_empty[(it * 4 + 2 * pair) % SB_SLOTS])) : "memory");
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&slot_empty[(it * 4 + 2 * pair + 1) % SB_SLOTS])) : "memory");
+                    sb_commit(&acc_full[aslot]);
                     if (k >= 1 && !wgrad(k - 1)) { dead = true; break; }
                 }
             }
             if (!dead && k >= 1 && !wgrad(k - 1)) dead = true;
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&done_bar)) : "memory");
-            if (pr) { prof[3] = t_a; prof[4] = t_b; prof[5] = t_c; prof[6] = clock64() - t_start; }
+            sb_commit(&done_bar);
+            if (pr && lane == 0) { prof[3] = t_a; prof[4] = t_b; prof[5] = t_c; prof[6] = clock64() - t_start; }
         }
     } else {
-        // ---------------- epilogue (warps 0-3): lane = position 32 * warp + lane of the tile ----------------
+        // ---------------- epilogue (warps 0-3: the even class of every pair, warps 13-16: the odd one) ----------------
+        // lane = position 32 * q + lane of the tile; a warp may only read the TMEM lane quadrant warp % 4
+        const int q = warp & 3, cc = warp >= 13 ? 1 : 0;
         long long k = 0;
-        const int p = warp * 32 + lane;
-        uint8_t *a2row = sA2 + (p >> 3) * 128 + (p & 7) * 16;
+        const int p = q * 32 + lane;
+        uint8_t *a2row = sA2 + (p >> 3) * 128 + (p & 7) * 16 + cc * 8 * TCB_SBO;
         for (long long tile = blockIdx.x; tile < ntiles && !dead; tile += gridDim.x) {
             const long long P = tile * TC_M + p;
-            // conv1's ReLU mask words of this position (4 classes x 2 halves = 32 contiguous bytes), fetched before the waits
-            uint4 mw[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+            // conv1's ReLU mask words of this position and this warp's two classes (cc, 2 + cc), fetched before the waits
+            uint2 mw[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
             if (P < npos) {
-                mw[0] = __ldg(reinterpret_cast<const uint4 *>(relu_mask + P * 8));
-                mw[1] = __ldg(reinterpret_cast<const uint4 *>(relu_mask + P * 8) + 1);
+                mw[0] = __ldg(reinterpret_cast<const uint2 *>(relu_mask + P * 8 + cc * 2));
+                mw[1] = __ldg(reinterpret_cast<const uint2 *>(relu_mask + P * 8 + 4 + cc * 2));
             }
 #pragma unroll
             for (int pair = 0; pair < 2; pair++, k++) {
@@ -277,54 +312,49 @@ __global__ void __launch_bounds__(SB_THREADS, 1) conv2_dgrad_conv1_wgrad_kernel(
                 if (!sb_wait_warp(&acc_full[aslot], (uint32_t)((k / 3) & 1))) { dead = true; break; }
                 t_a += clock64() - tw;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint4 m4 = mw[pair];
+                uint32_t r[2][32];
 #pragma unroll
-                for (int cc = 0; cc < 2; cc++) {
-                    uint32_t r[2][32];
-#pragma unroll
-                    for (int half = 0; half < 2; half++) {
-                        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(aslot * 128 + cc * 64 + half * 32);
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                            : "=r"(r[half][0]), "=r"(r[half][1]), "=r"(r[half][2]), "=r"(r[half][3]), "=r"(r[half][4]), "=r"(r[half][5]),
-                              "=r"(r[half][6]), "=r"(r[half][7]), "=r"(r[half][8]), "=r"(r[half][9]), "=r"(r[half][10]), "=r"(r[half][11]),
-                              "=r"(r[half][12]), "=r"(r[half][13]), "=r"(r[half][14]), "=r"(r[half][15]), "=r"(r[half][16]), "=r"(r[half][17]),
-                              "=r"(r[half][18]), "=r"(r[half][19]), "=r"(r[half][20]), "=r"(r[half][21]), "=r"(r[half][22]), "=r"(r[half][23]),
-                              "=r"(r[half][24]), "=r"(r[half][25]), "=r"(r[half][26]), "=r"(r[half][27]), "=r"(r[half][28]), "=r"(r[half][29]),
-                              "=r"(r[half][30]), "=r"(r[half][31])
-                            : "r"(taddr));
-                    }
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cc == 1) {   // both classes of the pair are in registers: the accumulator slot may be overwritten
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) dg_mbar_arrive(&acc_empty[aslot]);
-                    }
-                    uint4 o[8];   // the position's 64 channels of this class: 8 chunks of 8 bf16, masked
-#pragma unroll
-                    for (int half = 0; half < 2; half++) {
-                        const uint32_t mb = cc ? (half ? m4.w : m4.z) : (half ? m4.y : m4.x);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            uint32_t w4[4];
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const __nv_bfloat162 pk =
-                                    __floats2bfloat162_rn(__uint_as_float(r[half][8 * j + 2 * i]), __uint_as_float(r[half][8 * j + 2 * i + 1]));
-                                w4[i] = *reinterpret_cast<const uint32_t *>(&pk) & (((mb >> (4 * j + i)) & 0x00010001u) * 0xFFFFu);
-                            }
-                            o[half * 4 + j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                        }
-                    }
-                    // GEMM 2 of the previous pair must have read the operand block before it is rewritten
-                    tw = clock64();
-                    if (cc == 0 && !sb_wait_warp(&a2_empty, (uint32_t)((k & 1) ^ 1))) dead = true;
-                    t_b += clock64() - tw;
-                    // row group g = (class of the pair, 8 channels): the 32 lanes of a store are 512 contiguous bytes
-#pragma unroll
-                    for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(a2row + (cc * 8 + j) * TCB_SBO) = o[j];
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(aslot * 128 + cc * 64 + half * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[half][0]), "=r"(r[half][1]), "=r"(r[half][2]), "=r"(r[half][3]), "=r"(r[half][4]), "=r"(r[half][5]),
+                          "=r"(r[half][6]), "=r"(r[half][7]), "=r"(r[half][8]), "=r"(r[half][9]), "=r"(r[half][10]), "=r"(r[half][11]),
+                          "=r"(r[half][12]), "=r"(r[half][13]), "=r"(r[half][14]), "=r"(r[half][15]), "=r"(r[half][16]), "=r"(r[half][17]),
+                          "=r"(r[half][18]), "=r"(r[half][19]), "=r"(r[half][20]), "=r"(r[half][21]), "=r"(r[half][22]), "=r"(r[half][23]),
+                          "=r"(r[half][24]), "=r"(r[half][25]), "=r"(r[half][26]), "=r"(r[half][27]), "=r"(r[half][28]), "=r"(r[half][29]),
+                          "=r"(r[half][30]), "=r"(r[half][31])
+                        : "r"(taddr));
                 }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // this warp's part of the accumulator slot is in registers: it may be overwritten
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) dg_mbar_arrive(&acc_empty[aslot]);
+                uint4 o[8];   // the position's 64 channels of this class: 8 chunks of 8 bf16, masked
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t mb = half ? mw[pair].y : mw[pair].x;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const __nv_bfloat162 pk =
+                                __floats2bfloat162_rn(__uint_as_float(r[half][8 * j + 2 * i]), __uint_as_float(r[half][8 * j + 2 * i + 1]));
+                            w4[i] = *reinterpret_cast<const uint32_t *>(&pk) & (((mb >> (4 * j + i)) & 0x00010001u) * 0xFFFFu);
+                        }
+                        o[half * 4 + j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                }
+                // GEMM 2 of the previous pair must have read the operand block before it is rewritten
+                tw = clock64();
+                if (!sb_wait_warp(&a2_empty, (uint32_t)((k & 1) ^ 1))) dead = true;
+                t_b += clock64() - tw;
+                // row group g = (class of the pair, 8 channels): the 32 lanes of a store are 512 contiguous bytes
+#pragma unroll
+                for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(a2row + j * TCB_SBO) = o[j];
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) dg_mbar_arrive(&a2_full);
@@ -333,7 +363,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) conv2_dgrad_conv1_wgrad_kernel(
         }
         if (pr && tid == 0) { prof[7] = t_a; prof[8] = t_b; prof[9] = clock64() - t_start; }
         // ---- dW4 / db4: lane = row (class-pair member * 64 + channel), columns = 16 taps + bias; one atomicAdd per value and CTA
-        if (my_tiles > 0 && !dead) {
+        if (my_tiles > 0 && !dead && cc == 0) {
             if (!sb_wait_warp(&done_bar, 0u)) dead = true;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (!dead) {
