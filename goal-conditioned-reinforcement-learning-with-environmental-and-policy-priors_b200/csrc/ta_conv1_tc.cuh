@@ -80,6 +80,20 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem, uint64_t descA, uint64_t d
                  : "memory");
 }
 
+// The same, executed by a CONVERGED warp: one elected lane issues.  Inside an `if (tid == 0)` the descriptors live in
+// vector registers and ptxas wraps every tcgen05.mma in R2UR moves and an ELECT / BRA.U.ANY loop (~15 instructions, ~100
+// cycles per MMA in the issuing thread); with warp-uniform control flow they stay in uniform registers.
+__device__ __forceinline__ void tc_mma_elect(uint32_t tmem, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
+        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t *bar) {
+    asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <typename XT>
 __device__ __forceinline__ float tc_value(XT v) {
     if constexpr (sizeof(XT) == 1) return c1_decode((uint32_t)v);
@@ -221,13 +235,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_fwd_tc_kernel(const XT *__re
         // ---- one MMA per output phase (TC_NT = 64 columns), epilogue straight out of TMEM -------------------
 #pragma unroll 1
         for (int phase = 0; phase < TC_N / TC_NT; phase++) {
-            if (tid == 0) {
+            if (warp == 0) {   // (converged: one elected lane issues, see tc_mma_elect)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t boff = (uint64_t)((phase * TC_NT / 8 * 256) >> 4);  // rows phase*64.. of W4
-                tc_mma(tmem_base, descA_hi, descB_hi + boff, 0u);
-                tc_mma(tmem_base, descA_lo, descB_hi + boff, 1u);
-                tc_mma(tmem_base, descA_hi, descB_lo + boff, 1u);
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+                tc_mma_elect(tmem_base, descA_hi, descB_hi + boff, TC_IDESC, 0u);
+                tc_mma_elect(tmem_base, descA_lo, descB_hi + boff, TC_IDESC, 1u);
+                tc_mma_elect(tmem_base, descA_hi, descB_lo + boff, TC_IDESC, 1u);
+                tc_commit_elect(&bar);
             }
             if (!dead && !tc_mbar_wait(&bar, parity)) dead = true;
             parity ^= 1u;
@@ -460,16 +474,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv1_bwd_tc_kernel(const XT *__re
             }
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {   // (converged: one elected lane issues, see tc_mma_elect)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + (uint32_t)(h * TCB_N);
 #pragma unroll
                 for (int ks = 0; ks < TC_M / 16; ks++) {  // 16 positions = 2 core matrices of 128 bytes per step
                     const uint64_t koff = (uint64_t)((ks * 256) >> 4);
-                    tcb_mma(d, descA + koff, descBh + koff, (any || ks) ? 1u : 0u);
-                    tcb_mma(d, descA + koff, descBl + koff, 1u);
+                    tc_mma_elect(d, descA + koff, descBh + koff, TCB_IDESC, (any || ks) ? 1u : 0u);
+                    tc_mma_elect(d, descA + koff, descBl + koff, TCB_IDESC, 1u);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+                tc_commit_elect(&bar);
             }
             if (!dead && !tc_mbar_wait(&bar, parity)) dead = true;   // sG / sP are free again
             parity ^= 1u;

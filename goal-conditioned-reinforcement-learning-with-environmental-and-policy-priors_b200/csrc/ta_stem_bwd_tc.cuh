@@ -44,19 +44,11 @@ __device__ __forceinline__ bool sb_wait_warp(uint64_t *bar, uint32_t parity) { r
 // tcgen05.mma with an explicit instruction descriptor.  The tensor core spends ~75 cycles on an M = 128, K = 16 step almost
 // regardless of N <= 128 (measured through the issuer's busy time: 36 N = 64 steps = 2.7 k cycles per tile), so taps that
 // share an A tile and write neighbouring classes go out as ONE N = 128 step, and GEMM 2's hi / lo operands as one N = 64 step.
-// The MMA warp runs CONVERGED (all 32 lanes execute the issue loop, one elected lane issues): with the loop inside an
-// `if (lane == 0)` the descriptors live in vector registers and every tcgen05.mma costs ~15 instructions of R2UR moves and
-// an ELECT / BRA.U.ANY loop (SASS) -- ~115 cycles per MMA in the issuing thread, more than the tensor core needs.
+// The MMA warp runs CONVERGED: all 32 lanes execute the issue loop, one elected lane issues (tc_mma_elect, ta_conv1_tc.cuh).
 __device__ __forceinline__ void sb_mma(uint32_t tmem, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
-        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
-        : "memory");
+    tc_mma_elect(tmem, descA, descB, idesc, accumulate);
 }
-__device__ __forceinline__ void sb_commit(uint64_t *bar) {
-    asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
-                 : "memory");
-}
+__device__ __forceinline__ void sb_commit(uint64_t *bar) { tc_commit_elect(bar); }
 // D f32, A / B bf16 K-major, M = 128
 constexpr uint32_t SB_IDESC_N64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 constexpr uint32_t SB_IDESC_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
