@@ -622,8 +622,8 @@ def main():
                          "observations (2-bit cell codes) + status bytes in 8 pieces, expanded by host threads into the caller's "
                          "uint8 [n,V,V,3] / float32 / uint8 arrays; synchronous per step") if e2e_d2h < n * 3 * V * V else
                         ("TwoarmyVecEnv.step_host -> ta_step_host: H2D actions from pinned memory, fused kernel, expanded observations "
-                         "copied by the DMA engine into the pinned array (the library's own choice: at most 4 host threads for this "
-                         "rank) + status bytes; synchronous per step")},
+                         "copied by the DMA engine into the pinned array (the library's own choice: a single rank with at most 4 host "
+                         "threads) + status bytes; synchronous per step")},
         "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -373,12 +373,14 @@ int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, 
     ta_host::Job &job = h->job;
     job.status = h_status; job.reward = reward_out; job.term = term_out; job.trunc = trunc_out;
     job.n = h->n; job.ntiles = ntiles; job.runs = runs; job.obs_bytes = obs_bytes; job.obs = obs_out;
-    // Few host threads for this rank (many ranks sharing a small host) and a pinned destination: the DMA engine alone
-    // (~54 GB/s of expanded observations) beats the threads' expansion (~11 GB/s each); TA_STEP_HOST_AUTO=0 disables the choice
+    // A single rank on a host with few cores and a pinned destination: the DMA engine alone (~54 GB/s of expanded
+    // observations) beats the threads' expansion (~11 GB/s each).  With several ranks on the node the DMA form does not
+    // scale (measured on 8 GPUs / 32 cores: 111 M env-steps/s for all ranks together against 196 M through the packed
+    // form with 4 threads per rank), so it is never chosen there.  TA_STEP_HOST_AUTO=0 disables the choice.
     if (!(flags & TA_STEP_HOST_DMA) && h->auto_dma < 0) {
-        const char *e = getenv("TA_STEP_HOST_AUTO");
+        const char *e = getenv("TA_STEP_HOST_AUTO"), *lw = getenv("LOCAL_WORLD_SIZE");
         h->auto_dma = 0;
-        if (!(e && atoi(e) == 0) && ta_host::default_threads() <= 4) {
+        if (!(e && atoi(e) == 0) && !(lw && atoi(lw) > 1) && ta_host::default_threads() <= 4) {
             cudaPointerAttributes pa;
             if (cudaPointerGetAttributes(&pa, obs_out) == cudaSuccess && pa.type == cudaMemoryTypeHost) h->auto_dma = 1;
             (void)cudaGetLastError();

@@ -145,8 +145,9 @@ int ta_step_packed(ta_handle h, const void *actions, int action_dtype, const uin
  *                      wire.  obs_out may be pageable; 16-byte alignment enables streaming stores.
  *   TA_STEP_HOST_DMA   the expanded observations are copied straight into obs_out by the DMA engine (fastest when
  *                      obs_out is pinned and host cores are scarce); reward / flags still travel as one status byte.
- * When this rank has at most 4 host threads and obs_out is pinned, the default switches itself to the DMA form
- * (decided on the handle's first call; TA_STEP_HOST_AUTO=0 keeps the threads).
+ * When the process is the only rank on the node (LOCAL_WORLD_SIZE unset or 1), has at most 4 host threads and obs_out
+ * is pinned, the default switches itself to the DMA form (decided on the handle's first call; TA_STEP_HOST_AUTO=0
+ * keeps the threads).  With several ranks per node the packed form is always used: the DMA form saturates the host.
  * Same bytes either way (tests/test_gpu_parity.py::test_step_host_equals_device_step). */
 #define TA_STEP_HOST_DMA 2
 int ta_step_host(ta_handle h, const void *actions, int action_dtype, int flags, uint8_t *obs_out,
