@@ -645,7 +645,25 @@ int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, int first
 }  // extern "C"
 
 namespace {
-int *g_tc_fail = nullptr;  // set by conv1_fwd_tc_kernel if its MMA-completion barrier never arrived
+// Everything the handle-free entry points cache is kept PER DEVICE (one process may drive several GPUs): the failure
+// flag of the tcgen05 kernels (set when a bounded MMA-barrier wait gave up), SM counts, CTAs per SM and the kernels'
+// shared-memory attributes, which are per-device state of the CUDA runtime.
+constexpr int MAX_DEV = 64;
+int *g_tc_fail_dev[MAX_DEV] = {};
+int cur_dev() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    return d & (MAX_DEV - 1);
+}
+int tc_fail_flag(int **out) {   // the current device's flag, allocated on first use
+    int *&f = g_tc_fail_dev[cur_dev()];
+    if (!f) {
+        CK(cudaMalloc(&f, sizeof(int)));
+        CK(cudaMemset(f, 0, sizeof(int)));
+    }
+    *out = f;
+    return TA_OK;
+}
 int g_use_tc = -1;         // -1: read TA_CONV1_TC on first use (default 1)
 
 int g_bwd_tc = -1;         // conv1 weight gradient on tcgen05: -1 = read TA_CONV1_BWD_TC on first use
@@ -714,7 +732,9 @@ int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4
     if ((uintptr_t)y_bf16 & 7u) return TA_E_INVALID;
     if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) != 0 : 1; }
     if (g_use_tc || relu_mask) {  // tcgen05 version of the layer (the only one that writes the ReLU bit mask) (TA_CONV1_TC=0 / ta_debug_conv1_tc(0) select the FP32-FMA kernel)
-        static int per_sm_u8 = 0, per_sm_f32 = 0, sms = 0;
+        static int per_sm_u8_d[MAX_DEV] = {}, per_sm_f32_d[MAX_DEV] = {}, sms_d[MAX_DEV] = {};
+        const int cd = cur_dev();
+        int &per_sm_u8 = per_sm_u8_d[cd], &per_sm_f32 = per_sm_f32_d[cd], &sms = sms_d[cd];
         if (!sms) {
             int dev = 0;
             CK(cudaGetDevice(&dev));
@@ -728,10 +748,8 @@ int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             if (getenv("TA_VERBOSE")) fprintf(stderr, "conv1_tc: %d / %d CTAs per SM (u8 / f32 input), %d SMs\n", per_sm_u8, per_sm_f32, sms);
         }
-        if (!g_tc_fail) {
-            CK(cudaMalloc(&g_tc_fail, sizeof(int)));
-            CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
-        }
+        int *g_tc_fail = nullptr;
+        if (int rc = tc_fail_flag(&g_tc_fail)) return rc;
         const int per_sm = x_dtype == TA_X_U8 ? per_sm_u8 : per_sm_f32;
         const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
         const long long cap = (long long)sms * per_sm;
@@ -764,7 +782,9 @@ int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4
 // the tcgen05 weight-gradient kernel; planes == nullptr: dy is one channels-last tensor; relu_mask (with planes): y is not read
 int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16, const void *planes,
                         const void *relu_mask, int64_t batch, float *dw4, float *db4, void *stream, int class_major = 0) {
-    static int per_sm[6] = {0, 0, 0, 0, 0, 0}, sms = 0;
+    static int per_sm_d[MAX_DEV][6] = {}, sms_d[MAX_DEV] = {};
+    const int cd = cur_dev();
+    int *per_sm = per_sm_d[cd], &sms = sms_d[cd];
     const int dyn = TCB_A_BYTES + 2 * TCB_B_BYTES;
     if (!sms) {
         int dev = 0;
@@ -779,10 +799,8 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
         if (getenv("TA_VERBOSE"))
             fprintf(stderr, "conv1_bwd_tc: %d / %d / %d CTAs per SM (dense / planes / planes + bit mask), %d SMs\n", per_sm[0], per_sm[2], per_sm[4], sms);
     }
-    if (!g_tc_fail) {
-        CK(cudaMalloc(&g_tc_fail, sizeof(int)));
-        CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
-    }
+    int *g_tc_fail = nullptr;
+    if (int rc = tc_fail_flag(&g_tc_fail)) return rc;
     if (batch * NCELL >= (1ll << 31)) return TA_E_INVALID;
     const long long ntiles = (batch * NCELL + TC_M - 1) / TC_M;
     const int variant = (planes ? (relu_mask ? 4 : 2) : 0) + (x_dtype == TA_X_U8 ? 0 : 1);
@@ -864,7 +882,8 @@ int ta_conv2_dgrad_planes(const void *dz_bf16, const void *wimg_bf16, const uint
                           void *planes_bf16, void *stream) {
     if (!dz_bf16 || !wimg_bf16 || !planes_bf16 || batch <= 0 || batch * (DG_P * DG_P) >= (1ll << 31)) return TA_E_INVALID;
     if (((uintptr_t)dz_bf16 | (uintptr_t)wimg_bf16 | (uintptr_t)planes_bf16) & 15u) return TA_E_INVALID;
-    static int sms = 0;
+    static int sms_d[MAX_DEV] = {};
+    int &sms = sms_d[cur_dev()];
     const int ws = class_major != 0;   // class-major output: the warp-specialised kernel; position-major: the single-role one
     if (!sms) {
         int dev = 0;
@@ -873,10 +892,8 @@ int ta_conv2_dgrad_planes(const void *dz_bf16, const void *wimg_bf16, const uint
         CK(cudaFuncSetAttribute(conv2_dgrad_planes_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DGW_SMEM));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    if (!g_tc_fail) {
-        CK(cudaMalloc(&g_tc_fail, sizeof(int)));
-        CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
-    }
+    int *g_tc_fail = nullptr;
+    if (int rc = tc_fail_flag(&g_tc_fail)) return rc;
     const long long ntiles = (batch * (DG_P * DG_P) + TC_M - 1) / TC_M;
     const int g = (int)(ntiles < sms ? ntiles : sms);   // one persistent CTA per SM (208 / 216 KB of shared memory each)
     if (ws) {
@@ -915,7 +932,8 @@ int ta_conv2_dgrad_conv1_bwd(const void *dz_bf16, const void *wimg_bf16, const u
         x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
     if ((((uintptr_t)dz_bf16 | (uintptr_t)wimg_bf16 | (uintptr_t)relu_mask) & 15u)) return TA_E_INVALID;
-    static int sms = 0;
+    static int sms_d[MAX_DEV] = {};
+    int &sms = sms_d[cur_dev()];
     if (!sms) {
         int dev = 0;
         CK(cudaGetDevice(&dev));
@@ -923,10 +941,8 @@ int ta_conv2_dgrad_conv1_bwd(const void *dz_bf16, const void *wimg_bf16, const u
         CK(cudaFuncSetAttribute(conv2_dgrad_conv1_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    if (!g_tc_fail) {
-        CK(cudaMalloc(&g_tc_fail, sizeof(int)));
-        CK(cudaMemset(g_tc_fail, 0, sizeof(int)));
-    }
+    int *g_tc_fail = nullptr;
+    if (int rc = tc_fail_flag(&g_tc_fail)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(dw4, 0, 256 * 16 * sizeof(float), st));
     CK(cudaMemsetAsync(db4, 0, 256 * sizeof(float), st));
@@ -1162,6 +1178,7 @@ int ta_debug_conv1_bwd_tc(int on) {
 
 /* check for the tcgen05 conv1 kernel: 1 if any launch gave up waiting for its MMA (synchronises) */
 int ta_debug_conv1_tc_failed(void) {
+    int *g_tc_fail = g_tc_fail_dev[cur_dev()];   // (the current device's flag)
     if (!g_tc_fail) return 0;
     int v = 0;
     if (cudaMemcpy(&v, g_tc_fail, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
