@@ -11,6 +11,7 @@
 #include "ta_aux.cuh"
 #include "ta_conv1.cuh"
 #include "ta_conv1_tc.cuh"
+#include "ta_conv1_fwd_ws.cuh"
 #include "ta_dgrad_tc.cuh"
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
@@ -668,6 +669,26 @@ int g_use_tc = -1;         // -1: read TA_CONV1_TC on first use (default 1)
 
 int g_bwd_tc = -1;         // conv1 weight gradient on tcgen05: -1 = read TA_CONV1_BWD_TC on first use
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda); a rank-3 bf16 tensor with a 128-byte-swizzled box
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int tensor_map_3d_bf16(CUtensorMap *map, void *base, const cuuint64_t dims[3], const cuuint64_t strides[2], const cuuint32_t box[3]) {
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) return cuda_fail(cudaErrorNotSupported, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (encode_fn)fn;
+    }
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    return TA_OK;
+}
+
 // Resident CTAs per SM of a TMEM-allocating kernel from its own footprint (the occupancy API answers 1 for such
 // kernels): registers, shared memory with the large carve-out, and 512 TMEM columns per SM.
 int tc_ctas_per_sm(const void *kern, int threads, int dyn_smem, int tmem_cols, int *out) {
@@ -730,7 +751,44 @@ int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4
     if (!x || !w4 || !b4 || !y_bf16 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
     if ((uintptr_t)y_bf16 & 7u) return TA_E_INVALID;
-    if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) != 0 : 1; }
+    if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) : 1; }
+    if (g_use_tc >= 2 && !((uintptr_t)y_bf16 & 15u) && batch * NCELL < (1ll << 31)) {
+        // TA_CONV1_TC=2: the warp-specialised kernel with tensor-map stores (ta_conv1_fwd_ws.cuh) -- bit-identical to
+        // conv1_fwd_tc_kernel but not faster (150 us without / 208 us with the bit mask against 148 / 164 us per 4096 samples;
+        // its header says where the time goes), so conv1_fwd_tc_kernel stays the default
+        static int sms_d[MAX_DEV] = {};
+        int &sms = sms_d[cur_dev()];
+        if (!sms) {
+            int dev = 0;
+            CK(cudaGetDevice(&dev));
+            CK(cudaFuncSetAttribute(conv1_fwd_ws_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+            CK(cudaFuncSetAttribute(conv1_fwd_ws_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+            CK(cudaFuncSetAttribute(conv1_fwd_ws_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+            CK(cudaFuncSetAttribute(conv1_fwd_ws_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        int *g_tc_fail = nullptr;
+        if (int rc = tc_fail_flag(&g_tc_fail)) return rc;
+        // y as [batch * 33 image rows][33 pixels][64 channels]; one store = one image row
+        const cuuint64_t dims[3] = {64, (cuuint64_t)C1_OUT, (cuuint64_t)batch * C1_OUT}, strides[2] = {128, (cuuint64_t)C1_OUT * 128};
+        const cuuint32_t box[3] = {64, (cuuint32_t)C1_OUT, 1};
+        CUtensorMap map;
+        if (int rc = tensor_map_3d_bf16(&map, y_bf16, dims, strides, box)) return rc;
+        const long long ntiles = (batch * GS + FW_ROWS - 1) / FW_ROWS;
+        const int g = (int)(ntiles < sms ? ntiles : sms);   // one persistent CTA per SM (all 512 TMEM columns)
+        cudaStream_t st = (cudaStream_t)stream;
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("TA_FW_DBG"); dbg = e ? atoi(e) : 0; }
+        if (x_dtype == TA_X_U8 && relu_mask)
+            conv1_fwd_ws_kernel<uint8_t, true><<<g, FW_THREADS, FW_SMEM, st>>>((const uint8_t *)x, x_stride, w4, b4, batch, map, relu_mask, g_tc_fail, dbg);
+        else if (x_dtype == TA_X_U8)
+            conv1_fwd_ws_kernel<uint8_t, false><<<g, FW_THREADS, FW_SMEM, st>>>((const uint8_t *)x, x_stride, w4, b4, batch, map, nullptr, g_tc_fail, dbg);
+        else if (relu_mask)
+            conv1_fwd_ws_kernel<float, true><<<g, FW_THREADS, FW_SMEM, st>>>((const float *)x, x_stride, w4, b4, batch, map, relu_mask, g_tc_fail, dbg);
+        else
+            conv1_fwd_ws_kernel<float, false><<<g, FW_THREADS, FW_SMEM, st>>>((const float *)x, x_stride, w4, b4, batch, map, nullptr, g_tc_fail, dbg);
+        return launch_ok("conv1_fwd_ws_kernel");
+    }
     if (g_use_tc || relu_mask) {  // tcgen05 version of the layer (the only one that writes the ReLU bit mask) (TA_CONV1_TC=0 / ta_debug_conv1_tc(0) select the FP32-FMA kernel)
         static int per_sm_u8_d[MAX_DEV] = {}, per_sm_f32_d[MAX_DEV] = {}, sms_d[MAX_DEV] = {};
         const int cd = cur_dev();
@@ -899,24 +957,11 @@ int ta_conv2_dgrad_planes(const void *dz_bf16, const void *wimg_bf16, const uint
     if (ws) {
         // the class-major planes [4][npos][64] as a rank-3 tensor; the kernel stores boxes of 32 positions x 64 channels of one
         // class from 128-byte-swizzled shared memory
-        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static encode_fn encode = nullptr;
-        if (!encode) {
-            void *fn = nullptr;
-            cudaDriverEntryPointQueryResult qr;
-            CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
-            if (!fn || qr != cudaDriverEntryPointSuccess) return cuda_fail(cudaErrorNotSupported, "cuTensorMapEncodeTiled is not available in this driver");
-            encode = (encode_fn)fn;
-        }
         const cuuint64_t npos = (cuuint64_t)batch * (DG_P * DG_P);
         const cuuint64_t dims[3] = {64, npos, 4}, strides[2] = {128, npos * 128};
-        const cuuint32_t box[3] = {64, 32, 1}, estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {64, 32, 1};
         CUtensorMap map;
-        const CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, planes_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (class-major planes)");
+        if (int rc = tensor_map_3d_bf16(&map, planes_bf16, dims, strides, box)) return rc;
         conv2_dgrad_planes_ws_kernel<<<g, DGW_THREADS, DGW_SMEM, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dz_bf16, (const uint4 *)wimg_bf16,
                                                                                        relu_mask, batch, map, g_tc_fail, g_dgrad_prof);
         return launch_ok("conv2_dgrad_planes_ws_kernel");
@@ -1154,8 +1199,32 @@ __global__ void __launch_bounds__(32) write_probe_bulk(uint8_t *dst, long long n
         bulk_wait_read<0>();
     }
 }
+// mode 2 / 3: the store pattern of conv1_fwd_ws_kernel without its compute -- one CTA per SM, tile = 14 image rows of 4224
+// bytes (two groups of 7: even / odd rows), one bulk store per row from a 1024-aligned staging block, at most `depth` tiles
+// of stores outstanding per group (mode 2: depth 2 = the kernel's double buffer; mode 3: depth 8)
+__global__ void __launch_bounds__(64) write_probe_rows(uint8_t *dst, long long ntiles, int depth) {
+    extern __shared__ __align__(1024) uint8_t rows_buf[];
+    for (int i = threadIdx.x; i < 7 * 5120 / 4; i += 64) reinterpret_cast<uint32_t *>(rows_buf)[i] = 0x01020304u * (i + 1);
+    fence_proxy_async();
+    __syncthreads();
+    const int g = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int r = 0; r < 7; r++) bulk_s2g(dst + ((t * 14 + 2 * r + g) * 4224), rows_buf + r * 5120, 4224);
+            bulk_commit();
+            if (depth <= 2) bulk_wait_read<1>();
+            else bulk_wait_read<7>();
+        }
+        bulk_wait_read<0>();
+    }
+}
 int ta_debug_write_probe(void *dst, int64_t bytes, int mode, void *stream) {
     if (!dst || bytes <= 0) return TA_E_INVALID;
+    if (mode >= 2) {
+        CK(cudaFuncSetAttribute(write_probe_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 5120));
+        write_probe_rows<<<148, 64, 7 * 5120, (cudaStream_t)stream>>>((uint8_t *)dst, bytes / (14 * 4224), mode == 2 ? 2 : 8);
+        return launch_ok("write_probe_rows");
+    }
     if (mode == 0) write_probe_stg<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((uint4 *)dst, bytes / 16);
     else write_probe_bulk<<<148 * 16, 32, 0, (cudaStream_t)stream>>>((uint8_t *)dst, bytes / 3072);
     return launch_ok("write_probe");
@@ -1163,9 +1232,9 @@ int ta_debug_write_probe(void *dst, int64_t bytes, int mode, void *stream) {
 
 /* test hook: route ta_conv1_fwd through the tcgen05 kernel (1, default) or the FP32-FMA kernel (0); returns the
  * previous setting (-1 = not decided yet) */
-int ta_debug_conv1_tc(int on) {
+int ta_debug_conv1_tc(int on) {   // 0: FP32-FMA kernel, 1: conv1_fwd_tc_kernel (default), 2: conv1_fwd_ws_kernel; -1: back to TA_CONV1_TC / default
     const int prev = g_use_tc;
-    g_use_tc = on != 0;
+    g_use_tc = on < 0 ? -1 : (on > 2 ? 2 : on);
     return prev;
 }
 

@@ -20,6 +20,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import twoarmy_b200 as pkg
 L = pkg._capi.lib()
 L.ta_debug_write_probe.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
-for mode, name in ((0, "STG.128 grid-stride"), (1, "3 KB TMA bulk stores")):
+for mode, name in ((0, "STG.128 grid-stride"), (1, "3 KB TMA bulk stores"), (2, "4224 B rows, 2 tiles deep"), (3, "4224 B rows, 8 tiles deep")):
     fn = lambda: L.ta_debug_write_probe(C.c_void_p(x.data_ptr()), x.numel(), mode, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     ms = t(fn); print(f"{name:24s} 1 GiB: {ms:.3f} ms  {x.numel()/ms/1e6:.0f} GB/s write")

@@ -127,6 +127,44 @@ def test_conv2_dgrad_planes_tcgen05(B, with_mask, class_major):
 
 @pytest.mark.parametrize("B", [1, 7, 300, 1500])
 @pytest.mark.parametrize("codes", [True, False])
+@pytest.mark.parametrize("with_mask", [True, False])
+def test_conv1_fwd_ws_equals_single_role_kernel(B, codes, with_mask):
+    """conv1_fwd_ws_kernel (warp-specialised, seven-grid-row tiles, one N = 256 MMA per operand pair, tensor-map stores of
+    whole image rows) performs the same arithmetic as conv1_fwd_tc_kernel: outputs and ReLU bit masks are BIT-IDENTICAL, for
+    code and float inputs, batch sizes with partial last tiles, and nothing is written outside y (NaN-filled guard rows)."""
+    L, check = _lib()
+    g = torch.Generator(device="cuda").manual_seed(B + 11)
+    w4 = torch.randn((256, 16), generator=g, device="cuda") * 0.3
+    b4 = torch.randn((256,), generator=g, device="cuda") * 0.1
+    if codes:
+        x = torch.tensor([0, 1, 2, 4], dtype=torch.uint8, device="cuda")[torch.randint(0, 4, (B, 5, 289), generator=g, device="cuda")]
+        x_dtype = 1
+    else:
+        x, x_dtype = torch.randn((B, 5, 289), generator=g, device="cuda"), 0
+    outs = []
+    for mode in (2, 1):
+        prev = L.ta_debug_conv1_tc(mode)
+        try:
+            y = torch.full((B + 1, 33, 33, 64), float("nan"), dtype=torch.bfloat16, device="cuda")    # the last sample is a guard
+            mask = torch.full((B * 289 * 8 + 64,), -1, dtype=torch.int32, device="cuda")
+            if with_mask:
+                check(L.ta_conv1_fwd_mask(_p(x), x_dtype, x.stride(0), _p(w4), _p(b4), B, _p(y), _p(mask), _st()), "ta_conv1_fwd_mask")
+            else:
+                check(L.ta_conv1_fwd(_p(x), x_dtype, x.stride(0), _p(w4), _p(b4), B, _p(y), _st()), "ta_conv1_fwd")
+            torch.cuda.synchronize()
+        finally:
+            L.ta_debug_conv1_tc(prev)
+        assert L.ta_debug_conv1_tc_failed() == 0
+        assert bool(torch.isnan(y[B].float()).all()) and bool((mask[B * 289 * 8:] == -1).all())
+        assert bool(torch.isfinite(y[:B].float()).all())
+        outs.append((y[:B].view(torch.int16).clone(), mask[:B * 289 * 8].clone()))
+    assert bool((outs[0][0] == outs[1][0]).all())
+    if with_mask:
+        assert bool((outs[0][1] == outs[1][1]).all())
+
+
+@pytest.mark.parametrize("B", [1, 7, 300, 1500])
+@pytest.mark.parametrize("codes", [True, False])
 def test_conv2_dgrad_conv1_bwd_fused(B, codes):
     """ta_conv2_dgrad_conv1_bwd (one kernel: conv2's data gradient on tcgen05 -> ReLU mask -> conv1's weight / bias gradient
     GEMM, the planes never leaving the SM) against an independent float64 evaluation from the same bf16 inputs:

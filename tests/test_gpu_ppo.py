@@ -234,16 +234,18 @@ def test_conv1_weight_gradient_run_to_run_bound():
         assert float((gb - grads[0][1]).abs().max()) <= 1e-5 * float(grads[0][1].abs().max())
 
 
-@pytest.fixture(params=["tcgen05", "fma"])
+@pytest.fixture(params=["tcgen05-ws", "tcgen05", "fma"])
 def conv1_kernel(request):
-    """Run the test once through each kernel pair of the fused first layer (forward + weight gradient)."""
+    """Run the test once through each kernel set of the fused first layer: the warp-specialised tcgen05 forward with
+    tensor-map stores (TA_CONV1_TC=2) / the single-role tcgen05 forward (default) / the FP32-FMA forward, each with the matching
+    weight-gradient kernel (tcgen05 for the first two)."""
     import twoarmy_b200 as pkg
     L = pkg._capi.lib()
-    on = 1 if request.param == "tcgen05" else 0
-    prev, prev_bwd = L.ta_debug_conv1_tc(on), L.ta_debug_conv1_bwd_tc(on)
+    on = {"tcgen05-ws": 2, "tcgen05": 1, "fma": 0}[request.param]
+    prev, prev_bwd = L.ta_debug_conv1_tc(on), L.ta_debug_conv1_bwd_tc(1 if on else 0)
     yield request.param
     assert L.ta_debug_conv1_tc_failed() == 0          # no tcgen05 launch gave up on its MMA barrier
-    L.ta_debug_conv1_tc(1 if prev != 0 else 0)
+    L.ta_debug_conv1_tc(prev)
     L.ta_debug_conv1_bwd_tc(1 if prev_bwd != 0 else 0)
 
 
