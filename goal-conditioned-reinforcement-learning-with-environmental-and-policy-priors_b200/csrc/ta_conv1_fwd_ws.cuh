@@ -1,33 +1,38 @@
 // ta_conv1_fwd_ws.cuh -- TINet's fused first layer (ta_conv1_tc.cuh: LUT decode + UpsamplingNearest2d(4) + Conv2d(4,64,4,2)
 // + bias + ReLU as D[position, (phase, channel)] = P[position, 16] x W4^T[16, 256]) as a WARP-SPECIALISED persistent kernel
-// whose output leaves through TMA tensor-map stores.  EXPERIMENTAL (TA_CONV1_TC=2): bit-identical to conv1_fwd_tc_kernel,
-// which stays the default because this kernel is not faster -- measurements below.
+// whose output leaves through TMA tensor-map stores.  Default forward kernel (TA_CONV1_TC=1 selects conv1_fwd_tc_kernel, which
+// runs stage -> MMA -> epilogue serially inside 128-thread CTAs and scatters a position's four phases in 64-byte pieces); the
+// two are bit-identical (same arithmetic: bf16 hi / lo operands, fp32 accumulation, bias add, cvt.rn.relu.bf16x2, the mask
+// bits from the carry trick).  all_net.py:142-143,157,180-181.
 //   * a tile is SEVEN ROWS of the 17-wide position grid (119 positions; rows run on across samples: linear position index
 //     = (sample * 17 + m) * 17 + n), so that for a fixed output-row parity py the tile's output is seven whole image rows
 //     y = 2m + py of 33 pixels x 128 bytes = 4224 contiguous bytes each;
-//   * the epilogue writes the (px = 0, px = 1) pixels of a position into rows 2n, 2n + 1 of that image row's staging block
-//     in the TMA's 128-byte swizzle, and ONE tensor-map store per image row (box 64 channels x 33 pixels x 1 row of the
-//     [B * 33][33][64] view of y) moves it: 14 stores of 4 KB per tile instead of 3808 scattered 64-byte pieces;
+//   * the epilogue writes the pixel of its phase (py, px) into row 2n + px of that image row's staging block in the TMA's
+//     128-byte swizzle, and ONE tensor-map store per image row (box 64 channels x 33 pixels x 1 row of the [B * 33][33][64]
+//     view of y) moves it: 14 stores of 4 KB per tile instead of 3808 scattered 64-byte pieces;
 //   * all four phases come out of ONE N = 256 MMA per operand pair (3 MMAs per tile: hi*hi, lo*hi, hi*lo) into 256 TMEM
 //     columns, double-buffered (512).
-//   roles (544 threads): two groups of four decoder warps (the tile's P operand, thread = position; even / odd tiles), warp 8 MMA
-//   issuer (converged, elect.sync), eight epilogue warps -- warps 0-3 the py = 0 phases, warps 9-12 the py = 1 phases, one TMEM
-//   lane quadrant each; the four warps of a row parity form a group that owns its staging (2 buffers x 7 blocks x 5 KB) and
-//   meets only inside the group (named barriers), the roles through mbarriers.  Every mbarrier wait is bounded and raises `fail`.
-// Same arithmetic as conv1_fwd_tc_kernel (bf16 hi / lo operands, fp32 accumulation, bias add, cvt.rn.relu.bf16x2, the mask
-// bits from the carry trick), so the two kernels agree bit for bit; all_net.py:142-143,157,180-181.
+//   roles: SEVEN WARP GROUPS (896 threads) -- 0, 3, 5, 6: epilogue of phase (0,0), (1,0), (0,1), (1,1), one TMEM lane quadrant
+//   per warp; 1, 4: decoders of this CTA's even / odd tiles (the tile's P operand, thread = position); 2: the MMA issuer
+//   (warp 8, converged, elect.sync; its three sister warps idle).  The 896 threads start with 72 registers each; the decoder
+//   and MMA groups give registers up (setmaxnreg.dec 48) and the four epilogue groups take them (setmaxnreg.inc 88) -- sixteen
+//   epilogue warps do not fit otherwise (spills: 370-480 us).  The two warp groups of a row parity py share the staging of
+//   its image rows (2 buffers x 7 blocks x 5 KB) and meet only inside the pair (named barriers of 256 threads); the roles meet
+//   through mbarriers.  Every mbarrier wait is bounded and raises `fail`.
 //
 // Measured per 4096 samples (scripts/probe_conv1_fwd.py; ablation bits in `dbg`, TA_FW_DBG; conv1_fwd_tc_kernel: 148 us
 // without / 164 us with the ReLU bit mask):
-//   whole kernel                                     150 us without the mask, 208 us with it
-//   stores only (no epilogue arithmetic)              98 us = 5.8 TB/s: the store pattern itself reaches the write roofline
-//                                                     (the same 14 x 4224-byte stores per tile with no compute: 6.1 TB/s, write_bw.py)
-//   epilogue arithmetic only (no stores)              96 us without the mask, 150 us with it (its 64 extra integer ops per 32 channels)
-//   neither (decode -> MMA -> TMEM read -> barriers)  62 us; with one decoder group and 64-bit index arithmetic this was 116 us and
-//                                                     paced everything: a decoder warp is ONE dependent instruction stream on its scheduler
-// so the eight epilogue warps (two per scheduler, ~520 / ~780 dependent instructions per tile) are the bottleneck and their time does
-// not overlap the stores'.  Sixteen epilogue warps need more registers than 800 threads leave (spills: 370-480 us); the next step would be
-// setmaxnreg to move registers from the decoder / MMA warp groups to the epilogue groups.
+//   whole kernel                                     135 us without the mask, 156 us with it
+//   stores only (no epilogue arithmetic)              93 us = 6.1 TB/s: the store pattern reaches the write roofline
+//                                                     (the same 14 x 4224-byte stores per tile as a bare probe: 6.1 TB/s, write_bw.py)
+//   epilogue arithmetic only (no stores)              95 us without the mask, 115 us with it (64 extra integer ops per 32 channels)
+//   neither (decode -> MMA -> TMEM read -> barriers)  66 us
+// History: with eight epilogue warps (two phases each) the epilogue's dependent instruction stream was the bottleneck (150 /
+// 208 us); with ONE decoder group and 64-bit index arithmetic the decoders paced everything at 116 us -- a role that is one
+// warp per scheduler is a serial instruction stream and its instruction count is its time.  Stores and arithmetic still do not
+// overlap fully (135 vs max(93, 95)): the staging writes conflict two ways in their banks (rows 2n + px of consecutive lanes
+// have the same parity, so the swizzle only spreads them over four of the eight 16-byte bank groups) and share the
+// shared-memory port with the TMA's reads and the MMA operands.
 #pragma once
 #include <cuda.h>
 
@@ -36,7 +41,8 @@
 
 namespace ta {
 
-constexpr int FW_THREADS = 544;
+constexpr int FW_THREADS = 896;   // seven warp groups: 0 epi (py0,px0), 1 dec A, 2 MMA (+3 idle warps), 3 epi (py1,px0), 4 dec B, 5 epi (py0,px1), 6 epi (py1,px1)
+constexpr int FW_REGS_LOW = 48, FW_REGS_EPI = 88;   // setmaxnreg: 896 threads start with 72 registers each; 12 warps give 24 up, 16 warps take 16
 constexpr int FW_ROWS = 7, FW_POS = FW_ROWS * GS;             // 119 positions per tile
 constexpr int FW_SLOTS = FW_POS + TC_HALO;                    // 137 decoded positions per tile
 constexpr int FW_BLOCK = 5 * 1024;                            // staging of one image row: 33 x 128 B, 1024-aligned
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
             dg_mbar_init(&a_full[s], 128);     // the decoder threads
             dg_mbar_init(&a_empty[s], 1);      // one tcgen05.commit
             dg_mbar_init(&acc_full[s], 1);     // one tcgen05.commit
-            dg_mbar_init(&acc_empty[s], 8);    // the eight epilogue warps
+            dg_mbar_init(&acc_empty[s], 16);   // the sixteen epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -127,16 +133,17 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
     const long long npos = B * NCELL, nrows = B * GS, ntiles = (nrows + FW_ROWS - 1) / FW_ROWS;
     bool dead = false;
 
-    if ((warp >= 4 && warp < 8) || warp >= 13) {
+    if ((warp >= 4 && warp < 8) || (warp >= 16 && warp < 20)) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_LOW));
         // ---------------- decoders: the tile's A operand (hi, lo), thread = position ----------------
-        // TWO groups of 128 threads (warps 4-7: this CTA's even tiles = A stage 0, warps 13-16: the odd ones = stage 1), each with
+        // TWO groups of 128 threads (warps 4-7: this CTA's even tiles = A stage 0, warps 16-19: the odd ones = stage 1), each with
         // its own decode scratch and named barrier.  A decoder warp is ONE dependent instruction stream on its scheduler: one
         // group with 64-bit index arithmetic needed 3.3 k cycles per tile and paced the whole kernel (the rest of the pipeline
         // runs a tile in 1.3 k without it).
         // (a thread whose wait gave up keeps going without waiting: it must reach the named barrier of its next tile, where all
         // 128 leave together)
-        const int dgrp = warp >= 13 ? 1 : 0;
-        const int ptid = tid - (dgrp ? 416 : 128);
+        const int dgrp = warp >= 16 ? 1 : 0;
+        const int ptid = tid - (dgrp ? 512 : 128);
         const int bar_id = dgrp ? 4 : 1;
         const unsigned np32 = (unsigned)npos;
         uint4 *dec = sDec + dgrp * FW_SLOTS;
@@ -185,7 +192,9 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
             fence_proxy_async();
             dg_mbar_arrive(&a_full[dgrp]);
         }
-    } else if (warp == 8) {
+    } else if (warp >= 8 && warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_LOW));   // (the whole warp group; warps 9-11 have no other work)
+        if (warp == 8) {
         // ---------------- MMA issuer (all 32 lanes converged, one elected lane issues) ----------------
         const uint64_t dBh = tc_smem_desc(sB), dBl = tc_smem_desc(sB + TC_N * 32);
         int it = 0;
@@ -203,15 +212,20 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
             tc_commit_elect(&a_empty[st]);
             tc_commit_elect(&acc_full[st]);
         }
+        }
     } else {
-        // ---------------- epilogue: group g = output-row parity py (warps 0-3: py = 0, warps 9-12: py = 1) ----------------
-        // a warp reads the TMEM lane quadrant warp % 4 and handles the px = 0 and px = 1 phases of its positions
-        const int g = warp >= 9 ? 1 : 0, q = warp & 3;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_EPI));
+        // ---------------- epilogue: one output phase (py, px) per warp group, one TMEM lane quadrant (warp % 4) per warp --------
+        // group g = py (two warp groups = 256 threads) shares the staging of its image rows
+        const int wg = warp >> 2;                          // 0: (0,0), 3: (1,0), 5: (0,1), 6: (1,1)
+        const int g = (wg == 3 || wg == 6) ? 1 : 0, px = wg >= 5 ? 1 : 0, q = warp & 3;
+        const int phase = g * 2 + px;
         const int p = q * 32 + lane;                       // TMEM lane = position of the tile
         const int r = p / GS, n = p - r * GS;              // grid row of the tile, column
-        const bool leader = q == 0 && lane == 0;           // issues the group's stores
+        const bool leader = px == 0 && q == 0 && lane == 0;   // issues the group's stores
         const uint64_t map_u = reinterpret_cast<uint64_t>(&y_map);
         const int bar_id = 2 + g;
+        const int sw = (2 * n + px) & 7;
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const int buf = it & 1;
@@ -223,13 +237,10 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
             // the stores issued two tiles ago have read this staging buffer
             if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             if (dead) group_dead[g] = 1;
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (group_dead[g]) { dead = true; break; }
-#pragma unroll
-            for (int px = 0; px < 2; px++) {
-                const int phase = g * 2 + px;
+            {
                 uint8_t *srow = stage + r * FW_BLOCK + (2 * n + px) * 128;
-                const int sw = (2 * n + px) & 7;
                 const bool wr = valid && !(px && n == 16);   // (pixel x = 33 does not exist)
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
                             : "r"(taddr));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     }
-                    if (px == 1 && half == 1) {   // this warp's share of the accumulator buffer is in registers
+                    if (half == 1) {   // this warp's share of the accumulator buffer is in registers
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) dg_mbar_arrive(&acc_empty[buf]);
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
                 }
             }
             fence_proxy_async();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (leader && !(dbg & 1)) {
                 // one store per image row y = 2m + py of the tile's seven grid rows (row 33 of a sample does not exist; rows past
                 // the last sample are not stored)

@@ -751,11 +751,10 @@ int conv1_fwd_impl(const void *x, int x_dtype, int64_t x_stride, const float *w4
     if (!x || !w4 || !b4 || !y_bf16 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8))
         return TA_E_INVALID;
     if ((uintptr_t)y_bf16 & 7u) return TA_E_INVALID;
-    if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) : 1; }
+    if (g_use_tc < 0) { const char *e = getenv("TA_CONV1_TC"); g_use_tc = e ? atoi(e) : 2; }
     if (g_use_tc >= 2 && !((uintptr_t)y_bf16 & 15u) && batch * NCELL < (1ll << 31)) {
-        // TA_CONV1_TC=2: the warp-specialised kernel with tensor-map stores (ta_conv1_fwd_ws.cuh) -- bit-identical to
-        // conv1_fwd_tc_kernel but not faster (150 us without / 208 us with the bit mask against 148 / 164 us per 4096 samples;
-        // its header says where the time goes), so conv1_fwd_tc_kernel stays the default
+        // default: the warp-specialised kernel with tensor-map stores (ta_conv1_fwd_ws.cuh; 135 / 156 us without / with the bit
+        // mask per 4096 samples); TA_CONV1_TC=1 selects conv1_fwd_tc_kernel (148 / 164 us, bit-identical), 0 the FP32-FMA kernel
         static int sms_d[MAX_DEV] = {};
         int &sms = sms_d[cur_dev()];
         if (!sms) {
@@ -1232,7 +1231,7 @@ int ta_debug_write_probe(void *dst, int64_t bytes, int mode, void *stream) {
 
 /* test hook: route ta_conv1_fwd through the tcgen05 kernel (1, default) or the FP32-FMA kernel (0); returns the
  * previous setting (-1 = not decided yet) */
-int ta_debug_conv1_tc(int on) {   // 0: FP32-FMA kernel, 1: conv1_fwd_tc_kernel (default), 2: conv1_fwd_ws_kernel; -1: back to TA_CONV1_TC / default
+int ta_debug_conv1_tc(int on) {   // 0: FP32-FMA kernel, 1: conv1_fwd_tc_kernel, 2: conv1_fwd_ws_kernel (default); -1: back to TA_CONV1_TC / default
     const int prev = g_use_tc;
     g_use_tc = on < 0 ? -1 : (on > 2 ? 2 : on);
     return prev;

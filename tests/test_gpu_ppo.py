@@ -237,7 +237,7 @@ def test_conv1_weight_gradient_run_to_run_bound():
 @pytest.fixture(params=["tcgen05-ws", "tcgen05", "fma"])
 def conv1_kernel(request):
     """Run the test once through each kernel set of the fused first layer: the warp-specialised tcgen05 forward with
-    tensor-map stores (TA_CONV1_TC=2) / the single-role tcgen05 forward (default) / the FP32-FMA forward, each with the matching
+    tensor-map stores (default) / the single-role tcgen05 forward (TA_CONV1_TC=1) / the FP32-FMA forward, each with the matching
     weight-gradient kernel (tcgen05 for the first two)."""
     import twoarmy_b200 as pkg
     L = pkg._capi.lib()
