@@ -254,9 +254,16 @@ class RolloutBuffer:
         """Sample-major views ([T*N, ...]) in the field names the reference uses."""
         B = self.counter * self.N
         T = self.counter
+        # next_same: sample i + N is the NEXT record of the same env and episode, i.e. its frames 0..3 / positions 0..3 are this
+        # record's frames 1..4 (VecRollout pushes record t + 1 from record t unless the episode ended at step t), so
+        # V(s') of sample i is V(s) of sample i + N and PPO.values evaluates the critic on it once
+        nxt = torch.zeros((T, self.N), dtype=torch.bool, device=self.device)
+        if T > 1:
+            nxt[:T - 1] = self.ended[:T - 1] == 0
         return {"s": self.s[:T].reshape(B, 5, 289), "p": self.p[:T].reshape(B, 5, 2), "a": self.a[:T].reshape(B, 1),
                 "g": self.g.unsqueeze(0).expand(T, self.N, 2).reshape(B, 2), "r": self.r[:T].reshape(B, 1),
-                "d": self.d[:T].reshape(B, 1), "a_logp": self.a_logp[:T].reshape(B, 1)}
+                "d": self.d[:T].reshape(B, 1), "a_logp": self.a_logp[:T].reshape(B, 1),
+                "next_same": nxt.reshape(B), "next_stride": self.N}
 
 
 def with_her(buf: "RolloutBuffer", seed: int = 9981, env_id0: int = 0, first: int = 0):
@@ -331,6 +338,9 @@ class PPO:
         # and hyper-parameters): the small per-update tensors it reads are persistent copies (TA_PPO_KEEP_GRAPH=0: re-capture
         # in every update, as before)
         self.keep_graph = os.environ.get("TA_PPO_KEEP_GRAPH", "1") == "1"
+        # V(s') of a sample whose next record belongs to the same episode is V(s) of that record (PPO.values): one critic
+        # pass over the buffer instead of two (TA_PPO_SHARE_NEXT_VALUE=0: two full passes as in the reference)
+        self.share_next_value = os.environ.get("TA_PPO_SHARE_NEXT_VALUE", "1") == "1"
         self._static = None
         self._graph_cache = None
         self._step_key = None
@@ -385,22 +395,39 @@ class PPO:
 
     # ------------------------------------------------------------------ learning
     @torch.no_grad()
-    def values(self, s, p, g, chunk: int = 16384, src=None):
-        """(V(s[:,0:4]), V(s[:,1:5])) in chunks: the two critic passes of PPO.py:113-114."""
-        outs0, outs1 = [], []
+    def values(self, s, p, g, chunk: int = 16384, src=None, next_same=None, next_stride: int = 0):
+        """(V(s[:,0:4]), V(s[:,1:5])) in chunks: the two critic passes of PPO.py:113-114.
+        next_same (bool [B], with next_stride): where set, sample i + next_stride holds the state s' of sample i as ITS s
+        (RolloutBuffer.flat), so V(s') is read from the first pass and the second pass only runs on the remaining samples
+        (episode ends and the last time step): the same values, about half the critic work."""
         self.critic.eval()
         B = s.shape[0] if src is None else src.shape[0]
-        for i in range(0, B, chunk):
-            rows = slice(i, i + chunk) if src is None else src[i:i + chunk]
-            sc = s[rows]
-            if sc.dtype == torch.uint8 and not (sc.is_cuda and self.autocast):
-                sc = decode_matrix(sc)
-            pc, gc = p[rows], g[i:i + chunk]
-            x0, x1 = self._net_in(sc[:, 0:4]), self._net_in(sc[:, 1:5])
-            with self._amp():
-                outs0.append(self.critic(x0, pc[:, 0:4], gc))
-                outs1.append(self.critic(x1, pc[:, 1:5], gc))
-        return torch.cat(outs0), torch.cat(outs1)
+
+        def critic_pass(lo, rows_of, idx=None):
+            outs = []
+            n = B if idx is None else idx.numel()
+            for i in range(0, n, chunk):
+                rows = rows_of(i) if idx is None else idx[i:i + chunk]
+                sc = s[rows]
+                if sc.dtype == torch.uint8 and not (sc.is_cuda and self.autocast):
+                    sc = decode_matrix(sc)
+                pc, gc = p[rows], (g[i:i + chunk] if idx is None else g[rows])
+                with self._amp():
+                    outs.append(self.critic(self._net_in(sc[:, lo:lo + 4]), pc[:, lo:lo + 4], gc))
+            return torch.cat(outs) if outs else torch.empty((0, 1), device=s.device)
+
+        rows_of = (lambda i: slice(i, i + chunk)) if src is None else (lambda i: src[i:i + chunk])
+        v = critic_pass(0, rows_of)
+        if next_same is None or src is not None or next_stride <= 0:
+            return v, critic_pass(1, rows_of)
+        nxt = next_same.to(s.device).view(-1)
+        rest = torch.nonzero(~nxt).view(-1)                       # (one host synchronisation per update)
+        v_next = torch.empty_like(v)
+        shifted = torch.roll(v, -int(next_stride), 0)             # v[i + stride]; the wrapped tail is never selected (next_same is 0 there)
+        v_next[nxt] = shifted[nxt].to(v_next.dtype)
+        if rest.numel():
+            v_next[rest] = critic_pass(1, None, idx=rest).to(v_next.dtype)
+        return v, v_next
 
     def advantages(self, r, v, v_next):
         """PPO.py:112-115: target_v = r + gamma*V(s'), adv = target_v - V(s).  On a GPU this is
@@ -456,7 +483,8 @@ class PPO:
             assert g.shape[0] == src.shape[0] and r.shape[0] == src.shape[0]
             old_a_logp, a = old_a_logp[src], a[src]
         B = s.shape[0] if src is None else src.shape[0]
-        v, v_next = self.values(s, p, g, src=src)
+        v, v_next = self.values(s, p, g, src=src, next_same=buffer.get("next_same") if self.share_next_value else None,
+                                next_stride=int(buffer.get("next_stride", 0)))
         target_v, adv = self.advantages(r, v, v_next)
         bs = minibatch or self.batch_size
         self.actor.train()

@@ -500,3 +500,45 @@ def test_step_graph_kept_across_updates_equals_recapture():
     # the updates are not interchangeable: the value loss follows the rescaled rewards (what a stale target would miss)
     assert losses[1][2, 1] > 1.5 * losses[1][0, 1]
     assert float((outs[0] - outs[1]).abs().max()) < 5e-3
+
+
+def test_next_value_shared_with_next_record():
+    """RolloutBuffer.flat()'s `next_same` hint: where the episode did not end at step t, record t + 1 of the same env holds
+    record t's frames 1..4 / positions 1..4 as ITS frames 0..3 / positions 0..3 (checked here on a real rollout with episode
+    ends), so PPO.values reads V(s') from the first critic pass.  The values are those of the two full passes of the
+    reference (PPO.py:113-114): identical where shared (same kernels on identical inputs in equally sized chunks), within
+    bf16 rounding for the remaining samples (evaluated in one smaller batch), and an update() gives the same losses."""
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    torch.manual_seed(0)
+    agent = P.PPO(device="cuda:0")
+    env = pkg.TwoarmyVecEnv(4, 512, 17, seed=5, autoreset=False)
+    T, N = 96, 512
+    roll = P.VecRollout(env, agent, T)
+    buf = roll.collect()
+    flat = buf.flat()
+    nxt = flat["next_same"].view(T, N)
+    assert int(buf.ended[:T].sum()) > 0 and not bool(nxt[T - 1].any())
+    assert bool((nxt[:T - 1] == (buf.ended[:T - 1] == 0)).all())
+    same = nxt[:T - 1]
+    assert bool((buf.s[1:T][same][:, 0:4] == buf.s[:T - 1][same][:, 1:5]).all())
+    assert bool((buf.p[1:T][same][:, 0:4] == buf.p[:T - 1][same][:, 1:5]).all())
+    # and where the episode ended the next record is NOT the continuation (so the hint is needed, not just harmless)
+    ended = ~same
+    assert bool((buf.s[1:T][ended][:, 0:4] != buf.s[:T - 1][ended][:, 1:5]).flatten(1).any(1).any())
+    with torch.no_grad():
+        v2, vn2 = agent.values(flat["s"], flat["p"], flat["g"])
+        v1, vn1 = agent.values(flat["s"], flat["p"], flat["g"], next_same=flat["next_same"], next_stride=flat["next_stride"])
+    assert torch.equal(v1, v2)
+    shared = flat["next_same"]
+    assert float((vn1[shared] == vn2[shared]).float().mean()) >= 0.99
+    scale = float(vn2.abs().max())
+    assert float((vn1 - vn2).abs().max()) <= 2e-2 * scale + 1e-3
+    losses = []
+    for share in (True, False):
+        torch.manual_seed(0)
+        ag = P.PPO(device="cuda:0")
+        ag.share_next_value, ag.K_epochs = share, 1
+        torch.manual_seed(3)
+        losses.append(ag.update(flat, minibatch=4096))
+    np.testing.assert_allclose(losses[0], losses[1], rtol=2e-2, atol=1e-3)
