@@ -690,6 +690,14 @@ class PPO:
                 works = []
 
                 def reduce(t, last):
+                    probe = getattr(self, "_probe_events", None)
+                    if probe is not None:   # probe_step(): device time of each bucket's collective, not overlapped with anything
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        torch.distributed.all_reduce(t, group=group)
+                        e1.record()
+                        probe.append((name + ("/stem" if last else "/late_layers"), e0, e1))
+                        return
                     works.append(torch.distributed.all_reduce(t, group=group, async_op=True))
                     if last:
                         for w in works:
