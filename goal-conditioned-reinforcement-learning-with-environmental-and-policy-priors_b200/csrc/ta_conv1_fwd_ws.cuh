@@ -17,12 +17,12 @@
 //   (warp 8, converged, elect.sync; its three sister warps idle).  The 896 threads start with 72 registers each; the decoder
 //   and MMA groups give registers up (setmaxnreg.dec 48) and the four epilogue groups take them (setmaxnreg.inc 88) -- sixteen
 //   epilogue warps do not fit otherwise (spills: 370-480 us).  The two warp groups of a row parity py share the staging of
-//   its image rows (2 buffers x 7 blocks x 5 KB) and meet only inside the pair (named barriers of 256 threads); the roles meet
+//   its image rows (3 buffers x 7 blocks x 4352 B) and meet only inside the pair (named barriers of 256 threads); the roles meet
 //   through mbarriers.  Every mbarrier wait is bounded and raises `fail`.
 //
 // Measured per 4096 samples (scripts/probe_conv1_fwd.py; ablation bits in `dbg`, TA_FW_DBG; conv1_fwd_tc_kernel: 148 us
 // without / 164 us with the ReLU bit mask):
-//   whole kernel                                     135 us without the mask, 156 us with it
+//   whole kernel                                     134 us without the mask, 149 us with it (three staging buffers; 135 / 156 us with two)
 //   stores only (no epilogue arithmetic)              93 us = 6.1 TB/s: the store pattern reaches the write roofline
 //                                                     (the same 14 x 4224-byte stores per tile as a bare probe: 6.1 TB/s, write_bw.py)
 //   epilogue arithmetic only (no stores)              95 us without the mask, 115 us with it (64 extra integer ops per 32 channels)
@@ -30,9 +30,11 @@
 // History: with eight epilogue warps (two phases each) the epilogue's dependent instruction stream was the bottleneck (150 /
 // 208 us); with ONE decoder group and 64-bit index arithmetic the decoders paced everything at 116 us -- a role that is one
 // warp per scheduler is a serial instruction stream and its instruction count is its time.  Stores and arithmetic still do not
-// overlap fully (135 vs max(93, 95)): the staging writes conflict two ways in their banks (rows 2n + px of consecutive lanes
+// overlap fully (134 vs max(93, 95)): the staging writes conflict two ways in their banks (rows 2n + px of consecutive lanes
 // have the same parity, so the swizzle only spreads them over four of the eight 16-byte bank groups) and share the
-// shared-memory port with the TMA's reads and the MMA operands.
+// shared-memory port with the TMA's reads and the MMA operands.  A conflict-free staging order was measured too -- one block per
+// (image row, px) with lane = row, stored through a tensor map that walks x with element stride 2 (28 stores of 2 KB per tile,
+// bit-identical): 143 / 157 us, the strided stores cost more than the conflicts.
 #pragma once
 #include <cuda.h>
 
@@ -45,11 +47,14 @@ constexpr int FW_THREADS = 896;   // seven warp groups: 0 epi (py0,px0), 1 dec A
 constexpr int FW_REGS_LOW = 48, FW_REGS_EPI = 88;   // setmaxnreg: 896 threads start with 72 registers each; 12 warps give 24 up, 16 warps take 16
 constexpr int FW_ROWS = 7, FW_POS = FW_ROWS * GS;             // 119 positions per tile
 constexpr int FW_SLOTS = FW_POS + TC_HALO;                    // 137 decoded positions per tile
-constexpr int FW_BLOCK = 5 * 1024;                            // staging of one image row: 33 x 128 B, 1024-aligned
+constexpr int FW_NBUF = 3;                                    // staging buffers per epilogue group (stores of FW_NBUF - 1 tiles may be in flight)
+constexpr int FW_BLOCK = 34 * 128;                            // staging of one image row: 33 x 128 B (+ one spare row); block k starts at
+                                                              // row 34 k of the 1024-aligned staging area, so the TMA's address-based
+                                                              // 128-byte swizzle XORs row i of block k with (34 k + i) % 8 = (2 k + i) % 8
 constexpr int FW_OFF_B = 0;                                   // W4 hi / lo: 2 x 8 KB
 constexpr int FW_OFF_A = FW_OFF_B + 2 * TC_N * 32;            // A hi / lo, 2 stages: 4 x 4 KB
 constexpr int FW_OFF_STAGE = FW_OFF_A + 4 * TC_M * 32;        // 32768: [group 2][buffer 2][row 7] blocks
-constexpr int FW_OFF_DEC = FW_OFF_STAGE + 2 * 2 * FW_ROWS * FW_BLOCK;   // 176128
+constexpr int FW_OFF_DEC = (FW_OFF_STAGE + 2 * FW_NBUF * FW_ROWS * FW_BLOCK + 15) & ~15;   // 215552
 constexpr int FW_OFF_BIAS = FW_OFF_DEC + 2 * FW_SLOTS * 16;   // 180512
 constexpr int FW_SMEM = FW_OFF_BIAS + TC_N * 4;               // 181536
 constexpr uint32_t FW_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // N = 256
@@ -225,17 +230,18 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv1_fwd_ws_kernel(const XT *_
         const bool leader = px == 0 && q == 0 && lane == 0;   // issues the group's stores
         const uint64_t map_u = reinterpret_cast<uint64_t>(&y_map);
         const int bar_id = 2 + g;
-        const int sw = (2 * n + px) & 7;
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-            const int buf = it & 1;
-            uint8_t *stage = sStage + ((g * 2 + buf) * FW_ROWS) * FW_BLOCK;
+            const int buf = it & 1, sbuf = it % FW_NBUF;
+            const int blk0 = (g * FW_NBUF + sbuf) * FW_ROWS;   // index of the group's first staging block of this tile
+            uint8_t *stage = sStage + blk0 * FW_BLOCK;
+            const int sw = (2 * n + px + 2 * (blk0 + r)) & 7;
             const long long P = tile * FW_POS + p;
             const bool valid = p < FW_POS && P < npos;
             if (!dead && !(__all_sync(0xFFFFFFFFu, tc_mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1))))) dead = true;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // the stores issued two tiles ago have read this staging buffer
-            if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            // the stores issued FW_NBUF tiles ago have read this staging buffer
+            if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(FW_NBUF - 1) : "memory");
             if (dead) group_dead[g] = 1;
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (group_dead[g]) { dead = true; break; }
