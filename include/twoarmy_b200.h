@@ -262,6 +262,9 @@ int ta_her_plan(const float *p, const uint8_t *done, int T, int64_t n, int first
  *   w4, b4   float32 [256][16] / [256]: the conv weight / bias folded per output phase by the host
  *            (row (py*2+px)*64 + o, column (dy*2+dx)*4 + c)
  *   y_bf16   bfloat16 [batch][33][33][64] (channels-last), = relu(conv + bias)
+ * Three forward kernels (TA_CONV1_TC): 2 (default) warp-specialised tcgen05 with tensor-map stores (csrc/ta_conv1_fwd_ws.cuh;
+ * needs y_bf16 16-byte aligned, else the next one runs), 1 single-role tcgen05 (csrc/ta_conv1_tc.cuh) -- the two are
+ * bit-identical --, 0 FP32 FMA (csrc/ta_conv1.cuh).
  * ta_conv1_bwd: gradients of w4 / b4 (overwritten) given y and dL/dy; x needs no gradient. */
 #define TA_X_F32 0
 #define TA_X_U8 1
