@@ -237,3 +237,54 @@ def test_merged_parity_planes_are_the_strided_data_gradient():
             got = planes[:, c * cin:(c + 1) * cin]
             assert torch.allclose(got[:, :, :want.shape[2], :want.shape[3]], want, rtol=0, atol=1e-12)
             assert float(got[:, :, want.shape[2]:].abs().max() if want.shape[2] < oh + 1 else 0.0) == 0.0   # the extra row is zero
+
+
+def test_next_value_hint_reuses_the_first_critic_pass():
+    """RolloutBuffer.flat()'s `next_same` flags (record t + 1 continues record t's episode) let PPO.values read V(s') from the
+    first critic pass; on a buffer whose records really chain that is the value of the reference's second pass
+    (soa/agent/PPO.py:113-114), and an update() built on it has the same losses."""
+    P = _ppo()
+    torch.manual_seed(0)
+    agent = P.PPO(device="cpu", autocast=False)
+    T, N = 6, 4
+    buf = P.RolloutBuffer(T, N, torch.device("cpu"))
+    g = torch.Generator().manual_seed(3)
+    frames = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)[torch.randint(0, 4, (T + 4, N, 289), generator=g)]
+    pos = torch.randint(1, 16, (T + 4, N, 2), generator=g).float()
+    ended = torch.zeros((T, N), dtype=torch.uint8)
+    ended[2, 1] = 1; ended[4, 3] = 1; ended[0, 0] = 1
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)
+    s_prev = p_prev = None
+    for t in range(T):
+        # the rollout's rule (VecRollout / ta_stack_push): record t = record t - 1 shifted by one frame + the new frame, or, where
+        # the previous step ended the episode, four fresh frames + the new frame
+        if t == 0:
+            s_t = torch.stack([frames[j] for j in range(5)], 1)
+            p_t = torch.stack([pos[j] for j in range(5)], 1)
+        else:
+            s_t = torch.cat([s_prev[:, 1:5], frames[t + 4][:, None]], 1)
+            p_t = torch.cat([p_prev[:, 1:5], pos[t + 4][:, None]], 1)
+            broke = ended[t - 1].bool()
+            s_t[broke, :4] = codes[torch.randint(0, 4, (int(broke.sum()), 4, 289), generator=g)]
+            p_t[broke, :4] = torch.randint(1, 16, (int(broke.sum()), 4, 2), generator=g).float()
+        buf.store(s_t, torch.randint(0, 5, (N,), generator=g), p_t, torch.rand(N, generator=g) - 0.5, ended[t].float(),
+                  torch.log(torch.rand(N, generator=g) * 0.5 + 0.1))
+        buf.ended[t].copy_(ended[t])
+        s_prev, p_prev = s_t, p_t
+    buf.g.copy_(torch.tensor([[2.0, 14.0]]).repeat(N, 1))
+    flat = buf.flat()
+    nxt = flat["next_same"].view(T, N)
+    assert not bool(nxt[T - 1].any()) and bool((nxt[:T - 1] == (ended[:T - 1] == 0)).all()) and flat["next_stride"] == N
+    with torch.no_grad():
+        v2, vn2 = agent.values(flat["s"], flat["p"], flat["g"])
+        v1, vn1 = agent.values(flat["s"], flat["p"], flat["g"], next_same=flat["next_same"], next_stride=N)
+    assert torch.equal(v1, v2)
+    assert torch.allclose(vn1, vn2, atol=1e-6)
+    losses = []
+    for share in (True, False):
+        torch.manual_seed(0)
+        ag = P.PPO(device="cpu", autocast=False)
+        ag.share_next_value, ag.K_epochs, ag.batch_size = share, 2, 8
+        torch.manual_seed(1)
+        losses.append(ag.update(flat, sampler_generator=torch.default_generator))
+    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-5, atol=1e-7)
