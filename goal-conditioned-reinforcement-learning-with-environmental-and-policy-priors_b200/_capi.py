@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
     L.ta_debug_force_generic_obs.argtypes = [i32]
     L.ta_debug_conv1_tc.argtypes = [i32]
     L.ta_debug_conv1_bwd_tc.argtypes = [i32]
+    L.ta_debug_push_tma.argtypes = [i32]
     L.ta_debug_conv1_tc_failed.argtypes = []
     if L.ta_abi_version() != 1:
         raise TwoarmyLibraryError("ABI version mismatch between header and library")

@@ -23,10 +23,11 @@ def _stream(dev):
 
 def gae(reward: torch.Tensor, value: torch.Tensor, done: Optional[torch.Tensor] = None, gamma: float = 0.99,
         lam: float = 0.95, use_mask: bool = True, v_next: Optional[torch.Tensor] = None,
-        last_value: Optional[torch.Tensor] = None, normalize: bool = False, group=None):
+        last_value: Optional[torch.Tensor] = None, normalize: bool = False, group=None, out=None):
     """reward/value/done/v_next: [T, N] time-major fp32 (done uint8/bool); last_value: [N].
     Returns (adv, ret) fp32 [T, N].  normalize=True applies (adv-mean)/(std+1e-8) over all
-    T*N elements; with a torch.distributed group the three moments are all-reduced first."""
+    T*N elements; with a torch.distributed group the three moments are all-reduced first.
+    out = (adv, ret): optional preallocated contiguous fp32 [T, N] outputs."""
     assert reward.is_cuda and reward.dtype == torch.float32 and reward.dim() == 2
     T, N = reward.shape
     reward, value = reward.contiguous(), value.contiguous()
@@ -39,8 +40,13 @@ def gae(reward: torch.Tensor, value: torch.Tensor, done: Optional[torch.Tensor] 
         assert last_value.numel() == N and last_value.dtype == torch.float32
     if done is not None:
         done = done.contiguous().view(torch.uint8) if done.dtype == torch.bool else done.to(torch.uint8).contiguous()
-    adv = torch.empty_like(reward)
-    ret = torch.empty_like(reward)
+    if out is not None:
+        adv, ret = out
+        for o in (adv, ret):
+            assert o.shape == (T, N) and o.dtype == torch.float32 and o.is_contiguous() and o.device == reward.device
+    else:
+        adv = torch.empty_like(reward)
+        ret = torch.empty_like(reward)
     L = _capi.lib()
     st = _stream(reward.device)
     if not normalize:

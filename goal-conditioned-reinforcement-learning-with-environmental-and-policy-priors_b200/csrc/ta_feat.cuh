@@ -192,84 +192,127 @@ __global__ void __launch_bounds__(FEAT_THREADS) frame_codes_tile_kernel(const ui
     if (codes) tile_out(codes + e0 * NCELL, tile, total);
 }
 
-__global__ void __launch_bounds__(FEAT_THREADS) stack_push_codes_tile_kernel(const uint32_t *grid, const uint4 *sc0,
+// does the 16-byte chunk at byte q0 of a CTA's slice of [env][5][289] touch frames 0..3 of some env?  (Chunks that lie
+// wholly inside a new frame -- j in [1156, 1429] -- are produced by the column threads alone and never loaded.)
+__device__ __forceinline__ bool push_chunk_needed(int q0) {
+    const int j = q0 - STACK_ELEMS * (q0 / STACK_ELEMS);
+    return j < SHIFT_ELEMS || j + 16 > STACK_ELEMS;
+}
+
+// MINB = CTAs per SM the register allocation is bounded for (5: no bound hit, 48 registers; 6: 40; 8: 32 with a few spills)
+template <int MINB>
+__global__ void __launch_bounds__(FEAT_THREADS, MINB) stack_push_codes_tile_kernel(const uint32_t *grid, const uint4 *sc0,
                                                                             const uint8_t *s_prev, uint8_t *s_out,
                                                                             const float *p_prev, float *p_out,
-                                                                            const uint8_t *prev_done, int init_all, long long n) {
+                                                                            const uint8_t *prev_done, int init_flags, long long n) {
     __shared__ uint32_t sg[FEAT_ENVS * REC_WORDS];
     __shared__ uint32_t sa[FEAT_ENVS];
-    __shared__ uint8_t sdone[FEAT_ENVS];
-    __shared__ uint8_t sreset[NCELL + 3];
+    __shared__ uint32_t sdone_bits;
     __shared__ __align__(16) uint8_t tile[FEAT_ENVS * STACK_ELEMS];
     const long long e0 = (long long)blockIdx.x * FEAT_ENVS;
     const int cnt = (int)((n - e0) < FEAT_ENVS ? (n - e0) : FEAT_ENVS);
-    stage_records(grid, sc0, e0, cnt, sg, sa);
-    if (threadIdx.x < cnt) sdone[threadIdx.x] = (uint8_t)(init_all || (prev_done && prev_done[e0 + threadIdx.x]));
-    for (int c = threadIdx.x; c < NCELL; c += FEAT_THREADS) sreset[c] = (uint8_t)reset_frame_code(c);
     const int total = cnt * STACK_ELEMS;
-    // 1. every byte of the slice <- the byte one frame (289) further on in the previous stacks: aligned
-    //    16-byte loads at +288 plus the 17th byte.  Positions that are not "frames 0..3 of a running
-    //    env" receive garbage here and are overwritten in step 2.
-    if (!init_all) {
-        const uint8_t *in = s_prev + e0 * STACK_ELEMS;
-        const long long in_bytes = (n - e0) * STACK_ELEMS;  // bytes of s_prev from `in` to its end
-        // every load of the CTA's slice is issued before the first shared-memory store (the kernel is bound by the
-        // latency of these loads: ncu showed 38 % of all stall samples on the first use of `a`); the 17th byte of a
-        // chunk is the first byte of the next lane's chunk -- one shuffle instead of a second load per chunk
-        constexpr int NIT = (FEAT_ENVS * STACK_ELEMS + FEAT_THREADS * 16 - 1) / (FEAT_THREADS * 16);   // 6
-        uint4 av[NIT];
-        uint32_t lastv[NIT];
-        const int lane = threadIdx.x & 31;
+    // bit 0: every env starts from the reset frame; bits 8..: ablation switches of the measurement probe (TA_PUSH_DBG;
+    // 1 = no stack loads, 2 = no bulk store, 4 = no column decode) -- results are only defined with them clear
+    const int init_all = init_flags & 1, dbg = init_flags >> 8;
+    // Every global load of the CTA is ISSUED before the first shared-memory store, so the CTA pays one DRAM round trip:
+    // the records (two words per thread), the agent position / previous done flag (threads < cnt), the position stack
+    // and the six 16-byte chunks of the previous frame stacks.  (Staging the records first, as the other feature
+    // kernels do, put three dependent round trips in front of the stack loads -- LDG -> STS pairs in program order.)
+    constexpr int NREC = (FEAT_ENVS * REC_WORDS + FEAT_THREADS - 1) / FEAT_THREADS;   // 2
+    uint32_t recw[NREC];
+#pragma unroll
+    for (int k = 0; k < NREC; k++) {
+        const int i = k * FEAT_THREADS + threadIdx.x;
+        recw[k] = i < cnt * REC_WORDS ? __ldg(grid + e0 * REC_WORDS + i) : 0u;
+    }
+    uint32_t my_xy = 0u, my_done = (uint32_t)(init_all != 0);
+    if (threadIdx.x < cnt) {
+        my_xy = __ldg(reinterpret_cast<const uint32_t *>(sc0 + e0 + threadIdx.x)) & 0xFFFFu;  // x | y << 8
+        if (!init_all && prev_done) my_done = __ldg(prev_done + e0 + threadIdx.x);
+    }
+    const bool pact = p_out && threadIdx.x < cnt * 10;
+    float pprev = 0.0f;   // data_env rows 1..4 of the previous position stack (unused for frame 4 / restarted envs)
+    if (pact && !init_all && (threadIdx.x % 10) < 8) pprev = __ldg(p_prev + e0 * 10 + threadIdx.x + 2);
+    // 1. every byte of frames 0..3 of the slice <- the byte one frame (289) further on in the previous stacks: aligned
+    //    16-byte loads at +288 plus the 17th byte (the first byte of the next lane's chunk -- one shuffle instead of a
+    //    second load).  Chunks that lie wholly inside a new frame (18 of an env's 90) are not loaded at all; chunks of
+    //    restarted envs receive garbage here and are overwritten in step 2.
+    constexpr int NIT = (FEAT_ENVS * STACK_ELEMS + FEAT_THREADS * 16 - 1) / (FEAT_THREADS * 16);   // 6
+    uint4 av[NIT];
+    uint32_t lastv[NIT];
+    const uint8_t *in = s_prev + e0 * STACK_ELEMS;
+    const long long in_bytes = (n - e0) * STACK_ELEMS;  // bytes of s_prev from `in` to its end
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) { av[it] = make_uint4(0u, 0u, 0u, 0u); lastv[it] = 0u; }
+    if (!init_all && !(dbg & 1)) {
 #pragma unroll
         for (int it = 0; it < NIT; it++) {
             const int q0 = (it * FEAT_THREADS + threadIdx.x) * 16;
             av[it] = make_uint4(0u, 0u, 0u, 0u);
             lastv[it] = 0u;
-            const bool full = q0 < total && (long long)q0 + NCELL + 16 <= in_bytes;
+            const bool full = push_chunk_needed(q0) && q0 < total && (long long)q0 + NCELL + 16 <= in_bytes;
+            const bool nfull = push_chunk_needed(q0 + 16) && q0 + 16 < total && (long long)q0 + NCELL + 32 <= in_bytes;
             if (full) av[it] = __ldg(reinterpret_cast<const uint4 *>(in + q0 + NCELL - 1));
-            if (full && lane == 31) lastv[it] = in[q0 + NCELL + 15];
+            if (full && (lane == 31 || !nfull)) lastv[it] = __ldg(in + q0 + NCELL + 15);
         }
+    }
+    // which envs restart: a 16-bit mask for the whole CTA (the flags sit in the first 16 lanes of warp 0)
+    if (threadIdx.x < 32) {
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, threadIdx.x < cnt && my_done != 0);
+        if (threadIdx.x == 0) sdone_bits = b;
+    }
+#pragma unroll
+    for (int k = 0; k < NREC; k++) {
+        const int i = k * FEAT_THREADS + threadIdx.x;
+        if (i < cnt * REC_WORDS) sg[i] = recw[k];
+    }
+    if (threadIdx.x < cnt) sa[threadIdx.x] = my_xy;
+    if (!init_all) {
 #pragma unroll
         for (int it = 0; it < NIT; it++) {
             const int q0 = (it * FEAT_THREADS + threadIdx.x) * 16;
-            const bool full = q0 < total && (long long)q0 + NCELL + 16 <= in_bytes;
-            // the next lane's first loaded byte (its chunk starts 16 bytes further on); a lane whose neighbour did not take
-            // the fast path re-reads the byte itself
+            const bool need = push_chunk_needed(q0);
+            const bool full = need && q0 < total && (long long)q0 + NCELL + 16 <= in_bytes;
+            const bool nfull = push_chunk_needed(q0 + 16) && q0 + 16 < total && (long long)q0 + NCELL + 32 <= in_bytes;
+            // the next lane's first loaded byte (its chunk starts 16 bytes further on); lane 31 and lanes whose neighbour
+            // loaded nothing fetched the byte themselves above
             const uint32_t nb = __shfl_down_sync(0xFFFFFFFFu, av[it].x, 1) & 0xFFu;
-            const bool nfull = __shfl_down_sync(0xFFFFFFFFu, (int)full, 1) != 0;
-            uint4 o;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (full) {
-                uint32_t last = lane == 31 ? lastv[it] : nb;
-                if (lane != 31 && !nfull) last = in[q0 + NCELL + 15];
+                const uint32_t last = (lane == 31 || !nfull) ? lastv[it] : nb;
                 const uint4 a = av[it];
                 o = make_uint4(__funnelshift_r(a.x, a.y, 8), __funnelshift_r(a.y, a.z, 8), __funnelshift_r(a.z, a.w, 8),
                                (a.w >> 8) | (last << 24));
-            } else if (q0 < total) {  // the last chunks of the last env: stay inside the array
+            } else if (need && q0 < total) {  // the last chunks of the last env: stay inside the array
                 uint32_t w[4] = {0, 0, 0, 0};
                 for (int k = 0; k < 16; k++)
                     if ((long long)q0 + NCELL + k < in_bytes) w[k >> 2] |= (uint32_t)in[q0 + NCELL + k] << (8 * (k & 3));
                 o = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            if (q0 < total && q0 + 16 <= FEAT_ENVS * STACK_ELEMS) *reinterpret_cast<uint4 *>(tile + q0) = o;
+            if (need && q0 < total && q0 + 16 <= FEAT_ENVS * STACK_ELEMS) *reinterpret_cast<uint4 *>(tile + q0) = o;
         }
     }
     __syncthreads();
     // 2. the new frame of every env; the tiled reset frame for envs whose episode has just restarted
-    write_frame_columns(sg, sa, tile, cnt, STACK_ELEMS, SHIFT_ELEMS);
-    for (int e = 0; e < cnt; e++)
-        if (sdone[e])
-            for (int j = threadIdx.x; j < SHIFT_ELEMS; j += FEAT_THREADS) tile[e * STACK_ELEMS + j] = sreset[j % NCELL];
+    if (!(dbg & 4)) write_frame_columns(sg, sa, tile, cnt, STACK_ELEMS, SHIFT_ELEMS);
+    const uint32_t done_bits = sdone_bits;
+    for (uint32_t m = done_bits; m; m &= m - 1) {   // (_gen_grid is a formula: no table, no memory traffic)
+        const int e = __ffs(m) - 1;
+        for (int j = threadIdx.x; j < SHIFT_ELEMS; j += FEAT_THREADS) tile[e * STACK_ELEMS + j] = (uint8_t)reset_frame_code(j % NCELL);
+    }
     // 3. out (in place is fine: every read of s_prev / p_prev that matters happened before the
     //    barrier inside tile_out; reads beyond this CTA's slice only feed positions overwritten in 2)
     float pv = 0.0f;
-    const bool pact = p_out && threadIdx.x < cnt * 10;
     if (pact) {  // data_env: (y, x) rows; reset position (15, 3)
         const int e = threadIdx.x / 10, r = threadIdx.x - 10 * e, f = r >> 1, comp = r & 1;
         if (f == 4) pv = comp ? (float)(sa[e] & 0xFFu) : (float)(sa[e] >> 8);
-        else if (sdone[e]) pv = comp ? 3.0f : 15.0f;
-        else pv = p_prev[e0 * 10 + threadIdx.x + 2];
+        else if ((done_bits >> e) & 1u) pv = comp ? 3.0f : 15.0f;
+        else pv = pprev;
     }
-    tile_out(s_out + e0 * STACK_ELEMS, tile, total);
+    if (dbg & 2) { __syncthreads(); if (tile[threadIdx.x] == 0xEE) s_out[e0] = 1; }
+    else tile_out(s_out + e0 * STACK_ELEMS, tile, total);
     if (pact) p_out[e0 * 10 + threadIdx.x] = pv;
 }
 

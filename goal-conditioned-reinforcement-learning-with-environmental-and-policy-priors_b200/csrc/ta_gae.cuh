@@ -103,18 +103,22 @@ __device__ __forceinline__ float f4get(const float4 &v, int i) { return i == 0 ?
 // stats (nullable): the launch also accumulates (sum, sum of squares, count) of adv in float64 -- the moments of
 // PPO.py:115's normalisation -- so that normalising costs one more pass over adv instead of two.
 template <int GV_L, int GV_CH, int GV_X>
-__global__ void __launch_bounds__(GV_X * GV_CH)
+__global__ void __launch_bounds__(GV_X * GV_CH, 512 / (GV_X * GV_CH))
 gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const float *__restrict__ v_next,
                 const float *__restrict__ last_v, const uint8_t *__restrict__ done, float gamma, float lam, int use_mask,
                 int T, long long n, float *__restrict__ adv, float *__restrict__ ret, double *__restrict__ stats) {
-    __shared__ float sP[GV_CH][GV_X][4], sA[GV_CH][GV_X][4];
+    // chunk summaries [chunk][env of the quad][quad] (+ GV_PAD floats per chunk row: the warps of a narrow CTA hold
+    // several chunks, whose rows would otherwise fall on the same banks)
+    constexpr int GV_PAD = GV_X < 32 ? GV_X : 0, GV_ROW = 4 * GV_X + GV_PAD;
+    __shared__ float sP[GV_CH * GV_ROW], sA[GV_CH * GV_ROW], sC[4 * GV_X];
     const int lx = threadIdx.x, cy = threadIdx.y, CH = blockDim.y;
+    const int tid = cy * GV_X + lx, nth = GV_X * CH;
+    for (int sidx = tid; sidx < 4 * GV_X; sidx += nth) sC[sidx] = 0.0f;   // (same thread, same slots as in the scan below)
     const long long col = ((long long)blockIdx.x * GV_X + lx) * 4;  // first of this thread's 4 envs
     double st_s = 0.0, st_ss = 0.0;
     const bool valid = col < n;
     const int span = GV_L * CH;
     const float gl = __fmul_rn(gamma, lam);
-    float carry[4] = {0.f, 0.f, 0.f, 0.f};
     for (int base = ((T - 1) / span) * span; base >= 0; base -= span) {
         const int t0 = base + cy * GV_L;
         float tv[GV_L][4], dl[GV_L][4];
@@ -173,19 +177,29 @@ gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const 
                 acc = __fadd_rn(dl[j][i], __fmul_rn(cj, acc));
                 P *= cj;
             }
-            sP[cy][lx][i] = P;
-            sA[cy][lx][i] = acc;
+            sP[cy * GV_ROW + i * GV_X + lx] = P;
+            sA[cy * GV_ROW + i * GV_X + lx] = acc;
         }
         __syncthreads();
-        float ain[4], cnext[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float a = carry[i];
-            for (int k = CH - 1; k > cy; k--) a = sA[k][lx][i] + sP[k][lx][i] * a;
-            ain[i] = a;
-            for (int k = cy; k >= 0; k--) a = sA[k][lx][i] + sP[k][lx][i] * a;
-            cnext[i] = a;
+        // the 4 * GV_X independent suffix scans over the chunks (one per env column of the CTA), each by ONE thread:
+        // chunk k's slot receives A entering chunk k from the later chunks (conflict-free rows, no re-reading by
+        // every thread of the column -- that serial re-fold was a third of the small-rollout launch)
+        for (int sidx = tid; sidx < 4 * GV_X; sidx += nth) {   // (one scan per thread unless T is very short)
+            float a = sC[sidx];
+#pragma unroll 8
+            for (int k = GV_CH - 1; k >= 0; k--) {
+                if (k < CH) {
+                    const float pk = sP[k * GV_ROW + sidx], ak = sA[k * GV_ROW + sidx];
+                    sA[k * GV_ROW + sidx] = a;
+                    a = ak + pk * a;
+                }
+            }
+            sC[sidx] = a;   // A carried into the next pass (earlier time steps)
         }
+        __syncthreads();
+        float ain[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ain[i] = sA[cy * GV_ROW + i * GV_X + lx];
         // pass 2: the recurrence from the true A_in, outputs
         float A[4] = {ain[0], ain[1], ain[2], ain[3]};
 #pragma unroll
@@ -212,12 +226,9 @@ gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const 
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; i++) carry[i] = cnext[i];
     }
     if (stats) {  // CTA-wide sum through the (now free) scan buffers, then one atomic pair per CTA
-        double *red = reinterpret_cast<double *>(&sP[0][0][0]);  // GV_CH * GV_X * 4 floats = room for 2 doubles per thread
-        const int tid = cy * GV_X + lx, nth = GV_X * CH;
+        __shared__ double red[2 * GV_X * GV_CH];
         red[2 * tid] = st_s;
         red[2 * tid + 1] = st_ss;
         __syncthreads();

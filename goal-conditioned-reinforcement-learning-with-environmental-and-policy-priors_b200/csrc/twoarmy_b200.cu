@@ -16,6 +16,7 @@
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
 #include "ta_her.cuh"
+#include "ta_push_tma.cuh"
 #include "ta_host.cuh"
 #include "ta_stem_bwd_tc.cuh"
 #include "ta_step.cuh"
@@ -469,6 +470,85 @@ int ta_rollout(ta_handle h, const void *actions, int action_dtype, int T, uint8_
                        nullptr, stream);
 }
 
+}  // extern "C"
+namespace {
+int g_push_tma = -1;   // -1: read TA_PUSH_TMA on first use (default 1); ta_debug_push_tma() sets it
+int tc_fail_flag(int **out);
+
+// the persistent TMA form of the uint8 frame-stack push (ta_push_tma.cuh); *used = 0 when its preconditions do not hold
+int launch_push_tma(cudaStream_t st, const uint32_t *grid, const uint4 *sc0, const uint8_t *s_prev, uint8_t *s_out, const float *p_prev,
+                    float *p_out, const uint8_t *prev_done, long long n, int *used) {
+    *used = 0;
+    static int stages = 0, ctas = 0;   // TA_PUSH_TMA (default 1), TA_PUSH_STAGES (2..4), TA_PUSH_CTAS (per SM; 0 = what fits)
+    int &mode = g_push_tma;
+    if (mode < 0) { const char *e = getenv("TA_PUSH_TMA"); mode = e ? atoi(e) : 1; }
+    if (!stages) {
+        const char *e;
+        stages = 3;
+        if ((e = getenv("TA_PUSH_STAGES"))) stages = atoi(e);
+        if (stages < 2 || stages > 4) stages = 3;
+        if ((e = getenv("TA_PUSH_CTAS"))) ctas = atoi(e);
+    }
+    if (!mode || n < FEAT_ENVS || (n % FEAT_ENVS) != 0) return TA_OK;
+    if ((((uintptr_t)s_prev | (uintptr_t)s_out | (uintptr_t)prev_done | (uintptr_t)grid) & 15u) != 0) return TA_OK;
+    int *fail = nullptr;
+    if (int rc = tc_fail_flag(&fail)) return rc;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int smem = stages * PT_STAGE;
+    const void *kern = stages == 2 ? (const void *)stack_push_tma_kernel<2> : stages == 3 ? (const void *)stack_push_tma_kernel<3>
+                                                                                       : (const void *)stack_push_tma_kernel<4>;
+    static bool attr_set[64][5] = {};
+    if (!attr_set[dev & 63][stages]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_set[dev & 63][stages] = true;
+    }
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PT_THREADS, smem));
+    if (occ < 1) return TA_OK;
+    // two resident CTAs per SM by default: measured 34.0 us per 65536 envs against 35.5 with three (4096 tiles over 296 CTAs
+    // are 13-14 each, over 444 CTAs 9-10: the static round-robin's tail costs more than the third CTA hides)
+    const int want = ctas > 0 ? ctas : 2;
+    if (want < occ) occ = want;
+    const long long ntiles = n / FEAT_ENVS;
+    long long g = (long long)sms * occ;
+    if (g > ntiles) g = ntiles;
+    if (stages == 2) stack_push_tma_kernel<2><<<(unsigned)g, PT_THREADS, smem, st>>>(grid, sc0, s_prev, s_out, p_prev, p_out, prev_done, n, fail);
+    else if (stages == 3) stack_push_tma_kernel<3><<<(unsigned)g, PT_THREADS, smem, st>>>(grid, sc0, s_prev, s_out, p_prev, p_out, prev_done, n, fail);
+    else stack_push_tma_kernel<4><<<(unsigned)g, PT_THREADS, smem, st>>>(grid, sc0, s_prev, s_out, p_prev, p_out, prev_done, n, fail);
+    *used = 1;
+    return TA_OK;
+}
+}  // namespace
+extern "C" {
+
+// the uint8 frame-stack push; TA_PUSH_MINB (tuning knob) = CTAs per SM the kernel's registers are bounded for
+static void launch_push_codes(unsigned nb, cudaStream_t st, const uint32_t *grid, const uint4 *sc0, const uint8_t *s_prev,
+                              uint8_t *s_out, const float *p_prev, float *p_out, const uint8_t *prev_done, int init_all,
+                              long long n) {
+    static int minb = -1;
+    if (minb < 0) { const char *e = getenv("TA_PUSH_MINB"); minb = e ? atoi(e) : 5; }
+    static int dbg = -1;   // TA_PUSH_DBG: ablation switches of scripts/probe_push.py (results undefined when set)
+    if (dbg < 0) { const char *e = getenv("TA_PUSH_DBG"); dbg = e ? atoi(e) : 0; }
+    init_all = (init_all ? 1 : 0) | (dbg << 8);
+    static bool carved[64] = {};   // per device: ask for the largest shared-memory carveout (8 CTAs x 25 KB per SM)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!carved[dev & 63]) {
+        cudaFuncSetAttribute(stack_push_codes_tile_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(stack_push_codes_tile_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(stack_push_codes_tile_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carved[dev & 63] = true;
+    }
+    static int extra = -1;  // TA_PUSH_EXTRA_SMEM: unused dynamic shared memory per CTA (occupancy throttle of the probe)
+    if (extra < 0) { const char *e = getenv("TA_PUSH_EXTRA_SMEM"); extra = e ? atoi(e) : 0; if (extra < 0 || extra > 22000) extra = 0; }
+    if (minb >= 8) stack_push_codes_tile_kernel<8><<<nb, FEAT_THREADS, extra, st>>>(grid, sc0, s_prev, s_out, p_prev, p_out, prev_done, init_all, n);
+    else if (minb >= 6) stack_push_codes_tile_kernel<6><<<nb, FEAT_THREADS, extra, st>>>(grid, sc0, s_prev, s_out, p_prev, p_out, prev_done, init_all, n);
+    else stack_push_codes_tile_kernel<5><<<nb, FEAT_THREADS, extra, st>>>(grid, sc0, s_prev, s_out, p_prev, p_out, prev_done, init_all, n);
+}
+
 int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *place_out, void *stream) {
     if (!h) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
@@ -494,8 +574,11 @@ int ta_stack_roll_codes(ta_handle h, uint8_t *s_codes, float *p_stack, const uin
     if (!h || !s_codes) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
     if (!init && ((uintptr_t)s_codes & 15u) == 0) {  // the roll itself: the tile kernel, in place
-        stack_push_codes_tile_kernel<<<blocks_for(h->n, FEAT_ENVS), FEAT_THREADS, 0, (cudaStream_t)stream>>>(
-            h->grid, h->sc0, s_codes, s_codes, p_stack, p_stack, nullptr, 0, h->n);
+        int used = 0;
+        if (int rc = launch_push_tma((cudaStream_t)stream, h->grid, h->sc0, s_codes, s_codes, p_stack, p_stack, nullptr, h->n, &used)) return rc;
+        if (used) return launch_ok("stack_push_tma_kernel");
+        launch_push_codes(blocks_for(h->n, FEAT_ENVS), (cudaStream_t)stream, h->grid, h->sc0, s_codes, s_codes, p_stack, p_stack,
+                          nullptr, 0, h->n);
         return launch_ok("stack_push_codes_tile_kernel");
     }
     stack_roll_kernel<uint8_t><<<blocks_for(h->n, SM_ENVS), 320, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, s_codes, p_stack,
@@ -511,9 +594,15 @@ int ta_stack_push(ta_handle h, const void *s_prev, void *s_out, const float *p_p
     if ((((uintptr_t)s_prev | (uintptr_t)s_out) & 15u) != 0) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
     const unsigned nb = blocks_for(h->n, FEAT_ENVS);
+    if (dtype == TA_STACK_U8 && !init_all) {
+        int used = 0;
+        if (int rc = launch_push_tma((cudaStream_t)stream, h->grid, h->sc0, (const uint8_t *)s_prev, (uint8_t *)s_out, p_prev, p_out,
+                                     prev_done, h->n, &used)) return rc;
+        if (used) return launch_ok("stack_push_tma_kernel");
+    }
     if (dtype == TA_STACK_U8)
-        stack_push_codes_tile_kernel<<<nb, FEAT_THREADS, 0, (cudaStream_t)stream>>>(
-            h->grid, h->sc0, (const uint8_t *)s_prev, (uint8_t *)s_out, p_prev, p_out, prev_done, init_all, h->n);
+        launch_push_codes(nb, (cudaStream_t)stream, h->grid, h->sc0, (const uint8_t *)s_prev, (uint8_t *)s_out, p_prev, p_out,
+                          prev_done, init_all, h->n);
     else
         stack_push_kernel<float><<<nb, FEAT_THREADS, 0, (cudaStream_t)stream>>>(
             h->grid, h->sc0, (const float *)s_prev, (float *)s_out, p_prev, p_out, prev_done, init_all, h->n);
@@ -567,7 +656,7 @@ static int gae_launch(const float *reward, const float *v, const float *v_next, 
         if (gch < 0) { const char *e = getenv("TA_GAE_CH"); gch = e ? atoi(e) : 0; if (gch < 0 || gch > 16) gch = 0; }
         const int steps_chunks = (T + 7) / 8;
         static int gvar = -1;  // TA_GAE_SMALL (tuning knob for small rollouts): 0 off, 1 = 128-env CTAs x 16 chunks, 2 = 64-env CTAs, 3 = 32-env CTAs
-        if (gvar < 0) { const char *e = getenv("TA_GAE_SMALL"); gvar = e ? atoi(e) : 1; if (gvar < 0 || gvar > 3) gvar = 1; }
+        if (gvar < 0) { const char *e = getenv("TA_GAE_SMALL"); gvar = e ? atoi(e) : 3; if (gvar < 0 || gvar > 3) gvar = 3; }
         if (!gch && gvar && n / 128 < 2 * 148) {
             // small rollout (fewer than two 128-env CTAs per SM; BASELINE configs[3] is 128 x 16384): up to 16 chunks, so
             // that one pass covers 128 steps -- one DRAM round trip instead of two dependent ones
@@ -1238,6 +1327,11 @@ int ta_debug_conv1_tc(int on) {   // 0: FP32-FMA kernel, 1: conv1_fwd_tc_kernel,
 }
 
 /* test hook for the tcgen05 weight-gradient kernel: on/off (returns the previous setting) */
+int ta_debug_push_tma(int on) {   // 0: register kernel (stack_push_codes_tile_kernel), 1: stack_push_tma_kernel; -1: TA_PUSH_TMA / default
+    g_push_tma = on < 0 ? -1 : (on != 0);
+    return TA_OK;
+}
+
 int ta_debug_conv1_bwd_tc(int on) {
     const int prev = g_bwd_tc;
     g_bwd_tc = on != 0;

@@ -422,12 +422,23 @@ def test_vec_rollout_records_follow_reference_loop():
     assert len({x.tobytes() for x in actions}) == 4
 
 
-@pytest.mark.parametrize("n", [300, 16, 65])
-def test_stack_push_equals_roll_and_tile(n):
+@pytest.mark.parametrize("n,tma", [(300, 1), (16, 1), (65, 1), (1024, 1), (1024, 0), (32768, 1), (32768, 0)])
+def test_stack_push_equals_roll_and_tile(n, tma):
     """ta_stack_push (out of place, fused with the episode-start tiling) == ta_stack_roll in place
-    + ta_stack_roll(init) on the finished envs, for both dtypes."""
+    + ta_stack_roll(init) on the finished envs, for both dtypes.  The uint8 form runs as the persistent TMA kernel
+    (tma = 1, env counts that are multiples of 16; 32768 envs = 2048 tiles, more per CTA than its pipeline has stages)
+    and as the register kernel (tma = 0, and always for ragged counts)."""
     import importlib
     pkg = _pkg()
+    pkg._capi.lib().ta_debug_push_tma(tma)
+    try:
+        _stack_push_case(pkg, n, 70 if n <= 1024 else 10)
+    finally:
+        pkg._capi.lib().ta_debug_push_tma(-1)
+    assert pkg._capi.lib().ta_debug_conv1_tc_failed() == 0    # (the TMA kernel's bounded waits raise the same flag)
+
+
+def _stack_push_case(pkg, n, steps):
     env = pkg.TwoarmyVecEnv(4, n, 17, seed=3, autoreset=False)
     env.reset()
     dev = env.device
@@ -439,7 +450,7 @@ def test_stack_push_equals_roll_and_tile(n):
     prev_done = torch.ones(n, dtype=torch.uint8, device=dev)
     g = torch.Generator().manual_seed(1)
     amap = torch.tensor([0, 1, 2, 3, 6], dtype=torch.int32)
-    for t in range(70):
+    for t in range(steps):
         _, _, te, tr, _ = env.step(amap[torch.randint(0, 5, (n,), generator=g)])
         env.stack_roll(sf, pf); env.stack_roll_codes(sc, pc)
         outs = {}
