@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
     L.ta_her_plan.argtypes = [vp, vp, i32, i64, i32, u64, u64, vp, vp, vp, vp, vp]
     L.ta_gae.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp]
     L.ta_gae_stats.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp, vp]
+    L.ta_gae_normalized.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp, vp]
     L.ta_adv_stats.argtypes = [vp, i64, vp, vp]
     L.ta_adv_normalize.argtypes = [vp, i64, vp, vp]
     L.ta_relu_bwd_bias_scratch_floats.argtypes = [i64, i32]; L.ta_relu_bwd_bias_scratch_floats.restype = i64

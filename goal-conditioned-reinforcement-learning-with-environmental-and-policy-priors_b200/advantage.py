@@ -52,6 +52,14 @@ def gae(reward: torch.Tensor, value: torch.Tensor, done: Optional[torch.Tensor] 
     if not normalize:
         _capi.check(L.ta_gae(_ptr(reward), _ptr(value), _ptr(v_next), _ptr(last_value), _ptr(done), float(gamma), float(lam),
                              int(bool(use_mask)), T, N, _ptr(adv), _ptr(ret), st), "ta_gae")
+    elif group is None and not (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                and torch.distributed.get_world_size() > 1):
+        # one rank: the library normalises inside the GAE launch when the whole grid is resident at once (small rollouts),
+        # else moments from the GAE launch + one pass over adv
+        work = torch.empty(8 + 2 * 1024, dtype=torch.float64, device=reward.device)   # TA_GAE_WORK_DOUBLES
+        _capi.check(L.ta_gae_normalized(_ptr(reward), _ptr(value), _ptr(v_next), _ptr(last_value), _ptr(done), float(gamma),
+                                        float(lam), int(bool(use_mask)), T, N, _ptr(adv), _ptr(ret), _ptr(work), st),
+                    "ta_gae_normalized")
     else:
         # the moments of adv come out of the same launch; normalising is one more pass over adv
         stats = torch.empty(3, dtype=torch.float64, device=reward.device)

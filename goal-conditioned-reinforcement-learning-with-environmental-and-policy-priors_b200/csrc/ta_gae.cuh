@@ -97,20 +97,50 @@ constexpr int GV_MAX_THREADS = 1024;
 
 __device__ __forceinline__ float f4get(const float4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
+// (sum, sum of squares) of a CTA in a fixed order: every thread's pair goes to shared memory, the first (up to) 32 threads
+// add the entries tid, tid + 32, ... in that order, then a xor-shuffle tree (full first warp) or thread 0 alone (CTAs of fewer
+// than 32 threads) finishes; the result is left in red[0], red[1] (valid for thread 0).
+__device__ __forceinline__ void gae_cta_moments(double s, double ss, double *red, int tid, int nth) {
+    __syncthreads();   // (red may still be read from an earlier use)
+    red[2 * tid] = s;
+    red[2 * tid + 1] = ss;
+    __syncthreads();
+    if (nth >= 32) {
+        if (tid < 32) {
+            double a = 0.0, b = 0.0;
+            for (int k = tid; k < nth; k += 32) { a += red[2 * k]; b += red[2 * k + 1]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+            }
+            if (tid == 0) { red[0] = a; red[1] = b; }
+        }
+    } else if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < nth; k++) { a += red[2 * k]; b += red[2 * k + 1]; }
+        red[0] = a;
+        red[1] = b;
+    }
+}
+
 // GV_X = float4 columns per CTA (threadIdx.x): 32 for large batches; 8 (one 128-byte line per row) when the rollout is
 // small -- BASELINE configs[3] is 128 x 16384 = 36 MB -- so that there are several CTAs per SM and one pass covers all of
 // T (16 chunks x 8 steps): the launch is then bound by one DRAM round trip instead of two dependent ones.
 // stats (nullable): the launch also accumulates (sum, sum of squares, count) of adv in float64 -- the moments of
 // PPO.py:115's normalisation -- so that normalising costs one more pass over adv instead of two.
-template <int GV_L, int GV_CH, int GV_X>
+// COOP: the single-launch normalising form (sync = the ticket word, followed at sync + 10 by two float64 slots per CTA).
+template <int GV_L, int GV_CH, int GV_X, bool COOP = false>
 __global__ void __launch_bounds__(GV_X * GV_CH, 512 / (GV_X * GV_CH))
 gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const float *__restrict__ v_next,
                 const float *__restrict__ last_v, const uint8_t *__restrict__ done, float gamma, float lam, int use_mask,
-                int T, long long n, float *__restrict__ adv, float *__restrict__ ret, double *__restrict__ stats) {
+                int T, long long n, float *__restrict__ adv, float *__restrict__ ret, double *__restrict__ stats,
+                unsigned int *__restrict__ sync) {
     // chunk summaries [chunk][env of the quad][quad] (+ GV_PAD floats per chunk row: the warps of a narrow CTA hold
     // several chunks, whose rows would otherwise fall on the same banks)
     constexpr int GV_PAD = GV_X < 32 ? GV_X : 0, GV_ROW = 4 * GV_X + GV_PAD;
     __shared__ float sP[GV_CH * GV_ROW], sA[GV_CH * GV_ROW], sC[4 * GV_X];
+    __shared__ double red[2 * GV_X * GV_CH];   // per-thread partial moments (stats launches)
     const int lx = threadIdx.x, cy = threadIdx.y, CH = blockDim.y;
     const int tid = cy * GV_X + lx, nth = GV_X * CH;
     for (int sidx = tid; sidx < 4 * GV_X; sidx += nth) sC[sidx] = 0.0f;   // (same thread, same slots as in the scan below)
@@ -215,9 +245,13 @@ gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const 
                 ao[i] = __fadd_rn(dl[j][i], ca);
                 A[i] = ao[i];
             }
+            if (COOP) {   // normalising launch: adv stays in registers until the grid's moments are known
+#pragma unroll
+                for (int i = 0; i < 4; i++) dl[j][i] = ao[i];
+            }
             if (in) {
                 const long long idx = (long long)t * n + col;
-                *reinterpret_cast<float4 *>(adv + idx) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+                if (!COOP) *reinterpret_cast<float4 *>(adv + idx) = make_float4(ao[0], ao[1], ao[2], ao[3]);
                 *reinterpret_cast<float4 *>(ret + idx) = make_float4(ro[0], ro[1], ro[2], ro[3]);
                 if (stats) {
                     st_s += (double)ao[0] + (double)ao[1] + (double)ao[2] + (double)ao[3];
@@ -225,18 +259,54 @@ gae_vec4_kernel(const float *__restrict__ r, const float *__restrict__ v, const 
                 }
             }
         }
+        if (COOP) {
+            // ---- single-launch normalisation (the launcher guarantees: one pass, every CTA of the grid resident) --------
+            // per-CTA moments -> the CTA's own slot (no same-address float64 atomics: 512 CTAs finishing together spent
+            // ~5 us queueing on them) -> grid barrier on a ticket -> EVERY CTA adds all slots in the same fixed order ->
+            // (adv - mean) / (std + 1e-8) from the registers (adv_normalize_kernel's arithmetic, PPO.py:115): adv is
+            // written once, never re-read, and the result does not depend on the order CTAs finish in
+            double *slots = reinterpret_cast<double *>(sync) + 5;   // (sync = work + 3: slots start at work + 8)
+            gae_cta_moments(st_s, st_ss, red, tid, nth);
+            __shared__ float s_norm[2];
+            if (tid == 0) {
+                __stcg(slots + 2 * blockIdx.x, red[0]);
+                __stcg(slots + 2 * blockIdx.x + 1, red[1]);
+                __threadfence();
+                atomicAdd(sync, 1u);
+                for (int spin = 0; spin < (1 << 24); spin++)   // bounded: a grid that is not co-resident must not hang
+                    if (*reinterpret_cast<volatile unsigned int *>(sync) >= gridDim.x) break;
+                __threadfence();
+            }
+            __syncthreads();
+            double gs = 0.0, gss = 0.0;
+            for (int k = tid; k < (int)gridDim.x; k += nth) { gs += __ldcg(slots + 2 * k); gss += __ldcg(slots + 2 * k + 1); }
+            gae_cta_moments(gs, gss, red, tid, nth);
+            if (tid == 0) {
+                const double s0 = red[0], s1 = red[1], cnt = (double)T * (double)n;
+                const double mean = s0 / cnt;
+                double var = (s1 - s0 * mean) / (cnt > 1.0 ? cnt - 1.0 : 1.0);
+                var = var < 0.0 ? 0.0 : var;
+                s_norm[0] = (float)mean;
+                s_norm[1] = 1.0f / ((float)sqrt(var) + 1e-8f);
+                if (blockIdx.x == 0) { stats[0] = s0; stats[1] = s1; stats[2] = cnt; }
+            }
+            __syncthreads();
+            const float m = s_norm[0], inv = s_norm[1];
+#pragma unroll
+            for (int j = 0; j < GV_L; j++) {
+                const int t = t0 + j;
+                if (valid && t < T)
+                    *reinterpret_cast<float4 *>(adv + (long long)t * n + col) =
+                        make_float4((dl[j][0] - m) * inv, (dl[j][1] - m) * inv, (dl[j][2] - m) * inv, (dl[j][3] - m) * inv);
+            }
+        }
         __syncthreads();
     }
-    if (stats) {  // CTA-wide sum through the (now free) scan buffers, then one atomic pair per CTA
-        __shared__ double red[2 * GV_X * GV_CH];
-        red[2 * tid] = st_s;
-        red[2 * tid + 1] = st_ss;
-        __syncthreads();
+    if (stats && !COOP) {  // CTA-wide sums, then one atomic pair per CTA
+        gae_cta_moments(st_s, st_ss, red, tid, nth);
         if (tid == 0) {
-            double a = 0.0, b = 0.0;
-            for (int k = 0; k < nth; k++) { a += red[2 * k]; b += red[2 * k + 1]; }
-            atomicAdd(&stats[0], a);
-            atomicAdd(&stats[1], b);
+            atomicAdd(&stats[0], red[0]);
+            atomicAdd(&stats[1], red[1]);
             if (blockIdx.x == 0) atomicAdd(&stats[2], (double)T * (double)n);
         }
     }

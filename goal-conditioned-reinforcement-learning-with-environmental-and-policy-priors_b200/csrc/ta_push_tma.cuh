@@ -198,4 +198,88 @@ __global__ void __launch_bounds__(PT_THREADS) stack_push_tma_kernel(const uint32
     if (dead && fail) atomicExch(fail, 1);
 }
 
+// ---- matrix_env / data_env of every env (ta_feat.cuh: frame_codes_tile_kernel) in the same pipelined form -----------
+// Env_transact.matrix_env / data_env, soa/env_buffer.py:300-334.  The input of a 16-env tile is 1.5 KB (records + agent
+// words), its output 4.6 KB of codes (+ 18 KB of float32 LUT values): the one-tile-per-CTA kernel is a DRAM round trip
+// followed by a decode per CTA, 15 us per 65536 envs for 25 MB.  Here FP_STAGES input stages are prefetched by bulk copies,
+// a tile costs ONE CTA barrier, and the codes leave with a bulk store from a ring of FP_OUT output tiles.
+constexpr int FP_STAGES = 8;
+constexpr int FP_OUT = 3;
+constexpr int FP_IN = PT_REC_BYTES + PT_SC_BYTES;                    // 1536
+constexpr int FP_TILE = FEAT_ENVS * NCELL;                           // 4624
+constexpr int FP_TILE_PAD = (FP_TILE + 127) / 128 * 128;             // 4736
+
+__global__ void __launch_bounds__(PT_THREADS) frame_codes_pipe_kernel(const uint32_t *grid, const uint4 *sc0, uint8_t *codes,
+                                                                      float *matrix, float *place, long long n, int *fail) {
+    __shared__ __align__(128) uint8_t s_in[FP_STAGES * FP_IN];
+    __shared__ __align__(128) uint8_t s_out[FP_OUT * FP_TILE_PAD];
+    __shared__ uint64_t full[FP_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long ntiles = n / FEAT_ENVS;
+    const long long my_tiles = ((long long)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int s = 0; s < FP_STAGES; s++) pt_mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long k) {   // one thread: stage k % FP_STAGES <- the CTA's k-th tile
+        const int s = (int)(k % FP_STAGES);
+        const long long e0 = ((long long)blockIdx.x + k * gridDim.x) * FEAT_ENVS;
+        pt_mbar_expect(&full[s], FP_IN);
+        pt_bulk_g2s(s_in + s * FP_IN, grid + e0 * REC_WORDS, PT_REC_BYTES, &full[s]);
+        pt_bulk_g2s(s_in + s * FP_IN + PT_REC_BYTES, sc0 + e0, PT_SC_BYTES, &full[s]);
+    };
+    if (tid == 0)
+        for (long long k = 0; k < FP_STAGES && k < my_tiles; k++) issue(k);
+    bool dead = false;
+    for (long long k = 0; k < my_tiles; k++) {
+        const int s = (int)(k % FP_STAGES), o = (int)(k % FP_OUT);
+        const long long e0 = ((long long)blockIdx.x + k * gridDim.x) * FEAT_ENVS;
+        const uint32_t *sg = reinterpret_cast<const uint32_t *>(s_in + s * FP_IN);
+        const uint4 *ssc = reinterpret_cast<const uint4 *>(s_in + s * FP_IN + PT_REC_BYTES);
+        uint8_t *tile = s_out + o * FP_TILE_PAD;
+        if (!dead && !pt_mbar_wait(&full[s], (uint32_t)((k / FP_STAGES) & 1))) dead = true;
+        // (tile `o` is free: thread 0 waited for the store issued FP_OUT tiles ago before the previous tile's barrier)
+        if (tid < FEAT_ENVS * GS) {   // one (env, grid column) per thread
+            const int e = tid / GS, x = tid - GS * e;
+            const uint32_t *rec = sg + e * REC_WORDS;
+            const int bit = 2 * GS * x, w = bit >> 5, sh = bit & 31;
+            const uint32_t w1 = w + 1 < REC_WORDS ? rec[w + 1] : 0u, w2 = w + 2 < REC_WORDS ? rec[w + 2] : 0u;
+            const uint32_t lo = __funnelshift_r(rec[w], w1, sh), hi = __funnelshift_r(w1, w2, sh);
+            uint8_t *dst = tile + e * NCELL + x;
+#pragma unroll
+            for (int y = 0; y < GS; y++) {
+                const uint32_t cell = y < 16 ? (lo >> (2 * y)) & 3u : hi & 3u;
+                dst[y * GS] = (uint8_t)((0x0210u >> (4 * cell)) & 0xFu);
+            }
+            const uint32_t a = ssc[e].x & 0xFFFFu;
+            if ((int)(a & 0xFFu) == x && (a >> 8) < (uint32_t)GS) dst[(a >> 8) * GS] = 4;
+        }
+        if (place && tid < FEAT_ENVS * 2) {   // data_env: (y, x)
+            const uint32_t a = ssc[tid >> 1].x & 0xFFFFu;
+            place[e0 * 2 + tid] = (tid & 1) ? (float)(a & 0xFFu) : (float)(a >> 8);
+        }
+        if (tid == 0 && codes) bulk_wait_read<FP_OUT - 2>();   // frees the tile the NEXT iteration writes
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            if (codes) {
+                bulk_s2g(codes + e0 * NCELL, tile, (uint32_t)FP_TILE);
+                bulk_commit();
+            }
+            if (k + FP_STAGES < my_tiles) issue(k + FP_STAGES);
+        }
+        if (matrix) {   // the LUT applied: 4 codes -> one 16-byte store
+            float4 *out = reinterpret_cast<float4 *>(matrix + e0 * NCELL);
+            for (int q = tid; q < FP_TILE / 4; q += PT_THREADS) {
+                const uint32_t c4 = *reinterpret_cast<const uint32_t *>(tile + 4 * q);
+                out[q] = make_float4(matrix_value(c4 & 0xFFu), matrix_value((c4 >> 8) & 0xFFu), matrix_value((c4 >> 16) & 0xFFu),
+                                     matrix_value(c4 >> 24));
+            }
+        }
+    }
+    if (tid == 0 && codes) bulk_wait_read<0>();
+    if (dead && fail) atomicExch(fail, 1);
+}
+
 }  // namespace ta

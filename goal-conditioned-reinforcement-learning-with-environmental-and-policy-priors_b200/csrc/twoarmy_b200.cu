@@ -552,6 +552,28 @@ static void launch_push_codes(unsigned nb, cudaStream_t st, const uint32_t *grid
 int ta_state_matrix(ta_handle h, uint8_t *codes_out, float *matrix_out, float *place_out, void *stream) {
     if (!h) return TA_E_INVALID;
     CK(cudaSetDevice(h->device));
+    if ((((uintptr_t)codes_out | (uintptr_t)matrix_out) & 15u) == 0 && h->n >= FEAT_ENVS && (h->n % FEAT_ENVS) == 0) {
+        // the pipelined form (ta_push_tma.cuh); TA_FEAT_PIPE=0 / ta_debug_push_tma(0) select the one-tile-per-CTA kernel
+        int &mode = g_push_tma;
+        if (mode < 0) { const char *e = getenv("TA_PUSH_TMA"); mode = e ? atoi(e) : 1; }
+        static int pipe = -1, ctas = 6;   // (measured: 12.5 us with 4 CTAs per SM, 11.7 with 6 or 7, per 65536 envs)
+        if (pipe < 0) {
+            const char *e = getenv("TA_FEAT_PIPE"); pipe = e ? atoi(e) : 1;
+            if ((e = getenv("TA_FEAT_CTAS")) && atoi(e) >= 1 && atoi(e) <= 7) ctas = atoi(e);
+        }
+        if (mode && pipe) {
+            int *fail = nullptr;
+            if (int rc = tc_fail_flag(&fail)) return rc;
+            int dev = 0, sms = 0;
+            CK(cudaGetDevice(&dev));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            long long g = (long long)sms * ctas;
+            if (g > h->n / FEAT_ENVS) g = h->n / FEAT_ENVS;
+            frame_codes_pipe_kernel<<<(unsigned)g, PT_THREADS, 0, (cudaStream_t)stream>>>(h->grid, h->sc0, codes_out, matrix_out, place_out,
+                                                                                          h->n, fail);
+            return launch_ok("frame_codes_pipe_kernel");
+        }
+    }
     if ((((uintptr_t)codes_out | (uintptr_t)matrix_out) & 15u) == 0) {
         frame_codes_tile_kernel<<<blocks_for(h->n, FEAT_ENVS), FEAT_THREADS, 0, (cudaStream_t)stream>>>(
             h->grid, h->sc0, codes_out, matrix_out, place_out, h->n);
@@ -639,13 +661,17 @@ int ta_import_state(ta_handle h, const ta_env_state *in, void *stream) {
     return launch_ok("import_kernel");
 }
 
+// coop (nullable): a zeroed ticket word -- the launch then also normalises adv (single launch; only taken when one pass
+// covers T and the whole grid is resident at once, *coop_used says whether it was)
 static int gae_launch(const float *reward, const float *v, const float *v_next, const float *last_v, const uint8_t *done, float gamma,
-                      float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, double *stats3, void *stream) {
+                      float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, double *stats3, void *stream,
+                      unsigned int *coop = nullptr, int *coop_used = nullptr) {
+    if (coop_used) *coop_used = 0;
     if (!reward || !v || !adv_out || !ret_out || T <= 0 || n <= 0) return TA_E_INVALID;
     if (!v_next && !last_v) return TA_E_INVALID;
     if (use_mask && !done) return TA_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    if (stats3) CK(cudaMemsetAsync(stats3, 0, 3 * sizeof(double), st));
+    if (stats3) CK(cudaMemsetAsync(stats3, 0, (coop ? 5 : 3) * sizeof(double), st));   // (coop = stats3 + 3: the ticket word)
     const uintptr_t al = (uintptr_t)reward | (uintptr_t)v | (uintptr_t)v_next | (uintptr_t)last_v | (uintptr_t)adv_out |
                          (uintptr_t)ret_out;
     if ((n & 3) == 0 && (al & 15u) == 0 && ((uintptr_t)done & 3u) == 0) {  // four envs per thread, 16-byte accesses
@@ -661,22 +687,35 @@ static int gae_launch(const float *reward, const float *v, const float *v_next, 
             // small rollout (fewer than two 128-env CTAs per SM; BASELINE configs[3] is 128 x 16384): up to 16 chunks, so
             // that one pass covers 128 steps -- one DRAM round trip instead of two dependent ones
             const int chv = steps_chunks < 16 ? steps_chunks : 16;
+            if (coop && stats3 && steps_chunks <= 16) {   // normalise in the same launch when every CTA is resident at once
+                int dev = 0, sms = 0, occ = 0;
+                CK(cudaGetDevice(&dev));
+                CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gae_vec4_kernel<8, 16, 8, true>, 8 * chv, 0));
+                const unsigned nb = blocks_for(n / 4, 8);
+                if ((long long)nb <= (long long)occ * sms && nb <= TA_GAE_WORK_CTAS) {
+                    gae_vec4_kernel<8, 16, 8, true><<<nb, dim3(8, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out,
+                                                                            ret_out, stats3, coop);
+                    if (coop_used) *coop_used = 1;
+                    return launch_ok("gae_vec4_kernel (normalising)");
+                }
+            }
             if (gvar == 1)
                 gae_vec4_kernel<8, 16, 32><<<blocks_for(n / 4, 32), dim3(32, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask,
-                                                                                            T, n, adv_out, ret_out, stats3);
+                                                                                            T, n, adv_out, ret_out, stats3, nullptr);
             else if (gvar == 2)
                 gae_vec4_kernel<8, 16, 16><<<blocks_for(n / 4, 16), dim3(16, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask,
-                                                                                            T, n, adv_out, ret_out, stats3);
+                                                                                            T, n, adv_out, ret_out, stats3, nullptr);
             else
                 gae_vec4_kernel<8, 16, 8><<<blocks_for(n / 4, 8), dim3(8, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T,
-                                                                                          n, adv_out, ret_out, stats3);
+                                                                                          n, adv_out, ret_out, stats3, nullptr);
             return launch_ok("gae_vec4_kernel (small rollout)");
         }
         int want = gch ? gch : (n / 128 >= 4 * 148 ? 4 : 8);
         int chv = steps_chunks;
         if (chv > want) chv = want;
         gae_vec4_kernel<8, 16, 32><<<blocks_for(n / 4, 32), dim3(32, chv), 0, st>>>(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n,
-                                                                                    adv_out, ret_out, stats3);
+                                                                                    adv_out, ret_out, stats3, nullptr);
         return launch_ok("gae_vec4_kernel");
     }
     int ch = (T + GAE_L - 1) / GAE_L;
@@ -702,6 +741,22 @@ int ta_gae_stats(const float *reward, const float *v, const float *v_next, const
                  float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, double *stats3, void *stream) {
     if (!stats3) return TA_E_INVALID;
     return gae_launch(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out, ret_out, stats3, stream);
+}
+
+int ta_gae_normalized(const float *reward, const float *v, const float *v_next, const float *last_v, const uint8_t *done,
+                      float gamma, float lam, int use_mask, int T, int64_t n, float *adv_out, float *ret_out, double *work,
+                      void *stream) {
+    double *work5 = work;
+    if (!work5) return TA_E_INVALID;
+    // work = (sum, sum of squares, count, ticket, spare) zeroed by the launch, then 3 unused and two slots per CTA.  A small rollout (one pass over T, every CTA of the
+    // grid resident at once -- 128 x 16384 is) normalises inside the GAE launch; anything else takes the moments from the
+    // GAE launch and one ta_adv_normalize pass.
+    int used = 0;
+    if (int rc = gae_launch(reward, v, v_next, last_v, done, gamma, lam, use_mask, T, n, adv_out, ret_out, work5, stream,
+                            reinterpret_cast<unsigned int *>(work5 + 3), &used))
+        return rc;
+    if (used) return TA_OK;
+    return ta_adv_normalize(adv_out, (int64_t)T * n, work5, stream);
 }
 
 int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream) {

@@ -230,6 +230,16 @@ int ta_gae(const float *reward, const float *v, const float *v_next, const float
 int ta_gae_stats(const float *reward, const float *v, const float *v_next, const float *last_v,
                  const uint8_t *done, float gamma, float lam, int use_mask, int T, int64_t n,
                  float *adv_out, float *ret_out, double *stats3, void *stream);
+/* ta_gae followed by adv <- (adv - mean) / (std + 1e-8) (PPO.py:115) for ONE rank.  work: TA_GAE_WORK_DOUBLES float64
+ * of device scratch (overwritten; work[0..2] end as sum, sum of squares, count of the un-normalised adv).  A rollout whose
+ * whole grid is resident at once (T <= 128 and about n <= 18944 on a B200: BASELINE configs[3]'s 128 x 16384 is) is
+ * normalised inside the GAE launch -- adv is written once, and the moments are added in a fixed order (bitwise
+ * reproducible); larger ones take the fused moments plus one ta_adv_normalize pass. */
+#define TA_GAE_WORK_CTAS 1024
+#define TA_GAE_WORK_DOUBLES (8 + 2 * TA_GAE_WORK_CTAS)
+int ta_gae_normalized(const float *reward, const float *v, const float *v_next, const float *last_v,
+                      const uint8_t *done, float gamma, float lam, int use_mask, int T, int64_t n,
+                      float *adv_out, float *ret_out, double *work, void *stream);
 int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream);
 int ta_adv_normalize(float *adv, int64_t count, const double *stats3, void *stream);
 

@@ -46,10 +46,12 @@ def test_gae_matches_float64_oracle(T, N, lam, use_mask):
     assert np.max(np.abs(ret.cpu().numpy() - want_ret) / scale) < RTOL
 
 
-@pytest.mark.parametrize("T,N", [(128, 4096), (24, 65536), (40, 1003)])
+@pytest.mark.parametrize("T,N", [(128, 4096), (24, 65536), (40, 1003), (128, 16384), (16, 64), (130, 4096), (8, 18944), (8, 18976)])
 def test_gae_with_per_sample_v_next_and_normalisation(T, N):
-    """normalize=True: the moments come out of the GAE launch itself (ta_gae_stats; the 32-env-CTA kernel for small
-    rollouts, the 128-env-CTA kernel for large ones, the scalar kernel + separate pass when N % 4 != 0)."""
+    """normalize=True (ta_gae_normalized): rollouts whose grid is resident at once are normalised INSIDE the GAE launch
+    (grid barrier on a ticket: 128 x 4096, 128 x 16384 = BASELINE configs[3], 16 x 64 with CTAs of 16 threads, 8 x 18944 =
+    the last env count that fits); the others take the moments from the GAE launch plus one pass over adv (130 steps = two
+    passes over T, 18976 envs = one CTA too many, 65536 envs = the 128-env-CTA kernel, N % 4 != 0 = the scalar kernel)."""
     from oracle import oracle as O
     A = _adv()
     rng = np.random.default_rng(3)

@@ -354,6 +354,33 @@ def test_matrix_env_and_stack_roll_match_reference(golden):
                 assert np.array_equal(s.cpu().numpy(), ref_s)
 
 
+@pytest.mark.parametrize("n", [16, 48, 4096, 131072])
+def test_state_matrix_pipelined_equals_tile_kernel(n):
+    """ta_state_matrix's persistent bulk-copy pipeline (frame_codes_pipe_kernel: env counts that are multiples of 16)
+    == the one-tile-per-CTA kernel the reference fixtures pin (test_matrix_env_and_stack_roll_match_reference), for
+    codes, LUT values and positions; 131072 envs = 8192 tiles, more per CTA than the pipeline has input stages."""
+    pkg = _pkg()
+    L = pkg._capi.lib()
+    env = pkg.TwoarmyVecEnv(4, n, 17, seed=11, autoreset=True)
+    env.reset()
+    g = torch.Generator().manual_seed(2)
+    amap = torch.tensor([0, 1, 2, 3, 6], dtype=torch.int32)
+    try:
+        for t in range(6):
+            for _ in range(3):
+                env.step(amap[torch.randint(0, 5, (n,), generator=g)])
+            L.ta_debug_push_tma(0)
+            want = env.state_matrix(want_codes=True)
+            L.ta_debug_push_tma(1)
+            got = env.state_matrix(want_codes=True)
+            for a, b in zip(got, want):
+                assert torch.equal(a, b), t
+            assert int(got[2].max()) == 4 and int((got[2] == 4).sum()) == n     # one agent cell per env
+    finally:
+        L.ta_debug_push_tma(-1)
+    assert L.ta_debug_conv1_tc_failed() == 0
+
+
 def test_stack_roll_codes_equals_float_stack_roll(golden):
     """ta_stack_roll_codes decoded with the matrix_env LUT == ta_stack_roll (float)."""
     import importlib
