@@ -125,6 +125,9 @@ def lib() -> C.CDLL:
     L.ta_her_plan.argtypes = [vp, vp, i32, i64, i32, u64, u64, vp, vp, vp, vp, vp]
     L.ta_gae.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp]
     L.ta_gae_stats.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp, vp]
+    L.ta_pred_encoder.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ta_pred_decoder.argtypes = [vp, i64, vp, vp, vp, vp, vp, f32, vp, vp]
+    L.ta_lstm_gates.argtypes = [vp, vp, vp, vp, vp, i64, i64, i32, vp]
     L.ta_gae_normalized.argtypes = [vp, vp, vp, vp, vp, f32, f32, i32, i32, i64, vp, vp, vp, vp]
     L.ta_adv_stats.argtypes = [vp, i64, vp, vp]
     L.ta_adv_normalize.argtypes = [vp, i64, vp, vp]

@@ -396,4 +396,48 @@ __global__ void __launch_bounds__(128) gather_minibatch_kernel(const uint8_t *__
     }
 }
 
+// ---- LSTM cell gates (the frozen frame predictor of BASELINE configs[4]: soa/agent/net/all_net.py:53-98, nn.LSTM(1024, 1024, 3)) ----
+// torch.nn.LSTM's cell with the two gate GEMMs done by the caller:
+//     (i, f, g, o) = gx + gh + bias         gate order of torch.nn.LSTM: input, forget, cell, output
+//     c' = sigmoid(f) * c + sigmoid(i) * tanh(g);   h' = sigmoid(o) * tanh(c')
+// gx, gh: float32 [B][4H] pre-activations (x W_ih^T and h W_hh^T; gh nullable when one GEMM over [x, h] produced both),
+// bias float32 [4H] = b_ih + b_hh, c float32 [B][H] updated in place, h_out bf16 [B][ld_h] (the next GEMM's operand).
+// One thread = 4 hidden units of one sample: four 16-byte gate loads (x 2), one 16-byte cell load / store, one 8-byte h store.
+__global__ void __launch_bounds__(256) lstm_gates_kernel(const float *__restrict__ gx, const float *__restrict__ gh,
+                                                         const float *__restrict__ bias, float *__restrict__ c,
+                                                         __nv_bfloat16 *__restrict__ h_out, long long ld_h, long long B, int H) {
+    const int hq = H >> 2;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B * hq) return;
+    const long long b = q / hq;
+    const int j = (int)(q - b * hq) * 4;
+    float4 g4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const long long off = b * 4ll * H + (long long)k * H + j;
+        float4 a = __ldcs(reinterpret_cast<const float4 *>(gx + off));
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + k * H + j));
+        a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+        if (gh) {
+            const float4 hh = __ldcs(reinterpret_cast<const float4 *>(gh + off));
+            a.x += hh.x; a.y += hh.y; a.z += hh.z; a.w += hh.w;
+        }
+        g4[k] = a;
+    }
+    float4 cv = *reinterpret_cast<const float4 *>(c + b * H + j);
+    auto sig = [](float x) { return 1.0f / (1.0f + __expf(-x)); };
+    auto cell = [&](float i, float f, float g, float o, float &cc) {
+        cc = sig(f) * cc + sig(i) * tanhf(g);
+        return sig(o) * tanhf(cc);
+    };
+    const float h0 = cell(g4[0].x, g4[1].x, g4[2].x, g4[3].x, cv.x), h1 = cell(g4[0].y, g4[1].y, g4[2].y, g4[3].y, cv.y);
+    const float h2 = cell(g4[0].z, g4[1].z, g4[2].z, g4[3].z, cv.z), h3 = cell(g4[0].w, g4[1].w, g4[2].w, g4[3].w, cv.w);
+    *reinterpret_cast<float4 *>(c + b * H + j) = cv;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(h0, h1), hi = __floats2bfloat162_rn(h2, h3);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t *>(&lo);
+    pk.y = *reinterpret_cast<uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(h_out + b * ld_h + j) = pk;
+}
+
 }  // namespace ta

@@ -16,6 +16,7 @@
 #include "ta_feat.cuh"
 #include "ta_gae.cuh"
 #include "ta_her.cuh"
+#include "ta_pred.cuh"
 #include "ta_push_tma.cuh"
 #include "ta_host.cuh"
 #include "ta_stem_bwd_tc.cuh"
@@ -757,6 +758,54 @@ int ta_gae_normalized(const float *reward, const float *v, const float *v_next, 
         return rc;
     if (used) return TA_OK;
     return ta_adv_normalize(adv_out, (int64_t)T * n, work5, stream);
+}
+
+static int pred_grid(const void *kern, int smem, int64_t M, unsigned *grid) {
+    int dev = 0, sms = 0, occ = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PR_THREADS, smem));
+    long long g = (long long)sms * (occ > 0 ? occ : 1);
+    *grid = (unsigned)(M < g ? M : g);
+    return TA_OK;
+}
+
+int ta_pred_encoder(const void *x, int x_dtype, int64_t M, const float *w1, const float *s1, const float *t1, const float *w2,
+                    const float *s2, const float *t2, const float *w3, const float *s3, const float *t3, void *z_bf16, void *stream) {
+    if (!x || !z_bf16 || M <= 0 || !w1 || !s1 || !t1 || !w2 || !s2 || !t2 || !w3 || !s3 || !t3) return TA_E_INVALID;
+    if (x_dtype != TA_STACK_U8 && x_dtype != TA_STACK_F32) return TA_E_INVALID;
+    if ((((uintptr_t)w2 | (uintptr_t)w3) & 7u) != 0) return TA_E_INVALID;
+    const PredEncArgs a{w1, s1, t1, w2, s2, t2, w3, s3, t3};
+    unsigned g = 1;
+    if (x_dtype == TA_STACK_U8) {
+        if (int rc = pred_grid((const void *)pred_encoder_kernel<true>, PR_ENC_SMEM, M, &g)) return rc;
+        pred_encoder_kernel<true><<<g, PR_THREADS, PR_ENC_SMEM, (cudaStream_t)stream>>>(x, a, (__nv_bfloat16 *)z_bf16, M);
+    } else {
+        if (int rc = pred_grid((const void *)pred_encoder_kernel<false>, PR_ENC_SMEM, M, &g)) return rc;
+        pred_encoder_kernel<false><<<g, PR_THREADS, PR_ENC_SMEM, (cudaStream_t)stream>>>(x, a, (__nv_bfloat16 *)z_bf16, M);
+    }
+    return launch_ok("pred_encoder_kernel");
+}
+
+int ta_pred_decoder(const void *z_bf16, int64_t M, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                    float b3, float *out, void *stream) {
+    if (!z_bf16 || !out || M <= 0 || !w1 || !b1 || !w2 || !b2 || !w3) return TA_E_INVALID;
+    if ((((uintptr_t)w1 | (uintptr_t)w2) & 15u) != 0) return TA_E_INVALID;
+    const PredDecArgs a{w1, b1, w2, b2, w3, b3};
+    unsigned g = 1;
+    if (int rc = pred_grid((const void *)pred_decoder_kernel, PR_DEC_SMEM, M, &g)) return rc;
+    pred_decoder_kernel<<<g, PR_THREADS, PR_DEC_SMEM, (cudaStream_t)stream>>>((const __nv_bfloat16 *)z_bf16, a, out, M);
+    return launch_ok("pred_decoder_kernel");
+}
+
+int ta_lstm_gates(const float *gx, const float *gh, const float *bias, float *c, void *h_out_bf16, int64_t ld_h, int64_t B, int H,
+                  void *stream) {
+    if (!gx || !bias || !c || !h_out_bf16 || B <= 0 || H <= 0 || (H & 3) || ld_h < H || (ld_h & 3)) return TA_E_INVALID;
+    if ((((uintptr_t)gx | (uintptr_t)gh | (uintptr_t)bias | (uintptr_t)c) & 15u) || ((uintptr_t)h_out_bf16 & 7u)) return TA_E_INVALID;
+    lstm_gates_kernel<<<blocks_for(B * (H / 4), 256), 256, 0, (cudaStream_t)stream>>>(gx, gh, bias, c, (__nv_bfloat16 *)h_out_bf16, ld_h, B, H);
+    return launch_ok("lstm_gates_kernel");
 }
 
 int ta_adv_stats(const float *adv, int64_t count, double *stats3, void *stream) {

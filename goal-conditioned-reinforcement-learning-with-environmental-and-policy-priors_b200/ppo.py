@@ -362,9 +362,17 @@ class PPO:
         return flat
 
     # ------------------------------------------------------------------ acting
-    def _net_in(self, frames):
-        """What the actor / critic receive for 4 frames [B,4,289] (subclasses add predicted frames)."""
+    def _net_in(self, frames, rows=None, lo=None):
+        """What the actor / critic receive for 4 frames [B,4,289] (subclasses add predicted frames).  During update()
+        `rows` are the buffer rows the frames were gathered from and `lo` the first of the record's frames used (0 or 1),
+        so that a subclass can reuse what it computed per buffer row in _begin_update."""
         return frames
+
+    def _begin_update(self, s):
+        """Called by update() once the records `s` [B,5,289] are on the device, before the critic passes."""
+
+    def _end_update(self):
+        """Called when update() has issued its last optimiser step."""
 
     def _amp(self):
         return torch.autocast(device_type=self.device.type, dtype=torch.bfloat16, enabled=self.autocast)
@@ -413,7 +421,7 @@ class PPO:
                     sc = decode_matrix(sc)
                 pc, gc = p[rows], (g[i:i + chunk] if idx is None else g[rows])
                 with self._amp():
-                    outs.append(self.critic(self._net_in(sc[:, lo:lo + 4]), pc[:, lo:lo + 4], gc))
+                    outs.append(self.critic(self._net_in(sc[:, lo:lo + 4], rows, lo), pc[:, lo:lo + 4], gc))
             return torch.cat(outs) if outs else torch.empty((0, 1), device=s.device)
 
         rows_of = (lambda i: slice(i, i + chunk)) if src is None else (lambda i: src[i:i + chunk])
@@ -483,6 +491,7 @@ class PPO:
             assert g.shape[0] == src.shape[0] and r.shape[0] == src.shape[0]
             old_a_logp, a = old_a_logp[src], a[src]
         B = s.shape[0] if src is None else src.shape[0]
+        self._begin_update(s)
         v, v_next = self.values(s, p, g, src=src, next_same=buffer.get("next_same") if self.share_next_value else None,
                                 next_stride=int(buffer.get("next_stride", 0)))
         target_v, adv = self.advantages(r, v, v_next)
@@ -507,7 +516,7 @@ class PPO:
             sb = s[rows]
             if sb.dtype == torch.uint8 and not (sb.is_cuda and self.autocast):
                 sb = decode_matrix(sb)
-            sb = self._net_in(sb[:, 0:4])
+            sb = self._net_in(sb[:, 0:4], rows, 0)
             pb, gb = p[rows][:, 0:4], g[idx]
             for name in self._flat:
                 self._flat[name].zero_()
@@ -844,6 +853,7 @@ class PPO:
             del graph
             mark("graph_free_ms")
         self.last_action_loss, self.last_value_loss = (float(x) for x in self._last)
+        self._end_update()
         if dev.type == "cuda":
             # the tcgen05 kernels bound their MMA-barrier waits and raise a flag instead of hanging: fail loudly here
             from . import _capi

@@ -341,6 +341,28 @@ int ta_col2im_s2(const void *dcols_bf16, void *dx_bf16, int64_t batch, int H, in
 int ta_im2col_s2(const void *x_bf16, void *cols_bf16, int64_t batch, int H, int W, int C, int ksize, void *stream);
 /* Bias gradient of those convolutions: out[c] = sum over rows of x [rows][C] (channels-last bf16, C in
  * {64, 128, 256}); out float32 [C] is overwritten. */
+/* The frozen frame predictor's convolution stacks in eval mode (BASELINE configs[4]; PPO_Predictor.pred_states,
+ * soa/agent/PPO_Predictor.py:70-83), one fused kernel each, every activation in shared memory (csrc/ta_pred.cuh).
+ * ta_pred_encoder = Net_Encoder (soa/agent/net/all_net.py:7-51): x [M][289] uint8 matrix codes (TA_STACK_U8) or float32
+ *   LUT values (TA_STACK_F32) -> z bf16 [M][1024] (64 x 4 x 4).  Per layer: convolution weights (w1 [16][4][4];
+ *   w2 [5][5][16 in][16 out]; w3 [2][2][16 in][64 out]) and the folded eval-mode BatchNorm + bias as scale s / shift t
+ *   per output channel (y = relu(conv * s + t)).
+ * ta_pred_decoder = Net_Decoder (all_net.py:100-137) up to and including the average pool: z bf16 [M][1024] -> out
+ *   float32 [M][289].  w1 [2][2][64 in][16 out], w2 [5][5][16 in][16 out] (transposed-convolution taps), w3 [3][3][16] =
+ *   ConvTranspose2d(16,1,4,2) + AvgPool2d(4) folded into a 3x3 stride-2 padding-1 convolution, b3 its bias.
+ * twoarmy_b200.predictor builds these arrays from the modules' parameters. */
+int ta_pred_encoder(const void *x, int x_dtype, int64_t M, const float *w1, const float *s1, const float *t1,
+                    const float *w2, const float *s2, const float *t2, const float *w3, const float *s3,
+                    const float *t3, void *z_bf16, void *stream);
+int ta_pred_decoder(const void *z_bf16, int64_t M, const float *w1, const float *b1, const float *w2,
+                    const float *b2, const float *w3, float b3, float *out, void *stream);
+/* The cell update of torch.nn.LSTM (gate order i, f, g, o) for the frozen frame predictor of BASELINE configs[4]
+ * (soa/agent/net/all_net.py:53-98; twoarmy_b200.predictor.LSTM runs the gate GEMMs and calls this per layer and step):
+ *   pre = gx + gh + bias;  c <- sigmoid(f) c + sigmoid(i) tanh(g);  h <- sigmoid(o) tanh(c)
+ * gx, gh float32 [B][4H] (gh nullable), bias float32 [4H] (b_ih + b_hh), c float32 [B][H] in place, h_out bf16 [B][ld_h].
+ * H % 4 == 0; gx / gh / bias / c 16-byte aligned, h_out 8-byte aligned with ld_h % 4 == 0. */
+int ta_lstm_gates(const float *gx, const float *gh, const float *bias, float *c, void *h_out_bf16, int64_t ld_h,
+                  int64_t B, int H, void *stream);
 int ta_channel_sum_bf16(const void *x_bf16, int64_t rows, int C, float *out, void *stream);
 
 /* ---- the hand-scheduled PPO optimiser step (soa/agent/PPO.py:124-144 without autograd; fused_step.py) ----------------

@@ -542,3 +542,172 @@ def test_next_value_shared_with_next_record():
         torch.manual_seed(3)
         losses.append(ag.update(flat, minibatch=4096))
     np.testing.assert_allclose(losses[0], losses[1], rtol=2e-2, atol=1e-3)
+
+
+def test_lstm_gates_kernel_matches_torch_cell():
+    """ta_lstm_gates == torch.nn.LSTM's cell arithmetic (gate order i, f, g, o) on the same fp32 pre-activations:
+    c to fp32 rounding, h to the rounding of its bf16 output; with and without the second gate operand, and with the h
+    output written into the right half of a wider [x | h] operand (strided rows)."""
+    import ctypes as C
+    import twoarmy_b200 as pkg
+    L = pkg._capi.lib()
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(5)
+    for B, H, wide in ((3, 1024, False), (257, 1024, True), (64, 8, False)):
+        gx = torch.randn((B, 4 * H), device=dev, generator=g) * 2
+        gh = torch.randn((B, 4 * H), device=dev, generator=g)
+        bias = torch.randn(4 * H, device=dev, generator=g) * 0.1
+        c0 = torch.randn((B, H), device=dev, generator=g)
+        for use_gh in (True, False):
+            c = c0.clone()
+            buf = torch.zeros((B, 2 * H if wide else H), dtype=torch.bfloat16, device=dev)
+            h_out = buf[:, -H:]
+            pkg._capi.check(L.ta_lstm_gates(C.c_void_p(gx.data_ptr()), C.c_void_p(gh.data_ptr()) if use_gh else None,
+                                            C.c_void_p(bias.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(h_out.data_ptr()),
+                                            buf.stride(0), B, H, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ta_lstm_gates")
+            pre = (gx + (gh if use_gh else 0) + bias).double()
+            i, f, gg, o = pre.split(H, 1)
+            c_want = torch.sigmoid(f) * c0.double() + torch.sigmoid(i) * torch.tanh(gg)
+            h_want = torch.sigmoid(o) * torch.tanh(c_want)
+            assert float((c.double() - c_want).abs().max()) < 2e-6 * max(1.0, float(c_want.abs().max()))
+            assert float((h_out.double() - h_want).abs().max()) < 2 ** -8          # |h| < 1: one bf16 ulp
+            if wide:
+                assert float(buf[:, :H].abs().max()) == 0.0                         # the x half is not touched
+
+
+def test_fast_lstm_forward_matches_nn_lstm():
+    """predictor.LSTM's hand-scheduled forward (bf16 GEMMs with fp32 gates + ta_lstm_gates) against torch.nn.LSTM in fp32
+    with the same weights: the 4 teacher-forced outputs and the 3 self-fed steps (all_net.py:76-98)."""
+    import twoarmy_b200 as pkg
+    M = importlib.import_module(pkg.__name__ + ".predictor")
+    torch.manual_seed(3)
+    m = M.LSTM().to("cuda:0")
+    m.h_0, m.c_0 = m.h_0.to("cuda:0"), m.c_0.to("cuda:0")
+    with torch.no_grad():
+        for p in m.recurrent_model.parameters():     # (the default init is tiny; make the recurrence matter)
+            p.mul_(3.0)
+    z = torch.randn((37, 4, 64, 4, 4), device="cuda:0")
+    with torch.no_grad():
+        want, _ = m(z)                                                       # fp32, cuDNN (no autocast -> reference path)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got, zc = m(z)                                                   # the fast path
+    assert got.dtype == torch.bfloat16 and got.shape == want.shape == (37, 7, 64, 4, 4) and zc.shape == (37, 4, 1024)
+    err = float((got.float() - want).abs().max())
+    assert err < 0.03 * max(1.0, float(want.abs().max())), err
+    # and its fp32 form (the same schedule with fp32 operands) agrees with cuDNN to fp32 rounding
+    got32 = m._fast_forward(z.reshape(37, 4, 1024), torch.float32).reshape(37, 7, 64, 4, 4)
+    assert float((got32 - want).abs().max()) < 1e-3 * max(1.0, float(want.abs().max()))      # (cuDNN's fp32 RNN may use TF32)
+
+
+def test_prediction_table_equals_per_use_predictions():
+    """ppo_predictor.update computes the frozen predictor's frames once per buffer row (_begin_update); what the networks
+    receive from the table == what _cat computes from the frames themselves (bf16 GEMMs: equal up to the batch shape's
+    rounding), and an update with the table tracks one without (TA_PRED_CACHE=0)."""
+    import os
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    M = importlib.import_module(pkg.__name__ + ".predictor")
+    torch.manual_seed(0)
+    agent = M.ppo_predictor(device="cuda:0")
+    env = pkg.TwoarmyVecEnv(4, 128, 17, seed=2, autoreset=False)
+    buf = P.VecRollout(env, agent, 16).collect().flat()
+    s = buf["s"].to("cuda:0")
+    agent._begin_update(s)
+    assert agent._pred_valid and agent._pred_table.shape == (s.shape[0], 4, 289)
+    rows = torch.randperm(s.shape[0], device="cuda:0")[:300]
+    got = agent._net_in(s[rows][:, 0:4], rows, 0)
+    want = agent._cat(s[rows][:, 0:4])
+    assert got.shape == want.shape == (300, 8, 289) and torch.equal(got[:, :4], want[:, :4])
+    assert float((got - want).abs().max()) < 0.02 * max(1.0, float(want.abs().max()))
+    agent._end_update()
+    assert torch.equal(agent._net_in(s[rows][:, 0:4], rows, 0), want)     # table off: computed from the frames
+    state = {k: v.clone() for k, v in agent.actor.state_dict().items()}
+    outs = []
+    for cache in ("1", "0"):
+        os.environ["TA_PRED_CACHE"] = cache
+        try:
+            agent.actor.load_state_dict(state)
+            torch.manual_seed(1)
+            outs.append(agent.update(buf, minibatch=512, epochs=1))
+        finally:
+            os.environ.pop("TA_PRED_CACHE", None)
+    assert all(np.isfinite(x) for o in outs for x in o)
+
+
+def _predictor_agent_with_nontrivial_statistics():
+    import twoarmy_b200 as pkg
+    M = importlib.import_module(pkg.__name__ + ".predictor")
+    torch.manual_seed(4)
+    agent = M.ppo_predictor(device="cuda:0")
+    g = torch.Generator(device="cuda:0").manual_seed(9)
+    with torch.no_grad():
+        for m in agent.encoder.cnn_base:
+            if isinstance(m, torch.nn.BatchNorm2d):     # (fresh modules have mean 0 / var 1: make the fold matter)
+                m.running_mean.copy_(torch.randn(m.num_features, device="cuda:0", generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.num_features, device="cuda:0", generator=g) + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, device="cuda:0", generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, device="cuda:0", generator=g) * 0.1)
+        for net in (agent.encoder, agent.decoder):
+            for m in net.cnn_base:
+                if hasattr(m, "weight") and m.weight.dim() == 4:
+                    m.weight.mul_(4.0)
+                    m.bias.copy_(torch.randn(m.bias.shape, device="cuda:0", generator=g) * 0.1)
+        for p in agent.predictor.recurrent_model.parameters():
+            p.mul_(3.0)
+    return agent, M
+
+
+def test_fused_predictor_stacks_match_modules():
+    """ta_pred_encoder / ta_pred_decoder (one fused kernel per stack, eval-mode BatchNorm and the average pool folded)
+    against the torch modules in fp32: the encoder to the rounding of its bf16 output, the decoder -- fed the same bf16
+    codes -- to fp32 accumulation order; uint8 codes and float LUT values give the same result."""
+    import ctypes as C
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    agent, M = _predictor_agent_with_nontrivial_statistics()
+    L = pkg._capi.lib()
+    dev = "cuda:0"
+    Mimg = 4 * 77
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8, device=dev)[torch.randint(0, 4, (Mimg, 289), device=dev)]
+    e, d = agent._stack_arrays()
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    agent.encoder.eval(); agent.decoder.eval()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want_z = agent.encoder(P.decode_matrix(codes).float().view(Mimg, 1, 289))[0].reshape(Mimg, 1024)
+            zs = []
+            for x in (codes, P.decode_matrix(codes).float().contiguous()):
+                z = torch.empty((Mimg, 1024), dtype=torch.bfloat16, device=dev)
+                pkg._capi.check(L.ta_pred_encoder(ptr(x), 1 if x.dtype == torch.uint8 else 0, Mimg, ptr(e["w1"]), ptr(e["s1"]), ptr(e["t1"]),
+                                                  ptr(e["w2"]), ptr(e["s2"]), ptr(e["t2"]), ptr(e["w3"]), ptr(e["s3"]), ptr(e["t3"]), ptr(z), st),
+                                "ta_pred_encoder")
+                zs.append(z)
+            assert torch.equal(zs[0], zs[1])
+            assert float(want_z.abs().max()) > 0.5
+            err = (zs[0].float() - want_z).abs()
+            assert float((err - 2 ** -8 * want_z.abs()).max()) < 1e-4, float(err.max())      # one bf16 ulp + fp32 noise
+            zin = zs[0]
+            want = agent.decoder(zin.float().view(Mimg, 1, 64, 4, 4))[0].reshape(Mimg, 289)
+            out = torch.empty((Mimg, 289), dtype=torch.float32, device=dev)
+            pkg._capi.check(L.ta_pred_decoder(ptr(zin), Mimg, ptr(d["w1"]), ptr(d["b1"]), ptr(d["w2"]), ptr(d["b2"]), ptr(d["w3"]),
+                                              d["b3"], ptr(out), st), "ta_pred_decoder")
+            assert float(want.abs().max()) > 0.1
+            assert float((out - want).abs().max()) < 1e-4 * max(1.0, float(want.abs().max()))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_fused_pred_states_tracks_fp32_modules():
+    """pred_states on the GPU (fused stacks + hand-scheduled bf16 LSTM) against the unfused fp32 modules with the same
+    weights (autocast off): bf16 rounding of the latent and of the LSTM's operands only."""
+    agent, M = _predictor_agent_with_nontrivial_statistics()
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8, device="cuda:0")[torch.randint(0, 4, (50, 4, 289), device="cuda:0")]
+    got = agent.pred_states(codes)[0]
+    agent.autocast = False
+    want = agent.pred_states(codes)[0]
+    agent.autocast = True
+    assert got.shape == want.shape == (50, 4, 289) and got.dtype == torch.float32
+    assert float((got - want).abs().max()) < 0.03 * max(1.0, float(want.abs().max()))
