@@ -26,6 +26,7 @@ namespace ta {
 
 constexpr int PR_THREADS = 512;
 constexpr int PR_A1 = 16 * 33 * 33;   // the 16 x 33 x 33 activation both stacks pass through
+constexpr int PR_TAP = 16 * 16 + 8;   // floats per tap of the decoder's [tap][ci][co] weights in shared memory
 
 struct PredEncArgs {
     const float *w1, *s1, *t1;   // [16][4][4]; scale / shift [16]   (y = relu(conv * s + t), t includes the bias)
@@ -48,7 +49,16 @@ __global__ void __launch_bounds__(PR_THREADS) pred_encoder_kernel(const void *__
     const int tid = threadIdx.x;
     for (int i = tid; i < 6400; i += PR_THREADS) sw2[i] = a.w2[i];
     for (int i = tid; i < 4096; i += PR_THREADS) sw3[i] = a.w3[i];
-    for (int i = tid; i < 256; i += PR_THREADS) sw1[i] = a.w1[i];
+    // layer 1 folded: an output pixel of parity (py, px) sees a 2 x 2 patch of the 17 x 17 frame; the 16 taps fall on patch row r
+    // through ky in {0..3} / {} (even Y) or {0,1} / {2,3} (odd Y), the same for columns: sw1[phase][c][2r + s] = the taps' sum
+    for (int i = tid; i < 256; i += PR_THREADS) {
+        const int ph = i >> 6, c = (i >> 2) & 15, r = (i >> 1) & 1, q = i & 1, py = ph >> 1, px = ph & 1;
+        const int ky0 = py ? 2 * r : (r ? 4 : 0), ky1 = py ? 2 * r + 2 : (r ? 4 : 4), kx0 = px ? 2 * q : (q ? 4 : 0), kx1 = px ? 2 * q + 2 : 4;
+        float sum = 0.0f;
+        for (int ky = ky0; ky < ky1; ky++)
+            for (int kx = kx0; kx < kx1; kx++) sum += a.w1[c * 16 + ky * 4 + kx];
+        sw1[i] = sum;
+    }
     if (tid < 16) { sst[tid] = a.s1[tid]; sst[16 + tid] = a.t1[tid]; sst[32 + tid] = a.s2[tid]; sst[48 + tid] = a.t2[tid]; }
     if (tid < 64) { sst[64 + tid] = a.s3[tid]; sst[128 + tid] = a.t3[tid]; }
     for (long long m = blockIdx.x; m < M; m += gridDim.x) {
@@ -64,25 +74,21 @@ __global__ void __launch_bounds__(PR_THREADS) pred_encoder_kernel(const void *__
             const int Y = p / 33, X = p - 33 * Y;
             const int y0 = (2 * Y) >> 2, y1 = (2 * Y + 3) >> 2, x0 = (2 * X) >> 2, x1 = (2 * X + 3) >> 2;
             const float v00 = sin[y0 * GS + x0], v01 = sin[y0 * GS + x1], v10 = sin[y1 * GS + x0], v11 = sin[y1 * GS + x1];
-            const int ny0 = (Y & 1) ? 2 : 4, nx0 = (X & 1) ? 2 : 4;   // taps ky < ny0 fall on row y0, the rest on y1
+            const float4 *wp = reinterpret_cast<const float4 *>(sw1 + (((Y & 1) << 1) | (X & 1)) * 64);
 #pragma unroll 4
             for (int c = 0; c < 16; c++) {
-                float acc = 0.0f;
-#pragma unroll
-                for (int ky = 0; ky < 4; ky++) {
-#pragma unroll
-                    for (int kx = 0; kx < 4; kx++) {
-                        const float v = ky < ny0 ? (kx < nx0 ? v00 : v01) : (kx < nx0 ? v10 : v11);
-                        acc = fmaf(sw1[c * 16 + ky * 4 + kx], v, acc);
-                    }
-                }
+                const float4 w = wp[c];
+                const float acc = fmaf(w.x, v00, fmaf(w.y, v01, fmaf(w.z, v10, w.w * v11)));
                 a1[c * 1089 + p] = fmaxf(fmaf(acc, sst[c], sst[16 + c]), 0.0f);
             }
         }
         __syncthreads();
         // layer 2: Conv2d(16,16,5,4) -> 16 x 8 x 8.  Thread = (pixel, 2 output channels): 64 x 8 = 512 threads.
         {
-            const int p = tid & 63, cg = tid >> 6, Y = p >> 3, X = p & 7;
+            // a warp = 8 pixels of one output row x 4 channel pairs: its activation loads touch 8 banks (4-lane broadcasts),
+            // its weight loads 8 consecutive floats (with (pixel, channel pair) = (tid & 63, tid >> 6) the 4 rows of a warp fell
+            // on the same 8 banks: four-way conflicts on every activation load)
+            const int X = tid & 7, Y = (tid >> 5) & 7, cg = ((tid >> 8) << 2) | ((tid >> 3) & 3), p = Y * 8 + X;
             float acc0 = 0.0f, acc1 = 0.0f;
             for (int ci = 0; ci < 16; ci++) {
                 const float *ap = a1 + ci * 1089 + (4 * Y) * 33 + 4 * X;
@@ -134,15 +140,15 @@ __global__ void __launch_bounds__(PR_THREADS) pred_decoder_kernel(const __nv_bfl
                                                                   long long M) {
     extern __shared__ __align__(16) float pd_smem[];
     float *sw1 = pd_smem;                 // 4096
-    float *sw2 = sw1 + 4096;              // 6400
-    float *sw3 = sw2 + 6400;              // 144
+    float *sw2 = sw1 + 4096;              // 25 taps x PR_TAP (256 weights + 8 floats of padding: lanes on different taps, different banks)
+    float *sw3 = sw2 + 25 * PR_TAP;       // 144
     float *sb = sw3 + 144;                // b1 (16) b2 (16)
     float *a1 = sb + 32;                  // 17424   16 x 33 x 33
     float *a0 = a1 + PR_A1;               // 1024    16 x 8 x 8
     float *sz = a0 + 1024;                // 1024    64 x 4 x 4
     const int tid = threadIdx.x;
     for (int i = tid; i < 4096; i += PR_THREADS) sw1[i] = a.w1[i];
-    for (int i = tid; i < 6400; i += PR_THREADS) sw2[i] = a.w2[i];
+    for (int i = tid; i < 6400; i += PR_THREADS) sw2[(i >> 8) * PR_TAP + (i & 255)] = a.w2[i];
     for (int i = tid; i < 144; i += PR_THREADS) sw3[i] = a.w3[i];
     if (tid < 16) { sb[tid] = a.b1[tid]; sb[16 + tid] = a.b2[tid]; }
     for (long long m = blockIdx.x; m < M; m += gridDim.x) {
@@ -168,29 +174,33 @@ __global__ void __launch_bounds__(PR_THREADS) pred_decoder_kernel(const __nv_bfl
         __syncthreads();
         // ConvTranspose2d(16,16,5,4): out[c][y][x] = b + sum over (i, ky) with 4i + ky = y, (j, kx) with 4j + kx = x.  A pixel has
         // one such pair per axis, or two where y % 4 == 0 inside the map (ky = 0 of row y/4 and ky = 4 of row y/4 - 1).
-        // Work item = (pixel, 4 output channels): 1089 x 4.
-        for (int it = tid; it < 1089 * 4; it += PR_THREADS) {
-            const int p = it % 1089, cg = it / 1089, y = p / 33, x = p - 33 * y;
-            int iy[2], ky[2], ny = 0, jx[2], kx[2], nx = 0;
-            if (y < 32) { iy[ny] = y >> 2; ky[ny] = y & 3; ny++; }
-            if ((y & 3) == 0 && y > 0) { iy[ny] = (y >> 2) - 1; ky[ny] = 4; ny++; }
-            if (x < 32) { jx[nx] = x >> 2; kx[nx] = x & 3; nx++; }
-            if ((x & 3) == 0 && x > 0) { jx[nx] = (x >> 2) - 1; kx[nx] = 4; nx++; }
-            float acc[4] = {sb[16 + 4 * cg], sb[16 + 4 * cg + 1], sb[16 + 4 * cg + 2], sb[16 + 4 * cg + 3]};
-            for (int u = 0; u < ny; u++)
+        // Work item = (pixel, 8 output channels): 1089 x 2; one activation load and two 16-byte weight loads per 8 FMAs.
+        for (int it = tid; it < 1089 * 2; it += PR_THREADS) {
+            const int cg = it >= 1089, p = it - 1089 * cg, y = p / 33, x = p - 33 * y;
+            // first (always, except on the last row / column) the tap of row y >> 2, then the overlap tap of the row before
+            const int ny = ((y < 32) ? 1 : 0) + (((y & 3) == 0 && y > 0) ? 1 : 0), nx = ((x < 32) ? 1 : 0) + (((x & 3) == 0 && x > 0) ? 1 : 0);
+            float acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) acc[c] = sb[16 + 8 * cg + c];
+            for (int u = 0; u < ny; u++) {
+                const bool firsty = (u == 0 && y < 32);
+                const int iy = firsty ? (y >> 2) : (y >> 2) - 1, ky = firsty ? (y & 3) : 4;
                 for (int v2 = 0; v2 < nx; v2++) {
-                    const float *ap = a0 + iy[u] * 8 + jx[v2];
-                    const float *wp = sw2 + ((ky[u] * 5 + kx[v2]) * 16) * 16 + 4 * cg;
+                    const bool firstx = (v2 == 0 && x < 32);
+                    const int jx = firstx ? (x >> 2) : (x >> 2) - 1, kx = firstx ? (x & 3) : 4;
+                    const float *ap = a0 + iy * 8 + jx;
+                    const float *wp = sw2 + (ky * 5 + kx) * PR_TAP + 8 * cg;
 #pragma unroll 4
                     for (int ci = 0; ci < 16; ci++) {
                         const float v = ap[ci * 64];
-                        const float4 w = *reinterpret_cast<const float4 *>(wp + ci * 16);
-                        acc[0] = fmaf(w.x, v, acc[0]); acc[1] = fmaf(w.y, v, acc[1]);
-                        acc[2] = fmaf(w.z, v, acc[2]); acc[3] = fmaf(w.w, v, acc[3]);
+                        const float4 w0 = *reinterpret_cast<const float4 *>(wp + ci * 16), w1 = *reinterpret_cast<const float4 *>(wp + ci * 16 + 4);
+                        acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]); acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
+                        acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]); acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
                     }
                 }
+            }
 #pragma unroll
-            for (int c = 0; c < 4; c++) a1[(4 * cg + c) * 1089 + p] = fmaxf(acc[c], 0.0f);
+            for (int c = 0; c < 8; c++) a1[(8 * cg + c) * 1089 + p] = fmaxf(acc[c], 0.0f);
         }
         __syncthreads();
         // the folded tail: 3x3, stride 2, padding 1 over the 16 x 33 x 33 map -> 17 x 17
@@ -215,6 +225,6 @@ __global__ void __launch_bounds__(PR_THREADS) pred_decoder_kernel(const __nv_bfl
 }
 
 constexpr int PR_ENC_SMEM = (6400 + 4096 + 256 + 192 + PR_A1 + 1024 + 292) * 4;
-constexpr int PR_DEC_SMEM = (4096 + 6400 + 144 + 32 + PR_A1 + 1024 + 1024) * 4;
+constexpr int PR_DEC_SMEM = (4096 + 25 * PR_TAP + 144 + 32 + PR_A1 + 1024 + 1024) * 4;
 
 }  // namespace ta
