@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.ta_export_state.argtypes = [vp, vp, vp]
     L.ta_import_state.argtypes = [vp, vp, vp]
     L.ta_conv1_fwd.argtypes = [vp, i32, i64, vp, vp, i64, vp, vp]
+    L.ta_conv1_fwd_add.argtypes = [vp, i32, i64, vp, vp, i64, vp, i32, vp, vp]
     L.ta_conv1_bwd.argtypes = [vp, i32, i64, vp, vp, i64, vp, vp, vp]
     L.ta_parity_class_weights.argtypes = [vp, i64, i64, i64, i64, i32, i32, i32, vp, vp]
     L.ta_planes_to_dense_relu.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp]

@@ -215,6 +215,75 @@ class _Stem(torch.autograd.Function):
         return None, dw4, db4, gw2, gb2, gw3, gb3
 
 
+class _Stem8(torch.autograd.Function):
+    """_Stem for a first convolution with EIGHT input channels (Net_PPO_Predictor_actor / _critic, all_net.py:249-305: the
+    4 current frames + the 4 predicted ones).  The folded layer is linear in its input channels, so it is two passes of
+    the 4-channel kernel: z_b = w4b . patch(x_b) (no bias, no ReLU), then y1 = relu(b4 + w4a . patch(x_a) + z_b)
+    (ta_conv1_fwd_add); backward: conv2's data gradient as parity planes, read in place by the tcgen05 weight-gradient kernel
+    once per half (ta_conv1_bwd_planes with y1 as the ReLU mask), the bias gradient from the first."""
+
+    @staticmethod
+    def forward(ctx, xa, xb, w4a, b4, w4b, w2, b2, w3, b3):
+        xs = []
+        for x in (xa, xb):
+            assert x.is_cuda and x.dim() == 3 and x.shape[2] == 289 and x.shape[1] >= 4
+            if x.dtype not in (torch.uint8, torch.float32):
+                x = x.float()
+            if x.stride(2) != 1 or x.stride(1) != 289 or x.stride(0) < 4 * 289:
+                x = x.contiguous()
+            xs.append(x)
+        xa, xb = xs
+        B = xa.shape[0]
+        lib, st = _capi.lib(), C.c_void_p(torch.cuda.current_stream(xa.device).cuda_stream)
+        zb = torch.empty((B, 33, 33, 64), dtype=torch.bfloat16, device=xa.device)
+        y1 = torch.empty_like(zb)
+        w4a_d, w4b_d, b4_d = (t.detach().float().contiguous() for t in (w4a, w4b, b4))
+        zero = torch.zeros_like(b4_d)
+        dt = lambda x: 1 if x.dtype == torch.uint8 else 0
+        _capi.check(lib.ta_conv1_fwd_add(_ptr(xb), dt(xb), xb.stride(0), _ptr(w4b_d), _ptr(zero), B, None, 0, _ptr(zb), st), "ta_conv1_fwd_add")
+        _capi.check(lib.ta_conv1_fwd_add(_ptr(xa), dt(xa), xa.stride(0), _ptr(w4a_d), _ptr(b4_d), B, _ptr(zb), 1, _ptr(y1), st), "ta_conv1_fwd_add")
+        del zb
+        y2 = torch.cudnn_convolution_relu(y1.permute(0, 3, 1, 2), w2, b2, [2, 2], [0, 0], [1, 1], 1)
+        y3 = torch.cudnn_convolution_relu(y2, w3, b3, [2, 2], [0, 0], [1, 1], 1)
+        ctx.save_for_backward(xa, xb, y1, w2, y2, w3, y3)
+        return y3
+
+    @staticmethod
+    def backward(ctx, dy):
+        xa, xb, y1, w2, y2, w3, y3 = ctx.saved_tensors
+        lib, st = _capi.lib(), C.c_void_p(torch.cuda.current_stream(xa.device).cuda_stream)
+        dz3 = torch.ops.aten.threshold_backward(dy, y3, 0).contiguous(memory_format=torch.channels_last)
+        gw3, gb3 = _wgrad_bgrad(dz3, y2, w3, st)
+        p3 = _class_planes(dz3, w3)
+        Bn, Cc, H, W = y2.shape
+        dz2_nhwc = torch.empty((Bn, H, W, Cc), dtype=torch.bfloat16, device=xa.device)
+        y2_nhwc = y2.permute(0, 2, 3, 1)
+        assert y2_nhwc.is_contiguous()
+        _capi.check(lib.ta_planes_to_dense_relu(_ptr(p3), _ptr(y2_nhwc), _ptr(dz2_nhwc), Bn, H, W, Cc, w3.shape[2], st),
+                    "ta_planes_to_dense_relu")
+        dz2 = dz2_nhwc.permute(0, 3, 1, 2)
+        gw2, gb2 = _wgrad_bgrad(dz2, y1.permute(0, 3, 1, 2), w2, st)
+        p2 = _class_planes(dz2, w2)
+        outs = []
+        dt = lambda x: 1 if x.dtype == torch.uint8 else 0
+        for x in (xa, xb):
+            dw4 = torch.empty((256, 16), dtype=torch.float32, device=xa.device)
+            db4 = torch.empty((256,), dtype=torch.float32, device=xa.device)
+            _capi.check(lib.ta_conv1_bwd_planes(_ptr(x), dt(x), x.stride(0), _ptr(y1), None, _ptr(p2), 0, x.shape[0], _ptr(dw4), _ptr(db4), st),
+                        "ta_conv1_bwd_planes")
+            outs.append((dw4, db4))
+        return None, None, outs[0][0], outs[0][1], outs[1][0], gw2, gb2, gw3, gb3
+
+
+def stem8_relu(x8: torch.Tensor, conv1: torch.nn.Conv2d, conv2: torch.nn.Conv2d, conv3: torch.nn.Conv2d) -> torch.Tensor:
+    """stem_relu for x8 [B, 8, 289] (float32: 4 current + 4 predicted frames) and a conv1 with 8 input channels."""
+    w4a, b4 = fold(conv1.weight[:, 0:4], conv1.bias)
+    w4b, _ = fold(conv1.weight[:, 4:8], conv1.bias)
+    w2, b2 = _bf16_cl(conv2)
+    w3, b3 = _bf16_cl(conv3)
+    return _Stem8.apply(x8[:, 0:4], x8[:, 4:8], w4a, b4, w4b, w2, b2, w3, b3)
+
+
 def _bf16_cl(conv: torch.nn.Conv2d):
     return conv.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), conv.bias.to(torch.bfloat16)
 

@@ -57,7 +57,11 @@ __device__ __forceinline__ void c1_patch(const float4 *sx, int m, int n, float (
 template <typename XT>
 __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const XT *__restrict__ x, long long xstride,
                                                               const float *__restrict__ w4, const float *__restrict__ b4,
-                                                              long long B, __nv_bfloat16 *__restrict__ y) {
+                                                              long long B, __nv_bfloat16 *__restrict__ y,
+                                                              const __nv_bfloat16 *__restrict__ addend = nullptr, int relu = 1) {
+    // addend (nullable, bf16 like y): added to the pre-activation; relu == 0: the pre-activation itself is written.  Together they
+    // make a first layer with MORE than four input channels out of passes over four channels each (the layer is linear in
+    // its input channels): ta_conv1_fwd_add.
     __shared__ float4 sx[2][18 * 18];
     const int role = threadIdx.x & 63, plane = threadIdx.x >> 6;
     const int phase = role >> 4, cg = role & 15, py = phase >> 1, px = phase & 1;
@@ -81,15 +85,22 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const XT *__restr
             float p[16];
             c1_patch(sx[buf], m, n, p);
             // Blackwell's packed fp32 FMA (FFMA2): even / odd k accumulate in the two halves of a float2
-            float acc[4];
+            float acc[4], add[4] = {0.f, 0.f, 0.f, 0.f};
+            const long long yoff = ((2 * m + py) * C1_OUT + (2 * n + px)) * C1_CH + cg * 4;
+            if (addend) {
+                const uint2 av = __ldg(reinterpret_cast<const uint2 *>(addend + b * (long long)(C1_OUT * C1_OUT * C1_CH) + yoff));
+                const float2 a01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&av.x));
+                const float2 a23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&av.y));
+                add[0] = a01.x; add[1] = a01.y; add[2] = a23.x; add[3] = a23.y;
+            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 float2 a2 = make_float2(bias[i], 0.f);
 #pragma unroll
                 for (int k = 0; k < 16; k += 2)
                     a2 = __ffma2_rn(make_float2(w[i][k], w[i][k + 1]), make_float2(p[k], p[k + 1]), a2);
-                const float a = a2.x + a2.y;
-                acc[i] = a > 0.f ? a : 0.f;
+                const float a = a2.x + a2.y + add[i];
+                acc[i] = (a > 0.f || !relu) ? a : 0.f;
             }
             const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[0], acc[1]), hi = __floats2bfloat162_rn(acc[2], acc[3]);
             uint2 out;

@@ -1077,6 +1077,23 @@ int launch_conv1_bwd_tc(const void *x, int x_dtype, int64_t x_stride, const void
 
 extern "C" {
 
+int ta_conv1_fwd_add(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch,
+                     const void *addend_bf16, int relu, void *y_bf16, void *stream) {
+    if (!x || !w4 || !b4 || !y_bf16 || batch <= 0 || x_stride < 4 * NCELL || (x_dtype != TA_X_F32 && x_dtype != TA_X_U8)) return TA_E_INVALID;
+    if (((uintptr_t)y_bf16 | (uintptr_t)addend_bf16) & 7u) return TA_E_INVALID;
+    int grid = 1;
+    if (x_dtype == TA_X_U8) {
+        if (int rc = conv1_grid(conv1_fwd_kernel<uint8_t>, batch, &grid)) return rc;
+        conv1_fwd_kernel<uint8_t><<<grid, C1_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)x, x_stride, w4, b4, batch, (__nv_bfloat16 *)y_bf16,
+                                                                                 (const __nv_bfloat16 *)addend_bf16, relu);
+    } else {
+        if (int rc = conv1_grid(conv1_fwd_kernel<float>, batch, &grid)) return rc;
+        conv1_fwd_kernel<float><<<grid, C1_THREADS, 0, (cudaStream_t)stream>>>((const float *)x, x_stride, w4, b4, batch, (__nv_bfloat16 *)y_bf16,
+                                                                               (const __nv_bfloat16 *)addend_bf16, relu);
+    }
+    return launch_ok("conv1_fwd_kernel (add)");
+}
+
 int ta_conv1_bwd_planes(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const uint32_t *relu_mask,
                         const void *planes_bf16, int class_major, int64_t batch, float *dw4, float *db4, void *stream) {
     if (!x || (!y_bf16 && !relu_mask) || !planes_bf16 || !dw4 || !db4 || batch <= 0 || x_stride < 4 * NCELL ||

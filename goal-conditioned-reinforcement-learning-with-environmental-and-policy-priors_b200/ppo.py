@@ -139,6 +139,12 @@ class TINet(nn.Module):
                 stem = self.fused_stem and self.gemm_dgrad
                 # conv1 + conv2 + conv3 as one autograd node: the data gradients stay in parity planes (conv1._Stem)
                 x = _c1.stem_relu(xin, self.cnn_base[0], self.cnn_base[2], self.cnn_base[4]) if stem else _c1.conv1_relu(xin, self.cnn_base[0])
+            elif (self.fused_conv1 and self.fused_stem and self.gemm_dgrad and torch.is_autocast_enabled() and T == 8
+                  and state_matrix.dtype == torch.float32 and os.environ.get("TA_STEM8", "1") == "1"):
+                # 8 input channels (the predictor agent's networks): the folded layer as two 4-channel passes (conv1._Stem8)
+                from . import conv1 as _c1
+                stem = True
+                x = _c1.stem8_relu(state_matrix.contiguous(), self.cnn_base[0], self.cnn_base[2], self.cnn_base[4])
             else:
                 if state_matrix.dtype == torch.uint8:
                     state_matrix = decode_matrix(state_matrix)

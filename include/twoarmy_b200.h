@@ -282,6 +282,12 @@ int ta_conv1_fwd(const void *x, int x_dtype, int64_t x_stride, const float *w4, 
                  void *y_bf16, void *stream);
 int ta_conv1_bwd(const void *x, int x_dtype, int64_t x_stride, const void *y_bf16, const void *dy_bf16,
                  int64_t batch, float *dw4, float *db4, void *stream);
+/* ta_conv1_fwd with an addend and an optional ReLU: y = act(b4 + w4 . patch(x) + addend), act = ReLU (relu != 0) or the
+ * identity.  The folded first layer is linear in its input channels, so a first convolution with 8 input channels
+ * (Net_PPO_Predictor_actor / _critic, soa/agent/net/all_net.py:249-305: 4 current + 4 predicted frames) is two passes
+ * over 4 channels each: the second half without bias / ReLU, then the first half with the result as addend. */
+int ta_conv1_fwd_add(const void *x, int x_dtype, int64_t x_stride, const float *w4, const float *b4, int64_t batch,
+                     const void *addend_bf16, int relu, void *y_bf16, void *stream);
 /* Parity planes.  The data gradient of a k x k (k = 3, 4) stride-2 unpadded convolution splits by the parity (pa, pb)
  * of the input pixel: dx[2i+pa][2j+pb] only receives the taps ky = pa, kx = pb (mod 2), from dz[i - ky/2][j - kx/2] --
  * a stride-1 convolution of dz with a <= 2x2 sub-kernel.  All four classes come out of ONE stride-1 convolution

@@ -711,3 +711,50 @@ def test_fused_pred_states_tracks_fp32_modules():
     agent.autocast = True
     assert got.shape == want.shape == (50, 4, 289) and got.dtype == torch.float32
     assert float((got - want).abs().max()) < 0.03 * max(1.0, float(want.abs().max()))
+
+
+def test_stem8_matches_unfused_layers():
+    """The predictor agent's 8-channel TINet stem (conv1._Stem8: the folded first layer as two 4-channel passes joined by
+    an addend, conv2 / conv3 with parity-plane data gradients, the first layer's weight gradient once per half) against the
+    SAME network in fp32 (upsample + cuDNN layers, no autocast): its forward / gradient errors must not exceed those of
+    the unfused bf16-autocast path (upsample + cuDNN in bf16, which also rounds the layer's input) by more than half
+    plus 1 % -- two bf16 evaluations of one network differ from each other by several per cent (ReLUs near zero flip)."""
+    import os
+    import twoarmy_b200 as pkg
+    P = _ppo()
+    torch.manual_seed(0)
+    net = P.TINet(in_frames=8).cuda()
+    g = torch.Generator().manual_seed(2)
+    B = 301
+    codes = torch.tensor([0, 1, 2, 4], dtype=torch.uint8)[torch.randint(0, 4, (B, 4, 289), generator=g)].cuda()
+    pred = (torch.rand((B, 4, 289), generator=g) * 1.8 - 0.9).cuda()
+    x8 = torch.cat([P.decode_matrix(codes).float(), pred], 1).contiguous()
+    pos = torch.rand((B, 4, 2), generator=g).cuda() * 16
+    goal = torch.rand((B, 2), generator=g).cuda() * 16
+    gy = None
+    outs = {}
+    prms = [net.cnn_base[i].weight for i in (0, 2, 4)] + [net.cnn_base[i].bias for i in (0, 2, 4)]
+    names = ("conv1.weight", "conv2.weight", "conv3.weight", "conv1.bias", "conv2.bias", "conv3.bias")
+    old_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for mode in ("fp32", "bf16_unfused", "bf16_fused"):
+            os.environ["TA_STEM8"] = "1" if mode == "bf16_fused" else "0"
+            for prm in net.parameters():
+                prm.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode != "fp32"):
+                y = net(x8, pos, goal)
+            if gy is None:
+                gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).cuda()
+            (y.float() * gy).sum().backward()
+            outs[mode] = (y.detach().float().clone(), [prm.grad.detach().float().clone() for prm in prms])
+    finally:
+        os.environ.pop("TA_STEM8", None)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    ref_y, ref_g = outs["fp32"]
+    err = {m: {"forward": float((outs[m][0] - ref_y).norm() / ref_y.norm()),
+               **{n: float((a - b).norm() / b.norm()) for n, a, b in zip(names, outs[m][1], ref_g)}} for m in ("bf16_unfused", "bf16_fused")}
+    print("relative errors against fp32", err)
+    for k, v in err["bf16_fused"].items():
+        assert v <= 1.5 * err["bf16_unfused"][k] + 0.01, (k, err)
+    assert pkg._capi.lib().ta_debug_conv1_tc_failed() == 0
