@@ -302,6 +302,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the rollout / 7x7-view secondary measurements")
     ap.add_argument("--no-ppo", action="store_true", help="skip extra.ppo (the PPO rollout+update loop)")
+    ap.add_argument("--no-ppo-predictor", action="store_true", help="skip extra.ppo_predictor (BASELINE configs[4] at 8192 envs x 32 steps)")
+    ap.add_argument("--no-aux", action="store_true", help="skip extra.aux (featuriser / advantage kernels against the HBM roofline)")
     ap.add_argument("--rollout-T", type=int, default=16)
     ap.add_argument("--workload", default="step", choices=["step", "ppo", "aux"])
     ap.add_argument("--ppo-envs", type=int, default=16384, help="GLOBAL env count of the PPO workload")
@@ -586,6 +588,18 @@ def main():
     # ---- the PPO rollout+update loop (second half of BASELINE.json's metric) --------------
     if not args.no_ppo:
         extra["ppo"] = ppo_measure(args, rank, world, dev, dist)
+    # ---- PPO + frozen frame predictor (BASELINE configs[4]) under the same world: 8192 envs GLOBAL x 32 steps, K_epochs 2
+    if not args.no_ppo and not args.no_ppo_predictor:
+        import copy
+        pa = copy.copy(args)
+        pa.ppo_predictor, pa.ppo_envs, pa.ppo_horizon, pa.ppo_epochs, pa.ppo_steps = True, 8192, 32, 2, 2
+        extra["ppo_predictor"] = ppo_measure(pa, rank, world, dev, dist)
+    # ---- featuriser / advantage kernels against the HBM roofline (one GPU: the kernels do not communicate) ----
+    if world == 1 and not args.no_aux:
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import aux_kernels_bench
+        extra["aux"] = aux_kernels_bench.measure()
 
     if rank != 0:
         if dist:

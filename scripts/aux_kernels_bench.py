@@ -32,7 +32,8 @@ def timeit(fn, reps=48, warm=8):
     return e0.elapsed_time(e1) / (reps // 8 * 8) * 1e-3  # seconds
 
 
-def main():
+def measure():
+    """The table as a dict (bench.py puts it under extra.aux of its default line)."""
     adv_mod = importlib.import_module(pkg.__name__ + ".advantage")
     dev = torch.device("cuda:0")
     peak = 6536.7
@@ -112,7 +113,14 @@ def main():
         byt = 25 * T * N + 4 * N
         out[f"gae_norm_{tag}"] = {"us": s * 1e6, "alg_bytes": byt, "gbs": byt / s / 1e9, "frac": byt / s / 1e9 / peak}
         del r, v, d
-    print(json.dumps(out))
+    for e in envs:
+        e.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    print(json.dumps(measure()))
 
 
 if __name__ == "__main__":
