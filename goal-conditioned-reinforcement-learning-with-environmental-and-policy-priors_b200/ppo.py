@@ -593,7 +593,7 @@ class PPO:
         step(idx)
         torch.cuda.synchronize(self.device)
         out = {}
-        self._probe_events = []
+        self._probe_events = None
         try:
             from torch.profiler import ProfilerActivity, profile
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -610,10 +610,19 @@ class PPO:
             out["profiler_error"] = f"{type(exc).__name__}: {exc}"[:200]
             step(idx)
             torch.cuda.synchronize(self.device)
-        if self._probe_events:
-            out["allreduce_us_per_optimizer_step"] = {n: e0.elapsed_time(e1) * 1e3 for n, e0, e1 in self._probe_events}
-        self._probe_events = None
         import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            # each gradient bucket's collective timed alone with CUDA events, in a step of its own that all ranks enter
+            # together (inside the profiled step the ranks' CUPTI start-up skews them by tens of milliseconds, and a
+            # collective's time includes the wait for the slowest rank)
+            dist.barrier(group=group)
+            torch.cuda.synchronize(self.device)
+            self._probe_events = []
+            step(idx)
+            torch.cuda.synchronize(self.device)
+            if self._probe_events:
+                out["allreduce_us_per_optimizer_step"] = {n: e0.elapsed_time(e1) * 1e3 for n, e0, e1 in self._probe_events}
+            self._probe_events = None
         if self._fused is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             # the collective on its own (nothing else on the GPU): one network's whole flat gradient buffer, best of 5
             res = {}
