@@ -100,3 +100,73 @@ def test_pre_transition_records_replay_the_reference_loop():
                     break
                 t += 1
         assert sorted(got.get(e, [])) == sorted(want), e
+
+
+def test_fold_decoder_tail_is_exact():
+    """ConvTranspose2d(16, 1, 4, 2) + AvgPool2d(4) == the 3x3 stride-2 padding-1 convolution predictor.fold_decoder_tail
+    builds (what ta_pred_decoder's last stage computes), in float64."""
+    import torch.nn.functional as F
+    M = _mod()
+    torch.manual_seed(0)
+    dec = M.Net_Decoder().double()
+    x = torch.randn(3, 16, 33, 33, dtype=torch.float64)
+    with torch.no_grad():
+        want = dec.pool(dec.cnn_base[4](x))
+        taps, b = M.fold_decoder_tail(dec.cnn_base[4].weight.detach(), dec.cnn_base[4].bias.detach())
+        got = F.conv2d(x, taps.permute(2, 0, 1).unsqueeze(0), b.reshape(1), stride=2, padding=1)
+    assert want.shape == got.shape == (3, 1, 17, 17)
+    assert float((want - got).abs().max()) < 1e-12
+
+
+def test_hand_scheduled_lstm_matches_nn_lstm():
+    """LSTM._fast_forward (the GPU path's schedule: one input-gate GEMM per layer for the teacher-forced steps, a recurrent
+    GEMM + cell update per step, [x | h] GEMMs for the self-fed steps) in fp32 on the CPU == the reference's forward
+    through torch.nn.LSTM (all_net.py:76-98), with non-zero initial states."""
+    M = _mod()
+    torch.manual_seed(0)
+    m = M.LSTM()
+    m.h_0, m.c_0 = torch.randn(3, 1024) * 0.1, torch.randn(3, 1024) * 0.1
+    z = torch.randn(5, 4, 64, 4, 4)
+    with torch.no_grad():
+        want, zc = m(z)
+        got = m._fast_forward(z.reshape(5, 4, 1024), torch.float32).reshape(5, 7, 64, 4, 4)
+    assert want.shape == got.shape and zc.shape == (5, 4, 1024)
+    assert float((want - got).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_stack_arrays_fold_eval_batchnorm_and_layouts():
+    """ppo_predictor._stack_arrays (what ta_pred_encoder / ta_pred_decoder read): convolution taps in [ky][kx][ci][co]
+    order and eval-mode BatchNorm + bias folded into scale / shift reproduce the modules layer by layer (float32, CPU)."""
+    import torch.nn.functional as F
+    M = _mod()
+    torch.manual_seed(1)
+    agent = M.ppo_predictor(device="cpu", autocast=False)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for m in agent.encoder.cnn_base:
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    agent.encoder.eval(); agent.decoder.eval()
+    e, d = agent._stack_arrays()
+    enc, dec = agent.encoder.cnn_base, agent.decoder.cnn_base
+    with torch.no_grad():
+        x = torch.randn(2, 1, 68, 68, generator=g)
+        for (ci, w_key, s_key, t_key, stride) in ((0, "w1", "s1", "t1", 2), (3, "w2", "s2", "t2", 4), (6, "w3", "s3", "t3", 2)):
+            conv, bn = enc[ci], enc[ci + 1]
+            want = torch.relu(bn(conv(x)))
+            w = e[w_key].reshape(conv.weight.shape) if w_key == "w1" else e[w_key].permute(3, 2, 0, 1)   # back to [co][ci][ky][kx]
+            got = torch.relu(F.conv2d(x, w, None, stride=stride) * e[s_key].view(1, -1, 1, 1) + e[t_key].view(1, -1, 1, 1))
+            assert float((want - got).abs().max()) < 1e-4 * max(1.0, float(want.abs().max())), w_key
+            x = want
+        z = torch.randn(2, 64, 4, 4, generator=g)
+        for (ci, w_key, b_key, stride) in ((0, "w1", "b1", 2), (2, "w2", "b2", 4)):
+            want = torch.relu(dec[ci](z))
+            got = torch.relu(F.conv_transpose2d(z, d[w_key].permute(2, 3, 0, 1), d[b_key], stride=stride))      # [ci][co][ky][kx]
+            assert float((want - got).abs().max()) < 1e-5 * max(1.0, float(want.abs().max())), w_key
+            z = want
+        want = agent.decoder.pool(dec[4](z))
+        got = F.conv2d(z, d["w3"].permute(2, 0, 1).unsqueeze(0), torch.tensor([d["b3"]]), stride=2, padding=1)
+        assert float((want - got).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
