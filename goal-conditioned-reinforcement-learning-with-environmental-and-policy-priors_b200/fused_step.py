@@ -53,13 +53,14 @@ class FusedNet:
 
     # parameter order of net.parameters(): cnn_base.{0,2,4,6}.{weight,bias}, positionnet, fc0, fc1, head
     NAMES = ("w1", "b1", "w2", "b2", "w3", "b3", "w4c", "b4c", "wpos", "bpos", "wfc0", "bfc0", "wfc1", "bfc1", "wh", "bh")
+    IN_CH = 4    # input channels of the first convolution (FusedNet8: 8)
 
     def __init__(self, net: torch.nn.Module, kind: str, lr: float, eps: float):
         assert kind in ("actor", "critic")
         self.net, self.kind = net, kind
         self.lr, self.eps, self.betas = float(lr), float(eps), (0.9, 0.999)
         params = list(net.parameters())
-        assert len(params) == 16 and params[0].shape == (64, 4, 4, 4) and params[10].shape == (256, 2304)
+        assert len(params) == 16 and params[0].shape == (64, self.IN_CH, 4, 4) and params[10].shape == (256, 2304)
         dev = params[0].device
         self.device = dev
         self.nh = params[14].shape[0]                       # 5 (actor) / 1 (critic)
@@ -179,7 +180,7 @@ class FusedNet:
         a.nh = self.nh
         _capi.check(self._L.ta_tinet_grad(C.byref(a), self._st()), "ta_tinet_grad")
 
-    def forward_backward(self, sb, pg16, loss_fn, reduce_fn=None):
+    def forward_backward(self, sb, pg16, loss_fn, reduce_fn=None, extra=None):
         """sb uint8 [B,4,289] codes, pg16 bf16 [B,16]; loss_fn(head_out bf16 [B,8], d_out bf16 [B,8], db_head fp32 view)
         launches the loss kernel.  Leaves every gradient in self.G32 and the mean loss in self.loss.
         reduce_fn(flat_slice, last) is the gradient all-reduce hook: it is called with the late layers' slice of G32
@@ -190,9 +191,7 @@ class FusedNet:
         p16, g32 = self.p16, self.g32
         bf = torch.bfloat16
         # ---------------- forward
-        y1 = torch.empty((B, 33, 33, 64), dtype=bf, device=dev)
-        mask = torch.empty((B * 289 * 8,), dtype=torch.int32, device=dev)
-        _capi.check(L.ta_conv1_fwd_mask(_ptr(sb), 1, sb.stride(0), _ptr(self.w4), _ptr(self.b4), B, _ptr(y1), _ptr(mask), st), "ta_conv1_fwd_mask")
+        y1, mask = self._conv1_forward(sb, extra, B)
         y1v = y1.permute(0, 3, 1, 2)
         y2 = torch.cudnn_convolution_relu(y1v, p16["w2"], p16["b2"], [2, 2], [0, 0], [1, 1], 1)       # [B,64,16,16] channels-last
         y3 = torch.cudnn_convolution_relu(y2, p16["w3"], p16["b3"], [2, 2], [0, 0], [1, 1], 1)        # [B,128,7,7]
@@ -243,14 +242,29 @@ class FusedNet:
         dz2v = dz2.permute(0, 3, 1, 2)
         gw2 = torch.ops.aten.convolution_backward(dz2v, y1v, p16["w2"], None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
                                                   [False, True, False])[1].contiguous(memory_format=torch.channels_last)
+        self._stem_backward(dz2, dz2v, sb, extra, y1, mask, gw2, gw3, B)
+        if reduce_fn is not None:
+            reduce_fn(self.G32[:self.off[6]], True)
+        return self.loss
+
+    def _conv1_forward(self, sb, extra, B):
+        """LUT decode + Upsample(4) + conv1 + bias + ReLU on tcgen05 with the ReLU bit mask: (y1 bf16 [B,33,33,64], mask)."""
+        L, st, dev = self._L, self._st(), self.device
+        y1 = torch.empty((B, 33, 33, 64), dtype=torch.bfloat16, device=dev)
+        mask = torch.empty((B * 289 * 8,), dtype=torch.int32, device=dev)
+        _capi.check(L.ta_conv1_fwd_mask(_ptr(sb), 1, sb.stride(0), _ptr(self.w4), _ptr(self.b4), B, _ptr(y1), _ptr(mask), st), "ta_conv1_fwd_mask")
+        return y1, mask
+
+    def _stem_backward(self, dz2, dz2v, sb, extra, y1, mask, gw2, gw3, B):
+        """conv2's data gradient and conv1's weight / bias gradient; the stem's weight gradients into the flat fp32 buffer."""
+        L, st, dev = self._L, self._st(), self.device
+        bf = torch.bfloat16
         if self.tc_dgrad and self.stem_bwd_fused:
             # conv2's data gradient and conv1's weight / bias gradient in ONE tcgen05 kernel: the 605 MB of planes stay on the SM
             _capi.check(L.ta_conv2_dgrad_conv1_bwd(_ptr(dz2), _ptr(self.wimg2), _ptr(mask), _ptr(sb), 1, sb.stride(0), B,
                                                    _ptr(self.dw4), _ptr(self.db4), st), "ta_conv2_dgrad_conv1_bwd")
             self._finalise(conv1=True, dense=((gw2, "w2"), (gw3, "w3")))
-            if reduce_fn is not None:
-                reduce_fn(self.G32[:self.off[6]], True)
-            return self.loss
+            return
         if self.tc_dgrad:   # per-class tap lists on tcgen05 (warp-specialised), conv1's ReLU mask applied in the epilogue; class-major planes
             p2 = torch.empty((4, B * 289, 64), dtype=bf, device=dev)
             # (conv1's ReLU mask is applied by ta_conv1_bwd_planes, where it costs one multiply per word; in this kernel's
@@ -262,9 +276,6 @@ class FusedNet:
                                           _ptr(self.dw4), _ptr(self.db4), st), "ta_conv1_bwd_planes")
         # ---------------- the stem's weight gradients into the flat fp32 buffer
         self._finalise(conv1=True, dense=((gw2, "w2"), (gw3, "w3")))
-        if reduce_fn is not None:
-            reduce_fn(self.G32[:self.off[6]], True)
-        return self.loss
 
     def adam(self, grad_scale: float = 1.0):
         b1, b2 = self.betas
@@ -295,8 +306,88 @@ class FusedNet:
             self.step_t.fill_(float(e["step"]))
 
 
+class FusedNet8(FusedNet):
+    """FusedNet for the predictor agent's networks (Net_PPO_Predictor_actor / _critic, all_net.py:249-305): the first
+    convolution has 8 input channels -- the 4 current frames (uint8 codes) and the 4 predicted ones (float).  The folded
+    layer is linear in its input channels: forward = two passes of the 4-channel kernel joined by an addend
+    (ta_conv1_fwd_add), backward = conv2's data gradient as class-major parity planes (ta_conv2_dgrad_planes) read by the
+    tcgen05 weight-gradient kernel once per half with y1 as the ReLU mask (ta_conv1_bwd_planes); ta_tinet_prep /
+    ta_tinet_grad fold / unfold each half of the weight through its element strides."""
+
+    IN_CH = 8
+
+    def __init__(self, net, kind, lr, eps):
+        dev = next(net.parameters()).device
+        self.w4b = torch.empty((256, 16), dtype=torch.float32, device=dev)
+        self.b4_unused = torch.empty((256,), dtype=torch.float32, device=dev)
+        self.b4_zero = torch.zeros((256,), dtype=torch.float32, device=dev)
+        self.dw4b = torch.empty((256, 16), dtype=torch.float32, device=dev)
+        self.db4b = torch.empty((256,), dtype=torch.float32, device=dev)
+        self.gb1_unused = torch.empty((64,), dtype=torch.float32, device=dev)
+        super().__init__(net, kind, lr, eps)
+
+    def _prep(self):
+        super()._prep()                       # folds input channels 0..3 (the strides step over all 8) and the other forms
+        w1 = self.p32["w1"]
+        a = _PrepArgs()
+        a.w1, a.b1 = w1.data_ptr() + 4 * w1.stride(1) * 4, self.p32["b1"].data_ptr()      # channels 4..7
+        a.s_o, a.s_c, a.s_y, a.s_x = w1.stride()
+        a.w4, a.b4 = self.w4b.data_ptr(), self.b4_unused.data_ptr()
+        a.fc0, a.fc0p = self.p16["wfc0"].data_ptr(), self.fc0p.data_ptr()                 # (rewritten with the same values)
+        a.pos, a.pos16 = self.p16["wpos"].data_ptr(), self.pos16.data_ptr()
+        a.head, a.head_b = self.p16["wh"].data_ptr(), self.p16["bh"].data_ptr()
+        a.head8, a.head_b8 = self.head8.data_ptr(), self.head_b8.data_ptr()
+        a.nh = self.nh
+        _capi.check(self._L.ta_tinet_prep(C.byref(a), self._st()), "ta_tinet_prep")
+
+    def _conv1_forward(self, sb, extra, B):
+        L, st, dev = self._L, self._st(), self.device
+        assert extra is not None and extra.dtype == torch.float32 and extra.shape == (B, 4, 289) and extra.is_contiguous()
+        zb = torch.empty((B, 33, 33, 64), dtype=torch.bfloat16, device=dev)
+        y1 = torch.empty_like(zb)
+        _capi.check(L.ta_conv1_fwd_add(_ptr(extra), 0, extra.stride(0), _ptr(self.w4b), _ptr(self.b4_zero), B, None, 0, _ptr(zb), st),
+                    "ta_conv1_fwd_add")
+        _capi.check(L.ta_conv1_fwd_add(_ptr(sb), 1, sb.stride(0), _ptr(self.w4), _ptr(self.b4), B, _ptr(zb), 1, _ptr(y1), st),
+                    "ta_conv1_fwd_add")
+        return y1, None
+
+    def _stem_backward(self, dz2, dz2v, sb, extra, y1, mask, gw2, gw3, B):
+        L, st, dev = self._L, self._st(), self.device
+        if self.tc_dgrad:
+            p2 = torch.empty((4, B * 289, 64), dtype=torch.bfloat16, device=dev)
+            _capi.check(L.ta_conv2_dgrad_planes(_ptr(dz2), _ptr(self.wimg2), None, B, 1, _ptr(p2), st), "ta_conv2_dgrad_planes")
+        else:
+            p2 = F.conv2d(dz2v, self.pcw2, padding=1).permute(0, 2, 3, 1).contiguous()
+        cm = 1 if self.tc_dgrad else 0
+        _capi.check(L.ta_conv1_bwd_planes(_ptr(sb), 1, sb.stride(0), _ptr(y1), None, _ptr(p2), cm, B, _ptr(self.dw4), _ptr(self.db4), st),
+                    "ta_conv1_bwd_planes")
+        _capi.check(L.ta_conv1_bwd_planes(_ptr(extra), 0, extra.stride(0), _ptr(y1), None, _ptr(p2), cm, B, _ptr(self.dw4b), _ptr(self.db4b), st),
+                    "ta_conv1_bwd_planes")
+        self._finalise(conv1=True, dense=((gw2, "w2"), (gw3, "w3")))     # channels 0..3 of w1, b1, w2, w3
+        g_w1 = self.g32["w1"]
+        a = _GradArgs()
+        a.dw4, a.db4 = self.dw4b.data_ptr(), self.db4b.data_ptr()
+        a.g_w1, a.g_b1 = g_w1.data_ptr() + 4 * g_w1.stride(1) * 4, self.gb1_unused.data_ptr()   # channels 4..7; the bias is counted once
+        a.s_o, a.s_c, a.s_y, a.s_x = g_w1.stride()
+        a.nh = self.nh
+        _capi.check(L.ta_tinet_grad(C.byref(a), st), "ta_tinet_grad")
+
+
 def supported(agent) -> bool:
-    """The hand-scheduled step covers the plain PPO agent on a GPU under bf16 autocast (4-frame TINet)."""
+    """The hand-scheduled step covers the plain PPO agent (4-frame TINet, FusedNet) and the predictor agent (8-channel
+    first convolution, FusedNet8; TA_PPO_FUSED8=0 keeps it on the autograd path) on a GPU under bf16 autocast."""
+    import os
     from . import ppo as _ppo
-    return (type(agent) is _ppo.PPO and agent.device.type == "cuda" and agent.autocast and not agent.use_grad_clip
-            and isinstance(agent.actor, _ppo.Net_PPO_actor) and isinstance(agent.critic, _ppo.Net_PPO_critic))
+    if not (agent.device.type == "cuda" and agent.autocast and not agent.use_grad_clip):
+        return False
+    if type(agent) is _ppo.PPO:
+        return isinstance(agent.actor, _ppo.Net_PPO_actor) and isinstance(agent.critic, _ppo.Net_PPO_critic)
+    if type(agent).__name__ == "ppo_predictor" and os.environ.get("TA_PPO_FUSED8", "1") == "1":
+        return bool(getattr(agent, "_pred_valid", False)) and agent.actor.bone1.cnn_base[0].weight.shape[1] == 8
+    return False
+
+
+def make(agent, net, kind, lr, eps):
+    """FusedNet or FusedNet8 for one of the agent's networks."""
+    cls = FusedNet8 if next(net.parameters()).shape[1] == 8 else FusedNet
+    return cls(net, kind, lr, eps)

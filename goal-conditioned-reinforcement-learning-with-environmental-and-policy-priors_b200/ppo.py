@@ -649,8 +649,8 @@ class PPO:
         if not (self.fused_step and fused_step.supported(self)):
             return None
         if self._fused is None:
-            self._fused = {"actor": fused_step.FusedNet(self.actor, "actor", self.lr, 1e-5),
-                           "critic": fused_step.FusedNet(self.critic, "critic", self.lr, 1e-5)}
+            self._fused = {"actor": fused_step.make(self, self.actor, "actor", self.lr, 1e-5),
+                           "critic": fused_step.make(self, self.critic, "critic", self.lr, 1e-5)}
             for name, fn in self._fused.items():      # the all-reduce operand is the fused net's flat gradient buffer
                 self._flat[name] = fn.G32
                 opt = self.optimizer_actor if name == "actor" else self.optimizer_critic
@@ -673,6 +673,8 @@ class PPO:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(group)
         self._step_key = None
+        pred_table = self._pred_table if (fa.IN_CH == 8 and getattr(self, "_pred_valid", False)) else None
+        assert (fa.IN_CH == 8) == (pred_table is not None)
         if self.keep_graph and self.use_graph and src is None:
             # everything the step reads besides the (large, caller-owned) frame codes `s` moves into persistent tensors, so
             # that a graph captured over them can be replayed by later update() calls on the same rollout buffer
@@ -686,7 +688,8 @@ class PPO:
             st_t = self._static["t"]
             p, g, a, old_a_logp, adv, target_v = (st_t[k] for k in ("p", "g", "a", "old_a_logp", "adv", "target_v"))
             self._step_key = (sig, s.data_ptr(), tuple(s.shape), tuple(s.stride()), world, id(group), fa.lr, fc.lr, clip, ent,
-                              id(fa), id(fc), fa.tc_dgrad, fa.stem_bwd_fused, None if streams is None else tuple(id(x) for x in streams))
+                              id(fa), id(fc), fa.tc_dgrad, fa.stem_bwd_fused, None if streams is None else tuple(id(x) for x in streams),
+                              None if pred_table is None else pred_table.data_ptr())
 
         def step(idx):
             bs = idx.numel()
@@ -699,6 +702,10 @@ class PPO:
             tv_mb = torch.empty(bs, dtype=torch.float32, device=dev)
             _capi.check(L.ta_gather_minibatch(ptr(s), ptr(p), ptr(g), ptr(a), ptr(old_a_logp), ptr(adv), ptr(target_v), ptr(idx), ptr(src), bs,
                                               ptr(sb), ptr(pg16), ptr(a_mb), ptr(old_mb), ptr(adv_mb), ptr(tv_mb), st()), "ta_gather_minibatch")
+
+            extra = None
+            if pred_table is not None:   # the predictor agent: the 4 predicted frames of the gathered records (fused_step.FusedNet8)
+                extra = pred_table.index_select(0, idx if src is None else src[idx]).float()
 
             def actor_loss(out, d_out, db_head):
                 _capi.check(L.ta_ppo_actor_loss(ptr(out), ptr(a_mb), ptr(old_mb), ptr(adv_mb), bs, clip, ent, ptr(d_out), ptr(fa.loss),
@@ -727,7 +734,7 @@ class PPO:
                         for w in works:
                             w.wait()
 
-                fn.forward_backward(sb, pg16, loss_fn, reduce if world > 1 else None)
+                fn.forward_backward(sb, pg16, loss_fn, reduce if world > 1 else None, extra)
                 fn.adam(1.0 / world)          # the SUM's 1 / world is folded into Adam's gradient read
                 return fn.loss
 
@@ -743,7 +750,7 @@ class PPO:
                     lc = part(fc, "critic", self.critic, critic_loss)
                 for sx in streams:
                     cur.wait_stream(sx)
-                for t in (sb, pg16, a_mb, old_mb, adv_mb, tv_mb, idx):   # read on the side streams
+                for t in (sb, pg16, a_mb, old_mb, adv_mb, tv_mb, idx) + (() if extra is None else (extra,)):   # read on the side streams
                     t.record_stream(streams[0]); t.record_stream(streams[1])
             return la, lc
 

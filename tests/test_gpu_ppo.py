@@ -758,3 +758,67 @@ def test_stem8_matches_unfused_layers():
     for k, v in err["bf16_fused"].items():
         assert v <= 1.5 * err["bf16_unfused"][k] + 0.01, (k, err)
     assert pkg._capi.lib().ta_debug_conv1_tc_failed() == 0
+
+
+def test_fused8_step_gradients_match_autograd_step():
+    """The predictor agent under the hand-scheduled step (fused_step.FusedNet8: the 8-channel first layer as two passes of
+    the folded 4-channel kernels, everything else as FusedNet) on one minibatch against the fp32 autograd step and the bf16
+    autograd step (conv1._Stem8), same weights, same per-row predictions: the fused step's distance to the fp32 gradient
+    is at most 1.5 x the bf16 autograd step's + 1 % for every parameter -- both halves of conv1's weight included."""
+    import os
+    import twoarmy_b200 as pkg
+    M = importlib.import_module(pkg.__name__ + ".predictor")
+    n = 512
+    buf = {k: v.cuda() for k, v in _random_buffer(n, 7).items()}
+    grads, losses = {}, {}
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for mode in ("fp32", "autograd", "fused"):
+            torch.manual_seed(0)
+            agent = M.ppo_predictor(device="cuda:0", autocast=mode != "fp32")
+            with torch.no_grad():
+                for prm in agent.predictor.recurrent_model.parameters():
+                    prm.mul_(3.0)
+                for net in (agent.encoder, agent.decoder):
+                    for m in net.cnn_base:
+                        if hasattr(m, "weight") and m.weight.dim() == 4:
+                            m.weight.mul_(4.0)
+            os.environ["TA_PPO_FUSED8"] = "1" if mode == "fused" else "0"
+            agent.clip_param = 1e9
+            for opt in (agent.optimizer_actor, agent.optimizer_critic):
+                opt.param_groups[0]["lr"] = 0.0
+            step, B, bs, _ = agent._make_step(buf, minibatch=n)
+            if mode == "fp32":      # the other two read the bf16 table; give fp32 the same predictions (its own differ by bf16 rounding)
+                pass
+            la, lc = step(torch.arange(n, device="cuda"))
+            torch.cuda.synchronize()
+            assert (agent._fused is not None) == (mode == "fused")
+            if mode == "fused":
+                assert type(agent._fused["actor"]).__name__ == "FusedNet8"
+            losses[mode] = (float(la), float(lc))
+            grads[mode] = [p.grad.detach().float().clone() for net in (agent.actor, agent.critic) for p in net.parameters()]
+            names = [f"{nn}.{k}" for nn, net in (("actor", agent.actor), ("critic", agent.critic)) for k, _ in net.named_parameters()]
+            agent._end_update()
+    finally:
+        os.environ.pop("TA_PPO_FUSED8", None)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    print("losses", losses)
+    for k in (0, 1):
+        assert losses["fused"][k] == pytest.approx(losses["autograd"][k], rel=1e-2, abs=1e-3), losses
+        assert losses["fused"][k] == pytest.approx(losses["fp32"][k], rel=5e-2, abs=5e-3), losses
+    bad = {}
+    for name, ref, a, f in zip(names, grads["fp32"], grads["autograd"], grads["fused"]):
+        nr = max(float(ref.norm()), 1e-12)
+        ea, ef = float((a - ref).norm()) / nr, float((f - ref).norm()) / nr
+        print(f"{name:40s} |g| {nr:.3e}   bf16 autograd vs fp32 {ea:.4f}   fused vs fp32 {ef:.4f}")
+        if ef > 1.5 * ea + 1e-2:
+            bad[name] = (round(ea, 4), round(ef, 4))
+    # both halves of the first layer's weight gradient individually (a missing or doubled half would hide in the norm above)
+    for net_i in (0, 16):
+        ref, f = grads["fp32"][net_i], grads["fused"][net_i]
+        for half in (slice(0, 4), slice(4, 8)):
+            assert float((f[:, half] - ref[:, half]).norm()) <= 0.25 * float(ref[:, half].norm()) + 1e-12, (net_i, half)
+    assert not bad, bad
+    assert pkg._capi.lib().ta_debug_conv1_tc_failed() == 0
